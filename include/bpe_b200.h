@@ -1,0 +1,134 @@
+/* include/bpe_b200.h — C ABI of the B200-native BPE engine (libbpe_b200.so).
+ *
+ * Drop-in boundary for dbtreasure/zig-bpe's BasicTokenizer hot path. The reference has no
+ * FFI of its own (it is one Zig struct, src/basic_tokenizer.zig:52-349); this header is the
+ * thin layer its Zig host code binds with `extern fn` so that
+ *   BasicTokenizer.train   (src/basic_tokenizer.zig:140-153, hot loop :172-306)
+ *   BasicTokenizer.encode  (src/basic_tokenizer.zig:71-88)
+ *   BasicTokenizer.decode  (src/basic_tokenizer.zig:90-138)
+ * run on the GPU while the struct, allocator discipline, file I/O and merge (de)serialisation
+ * (src/basic_tokenizer.zig:319-348) stay on the host side.
+ *
+ * Conventions: plain pointers and sizes only; every host output buffer is allocated by the
+ * caller from the bounds documented per call; the library never returns memory it allocated;
+ * all device memory is owned by the bpe_ctx. A bpe_ctx is not thread-safe; distinct contexts
+ * are independent. There is no CPU fallback: every entry point fails with BPE_ERR_CUDA when
+ * no usable sm_100-class device is present.
+ */
+#ifndef BPE_B200_H
+#define BPE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bpe_ctx bpe_ctx;
+
+/* = `Merge{ pair: CharPair{first,second}, new_token }` (src/basic_tokenizer.zig:12-15,40-43), 6 bytes */
+typedef struct bpe_merge_t {
+    uint16_t first;
+    uint16_t second;
+    uint16_t new_token;
+} bpe_merge_t;
+
+/* Fills the reference's TimeStats buckets (src/utils/time_statistics.zig:4-34) from CUDA-event
+ * timings: pair counting -> just_count_pairs, argmax + tie-break -> sort_pairs,
+ * merge + compaction -> replace_pair; generate_pairs is always 0 (pairs are formed in registers). */
+typedef struct bpe_stats_t {
+    double sort_pairs_ms;
+    double replace_pair_ms;
+    double generate_pairs_ms;
+    double just_count_pairs_ms;
+    uint64_t sort_pairs_calls;
+    uint64_t replace_pair_calls;
+    uint64_t generate_pairs_calls;
+    uint64_t just_count_pairs_calls;
+    double total_ms;          /* whole call, host clock */
+    double device_ms;         /* resident-in-HBM -> merge list on host (CUDA events) */
+    uint64_t scanned_slots;   /* sum over merge steps of resident token slots scanned (roofline numerator / 2 B) */
+    uint64_t kernel_launches; /* kernels launched by this call */
+    uint64_t tie_steps;       /* steps whose top count was shared by >= 2 pairs */
+    uint64_t tie_slow_steps;  /* of those, resolved by the full table replay */
+    uint64_t compactions;
+} bpe_stats_t;
+
+enum {
+    BPE_OK = 0,
+    BPE_ERR_INVALID_VOCAB = 1, /* TrainError.InvalidVocabSize (src/basic_tokenizer.zig:147-149) */
+    BPE_ERR_OOM = 2,           /* TrainError.OutOfMemory: host or device allocation, or output cap too small */
+    BPE_ERR_INVALID_TOKEN = 3, /* error.InvalidToken (src/basic_tokenizer.zig:101,125,135) */
+    BPE_ERR_CUDA = 4,          /* CUDA / NCCL failure, or no device (no reference equivalent) */
+    BPE_ERR_INVALID_ARG = 5,   /* null pointer, bad option name, ... */
+    BPE_ERR_INTERNAL = 7       /* self-check failed (verify mode) */
+};
+
+/* ---- context ------------------------------------------------------------------------- */
+/* One context = one GPU (CUDA device ordinal `device`) and one stream. */
+int bpe_ctx_create(bpe_ctx** out, int device);
+/* Multi-GPU: one process (or thread) per GPU; `rank`-th contiguous shard of the corpus goes to
+ * rank `rank`. `nccl_unique_id` is the 128-byte ncclUniqueId obtained from
+ * bpe_nccl_unique_id() on rank 0 and broadcast by the caller (torch.distributed, MPI, ...). */
+int bpe_ctx_create_dist(bpe_ctx** out, int device, int rank, int world, const void* nccl_unique_id);
+int bpe_nccl_unique_id(void* out128);
+void bpe_ctx_destroy(bpe_ctx* ctx);
+/* Message for the last non-OK status returned on this context ("" if none). ctx may be NULL
+ * to get the message of the last failed bpe_ctx_create*. */
+const char* bpe_last_error(const bpe_ctx* ctx);
+
+/* Options (all default 0 unless noted):
+ *   "verify_recount"      1: after every merge step recount all pairs from the token sequence
+ *                            and compare with the incrementally maintained table (debug)
+ *   "force_slow_tiebreak" 1: resolve every tie step with the full table replay
+ *   "check_tiebreak"      1: on fast-path tie steps also run the replay and compare (debug)
+ *   "compact_pct"         live/slots percentage below which the sequence is compacted (default 85)
+ *   "table_log2"          log2 of the initial pair-table capacity (default: sized from n)
+ *   "max_steps"           stop training after this many merges (0 = no limit)
+ */
+int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value);
+
+/* ---- train (src/basic_tokenizer.zig:140-153; loop :172-205) -------------------------------
+ * text[n] bytes on the host. vocab_size as in the reference (u16; < 256 -> BPE_ERR_INVALID_VOCAB).
+ * out_merges: capacity vocab_size-256 entries. out_counts (nullable): count of the winning pair
+ * per merge, what the reference prints in verbose mode (:308-317). *out_n = merges learned
+ * (fewer than vocab_size-256 when the sequence runs out of pairs, :188-191).
+ * n == 0 or 1: zero merges (the reference underflows at :246 for n == 0; defined here as
+ * "no pairs"). In a dist context every rank passes its own shard and receives the same merges. */
+int bpe_train(bpe_ctx* ctx, const uint8_t* text, size_t n, uint16_t vocab_size,
+              bpe_merge_t* out_merges, uint64_t* out_counts, size_t* out_n, bpe_stats_t* stats);
+/* Same, text already resident in device memory (device pointer on ctx's device). */
+int bpe_train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t vocab_size,
+                     bpe_merge_t* out_merges, uint64_t* out_counts, size_t* out_n, bpe_stats_t* stats);
+
+/* ---- encode (src/basic_tokenizer.zig:71-88) ----------------------------------------------
+ * Applies merges[0..m) in list order, one left-to-right greedy pass each, exactly as the
+ * reference does. out: capacity n ids. In a dist context each rank encodes its own shard;
+ * shards are independent byte ranges, so shard boundaries are token boundaries. */
+int bpe_encode(bpe_ctx* ctx, const uint8_t* text, size_t n, const bpe_merge_t* merges, size_t m,
+               uint16_t* out, size_t* out_n, bpe_stats_t* stats);
+/* d_text and d_out (capacity n ids) are device pointers. */
+int bpe_encode_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bpe_merge_t* merges, size_t m,
+                      uint16_t* d_out, size_t* out_n, bpe_stats_t* stats);
+
+/* ---- decode (src/basic_tokenizer.zig:90-138) ---------------------------------------------
+ * ids < 256 are bytes; other ids expand through the first merge whose new_token matches
+ * (findMerge :109-116); unknown id -> BPE_ERR_INVALID_TOKEN. bpe_decode_size returns the byte
+ * length so the caller can allocate; bpe_decode writes at most cap bytes (BPE_ERR_OOM and the
+ * needed size in *out_n if cap is too small). */
+int bpe_decode_size(bpe_ctx* ctx, const uint16_t* toks, size_t n, const bpe_merge_t* merges, size_t m,
+                    size_t* out_n);
+int bpe_decode(bpe_ctx* ctx, const uint16_t* toks, size_t n, const bpe_merge_t* merges, size_t m,
+               uint8_t* out, size_t cap, size_t* out_n, bpe_stats_t* stats);
+/* d_toks and d_out are device pointers. */
+int bpe_decode_device(bpe_ctx* ctx, const uint16_t* d_toks, size_t n, const bpe_merge_t* merges, size_t m,
+                      uint8_t* d_out, size_t cap, size_t* out_n, bpe_stats_t* stats);
+
+/* Library / build identification, e.g. "bpe_b200 0.1 sm_100a". */
+const char* bpe_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPE_B200_H */

@@ -1,0 +1,188 @@
+// bpe_common.cuh — shared types, constants and small device helpers of the B200 BPE engine.
+//
+// Data layout in HBM:
+//   tok[]      resident token sequence, u16 ids (the reference's own width,
+//              src/basic_tokenizer.zig:162), HOLE = 0xFFFF marks a merged-away slot. train() can
+//              only create ids 256..65534 (vocabSize is u16 and ids stop at vocabSize-1), so
+//              0xFFFF is never a live id during training; encode switches to the u32 instantiation
+//              when a merge list mentions id 65535.
+//   pair table open-addressing hash table key -> count, key = first | second << 16 (the same 4
+//              bytes the reference hashes, src/basic_tokenizer.zig:40-43)
+//   zig cnt[]  per-home-slot population of the *reference's* hash table (Zig 0.13 AutoHashMap,
+//              Wyhash low bits), kept so the reference's tie-break (lowest slot among the
+//              max-count pairs, src/basic_tokenizer.zig:193,291-303) can be decided on the GPU.
+#pragma once
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef BPE_EMUL
+#include "cuda_emul.hpp"
+#else
+#include <cuda_runtime.h>
+#define BPE_LAUNCH(kern, grid, block, stream, ...) kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define BPE_LAUNCH_NS(kern, grid, block, stream, ...) kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
+
+namespace bpe {
+
+// ---- geometry ----------------------------------------------------------------------------
+#ifndef BPE_TILE
+#define BPE_TILE 4096  // token slots per tile (one CTA pass)
+#endif
+#ifndef BPE_THREADS
+#define BPE_THREADS 256
+#endif
+constexpr int TILE = BPE_TILE;
+constexpr int THREADS = BPE_THREADS;
+constexpr int SPT = TILE / THREADS;  // slots per thread
+static_assert(TILE % THREADS == 0, "tile must be a multiple of the block size");
+static_assert(SPT % 8 == 0 || SPT == 4 || SPT == 2 || SPT == 1, "slots per thread");
+
+constexpr int MAXTIE = 1024;          // tied keys listed per step; more -> table replay
+constexpr uint32_t EMPTY_KEY = 0xFFFFFFFFu;
+constexpr uint32_t ZCHUNK = 1024;     // reference-table slots per chunk in the occupancy scan
+
+template <class T> struct TokTraits;
+template <> struct TokTraits<uint16_t> { static constexpr uint32_t hole = 0xFFFFu; };
+template <> struct TokTraits<uint32_t> { static constexpr uint32_t hole = 0xFFFFFFFFu; };
+
+__host__ __device__ __forceinline__ uint32_t pair_key(uint32_t first, uint32_t second) {
+    return (first & 0xFFFFu) | (second << 16);
+}
+
+// error flags raised by kernels (StepCtl::err)
+enum : uint32_t {
+    ERR_TABLE_FULL = 1u << 0,
+    ERR_KEY_MISSING = 1u << 1,
+    ERR_COUNT_UNDERFLOW = 1u << 2,
+    ERR_VERIFY_MISMATCH = 1u << 3,
+    ERR_ZCNT_OVERFLOW = 1u << 4,
+};
+
+// tie-resolution verdicts (StepCtl::tie_status)
+enum : uint32_t { TIE_NONE = 0, TIE_FAST_OK = 1, TIE_NEED_REPLAY = 2 };
+
+// Device-resident control block: written by kernels, read back by the host once per step.
+struct StepCtl {
+    // current merge (A,B) -> X, set by the host (or the tie kernel) before the merge kernel
+    uint32_t A, B, X;
+    // argmax result
+    uint32_t max_count;
+    uint32_t ntied;        // number of keys with count == max_count (may exceed MAXTIE)
+    // table state
+    uint32_t live_keys;    // keys with count > 0 (= distinct adjacent pairs, D)
+    uint32_t n_inserted;   // keys ever inserted (load factor of our table)
+    // merge-step by-products
+    uint32_t cntXX;        // adjacent merged occurrences ("ABAB" -> "XX")
+    uint32_t cntAB;        // merged occurrences
+    uint32_t err;
+    // tie fast path
+    uint32_t tie_status;
+    uint32_t tie_winner;   // key
+    uint32_t last_pair_pos;  // slot index of the left token of the last pair (replay edge case)
+    uint32_t verify_mismatch;
+    uint32_t pad[2];
+    uint32_t tie_keys[MAXTIE];
+};
+
+// Per-tile neighbourhood, produced by halo_kernel before each merge pass: what a tile needs to
+// know about live tokens outside itself. hole value = "no such token" (sequence start/end).
+template <class TokT> struct TileHalo {
+    TokT l2, l1;      // last two live tokens before the tile (l1 nearest)
+    TokT r0, r1, r2;  // first three live tokens after the tile
+    uint32_t runA;    // A==B steps: number of consecutive live A immediately before the tile
+};
+
+// ---- pair table --------------------------------------------------------------------------
+struct PairTable {
+    uint32_t* keys;    // EMPTY_KEY when free
+    uint32_t* counts;
+    uint32_t mask;     // capacity - 1
+};
+
+__host__ __device__ __forceinline__ uint32_t tbl_hash(uint32_t k) {
+    k ^= k >> 16; k *= 0x85ebca6bu; k ^= k >> 13; k *= 0xc2b2ae35u; k ^= k >> 16;
+    return k;
+}
+
+// returns slot of key, or EMPTY_KEY if absent
+__device__ __forceinline__ uint32_t tbl_find(const PairTable& t, uint32_t key) {
+    uint32_t s = tbl_hash(key) & t.mask;
+    for (uint32_t probes = 0; probes <= t.mask; probes++) {
+        uint32_t k = ((volatile const uint32_t*)t.keys)[s];
+        if (k == key) return s;
+        if (k == EMPTY_KEY) return EMPTY_KEY;
+        s = (s + 1) & t.mask;
+    }
+    return EMPTY_KEY;
+}
+
+// returns slot of key, inserting it (count 0) if absent; EMPTY_KEY if the table is full
+__device__ __forceinline__ uint32_t tbl_find_or_insert(const PairTable& t, uint32_t key, uint32_t* n_inserted) {
+    uint32_t s = tbl_hash(key) & t.mask;
+    for (uint32_t probes = 0; probes <= t.mask; probes++) {
+        uint32_t k = ((volatile const uint32_t*)t.keys)[s];
+        if (k == key) return s;
+        if (k == EMPTY_KEY) {
+            uint32_t old = atomicCAS(&t.keys[s], EMPTY_KEY, key);
+            if (old == EMPTY_KEY) { atomicAdd(n_inserted, 1u); return s; }
+            if (old == key) return s;
+        }
+        s = (s + 1) & t.mask;
+    }
+    return EMPTY_KEY;
+}
+
+// ---- Zig 0.13 std.hash.Wyhash of the 4 key bytes, seed 0 ------
+// len = 4 -> a = b = (x << 32) | x, x = the key bytes as a little-endian u32 = pair_key().
+__host__ __device__ __forceinline__ void wy_mum(uint64_t a, uint64_t b, uint64_t* lo, uint64_t* hi) {
+#if defined(__CUDA_ARCH__)
+    *lo = a * b;
+    *hi = __umul64hi(a, b);
+#else
+    __uint128_t r = (__uint128_t)a * (__uint128_t)b;
+    *lo = (uint64_t)r;
+    *hi = (uint64_t)(r >> 64);
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t zig_hash_pair(uint32_t key) {
+    const uint64_t S0 = 0xa0761d6478bd642fULL, S1 = 0xe7037ed1a0b428dbULL;
+    uint64_t lo, hi;
+    wy_mum(S0, S1, &lo, &hi);       // seed 0: state0 = 0 ^ mix(0 ^ S0, S1)
+    const uint64_t st0 = lo ^ hi;
+    uint64_t a = ((uint64_t)key << 32) | (uint64_t)key;
+    uint64_t b = a;
+    a ^= S1;
+    b ^= st0;
+    wy_mum(a, b, &lo, &hi);
+    uint64_t x = lo ^ S0 ^ 4ULL, y = hi ^ S1;
+    wy_mum(x, y, &lo, &hi);
+    return lo ^ hi;
+}
+
+// capacity of the reference's table holding d distinct keys when no growth is pending
+// (Appendix A.3/A.4): smallest power of two >= 8 with floor(cap*80/100) >= d.
+__host__ __device__ __forceinline__ uint32_t zig_cap_for(uint32_t d) {
+    uint32_t cap = 8;
+    while ((uint64_t)cap * 80 / 100 < d) cap <<= 1;
+    return cap;
+}
+__host__ __device__ __forceinline__ uint32_t zig_max_load(uint32_t cap) { return (uint32_t)((uint64_t)cap * 80 / 100); }
+
+// population of reference home slots, two u16 counters per u32 word
+__device__ __forceinline__ void zcnt_add(uint32_t* zcnt, uint32_t zmask, uint32_t key, int delta, uint32_t* err) {
+    uint32_t h = (uint32_t)zig_hash_pair(key) & zmask;
+    uint32_t sh = (h & 1u) * 16u;
+    if (delta > 0) {
+        uint32_t old = atomicAdd(&zcnt[h >> 1], 1u << sh);
+        if (((old >> sh) & 0xFFFFu) == 0xFFFFu) atomicOr(err, (uint32_t)ERR_ZCNT_OVERFLOW);
+    } else {
+        atomicSub(&zcnt[h >> 1], 1u << sh);
+    }
+}
+__device__ __forceinline__ uint32_t zcnt_get(const uint32_t* zcnt, uint32_t h) {
+    return (zcnt[h >> 1] >> ((h & 1u) * 16u)) & 0xFFFFu;
+}
+
+}  // namespace bpe

@@ -1,0 +1,688 @@
+// bpe_engine.cu — host side of libbpe_b200.so: context, train / encode / decode drivers and the
+// C ABI of include/bpe_b200.h. Kernels live in bpe_kernels.cuh.
+//
+// Reference call stack replaced (src/basic_tokenizer.zig): train :140-153 -> expandVocabulary
+// :172-205 -> {generate :234-255, count :257-278, sort :280-306, replace :207-232} per merge;
+// encode :71-88; decode :90-138.
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bpe_b200.h"
+#include "bpe_kernels.cuh"
+#include "tiebreak_host.hpp"
+#include "dist_comm.hpp"
+
+using namespace bpe;
+
+// -----------------------------------------------------------------------------------------
+// context
+// -----------------------------------------------------------------------------------------
+struct bpe_ctx {
+    int device = 0;
+    cudaStream_t stream = 0;
+    std::string err;
+    // options
+    long verify_recount = 0, force_slow_tiebreak = 0, check_tiebreak = 0, compact_pct = 85, table_log2 = 0,
+         max_steps = 0, time_phases = 0;
+    DistComm dist;  // world == 1 when single GPU
+    uint64_t launches = 0;
+};
+
+static std::string g_create_err;
+
+static int fail(bpe_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, BPE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) {
+        if (p) { cudaFree(p); p = nullptr; }
+        bytes = n;
+        return cudaMalloc(&p, n ? n : 1);
+    }
+    template <class T> T* as() const { return (T*)p; }
+};
+struct HostBuf {
+    void* p = nullptr;
+    ~HostBuf() { if (p) cudaFreeHost(p); }
+    cudaError_t alloc(size_t n) { return cudaMallocHost(&p, n ? n : 1); }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+static inline unsigned grid_for(size_t n, int threads, unsigned max_blocks = 148 * 16) {
+    size_t b = (n + (size_t)threads - 1) / (size_t)threads;
+    if (b < 1) b = 1;
+    if (b > max_blocks) b = max_blocks;
+    return (unsigned)b;
+}
+static inline size_t round_up(size_t n, size_t m) { return (n + m - 1) / m * m; }
+static inline double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// -----------------------------------------------------------------------------------------
+// token sequence + per-tile scratch shared by train and encode
+// -----------------------------------------------------------------------------------------
+template <class TokT> struct Sequence {
+    DevBuf buf[2];
+    int cur = 0;
+    size_t cap_slots = 0;   // allocated slots per buffer (multiple of TILE)
+    size_t n_slots = 0;     // slots in use (multiple of TILE)
+    uint64_t live = 0;      // live tokens (host view; may lag the device by one step)
+    DevBuf halo, run_local, run_full, tile_live, tile_off, total;
+    TokT* tok() const { return buf[cur].as<TokT>(); }
+    TokT* other() const { return buf[cur ^ 1].as<TokT>(); }
+    uint32_t ntiles() const { return (uint32_t)(n_slots / TILE); }
+};
+
+template <class TokT>
+static int seq_init(bpe_ctx* ctx, Sequence<TokT>& sq, const uint8_t* d_text, size_t n) {
+    sq.cap_slots = round_up(n ? n : 1, TILE);
+    sq.n_slots = sq.cap_slots;
+    sq.live = n;
+    CU(sq.buf[0].alloc(sq.cap_slots * sizeof(TokT)));
+    CU(sq.buf[1].alloc(sq.cap_slots * sizeof(TokT)));
+    size_t nt = sq.cap_slots / TILE;
+    CU(sq.halo.alloc(nt * sizeof(TileHalo<TokT>)));
+    CU(sq.run_local.alloc(nt * sizeof(uint32_t)));
+    CU(sq.run_full.alloc(nt));
+    CU(sq.tile_live.alloc(nt * sizeof(uint32_t)));
+    CU(sq.tile_off.alloc(nt * sizeof(unsigned long long)));
+    CU(sq.total.alloc(sizeof(unsigned long long)));
+    BPE_LAUNCH_NS(widen_kernel<TokT>, grid_for(sq.cap_slots, 256), 256, ctx->stream, d_text, n, sq.tok(), sq.cap_slots);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return BPE_OK;
+}
+
+// squeeze holes out; *new_live receives the live count measured on the device
+template <class TokT>
+static int seq_compact(bpe_ctx* ctx, Sequence<TokT>& sq, uint64_t* new_live) {
+    const uint32_t nt = sq.ntiles();
+    BPE_LAUNCH(tile_count_kernel<TokT>, nt, THREADS, ctx->stream, sq.tok(), sq.tile_live.template as<uint32_t>());
+    BPE_LAUNCH(tile_scan_kernel, 1, THREADS, ctx->stream, sq.tile_live.template as<uint32_t>(), nt,
+               sq.tile_off.template as<unsigned long long>(), sq.total.template as<unsigned long long>());
+    BPE_LAUNCH((compact_scatter_kernel<TokT, TokT>), nt, THREADS, ctx->stream, sq.tok(),
+               sq.tile_off.template as<unsigned long long>(), sq.other());
+    ctx->launches += 3;
+    unsigned long long total = 0;
+    CU(cudaMemcpyAsync(&total, sq.total.p, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    size_t ns = round_up(total ? (size_t)total : 1, TILE);
+    if (ns > (size_t)total) {
+        BPE_LAUNCH_NS(fill_holes_kernel<TokT>, grid_for(ns - total, 256), 256, ctx->stream, sq.other(), (size_t)total, ns);
+        ctx->launches++;
+    }
+    CU(cudaGetLastError());
+    sq.cur ^= 1;
+    sq.n_slots = ns;
+    sq.live = total;
+    if (new_live) *new_live = total;
+    return BPE_OK;
+}
+
+// -----------------------------------------------------------------------------------------
+// pair table (+ reference-home population)
+// -----------------------------------------------------------------------------------------
+struct TableMem {
+    DevBuf keys, counts, zcnt, chunkfn;
+    uint32_t cap = 0;
+    uint32_t zcap = 0;  // capacity of the reference's table that zcnt currently models (0 = stale)
+    PairTable view() const { PairTable t; t.keys = keys.as<uint32_t>(); t.counts = counts.as<uint32_t>(); t.mask = cap - 1; return t; }
+    uint32_t zmask() const { return zcap ? zcap - 1 : 0; }
+};
+
+static int table_alloc(bpe_ctx* ctx, TableMem& tm, uint32_t cap) {
+    tm.cap = cap;
+    tm.zcap = 0;
+    CU(tm.keys.alloc((size_t)cap * 4));
+    CU(tm.counts.alloc((size_t)cap * 4));
+    CU(tm.zcnt.alloc((size_t)cap * 4));  // 2*cap u16 home counters: enough for zig cap <= 2*cap
+    CU(tm.chunkfn.alloc(((size_t)2 * cap / ZCHUNK + 1) * sizeof(ChunkFn)));
+    CU(cudaMemsetAsync(tm.keys.p, 0xFF, (size_t)cap * 4, ctx->stream));
+    CU(cudaMemsetAsync(tm.counts.p, 0, (size_t)cap * 4, ctx->stream));
+    return BPE_OK;
+}
+
+// make zcnt model the reference table capacity for d live keys (rebuild only when it changes)
+static int table_ensure_zcnt(bpe_ctx* ctx, TableMem& tm, StepCtl* d_ctl, uint32_t d) {
+    uint32_t want = zig_cap_for(d);
+    if (want == tm.zcap) return BPE_OK;
+    if ((size_t)want > (size_t)2 * tm.cap) return fail(ctx, BPE_ERR_INTERNAL, "reference table capacity %u exceeds zcnt buffer", want);
+    tm.zcap = want;
+    CU(cudaMemsetAsync(tm.zcnt.p, 0, std::max<size_t>((size_t)want * 2, 4), ctx->stream));
+    BPE_LAUNCH_NS(zig_rebuild_kernel, grid_for(tm.cap, 256), 256, ctx->stream, tm.view(), tm.zcnt.as<uint32_t>(), tm.zmask(), d_ctl);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return BPE_OK;
+}
+
+// -----------------------------------------------------------------------------------------
+// train
+// -----------------------------------------------------------------------------------------
+struct PhaseTimer {  // CUDA-event phase buckets (only when time_phases is on)
+    bool on = false;
+    cudaEvent_t ev[2];
+    cudaStream_t st = 0;
+    void init(bool enable, cudaStream_t s) { on = enable; st = s; if (on) { cudaEventCreate(&ev[0]); cudaEventCreate(&ev[1]); } }
+    ~PhaseTimer() { if (on) { cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]); } }
+    void begin() { if (on) cudaEventRecord(ev[0], st); }
+    void end(double* acc, uint64_t* calls) {
+        if (!on) return;
+        cudaEventRecord(ev[1], st);
+        cudaEventSynchronize(ev[1]);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev[0], ev[1]);
+        *acc += ms;
+        (*calls)++;
+    }
+};
+
+__global__ void set_merge_kernel(StepCtl* ctl, uint32_t A, uint32_t B, uint32_t X) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->A = A; ctl->B = B; ctl->X = X; }
+}
+__global__ void reset_argmax_kernel(StepCtl* ctl) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->max_count = 0; ctl->ntied = 0; ctl->tie_status = TIE_NONE; }
+}
+// folds cntXX/cntAB into the table through apply_kernel's arguments being device-resident:
+// the wrapper reads them on the device so no host round trip sits between merge and apply.
+__global__ void apply_from_ctl_kernel(PairTable tbl, uint32_t* cntL, uint32_t* cntR, StepCtl* ctl,
+                                      uint32_t* zcnt, uint32_t zmask, uint32_t n_ids, uint32_t* merged_out) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t A = ctl->A, B = ctl->B, X = ctl->X;
+    if (p < n_ids) {
+        uint32_t c = cntL[p];
+        if (c) {
+            cntL[p] = 0;
+            tbl_sub(tbl, pair_key(p, A), c, ctl, zcnt, zmask);
+            tbl_add(tbl, pair_key(p, X), c, ctl, zcnt, zmask);
+        }
+        c = cntR[p];
+        if (c) {
+            cntR[p] = 0;
+            tbl_sub(tbl, pair_key(B, p), c, ctl, zcnt, zmask);
+            tbl_add(tbl, pair_key(X, p), c, ctl, zcnt, zmask);
+        }
+    }
+    if (p == 0) {
+        const uint32_t xx = ctl->cntXX, ab = ctl->cntAB;
+        if (xx) {
+            tbl_sub(tbl, pair_key(B, A), xx, ctl, zcnt, zmask);
+            tbl_add(tbl, pair_key(X, X), xx, ctl, zcnt, zmask);
+        }
+        if (ab) tbl_sub(tbl, pair_key(A, B), ab, ctl, zcnt, zmask);
+        *merged_out = ab;
+        ctl->cntXX = 0;
+        ctl->cntAB = 0;
+    }
+}
+
+struct TrainRun {
+    bpe_ctx* ctx;
+    Sequence<uint16_t> sq;
+    TableMem tm;
+    DevBuf cntL, cntR, hist, ctl, merged, firstpos, recount, live_chk;
+    HostBuf h_ctl;
+    bpe_stats_t st;
+    StepCtl* d_ctl() const { return ctl.as<StepCtl>(); }
+    StepCtl* hc() const { return h_ctl.as<StepCtl>(); }
+};
+
+static int read_ctl(bpe_ctx* ctx, TrainRun& R, bool with_ties) {
+    size_t bytes = with_ties ? sizeof(StepCtl) : offsetof(StepCtl, tie_keys) + 8 * sizeof(uint32_t);
+    CU(cudaMemcpyAsync(R.h_ctl.p, R.ctl.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BPE_OK;
+}
+
+static int launch_halo(bpe_ctx* ctx, Sequence<uint16_t>& sq, StepCtl* d_ctl, bool aeqb) {
+    const uint32_t nt = sq.ntiles();
+    const uint16_t H = 0xFFFF;
+    BPE_LAUNCH_NS(halo_kernel<uint16_t>, grid_for(nt, 128, 1u << 30), 128, ctx->stream, sq.tok(), sq.n_slots, nt,
+                  sq.halo.as<TileHalo<uint16_t>>(), d_ctl, aeqb ? 1 : 0, sq.run_local.as<uint32_t>(),
+                  sq.run_full.as<uint8_t>(), H, H, H, H, H);
+    ctx->launches++;
+    if (aeqb) {
+        BPE_LAUNCH_NS(run_chain_kernel<uint16_t>, 1, 1, ctx->stream, nt, sq.halo.as<TileHalo<uint16_t>>(),
+                      sq.run_local.as<uint32_t>(), sq.run_full.as<uint8_t>(), 0u);
+        ctx->launches++;
+    }
+    CU(cudaGetLastError());
+    return BPE_OK;
+}
+
+// full table replay for one tie step (see tiebreak_host.hpp)
+static int replay_winner(bpe_ctx* ctx, TrainRun& R, const std::vector<uint32_t>& tied_hint, uint32_t max_count,
+                         uint32_t* winner) {
+    int rc = launch_halo(ctx, R.sq, R.d_ctl(), false);
+    if (rc) return rc;
+    const uint32_t cap = R.tm.cap;
+    if (R.firstpos.bytes < (size_t)cap * 4) CU(R.firstpos.alloc((size_t)cap * 4));
+    CU(cudaMemsetAsync(R.firstpos.p, 0xFF, (size_t)cap * 4, ctx->stream));
+    CU(cudaMemsetAsync(&R.d_ctl()->last_pair_pos, 0, 4, ctx->stream));
+    FirstPosOp op; op.tbl = R.tm.view(); op.firstpos = R.firstpos.as<uint32_t>(); op.ctl = R.d_ctl();
+    BPE_LAUNCH((pair_visit_kernel<uint16_t, FirstPosOp>), R.sq.ntiles(), THREADS, ctx->stream, R.sq.tok(),
+               R.sq.halo.as<TileHalo<uint16_t>>(), op);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    std::vector<uint32_t> keys(cap), counts(cap), fpos(cap);
+    CU(cudaMemcpyAsync(keys.data(), R.tm.keys.p, (size_t)cap * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(counts.data(), R.tm.counts.p, (size_t)cap * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(fpos.data(), R.firstpos.p, (size_t)cap * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    rc = read_ctl(ctx, R, false);
+    if (rc) return rc;
+    if (R.hc()->err) return fail(ctx, BPE_ERR_INTERNAL, "device error flags 0x%x during replay", R.hc()->err);
+    std::vector<ReplayKey> rk;
+    std::vector<uint32_t> tied;
+    for (uint32_t i = 0; i < cap; i++) {
+        if (keys[i] == EMPTY_KEY || counts[i] == 0) continue;
+        if (fpos[i] == 0xFFFFFFFFu) return fail(ctx, BPE_ERR_INTERNAL, "live pair without occurrence");
+        ReplayKey k; k.key = keys[i]; k.home_hash = (uint32_t)zig_hash_pair(keys[i]); k.first_pos = fpos[i];
+        rk.push_back(k);
+        if (counts[i] == max_count) tied.push_back(keys[i]);
+    }
+    (void)tied_hint;
+    ZigTableReplay rep;
+    rep.run(rk, R.hc()->last_pair_pos);
+    uint32_t w = rep.winner(rk, tied);
+    if (w == ZigTableReplay::NONE) return fail(ctx, BPE_ERR_INTERNAL, "replay found no tied key");
+    *winner = w;
+    return BPE_OK;
+}
+
+static int verify_state(bpe_ctx* ctx, TrainRun& R, uint32_t step) {
+    int rc = launch_halo(ctx, R.sq, R.d_ctl(), false);
+    if (rc) return rc;
+    const uint32_t cap = R.tm.cap;
+    if (R.recount.bytes < (size_t)cap * 4) CU(R.recount.alloc((size_t)cap * 4));
+    if (!R.live_chk.p) CU(R.live_chk.alloc(4));
+    CU(cudaMemsetAsync(R.recount.p, 0, (size_t)cap * 4, ctx->stream));
+    CU(cudaMemsetAsync(R.live_chk.p, 0, 4, ctx->stream));
+    RecountOp op; op.tbl = R.tm.view(); op.recount = R.recount.as<uint32_t>(); op.ctl = R.d_ctl();
+    BPE_LAUNCH((pair_visit_kernel<uint16_t, RecountOp>), R.sq.ntiles(), THREADS, ctx->stream, R.sq.tok(),
+               R.sq.halo.as<TileHalo<uint16_t>>(), op);
+    BPE_LAUNCH_NS(verify_counts_kernel, grid_for(cap, 256), 256, ctx->stream, R.tm.view(), R.recount.as<uint32_t>(),
+                  R.d_ctl(), R.live_chk.as<uint32_t>());
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    uint32_t live = 0;
+    CU(cudaMemcpyAsync(&live, R.live_chk.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    rc = read_ctl(ctx, R, false);
+    if (rc) return rc;
+    if (R.hc()->err || R.hc()->verify_mismatch || live != R.hc()->live_keys)
+        return fail(ctx, BPE_ERR_INTERNAL, "verify failed after step %u: err=0x%x mismatches=%u live=%u table_live=%u", step,
+                    R.hc()->err, R.hc()->verify_mismatch, live, R.hc()->live_keys);
+    return BPE_OK;
+}
+
+static int grow_table(bpe_ctx* ctx, TrainRun& R) {
+    TableMem nt;
+    uint32_t live = R.hc()->live_keys;
+    uint32_t cap = R.tm.cap;
+    while ((uint64_t)live * 4 > cap) cap <<= 1;  // keep live keys under 25 % after the rebuild
+    int rc = table_alloc(ctx, nt, cap);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(&R.d_ctl()->n_inserted, 0, 4, ctx->stream));
+    BPE_LAUNCH_NS(table_rehash_kernel, grid_for(R.tm.cap, 256), 256, ctx->stream, R.tm.view(), nt.view(), R.d_ctl(), 1);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::swap(R.tm.keys.p, nt.keys.p); std::swap(R.tm.keys.bytes, nt.keys.bytes);
+    std::swap(R.tm.counts.p, nt.counts.p); std::swap(R.tm.counts.bytes, nt.counts.bytes);
+    std::swap(R.tm.zcnt.p, nt.zcnt.p); std::swap(R.tm.zcnt.bytes, nt.zcnt.bytes);
+    std::swap(R.tm.chunkfn.p, nt.chunkfn.p); std::swap(R.tm.chunkfn.bytes, nt.chunkfn.bytes);
+    R.tm.cap = cap;
+    R.tm.zcap = 0;
+    return BPE_OK;
+}
+
+static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t vocab_size, bpe_merge_t* out_merges,
+                        uint64_t* out_counts, size_t* out_n, bpe_stats_t* stats_out) {
+    if (!out_n) return fail(ctx, BPE_ERR_INVALID_ARG, "out_n is null");
+    *out_n = 0;
+    if (vocab_size < 256) return fail(ctx, BPE_ERR_INVALID_VOCAB, "vocab_size %u < 256", (unsigned)vocab_size);
+    size_t want = (size_t)vocab_size - 256;
+    if (ctx->max_steps > 0 && (size_t)ctx->max_steps < want) want = (size_t)ctx->max_steps;
+    if (want && !out_merges) return fail(ctx, BPE_ERR_INVALID_ARG, "out_merges is null");
+    if (n >= 0xFFFFFFF0ull) return fail(ctx, BPE_ERR_INVALID_ARG, "shard of %zu bytes exceeds the 32-bit position range", n);
+    const double t_host0 = now_ms();
+    const uint64_t launches0 = ctx->launches;
+    TrainRun R;
+    R.ctx = ctx;
+    memset(&R.st, 0, sizeof R.st);
+    if (want == 0 || n < 2) {  // no pairs (:188-191; n == 0 underflows in the reference, defined as no pairs)
+        if (stats_out) { *stats_out = R.st; stats_out->total_ms = now_ms() - t_host0; }
+        return BPE_OK;
+    }
+    CU(cudaSetDevice(ctx->device));
+    cudaEvent_t ev0, ev1;
+    CU(cudaEventCreate(&ev0));
+    CU(cudaEventCreate(&ev1));
+    CU(cudaEventRecord(ev0, ctx->stream));
+    PhaseTimer pt;
+    pt.init(ctx->time_phases != 0, ctx->stream);
+
+    int rc = seq_init(ctx, R.sq, d_text, n);
+    if (rc) return rc;
+    CU(R.cntL.alloc(65536 * 4)); CU(R.cntR.alloc(65536 * 4)); CU(R.hist.alloc(65536 * 4));
+    CU(R.ctl.alloc(sizeof(StepCtl))); CU(R.merged.alloc(4));
+    CU(R.h_ctl.alloc(sizeof(StepCtl)));
+    CU(cudaMemsetAsync(R.cntL.p, 0, 65536 * 4, ctx->stream));
+    CU(cudaMemsetAsync(R.cntR.p, 0, 65536 * 4, ctx->stream));
+    CU(cudaMemsetAsync(R.hist.p, 0, 65536 * 4, ctx->stream));
+    CU(cudaMemsetAsync(R.ctl.p, 0, sizeof(StepCtl), ctx->stream));
+    CU(cudaMemsetAsync(R.merged.p, 0, 4, ctx->stream));
+    uint32_t cap = 1u << 19;
+    if (ctx->table_log2 > 0) cap = 1u << ctx->table_log2;
+    else while ((size_t)cap < n / 64 && cap < (1u << 28)) cap <<= 1;
+    rc = table_alloc(ctx, R.tm, cap);
+    if (rc) return rc;
+
+    // initial count (countCodePointPairs :257-278 on the byte sequence)
+    pt.begin();
+    BPE_LAUNCH_NS(byte_pair_hist_kernel, grid_for(n, 256), 256, ctx->stream, d_text, n, -1, R.hist.as<uint32_t>());
+    BPE_LAUNCH_NS(seed_table_kernel, 65536 / 256, 256, ctx->stream, R.hist.as<uint32_t>(), R.tm.view(), R.d_ctl(),
+                  (uint32_t*)nullptr, 0u);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    pt.end(&R.st.just_count_pairs_ms, &R.st.just_count_pairs_calls);
+
+    std::vector<bpe_merge_t> merges;
+    std::vector<uint64_t> mcounts;
+    uint32_t pending_merged = 0;  // merged occurrences of the previous step not yet subtracted from live
+    bool have_pending = false;
+    for (size_t step = 0; step < want; step++) {
+        // ---- argmax (sortCodePointPairs + [0]) ----
+        pt.begin();
+        BPE_LAUNCH_NS(reset_argmax_kernel, 1, 1, ctx->stream, R.d_ctl());
+        BPE_LAUNCH(argmax_kernel, grid_for(R.tm.cap, THREADS), THREADS, ctx->stream, R.tm.view(), R.d_ctl());
+        BPE_LAUNCH_NS(ties_kernel, grid_for(R.tm.cap, 256), 256, ctx->stream, R.tm.view(), R.d_ctl());
+        ctx->launches += 3;
+        CU(cudaGetLastError());
+        if (have_pending) CU(cudaMemcpyAsync(&pending_merged, R.merged.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        rc = read_ctl(ctx, R, true);
+        if (rc) return rc;
+        StepCtl* hc = R.hc();
+        if (hc->err) return fail(ctx, BPE_ERR_INTERNAL, "device error flags 0x%x at step %zu", hc->err, step);
+        if (have_pending) { R.sq.live -= pending_merged; have_pending = false; }
+        if (hc->max_count == 0) { pt.end(&R.st.sort_pairs_ms, &R.st.sort_pairs_calls); break; }  // "No more pairs to merge" (:188-191)
+        uint32_t winner = hc->tie_keys[0];
+        if (hc->ntied > 1) {
+            R.st.tie_steps++;
+            const uint32_t D = hc->live_keys;
+            bool fast_ok = false;
+            uint32_t fast_winner = 0;
+            bool try_fast = !ctx->force_slow_tiebreak && hc->ntied <= (uint32_t)MAXTIE && D != zig_max_load(zig_cap_for(D));
+            if (try_fast) {
+                rc = table_ensure_zcnt(ctx, R.tm, R.d_ctl(), D);
+                if (rc) return rc;
+                const uint32_t zcap = R.tm.zcap;
+                const uint32_t zchunk = zcap < ZCHUNK ? zcap : ZCHUNK;
+                const uint32_t nch = zcap / zchunk;
+                BPE_LAUNCH(zig_chunk_kernel, nch, THREADS, ctx->stream, R.tm.zcnt.as<uint32_t>(), zchunk, R.tm.chunkfn.as<ChunkFn>());
+                BPE_LAUNCH(zig_resolve_kernel, 1, MAXTIE, ctx->stream, R.tm.zcnt.as<uint32_t>(), zcap, zchunk,
+                           R.tm.chunkfn.as<ChunkFn>(), nch, R.d_ctl());
+                ctx->launches += 2;
+                CU(cudaGetLastError());
+                std::vector<uint32_t> tied(hc->tie_keys, hc->tie_keys + hc->ntied);
+                uint32_t maxc = hc->max_count;
+                rc = read_ctl(ctx, R, false);
+                if (rc) return rc;
+                hc = R.hc();
+                if (hc->err) return fail(ctx, BPE_ERR_INTERNAL, "device error flags 0x%x in tie kernels", hc->err);
+                if (hc->tie_status == TIE_FAST_OK) { fast_ok = true; fast_winner = hc->tie_winner; }
+                hc->max_count = maxc;
+            }
+            if (fast_ok && !ctx->check_tiebreak) winner = fast_winner;
+            else {
+                uint32_t maxc = hc->max_count;
+                uint32_t w = 0;
+                rc = replay_winner(ctx, R, std::vector<uint32_t>(), maxc, &w);
+                if (rc) return rc;
+                R.hc()->max_count = maxc;
+                if (fast_ok && w != fast_winner)
+                    return fail(ctx, BPE_ERR_INTERNAL, "tie fast path chose (%u,%u), replay chose (%u,%u) at step %zu",
+                                fast_winner & 0xFFFF, fast_winner >> 16, w & 0xFFFF, w >> 16, step);
+                if (!fast_ok) R.st.tie_slow_steps++;
+                winner = w;
+            }
+            hc = R.hc();
+        }
+        pt.end(&R.st.sort_pairs_ms, &R.st.sort_pairs_calls);
+        const uint32_t A = winner & 0xFFFFu, B = winner >> 16, X = 256u + (uint32_t)step;
+        bpe_merge_t m; m.first = (uint16_t)A; m.second = (uint16_t)B; m.new_token = (uint16_t)X;
+        merges.push_back(m);
+        mcounts.push_back(hc->max_count);
+
+        // ---- housekeeping decided from the status just read ----
+        if ((uint64_t)hc->n_inserted * 2 > R.tm.cap) { rc = grow_table(ctx, R); if (rc) return rc; }
+        if (R.sq.n_slots > (size_t)TILE && R.sq.live * 100 < (uint64_t)R.sq.n_slots * (uint64_t)ctx->compact_pct) {
+            pt.begin();
+            uint64_t live = 0;
+            rc = seq_compact(ctx, R.sq, &live);
+            if (rc) return rc;
+            R.st.compactions++;
+            pt.end(&R.st.replace_pair_ms, &R.st.replace_pair_calls);
+        }
+        // keep the reference-home population current so births/deaths can update it in place
+        rc = table_ensure_zcnt(ctx, R.tm, R.d_ctl(), hc->live_keys);
+        if (rc) return rc;
+
+        // ---- replace (replaceTopPairWithNewToken :207-232) + incremental recount ----
+        pt.begin();
+        BPE_LAUNCH_NS(set_merge_kernel, 1, 1, ctx->stream, R.d_ctl(), A, B, X);
+        ctx->launches++;
+        rc = launch_halo(ctx, R.sq, R.d_ctl(), A == B);
+        if (rc) return rc;
+        if (A == B)
+            BPE_LAUNCH((merge_kernel<uint16_t, true, true>), R.sq.ntiles(), THREADS, ctx->stream, R.sq.tok(),
+                       R.sq.halo.as<TileHalo<uint16_t>>(), R.d_ctl(), R.cntL.as<uint32_t>(), R.cntR.as<uint32_t>());
+        else
+            BPE_LAUNCH((merge_kernel<uint16_t, false, true>), R.sq.ntiles(), THREADS, ctx->stream, R.sq.tok(),
+                       R.sq.halo.as<TileHalo<uint16_t>>(), R.d_ctl(), R.cntL.as<uint32_t>(), R.cntR.as<uint32_t>());
+        ctx->launches++;
+        R.st.scanned_slots += R.sq.n_slots;
+        pt.end(&R.st.replace_pair_ms, &R.st.replace_pair_calls);
+        pt.begin();
+        BPE_LAUNCH_NS(apply_from_ctl_kernel, (X + 1 + 255) / 256, 256, ctx->stream, R.tm.view(), R.cntL.as<uint32_t>(),
+                      R.cntR.as<uint32_t>(), R.d_ctl(), R.tm.zcnt.as<uint32_t>(), R.tm.zmask(), X + 1, R.merged.as<uint32_t>());
+        ctx->launches++;
+        CU(cudaGetLastError());
+        pt.end(&R.st.just_count_pairs_ms, &R.st.just_count_pairs_calls);
+        have_pending = true;
+        if (ctx->verify_recount) { rc = verify_state(ctx, R, (uint32_t)step); if (rc) return rc; }
+    }
+    CU(cudaEventRecord(ev1, ctx->stream));
+    CU(cudaEventSynchronize(ev1));
+    float dev_ms = 0;
+    CU(cudaEventElapsedTime(&dev_ms, ev0, ev1));
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    for (size_t i = 0; i < merges.size(); i++) {
+        out_merges[i] = merges[i];
+        if (out_counts) out_counts[i] = mcounts[i];
+    }
+    *out_n = merges.size();
+    R.st.device_ms = dev_ms;
+    R.st.total_ms = now_ms() - t_host0;
+    R.st.kernel_launches = ctx->launches - launches0;
+    if (stats_out) *stats_out = R.st;
+    return BPE_OK;
+}
+
+// -----------------------------------------------------------------------------------------
+// encode (src/basic_tokenizer.zig:71-88): one merge pass per list entry, in list order
+// -----------------------------------------------------------------------------------------
+template <class TokT>
+static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bpe_merge_t* merges, size_t m,
+                         uint16_t* d_out, size_t* out_n, bpe_stats_t* st) {
+    Sequence<TokT> sq;
+    int rc = seq_init(ctx, sq, d_text, n);
+    if (rc) return rc;
+    DevBuf ctl, dummy;
+    HostBuf h_ctl;
+    CU(ctl.alloc(sizeof(StepCtl)));
+    CU(h_ctl.alloc(sizeof(StepCtl)));
+    CU(cudaMemsetAsync(ctl.p, 0, sizeof(StepCtl), ctx->stream));
+    StepCtl* d_ctl = ctl.as<StepCtl>();
+    StepCtl* hc = h_ctl.as<StepCtl>();
+    const TokT H = (TokT)TokTraits<TokT>::hole;
+    auto one_pass = [&](uint32_t A, uint32_t B, uint32_t X) -> int {
+        BPE_LAUNCH_NS(set_merge_kernel, 1, 1, ctx->stream, d_ctl, A, B, X);
+        const uint32_t nt = sq.ntiles();
+        BPE_LAUNCH_NS(halo_kernel<TokT>, grid_for(nt, 128, 1u << 30), 128, ctx->stream, sq.tok(), sq.n_slots, nt,
+                      sq.halo.template as<TileHalo<TokT>>(), d_ctl, A == B ? 1 : 0, sq.run_local.template as<uint32_t>(),
+                      sq.run_full.template as<uint8_t>(), H, H, H, H, H);
+        ctx->launches += 2;
+        if (A == B) {
+            BPE_LAUNCH_NS(run_chain_kernel<TokT>, 1, 1, ctx->stream, nt, sq.halo.template as<TileHalo<TokT>>(),
+                          sq.run_local.template as<uint32_t>(), sq.run_full.template as<uint8_t>(), 0u);
+            BPE_LAUNCH((merge_kernel<TokT, true, true>), nt, THREADS, ctx->stream, sq.tok(),
+                       sq.halo.template as<TileHalo<TokT>>(), d_ctl, (uint32_t*)nullptr, (uint32_t*)nullptr);
+            ctx->launches += 2;
+        } else {
+            BPE_LAUNCH((merge_kernel<TokT, false, true>), nt, THREADS, ctx->stream, sq.tok(),
+                       sq.halo.template as<TileHalo<TokT>>(), d_ctl, (uint32_t*)nullptr, (uint32_t*)nullptr);
+            ctx->launches++;
+        }
+        if (st) st->scanned_slots += sq.n_slots;
+        return BPE_OK;
+    };
+    (void)one_pass; (void)hc; (void)merges; (void)m; (void)d_out; (void)out_n;
+    return fail(ctx, BPE_ERR_INTERNAL, "encode not wired yet");
+}
+
+// -----------------------------------------------------------------------------------------
+// C ABI
+// -----------------------------------------------------------------------------------------
+extern "C" {
+
+const char* bpe_version(void) {
+#ifdef BPE_EMUL
+    return "bpe_b200 0.1 (CPU emulation build: tests only)";
+#else
+    return "bpe_b200 0.1 sm_100a";
+#endif
+}
+
+const char* bpe_last_error(const bpe_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int bpe_ctx_create(bpe_ctx** out, int device) {
+    bpe_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, BPE_ERR_INVALID_ARG, "out is null");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, BPE_ERR_CUDA, "no CUDA device available (%s): this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev) return fail(nullptr, BPE_ERR_INVALID_ARG, "device %d out of range (have %d)", device, ndev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, BPE_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major < 10) return fail(nullptr, BPE_ERR_CUDA, "device %d (%s) is sm_%d%d; this build needs sm_100", device, prop.name, prop.major, prop.minor);
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, BPE_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    ctx = new bpe_ctx();
+    ctx->device = device;
+    if (cudaStreamCreate(&ctx->stream) != cudaSuccess) { delete ctx; return fail(nullptr, BPE_ERR_CUDA, "cudaStreamCreate failed"); }
+    *out = ctx;
+    return BPE_OK;
+}
+
+int bpe_nccl_unique_id(void* out128) { return dist_unique_id(out128, &g_create_err) ? BPE_OK : BPE_ERR_CUDA; }
+
+int bpe_ctx_create_dist(bpe_ctx** out, int device, int rank, int world, const void* nccl_unique_id) {
+    int rc = bpe_ctx_create(out, device);
+    if (rc) return rc;
+    if (world > 1) {
+        std::string err;
+        if (!(*out)->dist.init(rank, world, nccl_unique_id, (*out)->stream, &err)) {
+            bpe_ctx_destroy(*out);
+            *out = nullptr;
+            return fail(nullptr, BPE_ERR_CUDA, "NCCL init failed: %s", err.c_str());
+        }
+    }
+    return BPE_OK;
+}
+
+void bpe_ctx_destroy(bpe_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    ctx->dist.destroy();
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value) {
+    if (!ctx || !name) return BPE_ERR_INVALID_ARG;
+    std::string s(name);
+    if (s == "verify_recount") ctx->verify_recount = value;
+    else if (s == "force_slow_tiebreak") ctx->force_slow_tiebreak = value;
+    else if (s == "check_tiebreak") ctx->check_tiebreak = value;
+    else if (s == "compact_pct") ctx->compact_pct = value;
+    else if (s == "table_log2") ctx->table_log2 = value;
+    else if (s == "max_steps") ctx->max_steps = value;
+    else if (s == "time_phases") ctx->time_phases = value;
+    else return fail(ctx, BPE_ERR_INVALID_ARG, "unknown option '%s'", name);
+    return BPE_OK;
+}
+
+int bpe_train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t vocab_size, bpe_merge_t* out_merges,
+                     uint64_t* out_counts, size_t* out_n, bpe_stats_t* stats) {
+    if (!ctx) return BPE_ERR_INVALID_ARG;
+    return train_device(ctx, d_text, n, vocab_size, out_merges, out_counts, out_n, stats);
+}
+
+int bpe_train(bpe_ctx* ctx, const uint8_t* text, size_t n, uint16_t vocab_size, bpe_merge_t* out_merges,
+              uint64_t* out_counts, size_t* out_n, bpe_stats_t* stats) {
+    if (!ctx) return BPE_ERR_INVALID_ARG;
+    if (n && !text) return fail(ctx, BPE_ERR_INVALID_ARG, "text is null");
+    const double t0 = now_ms();
+    CU(cudaSetDevice(ctx->device));
+    DevBuf d;
+    if (cudaMalloc(&d.p, n ? n : 1) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", n);
+    CU(cudaMemcpyAsync(d.p, text, n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = train_device(ctx, d.as<uint8_t>(), n, vocab_size, out_merges, out_counts, out_n, stats);
+    if (stats) stats->total_ms = now_ms() - t0;
+    return rc;
+}
+
+int bpe_encode_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bpe_merge_t* merges, size_t m,
+                      uint16_t* d_out, size_t* out_n, bpe_stats_t* stats) {
+    if (!ctx) return BPE_ERR_INVALID_ARG;
+    return encode_passes<uint16_t>(ctx, d_text, n, merges, m, d_out, out_n, stats);
+}
+int bpe_encode(bpe_ctx* ctx, const uint8_t*, size_t, const bpe_merge_t*, size_t, uint16_t*, size_t*, bpe_stats_t*) {
+    return fail(ctx, BPE_ERR_INTERNAL, "encode not wired yet");
+}
+int bpe_decode_size(bpe_ctx* ctx, const uint16_t*, size_t, const bpe_merge_t*, size_t, size_t*) {
+    return fail(ctx, BPE_ERR_INTERNAL, "decode not wired yet");
+}
+int bpe_decode(bpe_ctx* ctx, const uint16_t*, size_t, const bpe_merge_t*, size_t, uint8_t*, size_t, size_t*, bpe_stats_t*) {
+    return fail(ctx, BPE_ERR_INTERNAL, "decode not wired yet");
+}
+int bpe_decode_device(bpe_ctx* ctx, const uint16_t*, size_t, const bpe_merge_t*, size_t, uint8_t*, size_t, size_t*, bpe_stats_t*) {
+    return fail(ctx, BPE_ERR_INTERNAL, "decode not wired yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,665 @@
+// bpe_kernels.cuh — device kernels of the B200 BPE engine (train / encode hot path).
+//
+// Reference functions replaced (all in /root/reference/src/basic_tokenizer.zig):
+//   generateInitialTokens :155-170   -> widen_kernel
+//   generateCodePointPairs :234-255  -> fused away (pairs are formed from the staged tile)
+//   countCodePointPairs :257-278     -> byte_pair_hist_kernel + seed_table_kernel once, then
+//                                       incremental deltas from merge_kernel via apply_kernel
+//   sortCodePointPairs :280-306, [0] :193 -> argmax_kernel + ties_kernel + zig_* tie kernels
+//   replaceTopPairWithNewToken :207-232   -> halo_kernel + merge_kernel (+ compaction kernels)
+//   encode :71-88                    -> the same halo/merge kernels driven by the merge list
+#pragma once
+#include "bpe_common.cuh"
+
+namespace bpe {
+
+// =========================================================================================
+// small block-level helpers (blockDim.x == THREADS unless stated)
+// =========================================================================================
+template <int N>
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* sh /*[N]*/, uint32_t* total) {
+    const int t = threadIdx.x;
+    sh[t] = v;
+    __syncthreads();
+    for (int off = 1; off < N; off <<= 1) {
+        uint32_t add = (t >= off) ? sh[t - off] : 0u;
+        __syncthreads();
+        sh[t] += add;
+        __syncthreads();
+    }
+    uint32_t incl = sh[t];
+    if (total) *total = sh[N - 1];
+    __syncthreads();
+    return incl - v;
+}
+
+// =========================================================================================
+// load: u8 text -> token slots, padded with holes up to a whole number of tiles
+// =========================================================================================
+template <class TokT>
+__global__ void widen_kernel(const uint8_t* __restrict__ text, size_t n, TokT* __restrict__ tok, size_t n_pad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n_pad; i += stride) tok[i] = i < n ? (TokT)text[i] : (TokT)TokTraits<TokT>::hole;
+}
+
+template <class TokT>
+__global__ void fill_holes_kernel(TokT* tok, size_t from, size_t to) {
+    size_t i = from + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < to; i += stride) tok[i] = (TokT)TokTraits<TokT>::hole;
+}
+
+// =========================================================================================
+// initial pair count over bytes: dense 256x256 histogram, hist[first | second << 8]
+// next_byte: first byte of the following shard (multi-GPU), -1 if none
+// =========================================================================================
+__global__ void byte_pair_hist_kernel(const uint8_t* __restrict__ text, size_t n, int next_byte,
+                                      uint32_t* __restrict__ hist) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        uint32_t a = text[i];
+        int b = (i + 1 < n) ? (int)text[i + 1] : next_byte;
+        if (b >= 0) atomicAdd(&hist[a | ((uint32_t)b << 8)], 1u);
+    }
+}
+
+// hist (already summed over GPUs) -> pair table + reference-home population
+__global__ void seed_table_kernel(const uint32_t* __restrict__ hist, PairTable tbl, StepCtl* ctl,
+                                  uint32_t* zcnt, uint32_t zmask) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 65536u) return;
+    uint32_t c = hist[i];
+    if (!c) return;
+    uint32_t key = pair_key(i & 255u, i >> 8);
+    uint32_t s = tbl_find_or_insert(tbl, key, &ctl->n_inserted);
+    if (s == EMPTY_KEY) { atomicOr(&ctl->err, (uint32_t)ERR_TABLE_FULL); return; }
+    atomicAdd(&tbl.counts[s], c);
+    atomicAdd(&ctl->live_keys, 1u);
+    if (zcnt) zcnt_add(zcnt, zmask, key, +1, &ctl->err);
+}
+
+// =========================================================================================
+// argmax over the pair table, then the list of keys that share the maximum
+// =========================================================================================
+__global__ void argmax_kernel(PairTable tbl, StepCtl* ctl) {
+    __shared__ uint32_t sh[THREADS];
+    uint32_t m = 0;
+    size_t cap = (size_t)tbl.mask + 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t c = tbl.counts[i];
+        m = c > m ? c : m;
+    }
+    sh[threadIdx.x] = m;
+    __syncthreads();
+    for (int off = THREADS / 2; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) { uint32_t o = sh[threadIdx.x + off]; if (o > sh[threadIdx.x]) sh[threadIdx.x] = o; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && sh[0]) atomicMax(&ctl->max_count, sh[0]);
+}
+
+__global__ void ties_kernel(PairTable tbl, StepCtl* ctl) {
+    const uint32_t m = ctl->max_count;
+    if (m == 0) return;
+    size_t cap = (size_t)tbl.mask + 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
+        if (tbl.counts[i] == m) {
+            uint32_t idx = atomicAdd(&ctl->ntied, 1u);
+            if (idx < (uint32_t)MAXTIE) ctl->tie_keys[idx] = tbl.keys[i];
+        }
+    }
+}
+
+// =========================================================================================
+// halo_kernel: one thread per tile gathers the live tokens around the tile.
+// ext_*: live tokens beyond this GPU's shard (hole = none). For A==B steps it also measures
+// the run of A that ends at the tile's left edge (run_local / run_full, chained by
+// run_chain_kernel so the cost stays linear on degenerate inputs such as "aaaa...").
+// =========================================================================================
+template <class TokT>
+__global__ void halo_kernel(const TokT* __restrict__ tok, size_t n_slots, uint32_t ntiles, TileHalo<TokT>* halo,
+                            const StepCtl* ctl, int aeqb, uint32_t* run_local, uint8_t* run_full,
+                            TokT ext_l2, TokT ext_l1, TokT ext_r0, TokT ext_r1, TokT ext_r2) {
+    const TokT H = (TokT)TokTraits<TokT>::hole;
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    TileHalo<TokT> h;
+    // left: last two live tokens before slot t*TILE
+    TokT l[2] = {H, H};
+    int nl = 0;
+    for (size_t i = (size_t)t * TILE; i > 0 && nl < 2;) {
+        --i;
+        TokT v = tok[i];
+        if (v != H) l[nl++] = v;
+    }
+    if (nl == 0) { l[0] = ext_l1; l[1] = ext_l2; }
+    else if (nl == 1) { l[1] = ext_l1; }
+    h.l1 = l[0];
+    h.l2 = (l[0] == H) ? H : l[1];
+    // right: first three live tokens at/after slot (t+1)*TILE
+    TokT r[3] = {H, H, H};
+    int nr = 0;
+    for (size_t i = (size_t)(t + 1) * TILE; i < n_slots && nr < 3; i++) {
+        TokT v = tok[i];
+        if (v != H) r[nr++] = v;
+    }
+    const TokT er[3] = {ext_r0, ext_r1, ext_r2};
+    for (int k = 0; nr < 3 && k < 3; k++) {
+        if (er[k] == H) break;
+        r[nr++] = er[k];
+    }
+    h.r0 = r[0]; h.r1 = r[1]; h.r2 = r[2];
+    h.runA = 0;
+    halo[t] = h;
+    if (aeqb) {
+        // live A's walking back from the tile's left edge, inside the previous tile only
+        const TokT A = (TokT)ctl->A;
+        uint32_t cnt = 0;
+        uint8_t full = 1;
+        if (t == 0) { full = 0; }
+        else {
+            size_t lo = (size_t)(t - 1) * TILE;
+            for (size_t i = (size_t)t * TILE; i > lo;) {
+                --i;
+                TokT v = tok[i];
+                if (v == H) continue;
+                if (v == A) cnt++; else { full = 0; break; }
+            }
+        }
+        run_local[t] = cnt;
+        run_full[t] = full;
+    }
+}
+
+// sequential chain over tiles (A==B steps only): runA[t] = A's immediately before tile t
+template <class TokT>
+__global__ void run_chain_kernel(uint32_t ntiles, TileHalo<TokT>* halo, const uint32_t* run_local,
+                                 const uint8_t* run_full, uint32_t ext_run) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    uint32_t run = ext_run;
+    halo[0].runA = run;
+    for (uint32_t t = 1; t < ntiles; t++) {
+        run = run_local[t] + (run_full[t] ? run : 0u);
+        halo[t].runA = run;
+    }
+}
+
+// =========================================================================================
+// tile staging: ext[] = [holes | l2 l1 | TILE slots | r0 r1 r2 | holes], tile data at OFF
+// =========================================================================================
+constexpr int OFF = 8;
+constexpr int EXT = TILE + 16;
+constexpr int EXT_END = OFF + TILE + 3;  // one past the last index that may hold a token
+
+template <class TokT>
+__device__ __forceinline__ void stage_tile(TokT* ext, const TokT* __restrict__ tok, size_t base,
+                                           const TileHalo<TokT>& h) {
+    constexpr int VEC = 16 / sizeof(TokT);
+    const uint4* src = reinterpret_cast<const uint4*>(tok + base);
+    uint4* dst = reinterpret_cast<uint4*>(ext + OFF);
+    for (int i = threadIdx.x; i < TILE / VEC; i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x == 0) {
+        const TokT H = (TokT)TokTraits<TokT>::hole;
+        for (int i = 0; i < OFF - 2; i++) ext[i] = H;
+        ext[OFF - 2] = h.l2;
+        ext[OFF - 1] = h.l1;
+        ext[OFF + TILE + 0] = h.r0;
+        ext[OFF + TILE + 1] = h.r1;
+        ext[OFF + TILE + 2] = h.r2;
+        for (int i = OFF + TILE + 3; i < EXT; i++) ext[i] = H;
+    }
+}
+template <class TokT> __device__ __forceinline__ int next_live(const TokT* ext, int i) {
+    const TokT H = (TokT)TokTraits<TokT>::hole;
+    for (int j = i + 1; j < EXT_END; j++) if (ext[j] != H) return j;
+    return -1;
+}
+template <class TokT> __device__ __forceinline__ int prev_live(const TokT* ext, int i) {
+    const TokT H = (TokT)TokTraits<TokT>::hole;
+    for (int j = i - 1; j >= OFF - 2; j--) if (ext[j] != H) return j;
+    return -1;
+}
+
+// =========================================================================================
+// merge_kernel: replace every occurrence of (A,B) by X, left to right, non-overlapping, exactly
+// as replaceTopPairWithNewToken (:207-232) / the encode pass (:75-85) do. One CTA per tile.
+// Each thread writes only its own slots: the slot holding A becomes X, the slot holding the
+// consumed B becomes a hole. With DELTAS it also emits the count changes of the neighbouring
+// pairs: cntL[p] merges had unmerged left neighbour p ((p,A)-1,(p,X)+1), cntR[n] had right
+// neighbour n that does not start another occurrence ((B,n)-1,(X,n)+1), cntXX adjacent
+// occurrences ((B,A)-1,(X,X)+1), cntAB occurrences ((A,B)-1 each).
+// =========================================================================================
+template <class TokT, bool AEQB, bool DELTAS>
+__global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, const TileHalo<TokT>* __restrict__ halo,
+                                                        StepCtl* ctl, uint32_t* __restrict__ cntL,
+                                                        uint32_t* __restrict__ cntR) {
+    __shared__ __align__(16) TokT ext[EXT];
+    const TokT H = (TokT)TokTraits<TokT>::hole;
+    const TokT A = (TokT)ctl->A, B = (TokT)ctl->B, X = (TokT)ctl->X;
+    const size_t base = (size_t)blockIdx.x * TILE;
+    const TileHalo<TokT> h = halo[blockIdx.x];
+    stage_tile(ext, tok, base, h);
+    __syncthreads();
+
+    const int s0 = OFF + (int)threadIdx.x * SPT;
+    uint32_t run = 0;       // AEQB: consecutive live A's immediately before the current slot
+    bool run_known = false;
+    uint32_t nAB = 0, nXX = 0;
+    for (int s = s0; s < s0 + SPT; s++) {
+        const TokT t = ext[s];
+        if (t == H) continue;
+        bool start = false;
+        int j = -1;
+        if (!AEQB) {
+            if (t == A) {
+                j = next_live(ext, s);
+                start = (j >= 0 && ext[j] == B);
+            } else if (t == B) {
+                int p = prev_live(ext, s);
+                if (p >= 0 && ext[p] == A) tok[base + (size_t)(s - OFF)] = H;  // consumed by the A on its left
+            }
+        } else {
+            if (t == A) {
+                if (!run_known) {
+                    // count live A's before s inside the tile; if the tile start is reached the
+                    // run continues into earlier tiles (h.runA)
+                    uint32_t c = 0;
+                    bool hit = false;
+                    for (int q = s - 1; q >= OFF; q--) {
+                        TokT v = ext[q];
+                        if (v == H) continue;
+                        if (v == A) c++; else { hit = true; break; }
+                    }
+                    run = hit ? c : c + h.runA;
+                    run_known = true;
+                }
+                const uint32_t off = run;
+                run++;
+                if (off & 1u) {
+                    tok[base + (size_t)(s - OFF)] = H;  // second element of the occurrence at off-1
+                } else {
+                    j = next_live(ext, s);
+                    start = (j >= 0 && ext[j] == A);
+                }
+            } else {
+                run = 0;
+                run_known = true;
+            }
+        }
+        if (!start) continue;
+        tok[base + (size_t)(s - OFF)] = X;
+        if (DELTAS) {
+            nAB++;
+            // left side: always owned by this occurrence
+            int p = prev_live(ext, s);
+            if (p >= 0) {
+                const TokT tp = ext[p];
+                bool merged_second;
+                if (AEQB) merged_second = (tp == A);  // same run, odd offset
+                else {
+                    merged_second = false;
+                    if (tp == B) { int pp = prev_live(ext, p); merged_second = (pp >= 0 && ext[pp] == A); }
+                }
+                if (merged_second) nXX++; else atomicAdd(&cntL[tp], 1u);
+            }
+            // right side: owned only if the next live token does not start another occurrence
+            int n = next_live(ext, j);
+            if (n >= 0) {
+                const TokT tn = ext[n];
+                bool is_start = false;
+                if (tn == A) { int nn = next_live(ext, n); is_start = (nn >= 0 && ext[nn] == B); }
+                if (!is_start) atomicAdd(&cntR[tn], 1u);
+            }
+        }
+    }
+    if (DELTAS) {
+        if (nAB) atomicAdd(&ctl->cntAB, nAB);
+        if (nXX) atomicAdd(&ctl->cntXX, nXX);
+    }
+}
+
+// =========================================================================================
+// apply_kernel: fold the per-neighbour merge deltas into the pair table (and into the
+// reference-home population on births / deaths). One thread per token id.
+// =========================================================================================
+__device__ __forceinline__ void tbl_sub(const PairTable& tbl, uint32_t key, uint32_t c, StepCtl* ctl,
+                                        uint32_t* zcnt, uint32_t zmask) {
+    uint32_t s = tbl_find(tbl, key);
+    if (s == EMPTY_KEY) { atomicOr(&ctl->err, (uint32_t)ERR_KEY_MISSING); return; }
+    uint32_t old = atomicSub(&tbl.counts[s], c);
+    if (old < c) { atomicOr(&ctl->err, (uint32_t)ERR_COUNT_UNDERFLOW); return; }
+    if (old == c) {  // death
+        atomicSub(&ctl->live_keys, 1u);
+        if (zcnt) zcnt_add(zcnt, zmask, key, -1, &ctl->err);
+    }
+}
+__device__ __forceinline__ void tbl_add(const PairTable& tbl, uint32_t key, uint32_t c, StepCtl* ctl,
+                                        uint32_t* zcnt, uint32_t zmask) {
+    uint32_t s = tbl_find_or_insert(tbl, key, &ctl->n_inserted);
+    if (s == EMPTY_KEY) { atomicOr(&ctl->err, (uint32_t)ERR_TABLE_FULL); return; }
+    uint32_t old = atomicAdd(&tbl.counts[s], c);
+    if (old == 0) {  // birth
+        atomicAdd(&ctl->live_keys, 1u);
+        if (zcnt) zcnt_add(zcnt, zmask, key, +1, &ctl->err);
+    }
+}
+
+__global__ void apply_kernel(PairTable tbl, uint32_t* __restrict__ cntL, uint32_t* __restrict__ cntR,
+                             StepCtl* ctl, uint32_t* zcnt, uint32_t zmask, uint32_t n_ids,
+                             uint32_t cntXX, uint32_t cntAB) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t A = ctl->A, B = ctl->B, X = ctl->X;
+    if (p < n_ids) {
+        uint32_t c = cntL[p];
+        if (c) {
+            cntL[p] = 0;
+            tbl_sub(tbl, pair_key(p, A), c, ctl, zcnt, zmask);
+            tbl_add(tbl, pair_key(p, X), c, ctl, zcnt, zmask);
+        }
+        c = cntR[p];
+        if (c) {
+            cntR[p] = 0;
+            tbl_sub(tbl, pair_key(B, p), c, ctl, zcnt, zmask);
+            tbl_add(tbl, pair_key(X, p), c, ctl, zcnt, zmask);
+        }
+    }
+    if (p == 0) {
+        if (cntXX) {
+            tbl_sub(tbl, pair_key(B, A), cntXX, ctl, zcnt, zmask);
+            tbl_add(tbl, pair_key(X, X), cntXX, ctl, zcnt, zmask);
+        }
+        if (cntAB) tbl_sub(tbl, pair_key(A, B), cntAB, ctl, zcnt, zmask);
+    }
+}
+
+// =========================================================================================
+// Tie fast path. The reference picks, among the pairs sharing the maximum count, the one in the
+// lowest slot of its hash table (Appendix A). For linear probing without deletions the *set* of
+// occupied slots does not depend on insertion order, so from the population of home slots
+// (zcnt) the carry recurrence  o[x] = max(0, o[x-1] + cnt[x] - 1)  gives exactly which slots are
+// free. If the tied key with the smallest home h1 reaches a free slot before the next tied home
+// and no tied key can wrap past the end of the table, that key owns the lowest slot. Otherwise
+// the step is handed to the full replay (TIE_NEED_REPLAY).
+// =========================================================================================
+struct ChunkFn { int32_t add; int32_t lo; };  // f(o) = max(lo, o + add)
+__device__ __forceinline__ ChunkFn fn_compose(ChunkFn f, ChunkFn g) {  // g after f
+    ChunkFn r;
+    r.add = f.add + g.add;
+    int32_t a = f.lo + g.add;
+    r.lo = g.lo > a ? g.lo : a;
+    return r;
+}
+__device__ __forceinline__ int32_t fn_eval(ChunkFn f, int32_t o) { int32_t a = o + f.add; return f.lo > a ? f.lo : a; }
+
+__global__ void zig_rebuild_kernel(PairTable tbl, uint32_t* zcnt, uint32_t zmask, StepCtl* ctl) {
+    size_t cap = (size_t)tbl.mask + 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x)
+        if (tbl.counts[i] > 0) zcnt_add(zcnt, zmask, tbl.keys[i], +1, &ctl->err);
+}
+
+// one CTA (THREADS threads) per chunk of zchunk slots (zchunk = min(zcap, ZCHUNK))
+__global__ void zig_chunk_kernel(const uint32_t* __restrict__ zcnt, uint32_t zchunk, ChunkFn* __restrict__ fn) {
+    __shared__ ChunkFn sh[THREADS];
+    const uint32_t base = blockIdx.x * zchunk;
+    const uint32_t per = (zchunk + THREADS - 1) / THREADS;
+    ChunkFn f; f.add = 0; f.lo = 0;  // identity on o >= 0
+    for (uint32_t k = 0; k < per; k++) {
+        uint32_t x = threadIdx.x * per + k;
+        if (x < zchunk) {
+            ChunkFn g; g.add = (int32_t)zcnt_get(zcnt, base + x) - 1; g.lo = 0;
+            f = fn_compose(f, g);
+        }
+    }
+    sh[threadIdx.x] = f;
+    __syncthreads();
+    for (int off = 1; off < THREADS; off <<= 1) {  // ordered tree reduction
+        int i = (int)threadIdx.x;
+        if ((i % (2 * off)) == 0 && i + off < THREADS) sh[i] = fn_compose(sh[i], sh[i + off]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) fn[blockIdx.x] = sh[0];
+}
+
+// single CTA of MAXTIE threads
+__global__ void zig_resolve_kernel(const uint32_t* __restrict__ zcnt, uint32_t zcap, uint32_t zchunk,
+                                   const ChunkFn* __restrict__ fn, uint32_t nchunks, StepCtl* ctl) {
+    __shared__ ChunkFn agg[MAXTIE];
+    __shared__ int32_t pre[MAXTIE];
+    __shared__ uint32_t home[MAXTIE];
+    __shared__ uint32_t efree[MAXTIE];
+    __shared__ uint32_t bad;
+    const int t = (int)threadIdx.x;
+    const uint32_t ntied = ctl->ntied;
+    if (t == 0) bad = 0;
+    // 1. carry into every range of chunks
+    const uint32_t q = (nchunks + MAXTIE - 1) / MAXTIE;  // chunks per thread range
+    ChunkFn f; f.add = 0; f.lo = 0;
+    for (uint32_t k = 0; k < q; k++) {
+        uint32_t c = (uint32_t)t * q + k;
+        if (c < nchunks) f = fn_compose(f, fn[c]);
+    }
+    agg[t] = f;
+    __syncthreads();
+    if (t == 0) {
+        ChunkFn all; all.add = 0; all.lo = 0;
+        for (int r = 0; r < MAXTIE; r++) all = fn_compose(all, agg[r]);
+        int32_t o = fn_eval(all, 0);  // steady-state carry entering slot 0 (load < 1 => fixed point)
+        for (int r = 0; r < MAXTIE; r++) { pre[r] = o; o = fn_eval(agg[r], o); }
+    }
+    __syncthreads();
+    // 2. per tied key: first free slot at/after its home
+    if ((uint32_t)t < ntied && ntied <= (uint32_t)MAXTIE) {
+        const uint32_t key = ctl->tie_keys[t];
+        const uint32_t h = (uint32_t)zig_hash_pair(key) & (zcap - 1);
+        const uint32_t c = h / zchunk;
+        const uint32_t r = c / q;
+        int32_t o = pre[r];
+        for (uint32_t cc = r * q; cc < c; cc++) o = fn_eval(fn[cc], o);
+        for (uint32_t x = c * zchunk; x < h; x++) { int32_t a = o + (int32_t)zcnt_get(zcnt, x) - 1; o = a > 0 ? a : 0; }
+        uint32_t x = h;
+        bool wrapped = false;
+        while (true) {
+            int32_t occ = o + (int32_t)zcnt_get(zcnt, x);
+            if (occ == 0) break;  // free slot
+            o = occ - 1;
+            x++;
+            if (x == zcap) { wrapped = true; break; }
+        }
+        home[t] = h;
+        efree[t] = x;
+        if (wrapped) atomicOr(&bad, 1u);
+    }
+    __syncthreads();
+    // 3. winner = smallest home, if its probe run ends before every other tied home
+    if (t == 0) {
+        uint32_t status = TIE_NEED_REPLAY, winner = 0;
+        if (ntied >= 2 && ntied <= (uint32_t)MAXTIE && !bad) {
+            uint32_t b = 0;
+            for (uint32_t i = 1; i < ntied; i++) if (home[i] < home[b]) b = i;
+            bool ok = true;
+            for (uint32_t i = 0; i < ntied; i++) if (i != b && home[i] < efree[b]) { ok = false; break; }
+            if (ok) { status = TIE_FAST_OK; winner = ctl->tie_keys[b]; }
+        }
+        ctl->tie_status = status;
+        ctl->tie_winner = winner;
+    }
+}
+
+// =========================================================================================
+// pair_visit_kernel: one CTA per tile, calls op(pos, key) for every live adjacent pair whose left
+// token lies in the tile (pos = slot index of the left token). Used by the replay path
+// (first-occurrence positions) and by verify mode (full recount).
+// =========================================================================================
+struct FirstPosOp {
+    PairTable tbl; uint32_t* firstpos; StepCtl* ctl;
+    __device__ __forceinline__ void operator()(size_t pos, uint32_t key) const {
+        uint32_t s = tbl_find(tbl, key);
+        if (s == EMPTY_KEY) { atomicOr(&ctl->err, (uint32_t)ERR_KEY_MISSING); return; }
+        uint32_t p = (uint32_t)pos;
+        if (p < ((volatile uint32_t*)firstpos)[s]) atomicMin(&firstpos[s], p);
+        if (p > ((volatile uint32_t*)&ctl->last_pair_pos)[0]) atomicMax(&ctl->last_pair_pos, p);
+    }
+};
+struct RecountOp {
+    PairTable tbl; uint32_t* recount; StepCtl* ctl;
+    __device__ __forceinline__ void operator()(size_t, uint32_t key) const {
+        uint32_t s = tbl_find(tbl, key);
+        if (s == EMPTY_KEY) { atomicOr(&ctl->err, (uint32_t)ERR_KEY_MISSING); return; }
+        atomicAdd(&recount[s], 1u);
+    }
+};
+
+template <class TokT, class Op>
+__global__ void __launch_bounds__(THREADS) pair_visit_kernel(const TokT* __restrict__ tok,
+                                                             const TileHalo<TokT>* __restrict__ halo, Op op) {
+    __shared__ __align__(16) TokT ext[EXT];
+    const TokT H = (TokT)TokTraits<TokT>::hole;
+    const size_t base = (size_t)blockIdx.x * TILE;
+    stage_tile(ext, tok, base, halo[blockIdx.x]);
+    __syncthreads();
+    const int s0 = OFF + (int)threadIdx.x * SPT;
+    for (int s = s0; s < s0 + SPT; s++) {
+        TokT t = ext[s];
+        if (t == H) continue;
+        int j = next_live(ext, s);
+        if (j < 0) continue;
+        op(base + (size_t)(s - OFF), pair_key((uint32_t)t, (uint32_t)ext[j]));
+    }
+}
+
+__global__ void verify_counts_kernel(PairTable tbl, const uint32_t* __restrict__ recount, StepCtl* ctl,
+                                     uint32_t* live_out) {
+    size_t cap = (size_t)tbl.mask + 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t c = tbl.counts[i];
+        if (c != recount[i]) {
+            uint32_t k = atomicAdd(&ctl->verify_mismatch, 1u);
+            if (k < 8) printf("verify: key (%u,%u) table=%u recount=%u\n", tbl.keys[i] & 0xFFFFu, tbl.keys[i] >> 16, c, recount[i]);
+        }
+        if (c) atomicAdd(live_out, 1u);
+    }
+}
+
+// =========================================================================================
+// compaction: squeeze the holes out (ballot-free v1: per-tile counts, scan, scatter)
+// =========================================================================================
+template <class TokT>
+__global__ void __launch_bounds__(THREADS) tile_count_kernel(const TokT* __restrict__ tok, uint32_t* __restrict__ tile_live) {
+    __shared__ uint32_t sh[THREADS];
+    const TokT H = (TokT)TokTraits<TokT>::hole;
+    const size_t base = (size_t)blockIdx.x * TILE + (size_t)threadIdx.x * SPT;
+    uint32_t c = 0;
+    for (int k = 0; k < SPT; k++) c += (tok[base + k] != H);
+    sh[threadIdx.x] = c;
+    __syncthreads();
+    for (int off = THREADS / 2; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_live[blockIdx.x] = sh[0];
+}
+
+// single CTA: exclusive scan of tile_live[0..ntiles) into tile_off (u64), total -> *total
+__global__ void tile_scan_kernel(const uint32_t* __restrict__ tile_live, uint32_t ntiles,
+                                 unsigned long long* __restrict__ tile_off, unsigned long long* total) {
+    __shared__ unsigned long long part[THREADS];
+    const uint32_t per = (ntiles + THREADS - 1) / THREADS;
+    const uint32_t lo = threadIdx.x * per;
+    unsigned long long s = 0;
+    for (uint32_t k = 0; k < per; k++) if (lo + k < ntiles) s += tile_live[lo + k];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long acc = 0;
+        for (int i = 0; i < THREADS; i++) { unsigned long long v = part[i]; part[i] = acc; acc += v; }
+        *total = acc;
+    }
+    __syncthreads();
+    unsigned long long acc = part[threadIdx.x];
+    for (uint32_t k = 0; k < per; k++) if (lo + k < ntiles) { tile_off[lo + k] = acc; acc += tile_live[lo + k]; }
+}
+
+template <class TokT, class OutT>
+__global__ void __launch_bounds__(THREADS) compact_scatter_kernel(const TokT* __restrict__ tok,
+                                                                  const unsigned long long* __restrict__ tile_off,
+                                                                  OutT* __restrict__ dst) {
+    __shared__ uint32_t sh[THREADS];
+    const TokT H = (TokT)TokTraits<TokT>::hole;
+    const size_t base = (size_t)blockIdx.x * TILE + (size_t)threadIdx.x * SPT;
+    TokT v[SPT];
+    uint32_t c = 0;
+    for (int k = 0; k < SPT; k++) { v[k] = tok[base + k]; c += (v[k] != H); }
+    uint32_t off = block_exclusive_scan<THREADS>(c, sh, nullptr);
+    size_t o = (size_t)tile_off[blockIdx.x] + off;
+    for (int k = 0; k < SPT; k++) if (v[k] != H) dst[o++] = (OutT)v[k];
+}
+
+// =========================================================================================
+// pair table rebuild (growth / dropping dead keys)
+// =========================================================================================
+__global__ void table_rehash_kernel(PairTable src, PairTable dst, StepCtl* ctl, int drop_dead) {
+    size_t cap = (size_t)src.mask + 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t k = src.keys[i];
+        if (k == EMPTY_KEY) continue;
+        uint32_t c = src.counts[i];
+        if (drop_dead && c == 0) continue;
+        uint32_t s = tbl_find_or_insert(dst, k, &ctl->n_inserted);
+        if (s == EMPTY_KEY) { atomicOr(&ctl->err, (uint32_t)ERR_TABLE_FULL); continue; }
+        dst.counts[s] = c;
+    }
+}
+
+// =========================================================================================
+// decode (src/basic_tokenizer.zig:90-138): ids -> byte lengths -> offsets -> bytes
+// vocab expansions are flattened on the host: voc_off[id], voc_len[id], voc_bytes[]
+// =========================================================================================
+__global__ void __launch_bounds__(THREADS) decode_len_kernel(const uint16_t* __restrict__ toks, size_t n,
+                                                             const uint32_t* __restrict__ voc_len,
+                                                             uint32_t* __restrict__ tile_bytes, StepCtl* ctl) {
+    __shared__ uint32_t sh[THREADS];
+    const size_t base = (size_t)blockIdx.x * TILE + (size_t)threadIdx.x * SPT;
+    uint32_t c = 0;
+    for (int k = 0; k < SPT; k++) {
+        size_t i = base + k;
+        if (i < n) {
+            uint32_t l = voc_len[toks[i]];
+            if (l == 0) atomicOr(&ctl->err, (uint32_t)ERR_KEY_MISSING);  // unknown id
+            c += l;
+        }
+    }
+    sh[threadIdx.x] = c;
+    __syncthreads();
+    for (int off = THREADS / 2; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_bytes[blockIdx.x] = sh[0];
+}
+
+__global__ void __launch_bounds__(THREADS) decode_scatter_kernel(const uint16_t* __restrict__ toks, size_t n,
+                                                                 const uint32_t* __restrict__ voc_off,
+                                                                 const uint32_t* __restrict__ voc_len,
+                                                                 const uint8_t* __restrict__ voc_bytes,
+                                                                 const unsigned long long* __restrict__ tile_off,
+                                                                 uint8_t* __restrict__ out, size_t cap) {
+    __shared__ uint32_t sh[THREADS];
+    const size_t base = (size_t)blockIdx.x * TILE + (size_t)threadIdx.x * SPT;
+    uint32_t c = 0;
+    for (int k = 0; k < SPT; k++) { size_t i = base + k; if (i < n) c += voc_len[toks[i]]; }
+    uint32_t off = block_exclusive_scan<THREADS>(c, sh, nullptr);
+    size_t o = (size_t)tile_off[blockIdx.x] + off;
+    for (int k = 0; k < SPT; k++) {
+        size_t i = base + k;
+        if (i >= n) break;
+        uint32_t id = toks[i];
+        uint32_t l = voc_len[id];
+        const uint8_t* src = voc_bytes + voc_off[id];
+        for (uint32_t b = 0; b < l; b++) if (o + b < cap) out[o + b] = src[b];
+        o += l;
+    }
+}
+
+}  // namespace bpe

@@ -1,0 +1,91 @@
+// dist_comm.hpp — the multi-GPU exchange used by sharded training: NCCL over NVLink/NVSwitch,
+// one rank per GPU. NCCL is loaded lazily with dlopen so the single-GPU path has no dependency
+// on it (and so the library binds to whichever libnccl.so.2 the host process already loaded,
+// e.g. the one bundled with PyTorch).
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <string>
+
+#ifndef BPE_EMUL
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#endif
+
+namespace bpe {
+
+#ifndef BPE_EMUL
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclInt8 = 0, ncclChar = 0, ncclUint8 = 1, ncclInt32 = 2, ncclUint32 = 3, ncclInt64 = 4, ncclUint64 = 5 };
+enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 };
+
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load(std::string* err) {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+        for (int i = 0; names[i] && !lib; i++) lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) { if (err) *err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return false; }
+        GetUniqueId = (int (*)(ncclUniqueId*))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(lib, "ncclCommInitRank");
+        CommDestroy = (int (*)(ncclComm_t))dlsym(lib, "ncclCommDestroy");
+        AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclAllReduce");
+        AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclAllGather");
+        GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !AllGather) {
+            if (err) *err = "libnccl is missing required symbols";
+            return false;
+        }
+        return true;
+    }
+};
+inline NcclApi& nccl_api() { static NcclApi api; return api; }
+
+inline bool dist_unique_id(void* out128, std::string* err) {
+    NcclApi& api = nccl_api();
+    if (!api.load(err)) return false;
+    ncclUniqueId id;
+    int rc = api.GetUniqueId(&id);
+    if (rc != ncclSuccess) { if (err) *err = "ncclGetUniqueId failed"; return false; }
+    memcpy(out128, &id, 128);
+    return true;
+}
+
+struct DistComm {
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    cudaStream_t stream = 0;
+    bool init(int r, int w, const void* uid, cudaStream_t s, std::string* err) {
+        NcclApi& api = nccl_api();
+        if (!api.load(err)) return false;
+        ncclUniqueId id;
+        memcpy(&id, uid, 128);
+        int rc = api.CommInitRank(&comm, w, id, r);
+        if (rc != ncclSuccess) { if (err) *err = std::string("ncclCommInitRank: ") + (api.GetErrorString ? api.GetErrorString(rc) : "?"); return false; }
+        rank = r; world = w; stream = s;
+        return true;
+    }
+    void destroy() { if (comm) { nccl_api().CommDestroy(comm); comm = nullptr; } }
+    bool allreduce_u32_sum(uint32_t* buf, size_t n) { return nccl_api().AllReduce(buf, buf, n, ncclUint32, ncclSum, comm, stream) == ncclSuccess; }
+    bool allreduce_u64_sum(uint64_t* buf, size_t n) { return nccl_api().AllReduce(buf, buf, n, ncclUint64, ncclSum, comm, stream) == ncclSuccess; }
+    bool allreduce_u64_min(uint64_t* buf, size_t n) { return nccl_api().AllReduce(buf, buf, n, ncclUint64, ncclMin, comm, stream) == ncclSuccess; }
+    bool allgather_bytes(const void* src, void* dst, size_t bytes_per_rank) { return nccl_api().AllGather(src, dst, bytes_per_rank, ncclUint8, comm, stream) == ncclSuccess; }
+};
+#else
+inline bool dist_unique_id(void* out128, std::string*) { memset(out128, 0, 128); return true; }
+struct DistComm {
+    int rank = 0, world = 1;
+    bool init(int, int, const void*, int, std::string* err) { if (err) *err = "no NCCL in the emulation build"; return false; }
+    void destroy() {}
+};
+#endif
+
+}  // namespace bpe
