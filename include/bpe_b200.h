@@ -53,6 +53,13 @@ typedef struct bpe_stats_t {
     uint64_t tie_steps;       /* steps whose top count was shared by >= 2 pairs */
     uint64_t tie_slow_steps;  /* of those, resolved by the full table replay */
     uint64_t compactions;
+    /* per-kernel-class device time, filled when option "profile" = 1 (CUDA events recorded on
+     * the context's stream between launches, resolved after the run; no extra synchronisation):
+     * [0] load+initial count  [1] argmax+ties  [2] tie occupancy kernels  [3] table replay
+     * [4] halo  [5] merge  [6] apply deltas  [7] compaction  [8] table rebuild / zcnt rebuild
+     * [9] host gap (status read-back until the next launch)  [10..11] reserved */
+    double kernel_ms[12];
+    uint64_t kernel_calls[12];
 } bpe_stats_t;
 
 enum {
@@ -86,6 +93,8 @@ const char* bpe_last_error(const bpe_ctx* ctx);
  *   "compact_pct"         live/slots percentage below which the sequence is compacted (default 85)
  *   "table_log2"          log2 of the initial pair-table capacity (default: sized from n)
  *   "max_steps"           stop training after this many merges (0 = no limit)
+ *   "time_phases"         1: fill the reference's TimeStats buckets (synchronises per phase)
+ *   "profile"             1: fill bpe_stats_t.kernel_ms / kernel_calls
  */
 int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value);
 

@@ -1,0 +1,89 @@
+"""Kernel logic without a GPU: the same .cu sources compiled for the CPU emulation in
+tests/emul (small tiles so tile-boundary code paths are hit by tiny inputs), compared with the
+oracle. This tier only checks logic; the parity tests proper are the -m gpu tests."""
+import numpy as np
+import pytest
+
+from conftest import merges_array
+from test_oracle import MAIN_ZIG_STRING, MAIN_ZIG_TOKENS, REF_TEST_MERGES
+
+
+def _train_check(emu, ora, data, vocab, **opts):
+    for k, v in {"verify_recount": 0, "check_tiebreak": 1, "force_slow_tiebreak": 0, "compact_pct": 85, **opts}.items():
+        emu.set_option(k, v)
+    m, c = emu.train(data, vocab)
+    om, oc = ora.train(data, vocab, fast=True)
+    assert np.array_equal(merges_array(m), om)
+    assert np.array_equal(c, oc)
+    return emu.last_stats
+
+
+@pytest.mark.parametrize("data,vocab", [
+    (b"hello world hello", 300), (b"a" * 1000, 270), (b"ab" * 700 + b"a", 270), (b"aaab" * 300 + b"aa", 280),
+    (b"x", 300), (b"xy", 300), (b"", 300), (b"abcabc", 256),
+])
+def test_train_small(emu, ora, data, vocab):
+    _train_check(emu, ora, data, vocab, verify_recount=1)
+
+
+def test_train_random_alphabets(emu, ora):
+    rng = np.random.default_rng(3)
+    _train_check(emu, ora, bytes(rng.integers(97, 101, size=3000, dtype=np.uint8)), 290, verify_recount=1)
+    st = _train_check(emu, ora, bytes(rng.integers(0, 256, size=4000, dtype=np.uint8)), 330)
+    assert st["tie_steps"] > 0
+
+
+def test_train_forced_replay_and_no_compaction(emu, ora):
+    rng = np.random.default_rng(5)
+    data = bytes(rng.integers(97, 103, size=2500, dtype=np.uint8))
+    st = _train_check(emu, ora, data, 300, force_slow_tiebreak=1, compact_pct=0)
+    assert st["compactions"] == 0 and st["tie_slow_steps"] == st["tie_steps"]
+    st = _train_check(emu, ora, data, 300, compact_pct=100)
+    assert st["compactions"] > 0
+
+
+def test_train_golden_prefix(emu, ora, taylor):
+    st = _train_check(emu, ora, taylor[:40000], 300)
+    assert st["kernel_launches"] > 0
+
+
+def test_invalid_vocab(emu, zb):
+    with pytest.raises(zb.InvalidVocabSize):
+        emu.train(b"abc", 255)
+
+
+def test_encode_decode(emu, ora, golden_merges, taylor):
+    want = [257, ord("l"), ord("o"), ord(" "), 258, ord("r"), ord("l"), ord("d")]
+    assert list(emu.encode(b"hello world", REF_TEST_MERGES)) == want  # reference test :362-378
+    assert emu.decode(want, REF_TEST_MERGES) == b"hello world"  # :380-397
+    assert list(emu.encode(MAIN_ZIG_STRING, golden_merges)) == MAIN_ZIG_TOKENS
+    assert emu.decode(MAIN_ZIG_TOKENS, golden_merges) == MAIN_ZIG_STRING
+    chunk = taylor[:6000]
+    ids = emu.encode(chunk, golden_merges)
+    assert np.array_equal(ids, ora.encode(chunk, golden_merges, linear=False))
+    assert emu.decode(ids, golden_merges) == chunk
+
+
+@pytest.mark.parametrize("data,merges", [
+    (b"a" * 1001, [(97, 97, 256), (256, 256, 257), (257, 97, 258)]),
+    (b"Xbbbbb cXbb", [(ord("X"), ord("b"), ord("X"))]),
+    (b"aaaaaaa", [(97, 97, 97)]),
+    (b"aaXaX", [(97, ord("X"), ord("X"))]),
+    (b"abcabcab", [(97, 98, 65535), (65535, 99, 300), (300, 65535, 301)]),
+    (b"", [(97, 98, 256)]), (b"z", [(97, 98, 256)]), (b"abab", []),
+])
+def test_encode_edge_cases(emu, ora, data, merges):
+    ids = emu.encode(data, merges)
+    assert np.array_equal(ids, ora.encode(data, merges, linear=False))
+    if len(ids):
+        rc, want = ora.decode(ids, merges)
+        assert rc == 0 and emu.decode(ids, merges) == want
+
+
+def test_decode_errors(emu, zb):
+    with pytest.raises(zb.InvalidToken):
+        emu.decode([300], REF_TEST_MERGES)
+    with pytest.raises(zb.InvalidToken):  # a cycle would overflow the reference's stack; defined as InvalidToken
+        emu.decode([256], [(256, 97, 256)])
+    assert emu.decode([257], [(97, 98, 257), (99, 99, 257)]) == b"ab"  # first matching merge wins (:109-116)
+    assert emu.decode([], REF_TEST_MERGES) == b""

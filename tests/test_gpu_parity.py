@@ -1,0 +1,221 @@
+"""Parity tests proper: the CUDA path through the C ABI (libbpe_b200.so on cuda:0) against the
+oracle on the same inputs, bit-exact (integer / byte / index work), plus size-independent
+properties at BASELINE.json's C2 size. Reference tests restated: basic_tokenizer.zig:351-461."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, merges_array
+from test_oracle import MAIN_ZIG_STRING, MAIN_ZIG_TOKENS, REF_TEST_MERGES
+
+pytestmark = pytest.mark.gpu
+
+
+def _opts(eng, **opts):
+    for k, v in {"verify_recount": 0, "check_tiebreak": 0, "force_slow_tiebreak": 0, "compact_pct": 85, "table_log2": 0,
+                 "max_steps": 0, **opts}.items():
+        eng.set_option(k, v)
+
+
+def _train_check(gpu, ora, data, vocab, **opts):
+    _opts(gpu, **opts)
+    m, c = gpu.train(data, vocab)
+    om, oc = ora.train(data, vocab, fast=True)
+    assert np.array_equal(merges_array(m), om)
+    assert np.array_equal(c, oc)
+    _opts(gpu)
+    return gpu.last_stats
+
+
+# ---- the reference's own unit tests, through the host mirror --------------------------------
+def test_ref_train(zb, gpu):  # :399-432
+    tk = zb.BasicTokenizer(engine=gpu, quiet=True)
+    tk.train("hello world hello", 300, True)
+    assert len(tk.merges) > 0
+    enc = tk.encode("hello")
+    assert len(enc) == 1 and enc[0] == 259
+    assert tk.decode(enc) == b"hello"
+    assert len(tk.merges) == 12  # early stop once one token is left (:188-191)
+    with pytest.raises(zb.InvalidVocabSize):
+        tk.train("abc", 255)
+
+
+def test_ref_encode_decode(zb, gpu):  # :362-397
+    tk = zb.BasicTokenizer(engine=gpu, quiet=True)
+    for a, b, c in REF_TEST_MERGES:
+        tk.put((a, b), c)
+    want = [257, ord("l"), ord("o"), ord(" "), 258, ord("r"), ord("l"), ord("d")]
+    assert list(tk.encode("hello world")) == want
+    assert tk.decode(np.array(want, dtype=np.uint16)) == b"hello world"
+    with pytest.raises(zb.InvalidToken):
+        tk.decode([300])
+
+
+def test_ref_serialize_roundtrip(zb, gpu, tmp_path):  # :434-461
+    tk = zb.BasicTokenizer(engine=gpu, quiet=True)
+    for a, b, c in REF_TEST_MERGES:
+        tk.put((a, b), c)
+    p = tmp_path / "test_merges.txt"
+    tk.serializeMerges(p)
+    tk2 = zb.BasicTokenizer(engine=gpu, quiet=True)
+    tk2.deserializeMerges(p)
+    assert tk2.merges == tk.merges
+
+
+def test_verbose_output_format(zb, gpu, capsys):
+    tk = zb.BasicTokenizer(engine=gpu)
+    tk.train("hello world hello", 300, True)
+    err = capsys.readouterr().err
+    assert "merge 1/44: (101,108) -> 256 had 2 occurrences" in err  # printMergeInfo :308-317
+    assert "No more pairs to merge. Stopping early." in err  # :189
+    assert "Time statistics:" in err and "sortCodePointPairs:" in err
+
+
+# ---- golden vectors ---------------------------------------------------------------------------
+def test_golden_merges_txt(zb, gpu, taylor, tmp_path):
+    """main.zig: train(taylorswift.txt, 300) + serializeMerges == the committed merges.txt."""
+    tk = zb.BasicTokenizer(engine=gpu, quiet=True)
+    tk.train(taylor, 300, False)
+    p = tmp_path / "merges.txt"
+    tk.serializeMerges(p)
+    assert p.read_bytes() == open(os.path.join(GOLDEN, "merges_300.txt"), "rb").read()
+    enc = tk.encode(MAIN_ZIG_STRING)
+    assert list(enc) == MAIN_ZIG_TOKENS
+    assert tk.decode(enc) == MAIN_ZIG_STRING
+
+
+def test_c1_taylorswift_512(gpu, ora, taylor):
+    """BASELINE config 1: vocab 512, then encode / decode round trip of the whole file."""
+    _opts(gpu, check_tiebreak=1)
+    m, c = gpu.train(taylor, 512)
+    _opts(gpu)
+    text = "".join(f"{a},{b},{t}\n" for a, b, t in merges_array(m)).encode()
+    assert hashlib.sha256(text).hexdigest() == "fb698f9c0610b9779d549a59162c3d862ba0f9180a5687da4ce8c6e96dc9f588"
+    assert gpu.last_stats["tie_steps"] == 69
+    om, oc = ora.train(taylor, 512, fast=True)
+    assert np.array_equal(c, oc)
+    ids = gpu.encode(taylor, m)
+    assert np.array_equal(ids, ora.encode(taylor, om))
+    assert len(ids) == 78746  # Appendix B: final length after 256 merges
+    assert gpu.decode(ids, m) == taylor
+
+
+def test_whole_file_encode_golden(gpu, golden_merges, taylor):
+    ids = gpu.encode(taylor, golden_merges)
+    assert len(ids) == 128451
+    assert hashlib.sha256(ids.astype("<u2").tobytes()).hexdigest() == "71f70e539b770e3cf87adb5b9e04bf092f9b38d767351b7954a81d709c4facc3"
+    assert gpu.decode(ids, golden_merges) == taylor
+
+
+# ---- edge cases -------------------------------------------------------------------------------
+@pytest.mark.parametrize("data,vocab", [
+    (b"", 300), (b"x", 300), (b"xy", 300), (b"abcabc", 256), (b"a" * 100000, 280), (b"ab" * 50000 + b"a", 280),
+    (b"aaab" * 30000 + b"aa", 290), (bytes(range(256)) * 64, 300), (b"abc" * 4096 + b"ab", 270),
+])
+def test_train_edge_cases(gpu, ora, data, vocab):
+    _train_check(gpu, ora, data, vocab, verify_recount=1, check_tiebreak=1)
+
+
+def test_train_long_runs_across_tiles(gpu, ora):
+    # runs of one byte spanning many 4096-slot tiles, with odd/even lengths and odd offsets
+    data = b"xyz" + b"a" * 40961 + b"b" + b"a" * 8192 + b"cc" + b"a" * 12287 + b"q"
+    _train_check(gpu, ora, data, 300, verify_recount=1, check_tiebreak=1)
+    _train_check(gpu, ora, data, 300, compact_pct=0)
+
+
+def test_train_random(gpu, ora):
+    rng = np.random.default_rng(21)
+    for k, n, vocab in [(2, 50000, 300), (4, 100000, 400), (26, 200000, 600), (256, 300000, 700)]:
+        data = bytes(rng.integers(0, k, size=n, dtype=np.uint8))
+        _train_check(gpu, ora, data, vocab, check_tiebreak=1)
+
+
+def test_train_tiebreak_paths_agree(gpu, ora):
+    rng = np.random.default_rng(22)
+    data = bytes(rng.integers(97, 123, size=150000, dtype=np.uint8))
+    st_fast = _train_check(gpu, ora, data, 500)
+    st_slow = _train_check(gpu, ora, data, 500, force_slow_tiebreak=1)
+    assert st_fast["tie_steps"] == st_slow["tie_steps"] > 0
+    assert st_slow["tie_slow_steps"] == st_slow["tie_steps"]
+    assert st_fast["tie_slow_steps"] < st_fast["tie_steps"]
+
+
+def test_train_compaction_and_table_growth(gpu, ora, synth):
+    data = bytes(synth.generate(1_500_000, synth.SEED_C3, synth.BYTE))
+    st = _train_check(gpu, ora, data, 700, table_log2=12, compact_pct=95, verify_recount=0)
+    assert st["compactions"] >= 3
+    _train_check(gpu, ora, data[:300000], 400, compact_pct=0, verify_recount=1)
+
+
+def test_train_synth_utf8_4mb(gpu, ora, synth):
+    """C2-shaped input at a size the oracle finishes in seconds."""
+    data = bytes(synth.generate(4_000_000, synth.SEED_C2, synth.UTF8))
+    st = _train_check(gpu, ora, data, 256 + 400)
+    assert st["scanned_slots"] > 0 and st["kernel_launches"] > 400
+
+
+def test_encode_parity_synth(gpu, ora, synth):
+    data = bytes(synth.generate(1_000_000, synth.SEED_C3, synth.BYTE))
+    m, _ = gpu.train(data, 256 + 300)
+    ids = gpu.encode(data, m)
+    assert np.array_equal(ids, ora.encode(data, merges_array(m), linear=True))
+    assert np.array_equal(gpu.encode(data[:3000], m), ora.encode(data[:3000], merges_array(m), linear=False))
+    assert gpu.decode(ids, m) == data
+    # text the merges were not trained on, including bytes they never saw
+    other = bytes(synth.generate(500_000, synth.SEED_C5, synth.BYTE))
+    ids2 = gpu.encode(other, m)
+    assert np.array_equal(ids2, ora.encode(other, merges_array(m), linear=True))
+    assert gpu.decode(ids2, m) == other
+
+
+@pytest.mark.parametrize("data,merges", [
+    (b"a" * 100001, [(97, 97, 256), (256, 256, 257), (257, 97, 258)]),
+    (b"Xbbbbb cXbb" * 999, [(ord("X"), ord("b"), ord("X"))]),
+    (b"a" * 9999, [(97, 97, 97)]),
+    (b"aaXaX" * 5000, [(97, ord("X"), ord("X"))]),
+    (b"abcabcab" * 3000, [(97, 98, 65535), (65535, 99, 300), (300, 65535, 301)]),
+    (b"", [(97, 98, 256)]), (b"z", [(97, 98, 256)]), (b"abab", []),
+])
+def test_encode_edge_cases(gpu, ora, data, merges):
+    ids = gpu.encode(data, merges)
+    assert np.array_equal(ids, ora.encode(data, merges, linear=True))
+    if len(ids):
+        rc, want = ora.decode(ids, merges, cap=len(data) + 64)
+        assert rc == 0 and gpu.decode(ids, merges) == want
+
+
+def test_decode_semantics(gpu, zb):
+    with pytest.raises(zb.InvalidToken):
+        gpu.decode([256], [(256, 97, 256)])  # cyclic definition (stack overflow in the reference)
+    assert gpu.decode([257], [(97, 98, 257), (99, 99, 257)]) == b"ab"  # first matching merge wins (:109-116)
+    assert gpu.decode([], REF_TEST_MERGES) == b""
+    assert gpu.decode(np.arange(256, dtype=np.uint16), []) == bytes(range(256))
+
+
+# ---- BASELINE config 2 at full size: properties the domain offers ------------------------------
+def test_c2_full_size_properties(gpu, ora, synth):
+    n = 100_000_000
+    data = synth.generate(n, synth.SEED_C2, synth.UTF8)
+    m, c = gpu.train(data, 4096)
+    st = dict(gpu.last_stats)
+    ma = merges_array(m)
+    assert len(m) == 3840
+    assert list(ma[:, 2]) == list(range(256, 4096))
+    assert (ma[:, 0] < ma[:, 2]).all() and (ma[:, 1] < ma[:, 2]).all()  # components precede the new token
+    assert (np.diff(c.astype(np.int64)) <= 0).all()  # the maximum pair count never increases
+    assert len({(int(a), int(b)) for a, b, _ in ma}) == 3840
+    # first merges against the verbatim oracle at full size (the CPU-baseline sample)
+    om, oc = ora.train(data, 4096, max_steps=2, fast=False)
+    assert np.array_equal(ma[:2], om) and np.array_equal(c[:2], oc)
+    # first 40 merges against the incremental oracle
+    om, oc = ora.train(data[:n], 4096, max_steps=40, fast=True)
+    assert np.array_equal(ma[:40], om) and np.array_equal(c[:40], oc)
+    # encode -> decode round trip; the id stream re-encodes to itself (idempotence on bytes)
+    ids = gpu.encode(data, m)
+    assert len(ids) < n // 2
+    assert gpu.decode(ids, m) == data.tobytes()
+    sl = slice(12_345_678, 12_345_678 + 200_000)
+    assert np.array_equal(gpu.encode(data[sl], m), ora.encode(data[sl], ma, linear=True))
+    assert st["tie_slow_steps"] <= st["tie_steps"]

@@ -78,12 +78,18 @@ class bpe_stats_t(ctypes.Structure):
         ("tie_steps", c_uint64),
         ("tie_slow_steps", c_uint64),
         ("compactions", c_uint64),
+        ("kernel_ms", c_double * 12),
+        ("kernel_calls", c_uint64 * 12),
     ]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["kernel_ms"] = list(self.kernel_ms)
+        d["kernel_calls"] = list(self.kernel_calls)
+        return d
 
 
+KERNEL_CLASSES = ["init", "argmax", "tie", "replay", "halo", "merge", "apply", "compact", "table", "hostgap", "r10", "r11"]
 MERGE_DTYPE = np.dtype([("first", "<u2"), ("second", "<u2"), ("new_token", "<u2")])  # = bpe_merge_t, 6 bytes
 
 _lib = None
@@ -337,8 +343,10 @@ class TimeStats:
         self.just_count_pairs_calls = 0
 
 
-def print_time_stats(stats: TimeStats, total_time_ms: int, file=sys.stderr) -> None:
+def print_time_stats(stats: TimeStats, total_time_ms: int, file=None) -> None:
     """printTimeStats (utils/time_statistics.zig:36-60); 0 calls prints nan like the reference."""
+
+    file = file or sys.stderr
 
     def line(name, t, calls):
         avg = (t / (calls * 1000.0)) if calls else float("nan")

@@ -28,7 +28,7 @@ struct bpe_ctx {
     std::string err;
     // options
     long verify_recount = 0, force_slow_tiebreak = 0, check_tiebreak = 0, compact_pct = 85, table_log2 = 0,
-         max_steps = 0, time_phases = 0;
+         max_steps = 0, time_phases = 0, profile = 0;
     DistComm dist;  // world == 1 when single GPU
     uint64_t launches = 0;
 };
@@ -196,6 +196,36 @@ struct PhaseTimer {  // CUDA-event phase buckets (only when time_phases is on)
         cudaEventElapsedTime(&ms, ev[0], ev[1]);
         *acc += ms;
         (*calls)++;
+    }
+};
+
+// chained event marks: the interval between two consecutive marks is attributed to the bucket
+// of the earlier one. Nothing synchronises until finish().
+enum { K_INIT = 0, K_ARGMAX, K_TIE, K_REPLAY, K_HALO, K_MERGE, K_APPLY, K_COMPACT, K_TABLE, K_HOSTGAP, K_NB = 12 };
+struct EvProfile {
+    bool on = false;
+    cudaStream_t st = 0;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> bucket;
+    void init(bool enable, cudaStream_t s) { on = enable; st = s; }
+    ~EvProfile() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+    void mark(int b) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ev.push_back(e);
+        bucket.push_back(b);
+    }
+    void finish(double* ms, uint64_t* calls) {
+        if (!on || ev.empty()) return;
+        mark(-1);
+        cudaEventSynchronize(ev.back());
+        for (size_t i = 0; i + 1 < ev.size(); i++) {
+            float t = 0;
+            cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+            if (bucket[i] >= 0) { ms[bucket[i]] += t; calls[bucket[i]]++; }
+        }
     }
 };
 
@@ -382,6 +412,9 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     CU(cudaEventRecord(ev0, ctx->stream));
     PhaseTimer pt;
     pt.init(ctx->time_phases != 0, ctx->stream);
+    EvProfile prof;
+    prof.init(ctx->profile != 0, ctx->stream);
+    prof.mark(K_INIT);
 
     int rc = seq_init(ctx, R.sq, d_text, n);
     if (rc) return rc;
@@ -415,12 +448,14 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     for (size_t step = 0; step < want; step++) {
         // ---- argmax (sortCodePointPairs + [0]) ----
         pt.begin();
+        prof.mark(K_ARGMAX);
         BPE_LAUNCH_NS(reset_argmax_kernel, 1, 1, ctx->stream, R.d_ctl());
         BPE_LAUNCH(argmax_kernel, grid_for(R.tm.cap, THREADS), THREADS, ctx->stream, R.tm.view(), R.d_ctl());
         BPE_LAUNCH_NS(ties_kernel, grid_for(R.tm.cap, 256), 256, ctx->stream, R.tm.view(), R.d_ctl());
         ctx->launches += 3;
         CU(cudaGetLastError());
         if (have_pending) CU(cudaMemcpyAsync(&pending_merged, R.merged.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        prof.mark(K_HOSTGAP);
         rc = read_ctl(ctx, R, true);
         if (rc) return rc;
         StepCtl* hc = R.hc();
@@ -440,6 +475,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
                 const uint32_t zcap = R.tm.zcap;
                 const uint32_t zchunk = zcap < ZCHUNK ? zcap : ZCHUNK;
                 const uint32_t nch = zcap / zchunk;
+                prof.mark(K_TIE);
                 BPE_LAUNCH(zig_chunk_kernel, nch, THREADS, ctx->stream, R.tm.zcnt.as<uint32_t>(), zchunk, R.tm.chunkfn.as<ChunkFn>());
                 BPE_LAUNCH(zig_resolve_kernel, 1, MAXTIE, ctx->stream, R.tm.zcnt.as<uint32_t>(), zcap, zchunk,
                            R.tm.chunkfn.as<ChunkFn>(), nch, R.d_ctl());
@@ -447,6 +483,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
                 CU(cudaGetLastError());
                 std::vector<uint32_t> tied(hc->tie_keys, hc->tie_keys + hc->ntied);
                 uint32_t maxc = hc->max_count;
+                prof.mark(K_HOSTGAP);
                 rc = read_ctl(ctx, R, false);
                 if (rc) return rc;
                 hc = R.hc();
@@ -458,6 +495,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
             else {
                 uint32_t maxc = hc->max_count;
                 uint32_t w = 0;
+                prof.mark(K_REPLAY);
                 rc = replay_winner(ctx, R, std::vector<uint32_t>(), maxc, &w);
                 if (rc) return rc;
                 R.hc()->max_count = maxc;
@@ -476,9 +514,11 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
         mcounts.push_back(hc->max_count);
 
         // ---- housekeeping decided from the status just read ----
+        prof.mark(K_TABLE);
         if ((uint64_t)hc->n_inserted * 2 > R.tm.cap) { rc = grow_table(ctx, R); if (rc) return rc; }
         if (R.sq.n_slots > (size_t)TILE && R.sq.live * 100 < (uint64_t)R.sq.n_slots * (uint64_t)ctx->compact_pct) {
             pt.begin();
+            prof.mark(K_COMPACT);
             uint64_t live = 0;
             rc = seq_compact(ctx, R.sq, &live);
             if (rc) return rc;
@@ -486,15 +526,18 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
             pt.end(&R.st.replace_pair_ms, &R.st.replace_pair_calls);
         }
         // keep the reference-home population current so births/deaths can update it in place
+        prof.mark(K_TABLE);
         rc = table_ensure_zcnt(ctx, R.tm, R.d_ctl(), hc->live_keys);
         if (rc) return rc;
 
         // ---- replace (replaceTopPairWithNewToken :207-232) + incremental recount ----
         pt.begin();
+        prof.mark(K_HALO);
         BPE_LAUNCH_NS(set_merge_kernel, 1, 1, ctx->stream, R.d_ctl(), A, B, X);
         ctx->launches++;
         rc = launch_halo(ctx, R.sq, R.d_ctl(), A == B);
         if (rc) return rc;
+        prof.mark(K_MERGE);
         if (A == B)
             BPE_LAUNCH((merge_kernel<uint16_t, true, true>), R.sq.ntiles(), THREADS, ctx->stream, R.sq.tok(),
                        R.sq.halo.as<TileHalo<uint16_t>>(), R.d_ctl(), R.cntL.as<uint32_t>(), R.cntR.as<uint32_t>());
@@ -505,6 +548,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
         R.st.scanned_slots += R.sq.n_slots;
         pt.end(&R.st.replace_pair_ms, &R.st.replace_pair_calls);
         pt.begin();
+        prof.mark(K_APPLY);
         BPE_LAUNCH_NS(apply_from_ctl_kernel, (X + 1 + 255) / 256, 256, ctx->stream, R.tm.view(), R.cntL.as<uint32_t>(),
                       R.cntR.as<uint32_t>(), R.d_ctl(), R.tm.zcnt.as<uint32_t>(), R.tm.zmask(), X + 1, R.merged.as<uint32_t>());
         ctx->launches++;
@@ -515,6 +559,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     }
     CU(cudaEventRecord(ev1, ctx->stream));
     CU(cudaEventSynchronize(ev1));
+    prof.finish(R.st.kernel_ms, R.st.kernel_calls);
     float dev_ms = 0;
     CU(cudaEventElapsedTime(&dev_ms, ev0, ev1));
     cudaEventDestroy(ev0);
@@ -540,14 +585,21 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
     Sequence<TokT> sq;
     int rc = seq_init(ctx, sq, d_text, n);
     if (rc) return rc;
-    DevBuf ctl, dummy;
-    HostBuf h_ctl;
+    DevBuf ctl;
     CU(ctl.alloc(sizeof(StepCtl)));
-    CU(h_ctl.alloc(sizeof(StepCtl)));
     CU(cudaMemsetAsync(ctl.p, 0, sizeof(StepCtl), ctx->stream));
     StepCtl* d_ctl = ctl.as<StepCtl>();
-    StepCtl* hc = h_ctl.as<StepCtl>();
     const TokT H = (TokT)TokTraits<TokT>::hole;
+    uint32_t merged_seen = 0;  // device cntAB accumulates over passes; host subtracts what it has seen
+    auto read_merged = [&](uint32_t* fresh) -> int {
+        uint32_t acc = 0;
+        CU(cudaMemcpyAsync(&acc, &d_ctl->cntAB, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        *fresh = acc - merged_seen;
+        merged_seen = acc;
+        sq.live -= *fresh;
+        return BPE_OK;
+    };
     auto one_pass = [&](uint32_t A, uint32_t B, uint32_t X) -> int {
         BPE_LAUNCH_NS(set_merge_kernel, 1, 1, ctx->stream, d_ctl, A, B, X);
         const uint32_t nt = sq.ntiles();
@@ -558,19 +610,237 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
         if (A == B) {
             BPE_LAUNCH_NS(run_chain_kernel<TokT>, 1, 1, ctx->stream, nt, sq.halo.template as<TileHalo<TokT>>(),
                           sq.run_local.template as<uint32_t>(), sq.run_full.template as<uint8_t>(), 0u);
-            BPE_LAUNCH((merge_kernel<TokT, true, true>), nt, THREADS, ctx->stream, sq.tok(),
+            BPE_LAUNCH((merge_kernel<TokT, true, false>), nt, THREADS, ctx->stream, sq.tok(),
                        sq.halo.template as<TileHalo<TokT>>(), d_ctl, (uint32_t*)nullptr, (uint32_t*)nullptr);
             ctx->launches += 2;
         } else {
-            BPE_LAUNCH((merge_kernel<TokT, false, true>), nt, THREADS, ctx->stream, sq.tok(),
+            BPE_LAUNCH((merge_kernel<TokT, false, false>), nt, THREADS, ctx->stream, sq.tok(),
                        sq.halo.template as<TileHalo<TokT>>(), d_ctl, (uint32_t*)nullptr, (uint32_t*)nullptr);
             ctx->launches++;
         }
+        CU(cudaGetLastError());
         if (st) st->scanned_slots += sq.n_slots;
         return BPE_OK;
     };
-    (void)one_pass; (void)hc; (void)merges; (void)m; (void)d_out; (void)out_n;
-    return fail(ctx, BPE_ERR_INTERNAL, "encode not wired yet");
+    size_t since_check = 0;
+    for (size_t i = 0; i < m && n > 1; i++) {
+        const uint32_t A = merges[i].first, B = merges[i].second, X = merges[i].new_token;
+        rc = one_pass(A, B, X);
+        if (rc) return rc;
+        since_check++;
+        if (X == A) {
+            // the reference does not advance `i` after a hit (:78-81), so a merge whose new token
+            // equals its own first component keeps absorbing: repeat until a pass changes nothing
+            while (true) {
+                uint32_t fresh = 0;
+                rc = read_merged(&fresh);
+                if (rc) return rc;
+                if (!fresh) break;
+                rc = one_pass(A, B, X);
+                if (rc) return rc;
+            }
+            since_check = 0;
+        }
+        if (since_check >= 32 || i + 1 == m) {
+            uint32_t fresh = 0;
+            rc = read_merged(&fresh);
+            if (rc) return rc;
+            since_check = 0;
+            if (sq.n_slots > (size_t)TILE && sq.live * 100 < (uint64_t)sq.n_slots * (uint64_t)ctx->compact_pct && i + 1 < m) {
+                rc = seq_compact(ctx, sq, nullptr);
+                if (rc) return rc;
+                if (st) st->compactions++;
+            }
+        }
+    }
+    // final squeeze straight into the caller's u16 buffer
+    const uint32_t nt = sq.ntiles();
+    BPE_LAUNCH(tile_count_kernel<TokT>, nt, THREADS, ctx->stream, sq.tok(), sq.tile_live.template as<uint32_t>());
+    BPE_LAUNCH(tile_scan_kernel, 1, THREADS, ctx->stream, sq.tile_live.template as<uint32_t>(), nt,
+               sq.tile_off.template as<unsigned long long>(), sq.total.template as<unsigned long long>());
+    BPE_LAUNCH((compact_scatter_kernel<TokT, uint16_t>), nt, THREADS, ctx->stream, sq.tok(),
+               sq.tile_off.template as<unsigned long long>(), d_out);
+    ctx->launches += 3;
+    CU(cudaGetLastError());
+    unsigned long long total = 0;
+    CU(cudaMemcpyAsync(&total, sq.total.p, sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *out_n = (size_t)total;
+    return BPE_OK;
+}
+
+static int encode_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bpe_merge_t* merges, size_t m,
+                         uint16_t* d_out, size_t* out_n, bpe_stats_t* stats_out) {
+    if (!out_n) return fail(ctx, BPE_ERR_INVALID_ARG, "out_n is null");
+    *out_n = 0;
+    if (m && !merges) return fail(ctx, BPE_ERR_INVALID_ARG, "merges is null");
+    bpe_stats_t st;
+    memset(&st, 0, sizeof st);
+    const double t0 = now_ms();
+    const uint64_t l0 = ctx->launches;
+    if (n == 0) { if (stats_out) *stats_out = st; return BPE_OK; }
+    if (!d_out) return fail(ctx, BPE_ERR_INVALID_ARG, "out is null");
+    if (n >= 0xFFFFFFF0ull) return fail(ctx, BPE_ERR_INVALID_ARG, "input of %zu bytes exceeds the 32-bit position range", n);
+    CU(cudaSetDevice(ctx->device));
+    cudaEvent_t ev0, ev1;
+    CU(cudaEventCreate(&ev0));
+    CU(cudaEventCreate(&ev1));
+    CU(cudaEventRecord(ev0, ctx->stream));
+    // id 65535 is the u16 hole marker: lists that mention it run on u32 slots
+    bool wide = false;
+    for (size_t i = 0; i < m; i++)
+        if (merges[i].first == 0xFFFF || merges[i].second == 0xFFFF || merges[i].new_token == 0xFFFF) wide = true;
+    int rc = wide ? encode_passes<uint32_t>(ctx, d_text, n, merges, m, d_out, out_n, &st)
+                  : encode_passes<uint16_t>(ctx, d_text, n, merges, m, d_out, out_n, &st);
+    if (rc) return rc;
+    CU(cudaEventRecord(ev1, ctx->stream));
+    CU(cudaEventSynchronize(ev1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ev0, ev1));
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    st.device_ms = ms;
+    st.total_ms = now_ms() - t0;
+    st.kernel_launches = ctx->launches - l0;
+    st.replace_pair_calls = m;
+    st.replace_pair_ms = ms;
+    if (stats_out) *stats_out = st;
+    return BPE_OK;
+}
+
+// -----------------------------------------------------------------------------------------
+// decode (src/basic_tokenizer.zig:90-138)
+// -----------------------------------------------------------------------------------------
+struct Vocab {
+    std::vector<uint32_t> off, len;  // per id; len 0 = unknown id, 0xFFFFFFFF = expansion too large
+    std::vector<uint8_t> bytes;
+};
+static const uint32_t VOC_TOO_BIG = 0xFFFFFFFFu;
+static const uint32_t VOC_MAX_LEN = 1u << 19;
+
+// findMerge (:109-116) returns the FIRST merge whose new_token matches; decodeMerge (:118-138)
+// expands first then second, recursively. Ids whose expansion is undefined (unknown component or
+// a cycle, which would overflow the reference's stack) get len 0 and fail only if they are used.
+static void build_vocab(const bpe_merge_t* merges, size_t m, Vocab& v) {
+    const uint32_t NID = 65536;
+    std::vector<int32_t> def(NID, -1);
+    for (size_t i = 0; i < m; i++)
+        if (def[merges[i].new_token] < 0) def[merges[i].new_token] = (int32_t)i;
+    std::vector<uint8_t> state(NID, 0);  // 0 new, 1 open, 2 done
+    std::vector<std::vector<uint8_t>> exp(NID);
+    v.len.assign(NID, 0);
+    for (uint32_t b = 0; b < 256; b++) { exp[b].assign(1, (uint8_t)b); state[b] = 2; v.len[b] = 1; }
+    std::vector<uint32_t> stack;
+    for (uint32_t id = 256; id < NID; id++) {
+        if (state[id] || def[id] < 0) continue;
+        stack.push_back(id);
+        while (!stack.empty()) {
+            uint32_t t = stack.back();
+            if (state[t] == 2) { stack.pop_back(); continue; }
+            state[t] = 1;
+            const bpe_merge_t& mg = merges[def[t]];
+            uint32_t parts[2] = {mg.first, mg.second};
+            bool wait = false, bad = false, big = false;
+            for (uint32_t p : parts) {
+                if (p < 256) continue;
+                if (def[p] < 0) { bad = true; break; }
+                if (state[p] == 0) { stack.push_back(p); wait = true; break; }
+                if (state[p] == 1) { bad = true; break; }  // cycle
+                if (v.len[p] == 0) { bad = true; break; }
+                if (v.len[p] == VOC_TOO_BIG) big = true;
+            }
+            if (wait) continue;
+            if (bad) v.len[t] = 0;
+            else if (big || (uint64_t)v.len[parts[0]] + v.len[parts[1]] > VOC_MAX_LEN) v.len[t] = VOC_TOO_BIG;
+            else {
+                exp[t] = exp[parts[0]];
+                exp[t].insert(exp[t].end(), exp[parts[1]].begin(), exp[parts[1]].end());
+                v.len[t] = (uint32_t)exp[t].size();
+            }
+            state[t] = 2;
+            stack.pop_back();
+        }
+    }
+    v.off.assign(NID, 0);
+    size_t total = 0;
+    for (uint32_t id = 0; id < NID; id++) {
+        if (v.len[id] && v.len[id] != VOC_TOO_BIG) { v.off[id] = (uint32_t)total; total += exp[id].size(); }
+    }
+    v.bytes.resize(total ? total : 1);
+    for (uint32_t id = 0; id < NID; id++)
+        if (v.len[id] && v.len[id] != VOC_TOO_BIG) memcpy(&v.bytes[v.off[id]], exp[id].data(), exp[id].size());
+}
+
+__global__ void decode_flag_big_kernel(const uint16_t* __restrict__ toks, size_t n, const uint32_t* __restrict__ voc_len, StepCtl* ctl) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        uint32_t l = voc_len[toks[i]];
+        if (l == 0) atomicOr(&ctl->err, (uint32_t)ERR_KEY_MISSING);
+        else if (l == 0xFFFFFFFFu) atomicOr(&ctl->err, (uint32_t)ERR_TABLE_FULL);
+    }
+}
+
+// d_out == nullptr: size query only
+static int decode_device(bpe_ctx* ctx, const uint16_t* d_toks, size_t n, const bpe_merge_t* merges, size_t m,
+                         uint8_t* d_out, size_t cap, size_t* out_n, bpe_stats_t* stats_out) {
+    if (!out_n) return fail(ctx, BPE_ERR_INVALID_ARG, "out_n is null");
+    *out_n = 0;
+    if (m && !merges) return fail(ctx, BPE_ERR_INVALID_ARG, "merges is null");
+    bpe_stats_t st;
+    memset(&st, 0, sizeof st);
+    const double t0 = now_ms();
+    const uint64_t l0 = ctx->launches;
+    if (n == 0) { if (stats_out) *stats_out = st; return BPE_OK; }
+    CU(cudaSetDevice(ctx->device));
+    Vocab v;
+    build_vocab(merges, m, v);
+    DevBuf voff, vlen, vbytes, ctl, tile_bytes, tile_off, total;
+    const size_t nt = (n + TILE - 1) / TILE;
+    CU(voff.alloc(65536 * 4)); CU(vlen.alloc(65536 * 4)); CU(vbytes.alloc(v.bytes.size()));
+    CU(ctl.alloc(sizeof(StepCtl))); CU(tile_bytes.alloc(nt * 4)); CU(tile_off.alloc(nt * 8)); CU(total.alloc(8));
+    cudaEvent_t ev0, ev1;
+    CU(cudaEventCreate(&ev0));
+    CU(cudaEventCreate(&ev1));
+    CU(cudaEventRecord(ev0, ctx->stream));
+    CU(cudaMemcpyAsync(voff.p, v.off.data(), 65536 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(vlen.p, v.len.data(), 65536 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(vbytes.p, v.bytes.data(), v.bytes.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctl.p, 0, sizeof(StepCtl), ctx->stream));
+    BPE_LAUNCH_NS(decode_flag_big_kernel, grid_for(n, 256), 256, ctx->stream, d_toks, n, vlen.as<uint32_t>(), ctl.as<StepCtl>());
+    ctx->launches++;
+    uint32_t err = 0;
+    CU(cudaMemcpyAsync(&err, &ctl.as<StepCtl>()->err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (err & ERR_KEY_MISSING) return fail(ctx, BPE_ERR_INVALID_TOKEN, "token id without a merge (error.InvalidToken)");
+    if (err & ERR_TABLE_FULL) return fail(ctx, BPE_ERR_OOM, "a token expands to more than %u bytes", VOC_MAX_LEN);
+    BPE_LAUNCH(decode_len_kernel, (unsigned)nt, THREADS, ctx->stream, d_toks, n, vlen.as<uint32_t>(), tile_bytes.as<uint32_t>(), ctl.as<StepCtl>());
+    BPE_LAUNCH(tile_scan_kernel, 1, THREADS, ctx->stream, tile_bytes.as<uint32_t>(), (uint32_t)nt,
+               tile_off.as<unsigned long long>(), total.as<unsigned long long>());
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    unsigned long long tot = 0;
+    CU(cudaMemcpyAsync(&tot, total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *out_n = (size_t)tot;
+    if (d_out) {
+        if ((size_t)tot > cap) return fail(ctx, BPE_ERR_OOM, "decode needs %llu bytes, buffer has %zu", tot, cap);
+        BPE_LAUNCH(decode_scatter_kernel, (unsigned)nt, THREADS, ctx->stream, d_toks, n, voff.as<uint32_t>(), vlen.as<uint32_t>(),
+                   vbytes.as<uint8_t>(), tile_off.as<unsigned long long>(), d_out, cap);
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(ev1, ctx->stream));
+    CU(cudaEventSynchronize(ev1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ev0, ev1));
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    st.device_ms = ms;
+    st.total_ms = now_ms() - t0;
+    st.kernel_launches = ctx->launches - l0;
+    if (stats_out) *stats_out = st;
+    return BPE_OK;
 }
 
 // -----------------------------------------------------------------------------------------
@@ -643,6 +913,7 @@ int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value) {
     else if (s == "table_log2") ctx->table_log2 = value;
     else if (s == "max_steps") ctx->max_steps = value;
     else if (s == "time_phases") ctx->time_phases = value;
+    else if (s == "profile") ctx->profile = value;
     else return fail(ctx, BPE_ERR_INVALID_ARG, "unknown option '%s'", name);
     return BPE_OK;
 }
@@ -670,19 +941,69 @@ int bpe_train(bpe_ctx* ctx, const uint8_t* text, size_t n, uint16_t vocab_size, 
 int bpe_encode_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bpe_merge_t* merges, size_t m,
                       uint16_t* d_out, size_t* out_n, bpe_stats_t* stats) {
     if (!ctx) return BPE_ERR_INVALID_ARG;
-    return encode_passes<uint16_t>(ctx, d_text, n, merges, m, d_out, out_n, stats);
+    return encode_device(ctx, d_text, n, merges, m, d_out, out_n, stats);
 }
-int bpe_encode(bpe_ctx* ctx, const uint8_t*, size_t, const bpe_merge_t*, size_t, uint16_t*, size_t*, bpe_stats_t*) {
-    return fail(ctx, BPE_ERR_INTERNAL, "encode not wired yet");
+
+int bpe_encode(bpe_ctx* ctx, const uint8_t* text, size_t n, const bpe_merge_t* merges, size_t m, uint16_t* out,
+               size_t* out_n, bpe_stats_t* stats) {
+    if (!ctx) return BPE_ERR_INVALID_ARG;
+    if (!out_n) return fail(ctx, BPE_ERR_INVALID_ARG, "out_n is null");
+    *out_n = 0;
+    if (n == 0) { if (stats) memset(stats, 0, sizeof *stats); return BPE_OK; }
+    if (!text || !out) return fail(ctx, BPE_ERR_INVALID_ARG, "text/out is null");
+    const double t0 = now_ms();
+    CU(cudaSetDevice(ctx->device));
+    DevBuf d_in, d_out;
+    if (cudaMalloc(&d_in.p, n) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", n);
+    if (cudaMalloc(&d_out.p, n * 2) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", n * 2);
+    CU(cudaMemcpyAsync(d_in.p, text, n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = encode_device(ctx, d_in.as<uint8_t>(), n, merges, m, d_out.as<uint16_t>(), out_n, stats);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, d_out.p, *out_n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (stats) stats->total_ms = now_ms() - t0;
+    return BPE_OK;
 }
-int bpe_decode_size(bpe_ctx* ctx, const uint16_t*, size_t, const bpe_merge_t*, size_t, size_t*) {
-    return fail(ctx, BPE_ERR_INTERNAL, "decode not wired yet");
+
+int bpe_decode_device(bpe_ctx* ctx, const uint16_t* d_toks, size_t n, const bpe_merge_t* merges, size_t m,
+                      uint8_t* d_out, size_t cap, size_t* out_n, bpe_stats_t* stats) {
+    if (!ctx) return BPE_ERR_INVALID_ARG;
+    if (n && !d_out) return fail(ctx, BPE_ERR_INVALID_ARG, "out is null");
+    return decode_device(ctx, d_toks, n, merges, m, d_out, cap, out_n, stats);
 }
-int bpe_decode(bpe_ctx* ctx, const uint16_t*, size_t, const bpe_merge_t*, size_t, uint8_t*, size_t, size_t*, bpe_stats_t*) {
-    return fail(ctx, BPE_ERR_INTERNAL, "decode not wired yet");
+
+int bpe_decode_size(bpe_ctx* ctx, const uint16_t* toks, size_t n, const bpe_merge_t* merges, size_t m, size_t* out_n) {
+    if (!ctx) return BPE_ERR_INVALID_ARG;
+    if (!out_n) return fail(ctx, BPE_ERR_INVALID_ARG, "out_n is null");
+    *out_n = 0;
+    if (n == 0) return BPE_OK;
+    if (!toks) return fail(ctx, BPE_ERR_INVALID_ARG, "toks is null");
+    CU(cudaSetDevice(ctx->device));
+    DevBuf d_in;
+    if (cudaMalloc(&d_in.p, n * 2) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", n * 2);
+    CU(cudaMemcpyAsync(d_in.p, toks, n * 2, cudaMemcpyHostToDevice, ctx->stream));
+    return decode_device(ctx, d_in.as<uint16_t>(), n, merges, m, nullptr, 0, out_n, nullptr);
 }
-int bpe_decode_device(bpe_ctx* ctx, const uint16_t*, size_t, const bpe_merge_t*, size_t, uint8_t*, size_t, size_t*, bpe_stats_t*) {
-    return fail(ctx, BPE_ERR_INTERNAL, "decode not wired yet");
+
+int bpe_decode(bpe_ctx* ctx, const uint16_t* toks, size_t n, const bpe_merge_t* merges, size_t m, uint8_t* out,
+               size_t cap, size_t* out_n, bpe_stats_t* stats) {
+    if (!ctx) return BPE_ERR_INVALID_ARG;
+    if (!out_n) return fail(ctx, BPE_ERR_INVALID_ARG, "out_n is null");
+    *out_n = 0;
+    if (n == 0) { if (stats) memset(stats, 0, sizeof *stats); return BPE_OK; }
+    if (!toks || !out) return fail(ctx, BPE_ERR_INVALID_ARG, "toks/out is null");
+    const double t0 = now_ms();
+    CU(cudaSetDevice(ctx->device));
+    DevBuf d_in, d_out;
+    if (cudaMalloc(&d_in.p, n * 2) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", n * 2);
+    if (cudaMalloc(&d_out.p, cap ? cap : 1) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", cap);
+    CU(cudaMemcpyAsync(d_in.p, toks, n * 2, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = decode_device(ctx, d_in.as<uint16_t>(), n, merges, m, d_out.as<uint8_t>(), cap, out_n, stats);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, d_out.p, *out_n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (stats) stats->total_ms = now_ms() - t0;
+    return BPE_OK;
 }
 
 }  // extern "C"

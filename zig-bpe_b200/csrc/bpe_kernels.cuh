@@ -290,8 +290,8 @@ __global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, 
         }
         if (!start) continue;
         tok[base + (size_t)(s - OFF)] = X;
+        nAB++;
         if (DELTAS) {
-            nAB++;
             // left side: always owned by this occurrence
             int p = prev_live(ext, s);
             if (p >= 0) {
@@ -314,10 +314,8 @@ __global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, 
             }
         }
     }
-    if (DELTAS) {
-        if (nAB) atomicAdd(&ctl->cntAB, nAB);
-        if (nXX) atomicAdd(&ctl->cntXX, nXX);
-    }
+    if (nAB) atomicAdd(&ctl->cntAB, nAB);
+    if (DELTAS && nXX) atomicAdd(&ctl->cntXX, nXX);
 }
 
 // =========================================================================================
@@ -343,34 +341,6 @@ __device__ __forceinline__ void tbl_add(const PairTable& tbl, uint32_t key, uint
     if (old == 0) {  // birth
         atomicAdd(&ctl->live_keys, 1u);
         if (zcnt) zcnt_add(zcnt, zmask, key, +1, &ctl->err);
-    }
-}
-
-__global__ void apply_kernel(PairTable tbl, uint32_t* __restrict__ cntL, uint32_t* __restrict__ cntR,
-                             StepCtl* ctl, uint32_t* zcnt, uint32_t zmask, uint32_t n_ids,
-                             uint32_t cntXX, uint32_t cntAB) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t A = ctl->A, B = ctl->B, X = ctl->X;
-    if (p < n_ids) {
-        uint32_t c = cntL[p];
-        if (c) {
-            cntL[p] = 0;
-            tbl_sub(tbl, pair_key(p, A), c, ctl, zcnt, zmask);
-            tbl_add(tbl, pair_key(p, X), c, ctl, zcnt, zmask);
-        }
-        c = cntR[p];
-        if (c) {
-            cntR[p] = 0;
-            tbl_sub(tbl, pair_key(B, p), c, ctl, zcnt, zmask);
-            tbl_add(tbl, pair_key(X, p), c, ctl, zcnt, zmask);
-        }
-    }
-    if (p == 0) {
-        if (cntXX) {
-            tbl_sub(tbl, pair_key(B, A), cntXX, ctl, zcnt, zmask);
-            tbl_add(tbl, pair_key(X, X), cntXX, ctl, zcnt, zmask);
-        }
-        if (cntAB) tbl_sub(tbl, pair_key(A, B), cntAB, ctl, zcnt, zmask);
     }
 }
 
