@@ -4,6 +4,8 @@
 namespace emul {
 dim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
 uint64_t g_launches = 0;
+int g_sync_or_acc[2] = {0, 0};
+int g_sync_or_phase = 0;
 
 static ucontext_t g_sched;
 static std::vector<ucontext_t> g_ctx;
@@ -107,6 +109,8 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& body, bool uses_
             makecontext(&g_ctx[t], fiber_entry, 0);
             g_state[t] = 0;
         }
+        g_sync_or_acc[0] = g_sync_or_acc[1] = 0;
+        g_sync_or_phase = 0;
         int done = 0;
         while (done < n) {
             bool progressed = false;

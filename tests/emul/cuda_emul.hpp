@@ -49,6 +49,17 @@ extern uint64_t g_launches;
 #define blockDim (emul::g_blockDim)
 #define gridDim (emul::g_gridDim)
 static inline void __syncthreads() { emul::sync_threads(); }
+namespace emul { extern int g_sync_or_acc[2]; extern int g_sync_or_phase; }
+static inline int __syncthreads_or(int pred) {
+    // two alternating accumulators so that back-to-back calls do not interfere
+    int ph = emul::g_sync_or_phase;
+    if (pred) emul::g_sync_or_acc[ph] = 1;
+    emul::sync_threads();
+    int r = emul::g_sync_or_acc[ph];
+    if (threadIdx.x == 0) { emul::g_sync_or_phase = ph ^ 1; emul::g_sync_or_acc[ph ^ 1] = 0; }
+    emul::sync_threads();
+    return r;
+}
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
 static inline void __threadfence() {}
 

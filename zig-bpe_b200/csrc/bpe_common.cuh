@@ -82,7 +82,8 @@ struct StepCtl {
     uint32_t tie_winner;   // key
     uint32_t last_pair_pos;  // slot index of the left token of the last pair (replay edge case)
     uint32_t verify_mismatch;
-    uint32_t pad[2];
+    uint32_t n_heavy;      // entries appended to the heavy-key list (may exceed its capacity)
+    uint32_t hist_nonzero; // distinct byte pairs found by the initial count
     uint32_t tie_keys[MAXTIE];
 };
 

@@ -203,34 +203,53 @@ struct PhaseTimer {  // CUDA-event phase buckets (only when time_phases is on)
 // of the earlier one. Nothing synchronises until finish().
 enum { K_INIT = 0, K_ARGMAX, K_TIE, K_REPLAY, K_HALO, K_MERGE, K_APPLY, K_COMPACT, K_TABLE, K_HOSTGAP, K_NB = 12 };
 struct EvProfile {
+    static const size_t POOL = 2048;
     bool on = false;
     cudaStream_t st = 0;
     std::vector<cudaEvent_t> ev;
     std::vector<int> bucket;
-    void init(bool enable, cudaStream_t s) { on = enable; st = s; }
-    ~EvProfile() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
-    void mark(int b) {
+    size_t used = 0;
+    double* ms = nullptr;
+    uint64_t* calls = nullptr;
+    void init(bool enable, cudaStream_t s, double* ms_out, uint64_t* calls_out) {
+        on = enable; st = s; ms = ms_out; calls = calls_out;
         if (!on) return;
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        cudaEventRecord(e, st);
-        ev.push_back(e);
-        bucket.push_back(b);
+        ev.resize(POOL);
+        bucket.resize(POOL);
+        for (size_t i = 0; i < POOL; i++) cudaEventCreate(&ev[i]);
     }
-    void finish(double* ms, uint64_t* calls) {
-        if (!on || ev.empty()) return;
-        mark(-1);
-        cudaEventSynchronize(ev.back());
-        for (size_t i = 0; i + 1 < ev.size(); i++) {
+    ~EvProfile() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+    void drain(bool keep_last) {  // resolve recorded intervals; optionally carry the last mark over
+        if (used == 0) return;
+        cudaEventSynchronize(ev[used - 1]);
+        for (size_t i = 0; i + 1 < used; i++) {
             float t = 0;
             cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
             if (bucket[i] >= 0) { ms[bucket[i]] += t; calls[bucket[i]]++; }
         }
+        if (keep_last) { std::swap(ev[0], ev[used - 1]); bucket[0] = bucket[used - 1]; used = 1; }
+        else used = 0;
+    }
+    void mark(int b) {
+        if (!on) return;
+        if (used == POOL) drain(true);
+        cudaEventRecord(ev[used], st);
+        bucket[used] = b;
+        used++;
+    }
+    void finish() {
+        if (!on) return;
+        mark(-1);
+        drain(false);
     }
 };
 
 __global__ void set_merge_kernel(StepCtl* ctl, uint32_t A, uint32_t B, uint32_t X) {
     if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->A = A; ctl->B = B; ctl->X = X; }
+}
+__global__ void hist_nonzero_kernel(const uint32_t* __restrict__ hist, StepCtl* ctl) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 65536u && hist[i]) atomicAdd(&ctl->hist_nonzero, 1u);
 }
 __global__ void reset_argmax_kernel(StepCtl* ctl) {
     if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->max_count = 0; ctl->ntied = 0; ctl->tie_status = TIE_NONE; }
@@ -238,7 +257,7 @@ __global__ void reset_argmax_kernel(StepCtl* ctl) {
 // folds cntXX/cntAB into the table through apply_kernel's arguments being device-resident:
 // the wrapper reads them on the device so no host round trip sits between merge and apply.
 __global__ void apply_from_ctl_kernel(PairTable tbl, uint32_t* cntL, uint32_t* cntR, StepCtl* ctl,
-                                      uint32_t* zcnt, uint32_t zmask, uint32_t n_ids, uint32_t* merged_out) {
+                                      uint32_t* zcnt, uint32_t zmask, uint32_t n_ids, uint32_t* merged_out, HeavyList hl) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t A = ctl->A, B = ctl->B, X = ctl->X;
     if (p < n_ids) {
@@ -246,20 +265,20 @@ __global__ void apply_from_ctl_kernel(PairTable tbl, uint32_t* cntL, uint32_t* c
         if (c) {
             cntL[p] = 0;
             tbl_sub(tbl, pair_key(p, A), c, ctl, zcnt, zmask);
-            tbl_add(tbl, pair_key(p, X), c, ctl, zcnt, zmask);
+            tbl_add(tbl, pair_key(p, X), c, ctl, zcnt, zmask, hl);
         }
         c = cntR[p];
         if (c) {
             cntR[p] = 0;
             tbl_sub(tbl, pair_key(B, p), c, ctl, zcnt, zmask);
-            tbl_add(tbl, pair_key(X, p), c, ctl, zcnt, zmask);
+            tbl_add(tbl, pair_key(X, p), c, ctl, zcnt, zmask, hl);
         }
     }
     if (p == 0) {
         const uint32_t xx = ctl->cntXX, ab = ctl->cntAB;
         if (xx) {
             tbl_sub(tbl, pair_key(B, A), xx, ctl, zcnt, zmask);
-            tbl_add(tbl, pair_key(X, X), xx, ctl, zcnt, zmask);
+            tbl_add(tbl, pair_key(X, X), xx, ctl, zcnt, zmask, hl);
         }
         if (ab) tbl_sub(tbl, pair_key(A, B), ab, ctl, zcnt, zmask);
         *merged_out = ab;
@@ -272,7 +291,9 @@ struct TrainRun {
     bpe_ctx* ctx;
     Sequence<uint16_t> sq;
     TableMem tm;
-    DevBuf cntL, cntR, hist, ctl, merged, firstpos, recount, live_chk;
+    DevBuf cntL, cntR, hist, ctl, merged, firstpos, recount, live_chk, heavy;
+    uint32_t theta = 0;  // heavy-list threshold (0 = list invalid)
+    HeavyList hl() const { HeavyList h; h.slots = heavy.as<uint32_t>(); h.cap = (uint32_t)(heavy.bytes / 4); h.theta = theta; return h; }
     HostBuf h_ctl;
     bpe_stats_t st;
     StepCtl* d_ctl() const { return ctl.as<StepCtl>(); }
@@ -413,31 +434,37 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     PhaseTimer pt;
     pt.init(ctx->time_phases != 0, ctx->stream);
     EvProfile prof;
-    prof.init(ctx->profile != 0, ctx->stream);
+    prof.init(ctx->profile != 0, ctx->stream, R.st.kernel_ms, R.st.kernel_calls);
     prof.mark(K_INIT);
 
     int rc = seq_init(ctx, R.sq, d_text, n);
     if (rc) return rc;
     CU(R.cntL.alloc(65536 * 4)); CU(R.cntR.alloc(65536 * 4)); CU(R.hist.alloc(65536 * 4));
     CU(R.ctl.alloc(sizeof(StepCtl))); CU(R.merged.alloc(4));
+    CU(R.heavy.alloc((size_t)(1u << 20) * 4));
     CU(R.h_ctl.alloc(sizeof(StepCtl)));
     CU(cudaMemsetAsync(R.cntL.p, 0, 65536 * 4, ctx->stream));
     CU(cudaMemsetAsync(R.cntR.p, 0, 65536 * 4, ctx->stream));
     CU(cudaMemsetAsync(R.hist.p, 0, 65536 * 4, ctx->stream));
     CU(cudaMemsetAsync(R.ctl.p, 0, sizeof(StepCtl), ctx->stream));
     CU(cudaMemsetAsync(R.merged.p, 0, 4, ctx->stream));
-    uint32_t cap = 1u << 19;
-    if (ctx->table_log2 > 0) cap = 1u << ctx->table_log2;
-    else while ((size_t)cap < n / 64 && cap < (1u << 28)) cap <<= 1;
-    rc = table_alloc(ctx, R.tm, cap);
-    if (rc) return rc;
-
     // initial count (countCodePointPairs :257-278 on the byte sequence)
     pt.begin();
     BPE_LAUNCH_NS(byte_pair_hist_kernel, grid_for(n, 256), 256, ctx->stream, d_text, n, -1, R.hist.as<uint32_t>());
+    BPE_LAUNCH_NS(hist_nonzero_kernel, 65536 / 256, 256, ctx->stream, R.hist.as<uint32_t>(), R.d_ctl());
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    rc = read_ctl(ctx, R, false);
+    if (rc) return rc;
+    uint32_t cap = 1u << 19;
+    if (ctx->table_log2 > 0) cap = 1u << ctx->table_log2;
+    else while ((size_t)cap < n / 64 && cap < (1u << 28)) cap <<= 1;
+    while ((uint64_t)R.hc()->hist_nonzero * 4 > cap) cap <<= 1;  // the byte pairs alone must fit with room to spare
+    rc = table_alloc(ctx, R.tm, cap);
+    if (rc) return rc;
     BPE_LAUNCH_NS(seed_table_kernel, 65536 / 256, 256, ctx->stream, R.hist.as<uint32_t>(), R.tm.view(), R.d_ctl(),
                   (uint32_t*)nullptr, 0u);
-    ctx->launches += 2;
+    ctx->launches += 1;
     CU(cudaGetLastError());
     pt.end(&R.st.just_count_pairs_ms, &R.st.just_count_pairs_calls);
 
@@ -449,17 +476,41 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
         // ---- argmax (sortCodePointPairs + [0]) ----
         pt.begin();
         prof.mark(K_ARGMAX);
-        BPE_LAUNCH_NS(reset_argmax_kernel, 1, 1, ctx->stream, R.d_ctl());
-        BPE_LAUNCH(argmax_kernel, grid_for(R.tm.cap, THREADS), THREADS, ctx->stream, R.tm.view(), R.d_ctl());
-        BPE_LAUNCH_NS(ties_kernel, grid_for(R.tm.cap, 256), 256, ctx->stream, R.tm.view(), R.d_ctl());
-        ctx->launches += 3;
-        CU(cudaGetLastError());
-        if (have_pending) CU(cudaMemcpyAsync(&pending_merged, R.merged.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        prof.mark(K_HOSTGAP);
-        rc = read_ctl(ctx, R, true);
-        if (rc) return rc;
         StepCtl* hc = R.hc();
-        if (hc->err) return fail(ctx, BPE_ERR_INTERNAL, "device error flags 0x%x at step %zu", hc->err, step);
+        bool from_list = R.theta != 0;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            BPE_LAUNCH_NS(reset_argmax_kernel, 1, 1, ctx->stream, R.d_ctl());
+            if (from_list) {
+                // scan only the heavy keys (exact while the maximum stays >= theta)
+                const uint32_t nh_est = 1u << 16;
+                BPE_LAUNCH(heavy_argmax_kernel, grid_for(nh_est, THREADS, 148 * 4), THREADS, ctx->stream, R.tm.view(), R.hl(), R.d_ctl());
+                BPE_LAUNCH_NS(heavy_ties_kernel, grid_for(nh_est, 256, 148 * 4), 256, ctx->stream, R.tm.view(), R.hl(), R.d_ctl());
+            } else {
+                BPE_LAUNCH(argmax_kernel, grid_for(R.tm.cap, THREADS), THREADS, ctx->stream, R.tm.view(), R.d_ctl());
+                BPE_LAUNCH_NS(ties_kernel, grid_for(R.tm.cap, 256), 256, ctx->stream, R.tm.view(), R.d_ctl());
+            }
+            ctx->launches += 3;
+            CU(cudaGetLastError());
+            if (have_pending) CU(cudaMemcpyAsync(&pending_merged, R.merged.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            prof.mark(K_HOSTGAP);
+            rc = read_ctl(ctx, R, true);
+            if (rc) return rc;
+            hc = R.hc();
+            if (hc->err) return fail(ctx, BPE_ERR_INTERNAL, "device error flags 0x%x at step %zu", hc->err, step);
+            if (!from_list) break;
+            if (hc->max_count >= R.theta && hc->n_heavy <= R.hl().cap) break;  // list result is exact
+            from_list = false;  // maximum fell below theta (or the list overflowed): full pass
+            R.theta = 0;
+            prof.mark(K_ARGMAX);
+        }
+        if (!from_list && hc->max_count > 1) {
+            // (re)build the heavy list for the following steps
+            R.theta = hc->max_count / 2 > 1 ? hc->max_count / 2 : 1;
+            CU(cudaMemsetAsync(&R.d_ctl()->n_heavy, 0, 4, ctx->stream));
+            BPE_LAUNCH_NS(heavy_collect_kernel, grid_for(R.tm.cap, 256), 256, ctx->stream, R.tm.view(), R.hl(), R.d_ctl());
+            ctx->launches++;
+            CU(cudaGetLastError());
+        }
         if (have_pending) { R.sq.live -= pending_merged; have_pending = false; }
         if (hc->max_count == 0) { pt.end(&R.st.sort_pairs_ms, &R.st.sort_pairs_calls); break; }  // "No more pairs to merge" (:188-191)
         uint32_t winner = hc->tie_keys[0];
@@ -515,7 +566,16 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
 
         // ---- housekeeping decided from the status just read ----
         prof.mark(K_TABLE);
-        if ((uint64_t)hc->n_inserted * 2 > R.tm.cap) { rc = grow_table(ctx, R); if (rc) return rc; }
+        if ((uint64_t)hc->n_inserted * 2 > R.tm.cap) {
+            rc = grow_table(ctx, R);
+            if (rc) return rc;
+            if (R.theta) {  // slot indices changed: rebuild the heavy list with the same threshold
+                CU(cudaMemsetAsync(&R.d_ctl()->n_heavy, 0, 4, ctx->stream));
+                BPE_LAUNCH_NS(heavy_collect_kernel, grid_for(R.tm.cap, 256), 256, ctx->stream, R.tm.view(), R.hl(), R.d_ctl());
+                ctx->launches++;
+                CU(cudaGetLastError());
+            }
+        }
         if (R.sq.n_slots > (size_t)TILE && R.sq.live * 100 < (uint64_t)R.sq.n_slots * (uint64_t)ctx->compact_pct) {
             pt.begin();
             prof.mark(K_COMPACT);
@@ -550,7 +610,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
         pt.begin();
         prof.mark(K_APPLY);
         BPE_LAUNCH_NS(apply_from_ctl_kernel, (X + 1 + 255) / 256, 256, ctx->stream, R.tm.view(), R.cntL.as<uint32_t>(),
-                      R.cntR.as<uint32_t>(), R.d_ctl(), R.tm.zcnt.as<uint32_t>(), R.tm.zmask(), X + 1, R.merged.as<uint32_t>());
+                      R.cntR.as<uint32_t>(), R.d_ctl(), R.tm.zcnt.as<uint32_t>(), R.tm.zmask(), X + 1, R.merged.as<uint32_t>(), R.hl());
         ctx->launches++;
         CU(cudaGetLastError());
         pt.end(&R.st.just_count_pairs_ms, &R.st.just_count_pairs_calls);
@@ -559,7 +619,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     }
     CU(cudaEventRecord(ev1, ctx->stream));
     CU(cudaEventSynchronize(ev1));
-    prof.finish(R.st.kernel_ms, R.st.kernel_calls);
+    prof.finish();
     float dev_ms = 0;
     CU(cudaEventElapsedTime(&dev_ms, ev0, ev1));
     cudaEventDestroy(ev0);

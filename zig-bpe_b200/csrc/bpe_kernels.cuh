@@ -112,6 +112,55 @@ __global__ void ties_kernel(PairTable tbl, StepCtl* ctl) {
     }
 }
 
+// -----------------------------------------------------------------------------------------
+// Heavy-key list. The maximum pair count never increases (old pairs only lose occurrences and a
+// new pair (p,X)/(X,n)/(X,X) cannot occur more often than the (A,B) it came from), so it is
+// enough to scan the keys whose count was >= theta when the list was built, plus keys created
+// later with a count >= theta (appended by the apply kernel). The list is exact while
+// max >= theta; the host rebuilds it with a lower theta when the maximum falls below.
+// -----------------------------------------------------------------------------------------
+struct HeavyList { uint32_t* slots; uint32_t cap; uint32_t theta; };
+
+__global__ void heavy_collect_kernel(PairTable tbl, HeavyList hl, StepCtl* ctl) {
+    size_t cap = (size_t)tbl.mask + 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
+        if (tbl.counts[i] >= hl.theta) {
+            uint32_t idx = atomicAdd(&ctl->n_heavy, 1u);
+            if (idx < hl.cap) hl.slots[idx] = (uint32_t)i;
+        }
+    }
+}
+
+__global__ void heavy_argmax_kernel(PairTable tbl, HeavyList hl, StepCtl* ctl) {
+    __shared__ uint32_t sh[THREADS];
+    uint32_t n = ctl->n_heavy < hl.cap ? ctl->n_heavy : hl.cap;
+    uint32_t m = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t c = tbl.counts[hl.slots[i]];
+        m = c > m ? c : m;
+    }
+    sh[threadIdx.x] = m;
+    __syncthreads();
+    for (int off = THREADS / 2; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) { uint32_t o = sh[threadIdx.x + off]; if (o > sh[threadIdx.x]) sh[threadIdx.x] = o; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && sh[0]) atomicMax(&ctl->max_count, sh[0]);
+}
+
+__global__ void heavy_ties_kernel(PairTable tbl, HeavyList hl, StepCtl* ctl) {
+    const uint32_t m = ctl->max_count;
+    if (m == 0) return;
+    uint32_t n = ctl->n_heavy < hl.cap ? ctl->n_heavy : hl.cap;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t s = hl.slots[i];
+        if (tbl.counts[s] == m) {
+            uint32_t idx = atomicAdd(&ctl->ntied, 1u);
+            if (idx < (uint32_t)MAXTIE) ctl->tie_keys[idx] = tbl.keys[s];
+        }
+    }
+}
+
 // =========================================================================================
 // halo_kernel: one thread per tile gathers the live tokens around the tile.
 // ext_*: live tokens beyond this GPU's shard (hole = none). For A==B steps it also measures
@@ -231,86 +280,131 @@ template <class TokT> __device__ __forceinline__ int prev_live(const TokT* ext, 
 // neighbour n that does not start another occurrence ((B,n)-1,(X,n)+1), cntXX adjacent
 // occurrences ((B,A)-1,(X,X)+1), cntAB occurrences ((A,B)-1 each).
 // =========================================================================================
+// does any slot of the 16-byte vector equal `a`?
+template <class TokT> __device__ __forceinline__ bool vec_has(const uint4& v, uint32_t a);
+template <> __device__ __forceinline__ bool vec_has<uint16_t>(const uint4& v, uint32_t a) {
+    const uint32_t aa = a | (a << 16);
+    return (__vcmpeq2(v.x, aa) | __vcmpeq2(v.y, aa) | __vcmpeq2(v.z, aa) | __vcmpeq2(v.w, aa)) != 0u;
+}
+template <> __device__ __forceinline__ bool vec_has<uint32_t>(const uint4& v, uint32_t a) {
+    return v.x == a || v.y == a || v.z == a || v.w == a;
+}
+
 template <class TokT, bool AEQB, bool DELTAS>
 __global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, const TileHalo<TokT>* __restrict__ halo,
                                                         StepCtl* ctl, uint32_t* __restrict__ cntL,
                                                         uint32_t* __restrict__ cntR) {
     __shared__ __align__(16) TokT ext[EXT];
+    constexpr int VEC = 16 / (int)sizeof(TokT);   // slots per 16-byte vector
+    constexpr int NV = TILE / VEC / THREADS;       // vectors per thread (interleaved for coalescing)
+    static_assert(NV >= 1 && NV * VEC * THREADS == TILE, "tile geometry");
     const TokT H = (TokT)TokTraits<TokT>::hole;
-    const TokT A = (TokT)ctl->A, B = (TokT)ctl->B, X = (TokT)ctl->X;
+    const uint32_t Au = ctl->A, Bu = ctl->B;
+    const TokT A = (TokT)Au, B = (TokT)Bu, X = (TokT)ctl->X;
     const size_t base = (size_t)blockIdx.x * TILE;
+
+    // 1. stream the tile through registers; a tile that holds neither A nor B is left untouched
+    const uint4* src = reinterpret_cast<const uint4*>(tok + base);
+    uint4 v[NV];
+    bool hit[NV];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < NV; k++) v[k] = src[k * THREADS + (int)threadIdx.x];
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        hit[k] = vec_has<TokT>(v[k], Au) || (!AEQB && vec_has<TokT>(v[k], Bu));
+        any |= hit[k];
+    }
+    if (!__syncthreads_or(any ? 1 : 0)) return;
+
+    // 2. stage the tile (+ halo) so that neighbours can be looked up across thread boundaries
     const TileHalo<TokT> h = halo[blockIdx.x];
-    stage_tile(ext, tok, base, h);
+    uint4* dst = reinterpret_cast<uint4*>(ext + OFF);
+#pragma unroll
+    for (int k = 0; k < NV; k++) dst[k * THREADS + (int)threadIdx.x] = v[k];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < OFF - 2; i++) ext[i] = H;
+        ext[OFF - 2] = h.l2;
+        ext[OFF - 1] = h.l1;
+        ext[OFF + TILE + 0] = h.r0;
+        ext[OFF + TILE + 1] = h.r1;
+        ext[OFF + TILE + 2] = h.r2;
+        for (int i = OFF + TILE + 3; i < EXT; i++) ext[i] = H;
+    }
     __syncthreads();
 
-    const int s0 = OFF + (int)threadIdx.x * SPT;
-    uint32_t run = 0;       // AEQB: consecutive live A's immediately before the current slot
-    bool run_known = false;
     uint32_t nAB = 0, nXX = 0;
-    for (int s = s0; s < s0 + SPT; s++) {
-        const TokT t = ext[s];
-        if (t == H) continue;
-        bool start = false;
-        int j = -1;
-        if (!AEQB) {
-            if (t == A) {
-                j = next_live(ext, s);
-                start = (j >= 0 && ext[j] == B);
-            } else if (t == B) {
-                int p = prev_live(ext, s);
-                if (p >= 0 && ext[p] == A) tok[base + (size_t)(s - OFF)] = H;  // consumed by the A on its left
-            }
-        } else {
-            if (t == A) {
-                if (!run_known) {
-                    // count live A's before s inside the tile; if the tile start is reached the
-                    // run continues into earlier tiles (h.runA)
-                    uint32_t c = 0;
-                    bool hit = false;
-                    for (int q = s - 1; q >= OFF; q--) {
-                        TokT v = ext[q];
-                        if (v == H) continue;
-                        if (v == A) c++; else { hit = true; break; }
-                    }
-                    run = hit ? c : c + h.runA;
-                    run_known = true;
-                }
-                const uint32_t off = run;
-                run++;
-                if (off & 1u) {
-                    tok[base + (size_t)(s - OFF)] = H;  // second element of the occurrence at off-1
-                } else {
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        if (!hit[k]) continue;
+        const int s0 = OFF + (k * THREADS + (int)threadIdx.x) * VEC;
+        uint32_t run = 0;       // AEQB: consecutive live A's immediately before the current slot
+        bool run_known = false;
+        for (int s = s0; s < s0 + VEC; s++) {
+            const TokT t = ext[s];
+            if (t == H) continue;
+            bool start = false;
+            int j = -1;
+            if (!AEQB) {
+                if (t == A) {
                     j = next_live(ext, s);
-                    start = (j >= 0 && ext[j] == A);
+                    start = (j >= 0 && ext[j] == B);
+                } else if (t == B) {
+                    int p = prev_live(ext, s);
+                    if (p >= 0 && ext[p] == A) tok[base + (size_t)(s - OFF)] = H;  // consumed by the A on its left
                 }
             } else {
-                run = 0;
-                run_known = true;
-            }
-        }
-        if (!start) continue;
-        tok[base + (size_t)(s - OFF)] = X;
-        nAB++;
-        if (DELTAS) {
-            // left side: always owned by this occurrence
-            int p = prev_live(ext, s);
-            if (p >= 0) {
-                const TokT tp = ext[p];
-                bool merged_second;
-                if (AEQB) merged_second = (tp == A);  // same run, odd offset
-                else {
-                    merged_second = false;
-                    if (tp == B) { int pp = prev_live(ext, p); merged_second = (pp >= 0 && ext[pp] == A); }
+                if (t == A) {
+                    if (!run_known) {
+                        // count live A's before s inside the tile; if the tile start is reached
+                        // the run continues into earlier tiles (h.runA)
+                        uint32_t c = 0;
+                        bool stop = false;
+                        for (int q = s - 1; q >= OFF; q--) {
+                            TokT u = ext[q];
+                            if (u == H) continue;
+                            if (u == A) c++; else { stop = true; break; }
+                        }
+                        run = stop ? c : c + h.runA;
+                        run_known = true;
+                    }
+                    const uint32_t off = run;
+                    run++;
+                    if (off & 1u) {
+                        tok[base + (size_t)(s - OFF)] = H;  // second element of the occurrence at off-1
+                    } else {
+                        j = next_live(ext, s);
+                        start = (j >= 0 && ext[j] == A);
+                    }
+                } else {
+                    run = 0;
+                    run_known = true;
                 }
-                if (merged_second) nXX++; else atomicAdd(&cntL[tp], 1u);
             }
-            // right side: owned only if the next live token does not start another occurrence
-            int n = next_live(ext, j);
-            if (n >= 0) {
-                const TokT tn = ext[n];
-                bool is_start = false;
-                if (tn == A) { int nn = next_live(ext, n); is_start = (nn >= 0 && ext[nn] == B); }
-                if (!is_start) atomicAdd(&cntR[tn], 1u);
+            if (!start) continue;
+            tok[base + (size_t)(s - OFF)] = X;
+            nAB++;
+            if (DELTAS) {
+                // left side: always owned by this occurrence
+                int p = prev_live(ext, s);
+                if (p >= 0) {
+                    const TokT tp = ext[p];
+                    bool merged_second;
+                    if (AEQB) merged_second = (tp == A);  // same run, odd offset
+                    else {
+                        merged_second = false;
+                        if (tp == B) { int pp = prev_live(ext, p); merged_second = (pp >= 0 && ext[pp] == A); }
+                    }
+                    if (merged_second) nXX++; else atomicAdd(&cntL[tp], 1u);
+                }
+                // right side: owned only if the next live token does not start another occurrence
+                int n = next_live(ext, j);
+                if (n >= 0) {
+                    const TokT tn = ext[n];
+                    bool is_start = false;
+                    if (tn == A) { int nn = next_live(ext, n); is_start = (nn >= 0 && ext[nn] == B); }
+                    if (!is_start) atomicAdd(&cntR[tn], 1u);
+                }
             }
         }
     }
@@ -334,10 +428,14 @@ __device__ __forceinline__ void tbl_sub(const PairTable& tbl, uint32_t key, uint
     }
 }
 __device__ __forceinline__ void tbl_add(const PairTable& tbl, uint32_t key, uint32_t c, StepCtl* ctl,
-                                        uint32_t* zcnt, uint32_t zmask) {
+                                        uint32_t* zcnt, uint32_t zmask, const HeavyList& hl) {
     uint32_t s = tbl_find_or_insert(tbl, key, &ctl->n_inserted);
     if (s == EMPTY_KEY) { atomicOr(&ctl->err, (uint32_t)ERR_TABLE_FULL); return; }
     uint32_t old = atomicAdd(&tbl.counts[s], c);
+    if (hl.theta && old < hl.theta && old + c >= hl.theta) {  // newly heavy
+        uint32_t idx = atomicAdd(&ctl->n_heavy, 1u);
+        if (idx < hl.cap) hl.slots[idx] = s;
+    }
     if (old == 0) {  // birth
         atomicAdd(&ctl->live_keys, 1u);
         if (zcnt) zcnt_add(zcnt, zmask, key, +1, &ctl->err);
