@@ -94,7 +94,8 @@ const char* bpe_last_error(const bpe_ctx* ctx);
  *   "table_log2"          log2 of the initial pair-table capacity (default: sized from n)
  *   "max_steps"           stop training after this many merges (0 = no limit)
  *   "time_phases"         1: fill the reference's TimeStats buckets (synchronises per phase)
- *   "profile"             1: fill bpe_stats_t.kernel_ms / kernel_calls
+ *   "profile"             1: fill bpe_stats_t.kernel_ms / kernel_calls for every kernel class;
+ *                         2: only the merge kernel (two event records per merge step)
  */
 int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value);
 

@@ -31,6 +31,7 @@ struct bpe_ctx {
          max_steps = 0, time_phases = 0, profile = 0;
     DistComm dist;  // world == 1 when single GPU
     uint64_t launches = 0;
+    std::vector<cudaEvent_t> ev_pool;  // profiling events, created on first use
 };
 
 static std::string g_create_err;
@@ -203,43 +204,44 @@ struct PhaseTimer {  // CUDA-event phase buckets (only when time_phases is on)
 // of the earlier one. Nothing synchronises until finish().
 enum { K_INIT = 0, K_ARGMAX, K_TIE, K_REPLAY, K_HALO, K_MERGE, K_APPLY, K_COMPACT, K_TABLE, K_HOSTGAP, K_NB = 12 };
 struct EvProfile {
-    static const size_t POOL = 2048;
-    bool on = false;
+    int level = 0;  // 0 off, 1 all buckets, 2 merge kernel only (2 records per step)
     cudaStream_t st = 0;
-    std::vector<cudaEvent_t> ev;
+    std::vector<cudaEvent_t>* ev = nullptr;  // pool owned by the context (reused across calls)
     std::vector<int> bucket;
     size_t used = 0;
     double* ms = nullptr;
     uint64_t* calls = nullptr;
-    void init(bool enable, cudaStream_t s, double* ms_out, uint64_t* calls_out) {
-        on = enable; st = s; ms = ms_out; calls = calls_out;
-        if (!on) return;
-        ev.resize(POOL);
-        bucket.resize(POOL);
-        for (size_t i = 0; i < POOL; i++) cudaEventCreate(&ev[i]);
+    void init(int lvl, cudaStream_t s, std::vector<cudaEvent_t>* pool, double* ms_out, uint64_t* calls_out) {
+        level = lvl; st = s; ms = ms_out; calls = calls_out; ev = pool;
+        if (!level) return;
+        const size_t POOL = 1u << 15;
+        while (ev->size() < POOL) { cudaEvent_t e; cudaEventCreate(&e); ev->push_back(e); }
+        bucket.resize(ev->size());
     }
-    ~EvProfile() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
     void drain(bool keep_last) {  // resolve recorded intervals; optionally carry the last mark over
         if (used == 0) return;
-        cudaEventSynchronize(ev[used - 1]);
+        cudaEventSynchronize((*ev)[used - 1]);
         for (size_t i = 0; i + 1 < used; i++) {
+            if (bucket[i] < 0 || (level == 2 && bucket[i] != K_MERGE)) continue;
             float t = 0;
-            cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
-            if (bucket[i] >= 0) { ms[bucket[i]] += t; calls[bucket[i]]++; }
+            cudaEventElapsedTime(&t, (*ev)[i], (*ev)[i + 1]);
+            ms[bucket[i]] += t;
+            calls[bucket[i]]++;
         }
-        if (keep_last) { std::swap(ev[0], ev[used - 1]); bucket[0] = bucket[used - 1]; used = 1; }
+        if (keep_last) { std::swap((*ev)[0], (*ev)[used - 1]); bucket[0] = bucket[used - 1]; used = 1; }
         else used = 0;
     }
     void mark(int b) {
-        if (!on) return;
-        if (used == POOL) drain(true);
-        cudaEventRecord(ev[used], st);
+        if (!level) return;
+        if (level == 2 && b != K_MERGE && b != K_APPLY) return;
+        if (used == ev->size()) drain(true);
+        cudaEventRecord((*ev)[used], st);
         bucket[used] = b;
         used++;
     }
     void finish() {
-        if (!on) return;
-        mark(-1);
+        if (!level) return;
+        if (level == 1) mark(-1);
         drain(false);
     }
 };
@@ -434,7 +436,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     PhaseTimer pt;
     pt.init(ctx->time_phases != 0, ctx->stream);
     EvProfile prof;
-    prof.init(ctx->profile != 0, ctx->stream, R.st.kernel_ms, R.st.kernel_calls);
+    prof.init((int)ctx->profile, ctx->stream, &ctx->ev_pool, R.st.kernel_ms, R.st.kernel_calls);
     prof.mark(K_INIT);
 
     int rc = seq_init(ctx, R.sq, d_text, n);
@@ -959,6 +961,7 @@ void bpe_ctx_destroy(bpe_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     ctx->dist.destroy();
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
