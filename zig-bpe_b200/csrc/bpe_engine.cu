@@ -19,6 +19,33 @@
 
 using namespace bpe;
 
+// Device allocations are recycled through a per-context cache: a training call allocates several
+// GB (two token buffers, the pair table) and cudaMalloc/cudaFree of that size cost more than a
+// hundred merge steps. A freed block is reused by a later request of at most twice... its size.
+struct BufCache {
+    struct Blk { void* p; size_t bytes; };
+    std::vector<Blk> free_list;
+    size_t cached_bytes = 0;
+    static constexpr size_t MAX_CACHED = (size_t)24 << 30;
+    void* take(size_t n, size_t* got) {
+        size_t best = (size_t)-1;
+        for (size_t i = 0; i < free_list.size(); i++)
+            if (free_list[i].bytes >= n && free_list[i].bytes <= 2 * n + 4096 && (best == (size_t)-1 || free_list[i].bytes < free_list[best].bytes)) best = i;
+        if (best == (size_t)-1) return nullptr;
+        Blk b = free_list[best];
+        free_list.erase(free_list.begin() + (long)best);
+        cached_bytes -= b.bytes;
+        *got = b.bytes;
+        return b.p;
+    }
+    void give(void* p, size_t bytes) {
+        if (bytes < 4096 || cached_bytes + bytes > MAX_CACHED) { cudaFree(p); return; }
+        free_list.push_back(Blk{p, bytes});
+        cached_bytes += bytes;
+    }
+    void clear() { for (Blk& b : free_list) cudaFree(b.p); free_list.clear(); cached_bytes = 0; }
+};
+
 // -----------------------------------------------------------------------------------------
 // context
 // -----------------------------------------------------------------------------------------
@@ -31,6 +58,7 @@ struct bpe_ctx {
          max_steps = 0, time_phases = 0, profile = 0;
     DistComm dist;  // world == 1 when single GPU
     uint64_t launches = 0;
+    BufCache cache;
     std::vector<cudaEvent_t> ev_pool;  // profiling events, created on first use
 };
 
@@ -53,14 +81,36 @@ static int fail(bpe_ctx* ctx, int code, const char* fmt, ...) {
             return fail(ctx, BPE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+static thread_local BufCache* tl_cache = nullptr;  // set by the API entry points for the call's context
+
 struct DevBuf {
     void* p = nullptr;
-    size_t bytes = 0;
-    ~DevBuf() { if (p) cudaFree(p); }
+    size_t bytes = 0;      // requested size
+    size_t real = 0;       // size of the underlying block
+    BufCache* from = nullptr;
+    ~DevBuf() { release(); }
+    void release() {
+        if (!p) return;
+        if (from) from->give(p, real); else cudaFree(p);
+        p = nullptr;
+    }
     cudaError_t alloc(size_t n) {
-        if (p) { cudaFree(p); p = nullptr; }
+        release();
         bytes = n;
-        return cudaMalloc(&p, n ? n : 1);
+        from = tl_cache;
+        if (from) {
+            void* q = from->take(n ? n : 1, &real);
+            if (q) { p = q; return cudaSuccess; }
+        }
+        real = n ? n : 1;
+        cudaError_t e = cudaMalloc(&p, real);
+        if (e != cudaSuccess && from) {  // out of memory: drop the cache and retry once
+            cudaGetLastError();
+            from->clear();
+            e = cudaMalloc(&p, real);
+        }
+        if (e != cudaSuccess) p = nullptr;
+        return e;
     }
     template <class T> T* as() const { return (T*)p; }
 };
@@ -259,9 +309,9 @@ __global__ void reset_argmax_kernel(StepCtl* ctl) {
 // folds cntXX/cntAB into the table through apply_kernel's arguments being device-resident:
 // the wrapper reads them on the device so no host round trip sits between merge and apply.
 __global__ void apply_from_ctl_kernel(PairTable tbl, uint32_t* cntL, uint32_t* cntR, StepCtl* ctl,
-                                      uint32_t* zcnt, uint32_t zmask, uint32_t n_ids, uint32_t* merged_out, HeavyList hl) {
+                                      uint32_t* zcnt, uint32_t zmask, uint32_t n_ids, uint32_t* merged_out, HeavyList hl,
+                                      uint32_t A, uint32_t B, uint32_t X) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t A = ctl->A, B = ctl->B, X = ctl->X;
     if (p < n_ids) {
         uint32_t c = cntL[p];
         if (c) {
@@ -309,11 +359,11 @@ static int read_ctl(bpe_ctx* ctx, TrainRun& R, bool with_ties) {
     return BPE_OK;
 }
 
-static int launch_halo(bpe_ctx* ctx, Sequence<uint16_t>& sq, StepCtl* d_ctl, bool aeqb) {
+static int launch_halo(bpe_ctx* ctx, Sequence<uint16_t>& sq, uint32_t A, bool aeqb) {
     const uint32_t nt = sq.ntiles();
     const uint16_t H = 0xFFFF;
     BPE_LAUNCH_NS(halo_kernel<uint16_t>, grid_for(nt, 128, 1u << 30), 128, ctx->stream, sq.tok(), sq.n_slots, nt,
-                  sq.halo.as<TileHalo<uint16_t>>(), d_ctl, aeqb ? 1 : 0, sq.run_local.as<uint32_t>(),
+                  sq.halo.as<TileHalo<uint16_t>>(), A, aeqb ? 1 : 0, sq.run_local.as<uint32_t>(),
                   sq.run_full.as<uint8_t>(), H, H, H, H, H);
     ctx->launches++;
     if (aeqb) {
@@ -328,7 +378,7 @@ static int launch_halo(bpe_ctx* ctx, Sequence<uint16_t>& sq, StepCtl* d_ctl, boo
 // full table replay for one tie step (see tiebreak_host.hpp)
 static int replay_winner(bpe_ctx* ctx, TrainRun& R, const std::vector<uint32_t>& tied_hint, uint32_t max_count,
                          uint32_t* winner) {
-    int rc = launch_halo(ctx, R.sq, R.d_ctl(), false);
+    int rc = launch_halo(ctx, R.sq, 0, false);
     if (rc) return rc;
     const uint32_t cap = R.tm.cap;
     if (R.firstpos.bytes < (size_t)cap * 4) CU(R.firstpos.alloc((size_t)cap * 4));
@@ -365,7 +415,7 @@ static int replay_winner(bpe_ctx* ctx, TrainRun& R, const std::vector<uint32_t>&
 }
 
 static int verify_state(bpe_ctx* ctx, TrainRun& R, uint32_t step) {
-    int rc = launch_halo(ctx, R.sq, R.d_ctl(), false);
+    int rc = launch_halo(ctx, R.sq, 0, false);
     if (rc) return rc;
     const uint32_t cap = R.tm.cap;
     if (R.recount.bytes < (size_t)cap * 4) CU(R.recount.alloc((size_t)cap * 4));
@@ -401,10 +451,10 @@ static int grow_table(bpe_ctx* ctx, TrainRun& R) {
     ctx->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->stream));
-    std::swap(R.tm.keys.p, nt.keys.p); std::swap(R.tm.keys.bytes, nt.keys.bytes);
-    std::swap(R.tm.counts.p, nt.counts.p); std::swap(R.tm.counts.bytes, nt.counts.bytes);
-    std::swap(R.tm.zcnt.p, nt.zcnt.p); std::swap(R.tm.zcnt.bytes, nt.zcnt.bytes);
-    std::swap(R.tm.chunkfn.p, nt.chunkfn.p); std::swap(R.tm.chunkfn.bytes, nt.chunkfn.bytes);
+    auto swap_buf = [](DevBuf& a, DevBuf& b) {
+        std::swap(a.p, b.p); std::swap(a.bytes, b.bytes); std::swap(a.real, b.real); std::swap(a.from, b.from);
+    };
+    swap_buf(R.tm.keys, nt.keys); swap_buf(R.tm.counts, nt.counts); swap_buf(R.tm.zcnt, nt.zcnt); swap_buf(R.tm.chunkfn, nt.chunkfn);
     R.tm.cap = cap;
     R.tm.zcap = 0;
     return BPE_OK;
@@ -481,17 +531,23 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
         StepCtl* hc = R.hc();
         bool from_list = R.theta != 0;
         for (int attempt = 0; attempt < 2; attempt++) {
-            BPE_LAUNCH_NS(reset_argmax_kernel, 1, 1, ctx->stream, R.d_ctl());
             if (from_list) {
                 // scan only the heavy keys (exact while the maximum stays >= theta)
-                const uint32_t nh_est = 1u << 16;
-                BPE_LAUNCH(heavy_argmax_kernel, grid_for(nh_est, THREADS, 148 * 4), THREADS, ctx->stream, R.tm.view(), R.hl(), R.d_ctl());
-                BPE_LAUNCH_NS(heavy_ties_kernel, grid_for(nh_est, 256, 148 * 4), 256, ctx->stream, R.tm.view(), R.hl(), R.d_ctl());
+                if (R.hc()->n_heavy <= 16384) {  // short list (the usual case): one CTA does both passes
+                    BPE_LAUNCH(heavy_argmax_ties_kernel, 1, 1024, ctx->stream, R.tm.view(), R.hl(), R.d_ctl());
+                    ctx->launches += 1;
+                } else {
+                    BPE_LAUNCH_NS(reset_argmax_kernel, 1, 1, ctx->stream, R.d_ctl());
+                    BPE_LAUNCH(heavy_argmax_kernel, grid_for(R.hc()->n_heavy, THREADS, 148 * 4), THREADS, ctx->stream, R.tm.view(), R.hl(), R.d_ctl());
+                    BPE_LAUNCH_NS(heavy_ties_kernel, grid_for(R.hc()->n_heavy, 256, 148 * 4), 256, ctx->stream, R.tm.view(), R.hl(), R.d_ctl());
+                    ctx->launches += 3;
+                }
             } else {
+                BPE_LAUNCH_NS(reset_argmax_kernel, 1, 1, ctx->stream, R.d_ctl());
                 BPE_LAUNCH(argmax_kernel, grid_for(R.tm.cap, THREADS), THREADS, ctx->stream, R.tm.view(), R.d_ctl());
                 BPE_LAUNCH_NS(ties_kernel, grid_for(R.tm.cap, 256), 256, ctx->stream, R.tm.view(), R.d_ctl());
+                ctx->launches += 3;
             }
-            ctx->launches += 3;
             CU(cudaGetLastError());
             if (have_pending) CU(cudaMemcpyAsync(&pending_merged, R.merged.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
             prof.mark(K_HOSTGAP);
@@ -595,24 +651,22 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
         // ---- replace (replaceTopPairWithNewToken :207-232) + incremental recount ----
         pt.begin();
         prof.mark(K_HALO);
-        BPE_LAUNCH_NS(set_merge_kernel, 1, 1, ctx->stream, R.d_ctl(), A, B, X);
-        ctx->launches++;
-        rc = launch_halo(ctx, R.sq, R.d_ctl(), A == B);
+        rc = launch_halo(ctx, R.sq, A, A == B);
         if (rc) return rc;
         prof.mark(K_MERGE);
         if (A == B)
             BPE_LAUNCH((merge_kernel<uint16_t, true, true>), R.sq.ntiles(), THREADS, ctx->stream, R.sq.tok(),
-                       R.sq.halo.as<TileHalo<uint16_t>>(), R.d_ctl(), R.cntL.as<uint32_t>(), R.cntR.as<uint32_t>());
+                       R.sq.halo.as<TileHalo<uint16_t>>(), R.d_ctl(), R.cntL.as<uint32_t>(), R.cntR.as<uint32_t>(), A, B, X);
         else
             BPE_LAUNCH((merge_kernel<uint16_t, false, true>), R.sq.ntiles(), THREADS, ctx->stream, R.sq.tok(),
-                       R.sq.halo.as<TileHalo<uint16_t>>(), R.d_ctl(), R.cntL.as<uint32_t>(), R.cntR.as<uint32_t>());
+                       R.sq.halo.as<TileHalo<uint16_t>>(), R.d_ctl(), R.cntL.as<uint32_t>(), R.cntR.as<uint32_t>(), A, B, X);
         ctx->launches++;
         R.st.scanned_slots += R.sq.n_slots;
         pt.end(&R.st.replace_pair_ms, &R.st.replace_pair_calls);
         pt.begin();
         prof.mark(K_APPLY);
         BPE_LAUNCH_NS(apply_from_ctl_kernel, (X + 1 + 255) / 256, 256, ctx->stream, R.tm.view(), R.cntL.as<uint32_t>(),
-                      R.cntR.as<uint32_t>(), R.d_ctl(), R.tm.zcnt.as<uint32_t>(), R.tm.zmask(), X + 1, R.merged.as<uint32_t>(), R.hl());
+                      R.cntR.as<uint32_t>(), R.d_ctl(), R.tm.zcnt.as<uint32_t>(), R.tm.zmask(), X + 1, R.merged.as<uint32_t>(), R.hl(), A, B, X);
         ctx->launches++;
         CU(cudaGetLastError());
         pt.end(&R.st.just_count_pairs_ms, &R.st.just_count_pairs_calls);
@@ -663,21 +717,20 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
         return BPE_OK;
     };
     auto one_pass = [&](uint32_t A, uint32_t B, uint32_t X) -> int {
-        BPE_LAUNCH_NS(set_merge_kernel, 1, 1, ctx->stream, d_ctl, A, B, X);
         const uint32_t nt = sq.ntiles();
         BPE_LAUNCH_NS(halo_kernel<TokT>, grid_for(nt, 128, 1u << 30), 128, ctx->stream, sq.tok(), sq.n_slots, nt,
-                      sq.halo.template as<TileHalo<TokT>>(), d_ctl, A == B ? 1 : 0, sq.run_local.template as<uint32_t>(),
+                      sq.halo.template as<TileHalo<TokT>>(), A, A == B ? 1 : 0, sq.run_local.template as<uint32_t>(),
                       sq.run_full.template as<uint8_t>(), H, H, H, H, H);
-        ctx->launches += 2;
+        ctx->launches += 1;
         if (A == B) {
             BPE_LAUNCH_NS(run_chain_kernel<TokT>, 1, 1, ctx->stream, nt, sq.halo.template as<TileHalo<TokT>>(),
                           sq.run_local.template as<uint32_t>(), sq.run_full.template as<uint8_t>(), 0u);
             BPE_LAUNCH((merge_kernel<TokT, true, false>), nt, THREADS, ctx->stream, sq.tok(),
-                       sq.halo.template as<TileHalo<TokT>>(), d_ctl, (uint32_t*)nullptr, (uint32_t*)nullptr);
+                       sq.halo.template as<TileHalo<TokT>>(), d_ctl, (uint32_t*)nullptr, (uint32_t*)nullptr, A, B, X);
             ctx->launches += 2;
         } else {
             BPE_LAUNCH((merge_kernel<TokT, false, false>), nt, THREADS, ctx->stream, sq.tok(),
-                       sq.halo.template as<TileHalo<TokT>>(), d_ctl, (uint32_t*)nullptr, (uint32_t*)nullptr);
+                       sq.halo.template as<TileHalo<TokT>>(), d_ctl, (uint32_t*)nullptr, (uint32_t*)nullptr, A, B, X);
             ctx->launches++;
         }
         CU(cudaGetLastError());
@@ -908,6 +961,12 @@ static int decode_device(bpe_ctx* ctx, const uint16_t* d_toks, size_t n, const b
 // -----------------------------------------------------------------------------------------
 // C ABI
 // -----------------------------------------------------------------------------------------
+struct CacheScope {
+    BufCache* prev;
+    explicit CacheScope(bpe_ctx* ctx) : prev(tl_cache) { tl_cache = ctx ? &ctx->cache : nullptr; }
+    ~CacheScope() { tl_cache = prev; }
+};
+
 extern "C" {
 
 const char* bpe_version(void) {
@@ -962,6 +1021,7 @@ void bpe_ctx_destroy(bpe_ctx* ctx) {
     cudaSetDevice(ctx->device);
     ctx->dist.destroy();
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    ctx->cache.clear();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -984,12 +1044,14 @@ int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value) {
 int bpe_train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t vocab_size, bpe_merge_t* out_merges,
                      uint64_t* out_counts, size_t* out_n, bpe_stats_t* stats) {
     if (!ctx) return BPE_ERR_INVALID_ARG;
+    CacheScope cache_scope(ctx);
     return train_device(ctx, d_text, n, vocab_size, out_merges, out_counts, out_n, stats);
 }
 
 int bpe_train(bpe_ctx* ctx, const uint8_t* text, size_t n, uint16_t vocab_size, bpe_merge_t* out_merges,
               uint64_t* out_counts, size_t* out_n, bpe_stats_t* stats) {
     if (!ctx) return BPE_ERR_INVALID_ARG;
+    CacheScope cache_scope(ctx);
     if (n && !text) return fail(ctx, BPE_ERR_INVALID_ARG, "text is null");
     const double t0 = now_ms();
     CU(cudaSetDevice(ctx->device));
@@ -1004,12 +1066,14 @@ int bpe_train(bpe_ctx* ctx, const uint8_t* text, size_t n, uint16_t vocab_size, 
 int bpe_encode_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bpe_merge_t* merges, size_t m,
                       uint16_t* d_out, size_t* out_n, bpe_stats_t* stats) {
     if (!ctx) return BPE_ERR_INVALID_ARG;
+    CacheScope cache_scope(ctx);
     return encode_device(ctx, d_text, n, merges, m, d_out, out_n, stats);
 }
 
 int bpe_encode(bpe_ctx* ctx, const uint8_t* text, size_t n, const bpe_merge_t* merges, size_t m, uint16_t* out,
                size_t* out_n, bpe_stats_t* stats) {
     if (!ctx) return BPE_ERR_INVALID_ARG;
+    CacheScope cache_scope(ctx);
     if (!out_n) return fail(ctx, BPE_ERR_INVALID_ARG, "out_n is null");
     *out_n = 0;
     if (n == 0) { if (stats) memset(stats, 0, sizeof *stats); return BPE_OK; }
@@ -1031,12 +1095,14 @@ int bpe_encode(bpe_ctx* ctx, const uint8_t* text, size_t n, const bpe_merge_t* m
 int bpe_decode_device(bpe_ctx* ctx, const uint16_t* d_toks, size_t n, const bpe_merge_t* merges, size_t m,
                       uint8_t* d_out, size_t cap, size_t* out_n, bpe_stats_t* stats) {
     if (!ctx) return BPE_ERR_INVALID_ARG;
+    CacheScope cache_scope(ctx);
     if (n && !d_out) return fail(ctx, BPE_ERR_INVALID_ARG, "out is null");
     return decode_device(ctx, d_toks, n, merges, m, d_out, cap, out_n, stats);
 }
 
 int bpe_decode_size(bpe_ctx* ctx, const uint16_t* toks, size_t n, const bpe_merge_t* merges, size_t m, size_t* out_n) {
     if (!ctx) return BPE_ERR_INVALID_ARG;
+    CacheScope cache_scope(ctx);
     if (!out_n) return fail(ctx, BPE_ERR_INVALID_ARG, "out_n is null");
     *out_n = 0;
     if (n == 0) return BPE_OK;
@@ -1051,6 +1117,7 @@ int bpe_decode_size(bpe_ctx* ctx, const uint16_t* toks, size_t n, const bpe_merg
 int bpe_decode(bpe_ctx* ctx, const uint16_t* toks, size_t n, const bpe_merge_t* merges, size_t m, uint8_t* out,
                size_t cap, size_t* out_n, bpe_stats_t* stats) {
     if (!ctx) return BPE_ERR_INVALID_ARG;
+    CacheScope cache_scope(ctx);
     if (!out_n) return fail(ctx, BPE_ERR_INVALID_ARG, "out_n is null");
     *out_n = 0;
     if (n == 0) { if (stats) memset(stats, 0, sizeof *stats); return BPE_OK; }

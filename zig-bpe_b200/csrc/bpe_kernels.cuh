@@ -148,6 +148,37 @@ __global__ void heavy_argmax_kernel(PairTable tbl, HeavyList hl, StepCtl* ctl) {
     if (threadIdx.x == 0 && sh[0]) atomicMax(&ctl->max_count, sh[0]);
 }
 
+// single CTA: maximum and tie list in one launch (the heavy list is short)
+__global__ void heavy_argmax_ties_kernel(PairTable tbl, HeavyList hl, StepCtl* ctl) {
+    __shared__ uint32_t sh[1024];
+    __shared__ uint32_t s_ntied;
+    const uint32_t n = ctl->n_heavy < hl.cap ? ctl->n_heavy : hl.cap;
+    uint32_t m = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        uint32_t c = tbl.counts[hl.slots[i]];
+        m = c > m ? c : m;
+    }
+    sh[threadIdx.x] = m;
+    if (threadIdx.x == 0) s_ntied = 0;
+    __syncthreads();
+    for (int off = (int)blockDim.x / 2; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) { uint32_t o = sh[threadIdx.x + off]; if (o > sh[threadIdx.x]) sh[threadIdx.x] = o; }
+        __syncthreads();
+    }
+    m = sh[0];
+    if (m) {
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            uint32_t s = hl.slots[i];
+            if (tbl.counts[s] == m) {
+                uint32_t idx = atomicAdd(&s_ntied, 1u);
+                if (idx < (uint32_t)MAXTIE) ctl->tie_keys[idx] = tbl.keys[s];
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { ctl->max_count = m; ctl->ntied = s_ntied; ctl->tie_status = TIE_NONE; }
+}
+
 __global__ void heavy_ties_kernel(PairTable tbl, HeavyList hl, StepCtl* ctl) {
     const uint32_t m = ctl->max_count;
     if (m == 0) return;
@@ -169,7 +200,7 @@ __global__ void heavy_ties_kernel(PairTable tbl, HeavyList hl, StepCtl* ctl) {
 // =========================================================================================
 template <class TokT>
 __global__ void halo_kernel(const TokT* __restrict__ tok, size_t n_slots, uint32_t ntiles, TileHalo<TokT>* halo,
-                            const StepCtl* ctl, int aeqb, uint32_t* run_local, uint8_t* run_full,
+                            uint32_t Au, int aeqb, uint32_t* run_local, uint8_t* run_full,
                             TokT ext_l2, TokT ext_l1, TokT ext_r0, TokT ext_r1, TokT ext_r2) {
     const TokT H = (TokT)TokTraits<TokT>::hole;
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -204,7 +235,7 @@ __global__ void halo_kernel(const TokT* __restrict__ tok, size_t n_slots, uint32
     halo[t] = h;
     if (aeqb) {
         // live A's walking back from the tile's left edge, inside the previous tile only
-        const TokT A = (TokT)ctl->A;
+        const TokT A = (TokT)Au;
         uint32_t cnt = 0;
         uint8_t full = 1;
         if (t == 0) { full = 0; }
@@ -280,7 +311,19 @@ template <class TokT> __device__ __forceinline__ int prev_live(const TokT* ext, 
 // neighbour n that does not start another occurrence ((B,n)-1,(X,n)+1), cntXX adjacent
 // occurrences ((B,A)-1,(X,X)+1), cntAB occurrences ((A,B)-1 each).
 // =========================================================================================
-// does any slot of the 16-byte vector equal `a`?
+// bit i of the result is set when slot i of the 16-byte vector equals `a`
+template <class TokT> __device__ __forceinline__ uint32_t vec_mask(const uint4& v, uint32_t a);
+template <> __device__ __forceinline__ uint32_t vec_mask<uint16_t>(const uint4& v, uint32_t a) {
+    const uint32_t aa = a | (a << 16);
+    const uint32_t w[4] = {__vcmpeq2(v.x, aa), __vcmpeq2(v.y, aa), __vcmpeq2(v.z, aa), __vcmpeq2(v.w, aa)};
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) m |= ((w[i] & 1u) | ((w[i] >> 15) & 2u)) << (2 * i);
+    return m;
+}
+template <> __device__ __forceinline__ uint32_t vec_mask<uint32_t>(const uint4& v, uint32_t a) {
+    return (v.x == a ? 1u : 0u) | (v.y == a ? 2u : 0u) | (v.z == a ? 4u : 0u) | (v.w == a ? 8u : 0u);
+}
 template <class TokT> __device__ __forceinline__ bool vec_has(const uint4& v, uint32_t a);
 template <> __device__ __forceinline__ bool vec_has<uint16_t>(const uint4& v, uint32_t a) {
     const uint32_t aa = a | (a << 16);
@@ -290,35 +333,39 @@ template <> __device__ __forceinline__ bool vec_has<uint32_t>(const uint4& v, ui
     return v.x == a || v.y == a || v.z == a || v.w == a;
 }
 
+// Ownership of writes: the thread that holds the A of an occurrence writes X over it and, when the
+// consumed partner lies in the same tile, the hole over the partner. A partner that lies in the
+// next tile is blanked by that tile ("head duty": its left halo ends in an A that starts an
+// occurrence). So a tile without any A and without head duty is streamed and left untouched.
 template <class TokT, bool AEQB, bool DELTAS>
 __global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, const TileHalo<TokT>* __restrict__ halo,
                                                         StepCtl* ctl, uint32_t* __restrict__ cntL,
-                                                        uint32_t* __restrict__ cntR) {
+                                                        uint32_t* __restrict__ cntR, uint32_t Au, uint32_t Bu, uint32_t Xu) {
     __shared__ __align__(16) TokT ext[EXT];
+    __shared__ uint32_t sh_runA;
     constexpr int VEC = 16 / (int)sizeof(TokT);   // slots per 16-byte vector
     constexpr int NV = TILE / VEC / THREADS;       // vectors per thread (interleaved for coalescing)
     static_assert(NV >= 1 && NV * VEC * THREADS == TILE, "tile geometry");
     const TokT H = (TokT)TokTraits<TokT>::hole;
-    const uint32_t Au = ctl->A, Bu = ctl->B;
-    const TokT A = (TokT)Au, B = (TokT)Bu, X = (TokT)ctl->X;
+    const TokT A = (TokT)Au, B = (TokT)Bu, X = (TokT)Xu;
     const size_t base = (size_t)blockIdx.x * TILE;
 
-    // 1. stream the tile through registers; a tile that holds neither A nor B is left untouched
+    // 1. stream the tile through registers
     const uint4* src = reinterpret_cast<const uint4*>(tok + base);
     uint4 v[NV];
-    bool hit[NV];
     bool any = false;
 #pragma unroll
     for (int k = 0; k < NV; k++) v[k] = src[k * THREADS + (int)threadIdx.x];
 #pragma unroll
-    for (int k = 0; k < NV; k++) {
-        hit[k] = vec_has<TokT>(v[k], Au) || (!AEQB && vec_has<TokT>(v[k], Bu));
-        any |= hit[k];
+    for (int k = 0; k < NV; k++) any |= vec_has<TokT>(v[k], Au);
+    TileHalo<TokT> h;
+    if (threadIdx.x == 0) {
+        h = halo[blockIdx.x];
+        if (h.l1 == A) any = true;  // possible head duty
     }
     if (!__syncthreads_or(any ? 1 : 0)) return;
 
     // 2. stage the tile (+ halo) so that neighbours can be looked up across thread boundaries
-    const TileHalo<TokT> h = halo[blockIdx.x];
     uint4* dst = reinterpret_cast<uint4*>(ext + OFF);
 #pragma unroll
     for (int k = 0; k < NV; k++) dst[k * THREADS + (int)threadIdx.x] = v[k];
@@ -330,59 +377,64 @@ __global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, 
         ext[OFF + TILE + 1] = h.r1;
         ext[OFF + TILE + 2] = h.r2;
         for (int i = OFF + TILE + 3; i < EXT; i++) ext[i] = H;
+        sh_runA = h.runA;
     }
     __syncthreads();
 
     uint32_t nAB = 0, nXX = 0;
+    if (!AEQB && threadIdx.x == 0 && ext[OFF - 1] == A) {
+        // head duty: the A just before this tile starts an occurrence iff our first live token is B
+        int f = next_live(ext, OFF - 1);
+        if (f >= 0 && f < OFF + TILE && ext[f] == B) tok[base + (size_t)(f - OFF)] = H;
+    }
 #pragma unroll
     for (int k = 0; k < NV; k++) {
-        if (!hit[k]) continue;
+        uint32_t mask = vec_mask<TokT>(v[k], Au);
+        if (!mask) continue;
         const int s0 = OFF + (k * THREADS + (int)threadIdx.x) * VEC;
         uint32_t run = 0;       // AEQB: consecutive live A's immediately before the current slot
         bool run_known = false;
-        for (int s = s0; s < s0 + VEC; s++) {
-            const TokT t = ext[s];
-            if (t == H) continue;
+        while (mask) {
+            const int bit = __ffs((int)mask) - 1;
+            mask &= mask - 1;
+            const int s = s0 + bit;
             bool start = false;
             int j = -1;
             if (!AEQB) {
-                if (t == A) {
-                    j = next_live(ext, s);
-                    start = (j >= 0 && ext[j] == B);
-                } else if (t == B) {
-                    int p = prev_live(ext, s);
-                    if (p >= 0 && ext[p] == A) tok[base + (size_t)(s - OFF)] = H;  // consumed by the A on its left
-                }
+                j = next_live(ext, s);
+                start = (j >= 0 && ext[j] == B);
             } else {
-                if (t == A) {
-                    if (!run_known) {
-                        // count live A's before s inside the tile; if the tile start is reached
-                        // the run continues into earlier tiles (h.runA)
-                        uint32_t c = 0;
-                        bool stop = false;
-                        for (int q = s - 1; q >= OFF; q--) {
-                            TokT u = ext[q];
-                            if (u == H) continue;
-                            if (u == A) c++; else { stop = true; break; }
-                        }
-                        run = stop ? c : c + h.runA;
-                        run_known = true;
+                if (!run_known) {
+                    // live A's immediately before s inside the tile; if the tile start is reached
+                    // the run continues into earlier tiles (runA)
+                    uint32_t c = 0;
+                    bool stop = false;
+                    for (int q = s - 1; q >= OFF; q--) {
+                        TokT u = ext[q];
+                        if (u == H) continue;
+                        if (u == A) c++; else { stop = true; break; }
                     }
-                    const uint32_t off = run;
-                    run++;
-                    if (off & 1u) {
-                        tok[base + (size_t)(s - OFF)] = H;  // second element of the occurrence at off-1
-                    } else {
-                        j = next_live(ext, s);
-                        start = (j >= 0 && ext[j] == A);
-                    }
-                } else {
-                    run = 0;
+                    run = stop ? c : c + sh_runA;
                     run_known = true;
+                }
+                const uint32_t off = run;
+                // next A of this vector continues the run only if nothing but holes lies between
+                if (mask) {
+                    const int nb = __ffs((int)mask) - 1;
+                    bool contiguous = true;
+                    for (int q = s + 1; q < s0 + nb; q++) if (ext[q] != H) { contiguous = false; break; }
+                    if (contiguous) run = off + 1; else { run = 0; }
+                }
+                if (off & 1u) {
+                    tok[base + (size_t)(s - OFF)] = H;  // second element of the occurrence at off-1
+                } else {
+                    j = next_live(ext, s);
+                    start = (j >= 0 && ext[j] == A);
                 }
             }
             if (!start) continue;
             tok[base + (size_t)(s - OFF)] = X;
+            if (!AEQB && j < OFF + TILE) tok[base + (size_t)(j - OFF)] = H;
             nAB++;
             if (DELTAS) {
                 // left side: always owned by this occurrence
