@@ -63,19 +63,34 @@ enum : uint32_t {
 // tie-resolution verdicts (StepCtl::tie_status)
 enum : uint32_t { TIE_NONE = 0, TIE_FAST_OK = 1, TIE_NEED_REPLAY = 2 };
 
-// Device-resident control block: written by kernels, read back by the host once per step.
+// why the device-driven train loop stopped advancing (StepCtl::halt); kernels are no-ops while set
+enum : uint32_t {
+    H_NONE = 0,
+    H_DONE = 1,      // all requested merges learned
+    H_HEAVY = 2,     // heavy-key list no longer covers the maximum (or overflowed): host rebuilds it
+    H_ZCAP = 3,      // zcnt models another capacity of the reference's table: host rebuilds it
+    H_REPLAY = 4,    // tie that needs the full table replay on the host
+};
+// StepCtl::flags
+enum : uint32_t { F_FORCE_REPLAY = 1u << 0, F_CHECK_TIES = 1u << 1 };
+
+struct MergeRec { uint32_t key; uint32_t count; };  // one learned merge: pair key + its count
+
+// Device-resident control block. The train loop is driven from the device: select / tie kernels
+// choose the merge, halo / merge / apply kernels read it from here, and the host only reads this
+// block back once per batch of steps.
 struct StepCtl {
-    // current merge (A,B) -> X, set by the host (or the tie kernel) before the merge kernel
+    // current merge (A,B) -> X
     uint32_t A, B, X;
-    // argmax result
+    // argmax result of the current step
     uint32_t max_count;
     uint32_t ntied;        // number of keys with count == max_count (may exceed MAXTIE)
     // table state
     uint32_t live_keys;    // keys with count > 0 (= distinct adjacent pairs, D)
     uint32_t n_inserted;   // keys ever inserted (load factor of our table)
-    // merge-step by-products
-    uint32_t cntXX;        // adjacent merged occurrences ("ABAB" -> "XX")
-    uint32_t cntAB;        // merged occurrences
+    // encode passes: merged occurrences accumulate here
+    uint32_t cntXX;
+    uint32_t cntAB;
     uint32_t err;
     // tie fast path
     uint32_t tie_status;
@@ -84,6 +99,17 @@ struct StepCtl {
     uint32_t verify_mismatch;
     uint32_t n_heavy;      // entries appended to the heavy-key list (may exceed its capacity)
     uint32_t hist_nonzero; // distinct byte pairs found by the initial count
+    // device-driven stepping
+    uint32_t step;         // merges learned so far (= index of the merge being decided)
+    uint32_t want_steps;
+    uint32_t halt;         // H_*
+    uint32_t theta;        // heavy-list threshold (0 = list invalid)
+    uint32_t zcap;         // capacity of the reference table that zcnt models
+    uint32_t need_tie;     // the current step's tie is being settled by the zig_* kernels
+    uint32_t flags;        // F_*
+    uint32_t last_merged;  // occurrences merged by the last applied step
+    unsigned long long live_tokens;
+    unsigned long long fast_ties;   // tie steps settled by the zig_* kernels
     uint32_t tie_keys[MAXTIE];
 };
 

@@ -232,26 +232,8 @@ static int table_ensure_zcnt(bpe_ctx* ctx, TableMem& tm, StepCtl* d_ctl, uint32_
 // -----------------------------------------------------------------------------------------
 // train
 // -----------------------------------------------------------------------------------------
-struct PhaseTimer {  // CUDA-event phase buckets (only when time_phases is on)
-    bool on = false;
-    cudaEvent_t ev[2];
-    cudaStream_t st = 0;
-    void init(bool enable, cudaStream_t s) { on = enable; st = s; if (on) { cudaEventCreate(&ev[0]); cudaEventCreate(&ev[1]); } }
-    ~PhaseTimer() { if (on) { cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]); } }
-    void begin() { if (on) cudaEventRecord(ev[0], st); }
-    void end(double* acc, uint64_t* calls) {
-        if (!on) return;
-        cudaEventRecord(ev[1], st);
-        cudaEventSynchronize(ev[1]);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, ev[0], ev[1]);
-        *acc += ms;
-        (*calls)++;
-    }
-};
-
 // chained event marks: the interval between two consecutive marks is attributed to the bucket
-// of the earlier one. Nothing synchronises until finish().
+// of the earlier one. Nothing synchronises until the pool is exhausted or finish().
 enum { K_INIT = 0, K_ARGMAX, K_TIE, K_REPLAY, K_HALO, K_MERGE, K_APPLY, K_COMPACT, K_TABLE, K_HOSTGAP, K_NB = 12 };
 struct EvProfile {
     int level = 0;  // 0 off, 1 all buckets, 2 merge kernel only (2 records per step)
@@ -296,9 +278,6 @@ struct EvProfile {
     }
 };
 
-__global__ void set_merge_kernel(StepCtl* ctl, uint32_t A, uint32_t B, uint32_t X) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->A = A; ctl->B = B; ctl->X = X; }
-}
 __global__ void hist_nonzero_kernel(const uint32_t* __restrict__ hist, StepCtl* ctl) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 65536u && hist[i]) atomicAdd(&ctl->hist_nonzero, 1u);
@@ -306,69 +285,54 @@ __global__ void hist_nonzero_kernel(const uint32_t* __restrict__ hist, StepCtl* 
 __global__ void reset_argmax_kernel(StepCtl* ctl) {
     if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->max_count = 0; ctl->ntied = 0; ctl->tie_status = TIE_NONE; }
 }
-// folds cntXX/cntAB into the table through apply_kernel's arguments being device-resident:
-// the wrapper reads them on the device so no host round trip sits between merge and apply.
-__global__ void apply_from_ctl_kernel(PairTable tbl, uint32_t* cntL, uint32_t* cntR, StepCtl* ctl,
-                                      uint32_t* zcnt, uint32_t zmask, uint32_t n_ids, uint32_t* merged_out, HeavyList hl,
-                                      uint32_t A, uint32_t B, uint32_t X) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < n_ids) {
-        uint32_t c = cntL[p];
-        if (c) {
-            cntL[p] = 0;
-            tbl_sub(tbl, pair_key(p, A), c, ctl, zcnt, zmask);
-            tbl_add(tbl, pair_key(p, X), c, ctl, zcnt, zmask, hl);
-        }
-        c = cntR[p];
-        if (c) {
-            cntR[p] = 0;
-            tbl_sub(tbl, pair_key(B, p), c, ctl, zcnt, zmask);
-            tbl_add(tbl, pair_key(X, p), c, ctl, zcnt, zmask, hl);
-        }
-    }
-    if (p == 0) {
-        const uint32_t xx = ctl->cntXX, ab = ctl->cntAB;
-        if (xx) {
-            tbl_sub(tbl, pair_key(B, A), xx, ctl, zcnt, zmask);
-            tbl_add(tbl, pair_key(X, X), xx, ctl, zcnt, zmask, hl);
-        }
-        if (ab) tbl_sub(tbl, pair_key(A, B), ab, ctl, zcnt, zmask);
-        *merged_out = ab;
-        ctl->cntXX = 0;
-        ctl->cntAB = 0;
-    }
+// host-side decisions written into the control block (one tiny launch instead of several copies)
+__global__ void ctl_set_kernel(StepCtl* ctl, MergeRec* rec, int set_theta, uint32_t theta, int set_zcap, uint32_t zcap,
+                               int clear_halt, int commit, uint32_t key, uint32_t count) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    if (set_theta) ctl->theta = theta;
+    if (set_zcap) ctl->zcap = zcap;
+    if (commit) { commit_merge(ctl, rec, key, count); ctl->need_tie = 0; }
+    if (clear_halt) ctl->halt = H_NONE;
 }
 
 struct TrainRun {
     bpe_ctx* ctx;
     Sequence<uint16_t> sq;
     TableMem tm;
-    DevBuf cntL, cntR, hist, ctl, merged, firstpos, recount, live_chk, heavy;
+    DevBuf delta, hist, ctl, rec, firstpos, recount, live_chk, heavy;
+    uint32_t vcap = 0;   // stride of the cntL / cntR halves of `delta`
     uint32_t theta = 0;  // heavy-list threshold (0 = list invalid)
     HeavyList hl() const { HeavyList h; h.slots = heavy.as<uint32_t>(); h.cap = (uint32_t)(heavy.bytes / 4); h.theta = theta; return h; }
     HostBuf h_ctl;
     bpe_stats_t st;
+    EvProfile prof;
     StepCtl* d_ctl() const { return ctl.as<StepCtl>(); }
     StepCtl* hc() const { return h_ctl.as<StepCtl>(); }
+    MergeRec* d_rec() const { return rec.as<MergeRec>(); }
+    uint32_t* cntL() const { return delta.as<uint32_t>(); }
+    uint32_t* cntR() const { return delta.as<uint32_t>() + vcap; }
+    uint32_t* nxx() const { return delta.as<uint32_t>() + 2 * (size_t)vcap; }
+    uint32_t* nab() const { return delta.as<uint32_t>() + 2 * (size_t)vcap + 1; }
 };
 
 static int read_ctl(bpe_ctx* ctx, TrainRun& R, bool with_ties) {
-    size_t bytes = with_ties ? sizeof(StepCtl) : offsetof(StepCtl, tie_keys) + 8 * sizeof(uint32_t);
+    size_t bytes = with_ties ? sizeof(StepCtl) : offsetof(StepCtl, tie_keys);
     CU(cudaMemcpyAsync(R.h_ctl.p, R.ctl.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return BPE_OK;
 }
 
+// halo (+ run chain) for a host-chosen A (replay / verify passes)
 static int launch_halo(bpe_ctx* ctx, Sequence<uint16_t>& sq, uint32_t A, bool aeqb) {
     const uint32_t nt = sq.ntiles();
     const uint16_t H = 0xFFFF;
-    BPE_LAUNCH_NS(halo_kernel<uint16_t>, grid_for(nt, 128, 1u << 30), 128, ctx->stream, sq.tok(), sq.n_slots, nt,
-                  sq.halo.as<TileHalo<uint16_t>>(), A, aeqb ? 1 : 0, sq.run_local.as<uint32_t>(),
+    BPE_LAUNCH_NS((halo_kernel<uint16_t, false>), grid_for(nt, 128, 1u << 30), 128, ctx->stream, sq.tok(), sq.n_slots, nt,
+                  sq.halo.as<TileHalo<uint16_t>>(), (const StepCtl*)nullptr, A, aeqb ? 1 : 0, sq.run_local.as<uint32_t>(),
                   sq.run_full.as<uint8_t>(), H, H, H, H, H);
     ctx->launches++;
     if (aeqb) {
-        BPE_LAUNCH_NS(run_chain_kernel<uint16_t>, 1, 1, ctx->stream, nt, sq.halo.as<TileHalo<uint16_t>>(),
-                      sq.run_local.as<uint32_t>(), sq.run_full.as<uint8_t>(), 0u);
+        BPE_LAUNCH_NS((run_chain_kernel<uint16_t, false>), 1, 1, ctx->stream, nt, sq.halo.as<TileHalo<uint16_t>>(),
+                      sq.run_local.as<uint32_t>(), sq.run_full.as<uint8_t>(), 0u, (const StepCtl*)nullptr);
         ctx->launches++;
     }
     CU(cudaGetLastError());
@@ -376,8 +340,7 @@ static int launch_halo(bpe_ctx* ctx, Sequence<uint16_t>& sq, uint32_t A, bool ae
 }
 
 // full table replay for one tie step (see tiebreak_host.hpp)
-static int replay_winner(bpe_ctx* ctx, TrainRun& R, const std::vector<uint32_t>& tied_hint, uint32_t max_count,
-                         uint32_t* winner) {
+static int replay_winner(bpe_ctx* ctx, TrainRun& R, uint32_t max_count, uint32_t* winner) {
     int rc = launch_halo(ctx, R.sq, 0, false);
     if (rc) return rc;
     const uint32_t cap = R.tm.cap;
@@ -405,7 +368,6 @@ static int replay_winner(bpe_ctx* ctx, TrainRun& R, const std::vector<uint32_t>&
         rk.push_back(k);
         if (counts[i] == max_count) tied.push_back(keys[i]);
     }
-    (void)tied_hint;
     ZigTableReplay rep;
     rep.run(rk, R.hc()->last_pair_pos);
     uint32_t w = rep.winner(rk, tied);
@@ -439,11 +401,20 @@ static int verify_state(bpe_ctx* ctx, TrainRun& R, uint32_t step) {
     return BPE_OK;
 }
 
-static int grow_table(bpe_ctx* ctx, TrainRun& R) {
+static int collect_heavy(bpe_ctx* ctx, TrainRun& R) {
+    CU(cudaMemsetAsync(&R.d_ctl()->n_heavy, 0, 4, ctx->stream));
+    BPE_LAUNCH_NS(heavy_collect_kernel, grid_for(R.tm.cap, 256), 256, ctx->stream, R.tm.view(), R.hl(), R.d_ctl());
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return BPE_OK;
+}
+
+// rebuild the pair table (dropping dead keys) so that at least `need_free` more keys fit below 50 % load
+static int grow_table(bpe_ctx* ctx, TrainRun& R, uint64_t need_free) {
     TableMem nt;
     uint32_t live = R.hc()->live_keys;
     uint32_t cap = R.tm.cap;
-    while ((uint64_t)live * 4 > cap) cap <<= 1;  // keep live keys under 25 % after the rebuild
+    while (((uint64_t)live + need_free) * 2 > cap || (uint64_t)live * 4 > cap) cap <<= 1;
     int rc = table_alloc(ctx, nt, cap);
     if (rc) return rc;
     CU(cudaMemsetAsync(&R.d_ctl()->n_inserted, 0, 4, ctx->stream));
@@ -457,6 +428,38 @@ static int grow_table(bpe_ctx* ctx, TrainRun& R) {
     swap_buf(R.tm.keys, nt.keys); swap_buf(R.tm.counts, nt.counts); swap_buf(R.tm.zcnt, nt.zcnt); swap_buf(R.tm.chunkfn, nt.chunkfn);
     R.tm.cap = cap;
     R.tm.zcap = 0;
+    R.hc()->n_inserted = live;
+    return BPE_OK;
+}
+
+// make zcnt model the reference table for d live keys and tell the device
+static int sync_zcap(bpe_ctx* ctx, TrainRun& R, uint32_t d) {
+    int rc = table_ensure_zcnt(ctx, R.tm, R.d_ctl(), d);
+    if (rc) return rc;
+    BPE_LAUNCH_NS(ctl_set_kernel, 1, 1, ctx->stream, R.d_ctl(), R.d_rec(), 0, 0u, 1, R.tm.zcap, 0, 0, 0u, 0u);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return BPE_OK;
+}
+
+// the part of a step after the merge has been chosen: halo, merge, apply (all read the merge from ctl)
+static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids) {
+    const uint32_t nt = R.sq.ntiles();
+    const uint16_t H = 0xFFFF;
+    R.prof.mark(K_HALO);
+    BPE_LAUNCH_NS((halo_kernel<uint16_t, true>), grid_for(nt, 128, 1u << 30), 128, ctx->stream, R.sq.tok(), R.sq.n_slots, nt,
+                  R.sq.halo.as<TileHalo<uint16_t>>(), (const StepCtl*)R.d_ctl(), 0u, 0, R.sq.run_local.as<uint32_t>(),
+                  R.sq.run_full.as<uint8_t>(), H, H, H, H, H);
+    BPE_LAUNCH_NS((run_chain_kernel<uint16_t, true>), 1, 1, ctx->stream, nt, R.sq.halo.as<TileHalo<uint16_t>>(),
+                  R.sq.run_local.as<uint32_t>(), R.sq.run_full.as<uint8_t>(), 0u, (const StepCtl*)R.d_ctl());
+    R.prof.mark(K_MERGE);
+    BPE_LAUNCH((merge_kernel<uint16_t, true, true>), nt, THREADS, ctx->stream, R.sq.tok(), R.sq.halo.as<TileHalo<uint16_t>>(),
+               (const StepCtl*)R.d_ctl(), R.cntL(), R.cntR(), R.nxx(), R.nab(), 0u, 0u, 0u);
+    R.prof.mark(K_APPLY);
+    BPE_LAUNCH_NS(apply_kernel, (n_ids + 255) / 256, 256, ctx->stream, R.tm.view(), R.delta.as<uint32_t>(), R.vcap, R.d_ctl(),
+                  R.tm.zcnt.as<uint32_t>(), n_ids, R.hl());
+    ctx->launches += 4;
+    CU(cudaGetLastError());
     return BPE_OK;
 }
 
@@ -483,25 +486,23 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     CU(cudaEventCreate(&ev0));
     CU(cudaEventCreate(&ev1));
     CU(cudaEventRecord(ev0, ctx->stream));
-    PhaseTimer pt;
-    pt.init(ctx->time_phases != 0, ctx->stream);
-    EvProfile prof;
-    prof.init((int)ctx->profile, ctx->stream, &ctx->ev_pool, R.st.kernel_ms, R.st.kernel_calls);
+    const bool debug_sync = ctx->verify_recount != 0;  // per-step host checks: batches of one step
+    EvProfile& prof = R.prof;
+    prof.init(ctx->time_phases ? 1 : (int)ctx->profile, ctx->stream, &ctx->ev_pool, R.st.kernel_ms, R.st.kernel_calls);
     prof.mark(K_INIT);
 
     int rc = seq_init(ctx, R.sq, d_text, n);
     if (rc) return rc;
-    CU(R.cntL.alloc(65536 * 4)); CU(R.cntR.alloc(65536 * 4)); CU(R.hist.alloc(65536 * 4));
-    CU(R.ctl.alloc(sizeof(StepCtl))); CU(R.merged.alloc(4));
+    R.vcap = (uint32_t)vocab_size + 1;
+    CU(R.delta.alloc(((size_t)2 * R.vcap + 2) * 4)); CU(R.hist.alloc(65536 * 4));
+    CU(R.ctl.alloc(sizeof(StepCtl))); CU(R.rec.alloc(want * sizeof(MergeRec)));
     CU(R.heavy.alloc((size_t)(1u << 20) * 4));
     CU(R.h_ctl.alloc(sizeof(StepCtl)));
-    CU(cudaMemsetAsync(R.cntL.p, 0, 65536 * 4, ctx->stream));
-    CU(cudaMemsetAsync(R.cntR.p, 0, 65536 * 4, ctx->stream));
+    CU(cudaMemsetAsync(R.delta.p, 0, ((size_t)2 * R.vcap + 2) * 4, ctx->stream));
     CU(cudaMemsetAsync(R.hist.p, 0, 65536 * 4, ctx->stream));
     CU(cudaMemsetAsync(R.ctl.p, 0, sizeof(StepCtl), ctx->stream));
-    CU(cudaMemsetAsync(R.merged.p, 0, 4, ctx->stream));
+
     // initial count (countCodePointPairs :257-278 on the byte sequence)
-    pt.begin();
     BPE_LAUNCH_NS(byte_pair_hist_kernel, grid_for(n, 256), 256, ctx->stream, d_text, n, -1, R.hist.as<uint32_t>());
     BPE_LAUNCH_NS(hist_nonzero_kernel, 65536 / 256, 256, ctx->stream, R.hist.as<uint32_t>(), R.d_ctl());
     ctx->launches += 2;
@@ -518,161 +519,130 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
                   (uint32_t*)nullptr, 0u);
     ctx->launches += 1;
     CU(cudaGetLastError());
-    pt.end(&R.st.just_count_pairs_ms, &R.st.just_count_pairs_calls);
+    {   // device-side loop state
+        StepCtl init;
+        memset(&init, 0, sizeof init);
+        init.want_steps = (uint32_t)want;
+        init.live_tokens = n;
+        init.flags = (ctx->force_slow_tiebreak ? F_FORCE_REPLAY : 0u) | (ctx->check_tiebreak ? F_CHECK_TIES : 0u);
+        CU(cudaMemcpyAsync(&R.d_ctl()->step, &init.step, offsetof(StepCtl, tie_keys) - offsetof(StepCtl, step),
+                           cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));  // `init` lives on this stack frame
+    }
+    rc = read_ctl(ctx, R, false);
+    if (rc) return rc;
+    rc = sync_zcap(ctx, R, R.hc()->live_keys);
+    if (rc) return rc;
 
-    std::vector<bpe_merge_t> merges;
-    std::vector<uint64_t> mcounts;
-    uint32_t pending_merged = 0;  // merged occurrences of the previous step not yet subtracted from live
-    bool have_pending = false;
-    for (size_t step = 0; step < want; step++) {
-        // ---- argmax (sortCodePointPairs + [0]) ----
-        pt.begin();
-        prof.mark(K_ARGMAX);
+    uint32_t steps_done = 0;
+    bool finished = false;
+    while (!finished) {
         StepCtl* hc = R.hc();
-        bool from_list = R.theta != 0;
-        for (int attempt = 0; attempt < 2; attempt++) {
-            if (from_list) {
-                // scan only the heavy keys (exact while the maximum stays >= theta)
-                if (R.hc()->n_heavy <= 16384) {  // short list (the usual case): one CTA does both passes
-                    BPE_LAUNCH(heavy_argmax_ties_kernel, 1, 1024, ctx->stream, R.tm.view(), R.hl(), R.d_ctl());
-                    ctx->launches += 1;
-                } else {
-                    BPE_LAUNCH_NS(reset_argmax_kernel, 1, 1, ctx->stream, R.d_ctl());
-                    BPE_LAUNCH(heavy_argmax_kernel, grid_for(R.hc()->n_heavy, THREADS, 148 * 4), THREADS, ctx->stream, R.tm.view(), R.hl(), R.d_ctl());
-                    BPE_LAUNCH_NS(heavy_ties_kernel, grid_for(R.hc()->n_heavy, 256, 148 * 4), 256, ctx->stream, R.tm.view(), R.hl(), R.d_ctl());
-                    ctx->launches += 3;
-                }
-            } else {
+        // ---- housekeeping between batches (the table and the sequence are quiescent here) ----
+        const uint32_t max_batch = debug_sync ? 1u : 32u;
+        uint32_t K = (uint32_t)std::min<size_t>(max_batch, want - steps_done);
+        const uint64_t per_step_inserts = 2ull * (256 + steps_done + K + 1) + 1;
+        prof.mark(K_TABLE);
+        if (((uint64_t)hc->n_inserted + (uint64_t)K * per_step_inserts) * 4 > (uint64_t)R.tm.cap * 3) {
+            rc = grow_table(ctx, R, (uint64_t)K * per_step_inserts);
+            if (rc) return rc;
+            rc = sync_zcap(ctx, R, hc->live_keys);
+            if (rc) return rc;
+            if (R.theta) { rc = collect_heavy(ctx, R); if (rc) return rc; }  // slot indices changed
+        }
+        if (R.sq.n_slots > (size_t)TILE && R.sq.live * 100 < (uint64_t)R.sq.n_slots * (uint64_t)ctx->compact_pct) {
+            prof.mark(K_COMPACT);
+            rc = seq_compact(ctx, R.sq, nullptr);
+            if (rc) return rc;
+            R.st.compactions++;
+        }
+        // ---- one batch of device-driven steps ----
+        const uint32_t zch = R.tm.zcap < ZCHUNK ? 1u : R.tm.zcap / ZCHUNK;
+        const unsigned zgrid = zch < 592u ? zch : 592u;
+        for (uint32_t k = 0; k < K; k++) {
+            prof.mark(K_ARGMAX);
+            BPE_LAUNCH(select_kernel, 1, 1024, ctx->stream, R.tm.view(), R.hl(), R.d_ctl(), R.d_rec());
+            prof.mark(K_TIE);
+            BPE_LAUNCH(zig_chunk_kernel, zgrid, THREADS, ctx->stream, R.tm.zcnt.as<uint32_t>(), (const StepCtl*)R.d_ctl(),
+                       R.tm.chunkfn.as<ChunkFn>());
+            BPE_LAUNCH(zig_resolve_kernel, 1, MAXTIE, ctx->stream, R.tm.zcnt.as<uint32_t>(), R.tm.chunkfn.as<ChunkFn>(),
+                       R.d_ctl(), R.d_rec());
+            ctx->launches += 3;
+            rc = enqueue_step_tail(ctx, R, 256 + steps_done + k + 1);
+            if (rc) return rc;
+        }
+        prof.mark(K_HOSTGAP);
+        rc = read_ctl(ctx, R, true);
+        if (rc) return rc;
+        hc = R.hc();
+        if (hc->err) return fail(ctx, BPE_ERR_INTERNAL, "device error flags 0x%x near step %u", hc->err, hc->step);
+        R.st.scanned_slots += (uint64_t)(hc->step - steps_done) * R.sq.n_slots;
+        steps_done = hc->step;
+        R.sq.live = hc->live_tokens;
+        if (debug_sync && hc->halt == H_NONE) { rc = verify_state(ctx, R, steps_done); if (rc) return rc; hc = R.hc(); }
+        switch (hc->halt) {
+            case H_NONE: break;
+            case H_DONE: finished = true; break;
+            case H_ZCAP:
+                prof.mark(K_TABLE);
+                rc = sync_zcap(ctx, R, hc->live_keys);
+                if (rc) return rc;
+                BPE_LAUNCH_NS(ctl_set_kernel, 1, 1, ctx->stream, R.d_ctl(), R.d_rec(), 0, 0u, 0, 0u, 1, 0, 0u, 0u);
+                ctx->launches++;
+                break;
+            case H_HEAVY: {
+                // the list no longer covers the maximum: one full pass, then rebuild it at half the maximum
+                prof.mark(K_ARGMAX);
                 BPE_LAUNCH_NS(reset_argmax_kernel, 1, 1, ctx->stream, R.d_ctl());
                 BPE_LAUNCH(argmax_kernel, grid_for(R.tm.cap, THREADS), THREADS, ctx->stream, R.tm.view(), R.d_ctl());
-                BPE_LAUNCH_NS(ties_kernel, grid_for(R.tm.cap, 256), 256, ctx->stream, R.tm.view(), R.d_ctl());
-                ctx->launches += 3;
-            }
-            CU(cudaGetLastError());
-            if (have_pending) CU(cudaMemcpyAsync(&pending_merged, R.merged.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-            prof.mark(K_HOSTGAP);
-            rc = read_ctl(ctx, R, true);
-            if (rc) return rc;
-            hc = R.hc();
-            if (hc->err) return fail(ctx, BPE_ERR_INTERNAL, "device error flags 0x%x at step %zu", hc->err, step);
-            if (!from_list) break;
-            if (hc->max_count >= R.theta && hc->n_heavy <= R.hl().cap) break;  // list result is exact
-            from_list = false;  // maximum fell below theta (or the list overflowed): full pass
-            R.theta = 0;
-            prof.mark(K_ARGMAX);
-        }
-        if (!from_list && hc->max_count > 1) {
-            // (re)build the heavy list for the following steps
-            R.theta = hc->max_count / 2 > 1 ? hc->max_count / 2 : 1;
-            CU(cudaMemsetAsync(&R.d_ctl()->n_heavy, 0, 4, ctx->stream));
-            BPE_LAUNCH_NS(heavy_collect_kernel, grid_for(R.tm.cap, 256), 256, ctx->stream, R.tm.view(), R.hl(), R.d_ctl());
-            ctx->launches++;
-            CU(cudaGetLastError());
-        }
-        if (have_pending) { R.sq.live -= pending_merged; have_pending = false; }
-        if (hc->max_count == 0) { pt.end(&R.st.sort_pairs_ms, &R.st.sort_pairs_calls); break; }  // "No more pairs to merge" (:188-191)
-        uint32_t winner = hc->tie_keys[0];
-        if (hc->ntied > 1) {
-            R.st.tie_steps++;
-            const uint32_t D = hc->live_keys;
-            bool fast_ok = false;
-            uint32_t fast_winner = 0;
-            bool try_fast = !ctx->force_slow_tiebreak && hc->ntied <= (uint32_t)MAXTIE && D != zig_max_load(zig_cap_for(D));
-            if (try_fast) {
-                rc = table_ensure_zcnt(ctx, R.tm, R.d_ctl(), D);
-                if (rc) return rc;
-                const uint32_t zcap = R.tm.zcap;
-                const uint32_t zchunk = zcap < ZCHUNK ? zcap : ZCHUNK;
-                const uint32_t nch = zcap / zchunk;
-                prof.mark(K_TIE);
-                BPE_LAUNCH(zig_chunk_kernel, nch, THREADS, ctx->stream, R.tm.zcnt.as<uint32_t>(), zchunk, R.tm.chunkfn.as<ChunkFn>());
-                BPE_LAUNCH(zig_resolve_kernel, 1, MAXTIE, ctx->stream, R.tm.zcnt.as<uint32_t>(), zcap, zchunk,
-                           R.tm.chunkfn.as<ChunkFn>(), nch, R.d_ctl());
                 ctx->launches += 2;
                 CU(cudaGetLastError());
-                std::vector<uint32_t> tied(hc->tie_keys, hc->tie_keys + hc->ntied);
-                uint32_t maxc = hc->max_count;
-                prof.mark(K_HOSTGAP);
                 rc = read_ctl(ctx, R, false);
                 if (rc) return rc;
                 hc = R.hc();
-                if (hc->err) return fail(ctx, BPE_ERR_INTERNAL, "device error flags 0x%x in tie kernels", hc->err);
-                if (hc->tie_status == TIE_FAST_OK) { fast_ok = true; fast_winner = hc->tie_winner; }
-                hc->max_count = maxc;
-            }
-            if (fast_ok && !ctx->check_tiebreak) winner = fast_winner;
-            else {
-                uint32_t maxc = hc->max_count;
-                uint32_t w = 0;
-                prof.mark(K_REPLAY);
-                rc = replay_winner(ctx, R, std::vector<uint32_t>(), maxc, &w);
+                if (hc->max_count == 0) { finished = true; break; }  // "No more pairs to merge" (:188-191)
+                R.theta = hc->max_count / 2 > 1 ? hc->max_count / 2 : 1;
+                rc = collect_heavy(ctx, R);
                 if (rc) return rc;
-                R.hc()->max_count = maxc;
-                if (fast_ok && w != fast_winner)
-                    return fail(ctx, BPE_ERR_INTERNAL, "tie fast path chose (%u,%u), replay chose (%u,%u) at step %zu",
-                                fast_winner & 0xFFFF, fast_winner >> 16, w & 0xFFFF, w >> 16, step);
-                if (!fast_ok) R.st.tie_slow_steps++;
-                winner = w;
-            }
-            hc = R.hc();
-        }
-        pt.end(&R.st.sort_pairs_ms, &R.st.sort_pairs_calls);
-        const uint32_t A = winner & 0xFFFFu, B = winner >> 16, X = 256u + (uint32_t)step;
-        bpe_merge_t m; m.first = (uint16_t)A; m.second = (uint16_t)B; m.new_token = (uint16_t)X;
-        merges.push_back(m);
-        mcounts.push_back(hc->max_count);
-
-        // ---- housekeeping decided from the status just read ----
-        prof.mark(K_TABLE);
-        if ((uint64_t)hc->n_inserted * 2 > R.tm.cap) {
-            rc = grow_table(ctx, R);
-            if (rc) return rc;
-            if (R.theta) {  // slot indices changed: rebuild the heavy list with the same threshold
-                CU(cudaMemsetAsync(&R.d_ctl()->n_heavy, 0, 4, ctx->stream));
-                BPE_LAUNCH_NS(heavy_collect_kernel, grid_for(R.tm.cap, 256), 256, ctx->stream, R.tm.view(), R.hl(), R.d_ctl());
+                BPE_LAUNCH_NS(ctl_set_kernel, 1, 1, ctx->stream, R.d_ctl(), R.d_rec(), 1, R.theta, 0, 0u, 1, 0, 0u, 0u);
                 ctx->launches++;
-                CU(cudaGetLastError());
+                break;
             }
+            case H_REPLAY: {
+                R.st.tie_steps++;
+                prof.mark(K_REPLAY);
+                const uint32_t maxc = hc->max_count;
+                const bool had_fast = hc->tie_status == TIE_FAST_OK;
+                const uint32_t fast_winner = hc->tie_winner;
+                uint32_t w = 0;
+                rc = replay_winner(ctx, R, maxc, &w);
+                if (rc) return rc;
+                if (had_fast && w != fast_winner)
+                    return fail(ctx, BPE_ERR_INTERNAL, "tie fast path chose (%u,%u), replay chose (%u,%u) at step %u",
+                                fast_winner & 0xFFFF, fast_winner >> 16, w & 0xFFFF, w >> 16, steps_done);
+                if (!had_fast) R.st.tie_slow_steps++;
+                BPE_LAUNCH_NS(ctl_set_kernel, 1, 1, ctx->stream, R.d_ctl(), R.d_rec(), 0, 0u, 0, 0u, 1, 1, w, maxc);
+                ctx->launches++;
+                rc = enqueue_step_tail(ctx, R, 256 + steps_done + 1);
+                if (rc) return rc;
+                rc = read_ctl(ctx, R, false);
+                if (rc) return rc;
+                hc = R.hc();
+                if (hc->err) return fail(ctx, BPE_ERR_INTERNAL, "device error flags 0x%x near step %u", hc->err, hc->step);
+                R.st.scanned_slots += R.sq.n_slots;
+                steps_done = hc->step;
+                R.sq.live = hc->live_tokens;
+                if (debug_sync) { rc = verify_state(ctx, R, steps_done); if (rc) return rc; }
+                break;
+            }
+            default: return fail(ctx, BPE_ERR_INTERNAL, "unknown halt code %u", hc->halt);
         }
-        if (R.sq.n_slots > (size_t)TILE && R.sq.live * 100 < (uint64_t)R.sq.n_slots * (uint64_t)ctx->compact_pct) {
-            pt.begin();
-            prof.mark(K_COMPACT);
-            uint64_t live = 0;
-            rc = seq_compact(ctx, R.sq, &live);
-            if (rc) return rc;
-            R.st.compactions++;
-            pt.end(&R.st.replace_pair_ms, &R.st.replace_pair_calls);
-        }
-        // keep the reference-home population current so births/deaths can update it in place
-        prof.mark(K_TABLE);
-        rc = table_ensure_zcnt(ctx, R.tm, R.d_ctl(), hc->live_keys);
-        if (rc) return rc;
-
-        // ---- replace (replaceTopPairWithNewToken :207-232) + incremental recount ----
-        pt.begin();
-        prof.mark(K_HALO);
-        rc = launch_halo(ctx, R.sq, A, A == B);
-        if (rc) return rc;
-        prof.mark(K_MERGE);
-        if (A == B)
-            BPE_LAUNCH((merge_kernel<uint16_t, true, true>), R.sq.ntiles(), THREADS, ctx->stream, R.sq.tok(),
-                       R.sq.halo.as<TileHalo<uint16_t>>(), R.d_ctl(), R.cntL.as<uint32_t>(), R.cntR.as<uint32_t>(), A, B, X);
-        else
-            BPE_LAUNCH((merge_kernel<uint16_t, false, true>), R.sq.ntiles(), THREADS, ctx->stream, R.sq.tok(),
-                       R.sq.halo.as<TileHalo<uint16_t>>(), R.d_ctl(), R.cntL.as<uint32_t>(), R.cntR.as<uint32_t>(), A, B, X);
-        ctx->launches++;
-        R.st.scanned_slots += R.sq.n_slots;
-        pt.end(&R.st.replace_pair_ms, &R.st.replace_pair_calls);
-        pt.begin();
-        prof.mark(K_APPLY);
-        BPE_LAUNCH_NS(apply_from_ctl_kernel, (X + 1 + 255) / 256, 256, ctx->stream, R.tm.view(), R.cntL.as<uint32_t>(),
-                      R.cntR.as<uint32_t>(), R.d_ctl(), R.tm.zcnt.as<uint32_t>(), R.tm.zmask(), X + 1, R.merged.as<uint32_t>(), R.hl(), A, B, X);
-        ctx->launches++;
         CU(cudaGetLastError());
-        pt.end(&R.st.just_count_pairs_ms, &R.st.just_count_pairs_calls);
-        have_pending = true;
-        if (ctx->verify_recount) { rc = verify_state(ctx, R, (uint32_t)step); if (rc) return rc; }
+        if (steps_done >= want) finished = true;
     }
+    // merge list back to the host
+    std::vector<MergeRec> recs(steps_done);
+    if (steps_done) CU(cudaMemcpyAsync(recs.data(), R.rec.p, steps_done * sizeof(MergeRec), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaEventRecord(ev1, ctx->stream));
     CU(cudaEventSynchronize(ev1));
     prof.finish();
@@ -680,14 +650,24 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     CU(cudaEventElapsedTime(&dev_ms, ev0, ev1));
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
-    for (size_t i = 0; i < merges.size(); i++) {
-        out_merges[i] = merges[i];
-        if (out_counts) out_counts[i] = mcounts[i];
+    for (size_t i = 0; i < steps_done; i++) {
+        out_merges[i].first = (uint16_t)(recs[i].key & 0xFFFFu);
+        out_merges[i].second = (uint16_t)(recs[i].key >> 16);
+        out_merges[i].new_token = (uint16_t)(256 + i);
+        if (out_counts) out_counts[i] = recs[i].count;
     }
-    *out_n = merges.size();
+    *out_n = steps_done;
+    R.st.tie_steps += R.hc()->fast_ties;
     R.st.device_ms = dev_ms;
     R.st.total_ms = now_ms() - t_host0;
     R.st.kernel_launches = ctx->launches - launches0;
+    // reference TimeStats buckets from the kernel classes
+    R.st.sort_pairs_ms = R.st.kernel_ms[K_ARGMAX] + R.st.kernel_ms[K_TIE] + R.st.kernel_ms[K_REPLAY];
+    R.st.sort_pairs_calls = steps_done;
+    R.st.replace_pair_ms = R.st.kernel_ms[K_HALO] + R.st.kernel_ms[K_MERGE] + R.st.kernel_ms[K_COMPACT];
+    R.st.replace_pair_calls = steps_done;
+    R.st.just_count_pairs_ms = R.st.kernel_ms[K_INIT] + R.st.kernel_ms[K_APPLY];
+    R.st.just_count_pairs_calls = steps_done + 1;
     if (stats_out) *stats_out = R.st;
     return BPE_OK;
 }
@@ -718,21 +698,18 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
     };
     auto one_pass = [&](uint32_t A, uint32_t B, uint32_t X) -> int {
         const uint32_t nt = sq.ntiles();
-        BPE_LAUNCH_NS(halo_kernel<TokT>, grid_for(nt, 128, 1u << 30), 128, ctx->stream, sq.tok(), sq.n_slots, nt,
-                      sq.halo.template as<TileHalo<TokT>>(), A, A == B ? 1 : 0, sq.run_local.template as<uint32_t>(),
-                      sq.run_full.template as<uint8_t>(), H, H, H, H, H);
+        BPE_LAUNCH_NS((halo_kernel<TokT, false>), grid_for(nt, 128, 1u << 30), 128, ctx->stream, sq.tok(), sq.n_slots, nt,
+                      sq.halo.template as<TileHalo<TokT>>(), (const StepCtl*)nullptr, A, A == B ? 1 : 0,
+                      sq.run_local.template as<uint32_t>(), sq.run_full.template as<uint8_t>(), H, H, H, H, H);
         ctx->launches += 1;
         if (A == B) {
-            BPE_LAUNCH_NS(run_chain_kernel<TokT>, 1, 1, ctx->stream, nt, sq.halo.template as<TileHalo<TokT>>(),
-                          sq.run_local.template as<uint32_t>(), sq.run_full.template as<uint8_t>(), 0u);
-            BPE_LAUNCH((merge_kernel<TokT, true, false>), nt, THREADS, ctx->stream, sq.tok(),
-                       sq.halo.template as<TileHalo<TokT>>(), d_ctl, (uint32_t*)nullptr, (uint32_t*)nullptr, A, B, X);
-            ctx->launches += 2;
-        } else {
-            BPE_LAUNCH((merge_kernel<TokT, false, false>), nt, THREADS, ctx->stream, sq.tok(),
-                       sq.halo.template as<TileHalo<TokT>>(), d_ctl, (uint32_t*)nullptr, (uint32_t*)nullptr, A, B, X);
-            ctx->launches++;
+            BPE_LAUNCH_NS((run_chain_kernel<TokT, false>), 1, 1, ctx->stream, nt, sq.halo.template as<TileHalo<TokT>>(),
+                          sq.run_local.template as<uint32_t>(), sq.run_full.template as<uint8_t>(), 0u, (const StepCtl*)nullptr);
+            ctx->launches += 1;
         }
+        BPE_LAUNCH((merge_kernel<TokT, false, false>), nt, THREADS, ctx->stream, sq.tok(), sq.halo.template as<TileHalo<TokT>>(),
+                   (const StepCtl*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, &d_ctl->cntAB, A, B, X);
+        ctx->launches += 1;
         CU(cudaGetLastError());
         if (st) st->scanned_slots += sq.n_slots;
         return BPE_OK;

@@ -179,6 +179,65 @@ __global__ void heavy_argmax_ties_kernel(PairTable tbl, HeavyList hl, StepCtl* c
     if (threadIdx.x == 0) { ctl->max_count = m; ctl->ntied = s_ntied; ctl->tie_status = TIE_NONE; }
 }
 
+// record the decision for the current step
+__device__ __forceinline__ void commit_merge(StepCtl* ctl, MergeRec* rec, uint32_t key, uint32_t count) {
+    ctl->A = key & 0xFFFFu;
+    ctl->B = key >> 16;
+    ctl->X = 256u + ctl->step;
+    rec[ctl->step].key = key;
+    rec[ctl->step].count = count;
+}
+
+// select_kernel (single CTA): the device-driven replacement of "sort, take [0]" (:186-193). Scans
+// the heavy list for the maximum and its ties, then either commits the merge (unique maximum),
+// hands the tie to the zig_* kernels (need_tie), or halts the loop for the host.
+__global__ void select_kernel(PairTable tbl, HeavyList hl, StepCtl* ctl, MergeRec* rec) {
+    __shared__ uint32_t sh[1024];
+    __shared__ uint32_t s_ntied;
+    if (ctl->halt) return;
+    if (ctl->step >= ctl->want_steps) {
+        if (threadIdx.x == 0) ctl->halt = H_DONE;
+        return;
+    }
+    const uint32_t n = ctl->n_heavy < hl.cap ? ctl->n_heavy : hl.cap;
+    uint32_t m = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        uint32_t c = tbl.counts[hl.slots[i]];
+        m = c > m ? c : m;
+    }
+    sh[threadIdx.x] = m;
+    if (threadIdx.x == 0) s_ntied = 0;
+    __syncthreads();
+    for (int off = (int)blockDim.x / 2; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) { uint32_t o = sh[threadIdx.x + off]; if (o > sh[threadIdx.x]) sh[threadIdx.x] = o; }
+        __syncthreads();
+    }
+    m = sh[0];
+    const bool list_ok = (ctl->theta != 0) && (ctl->n_heavy <= hl.cap) && (m >= ctl->theta);
+    if (list_ok) {
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            uint32_t s = hl.slots[i];
+            if (tbl.counts[s] == m) {
+                uint32_t idx = atomicAdd(&s_ntied, 1u);
+                if (idx < (uint32_t)MAXTIE) ctl->tie_keys[idx] = tbl.keys[s];
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    ctl->max_count = m;
+    ctl->ntied = s_ntied;
+    ctl->tie_status = TIE_NONE;
+    ctl->need_tie = 0;
+    if (!list_ok) { ctl->halt = H_HEAVY; return; }
+    if (s_ntied == 1) { commit_merge(ctl, rec, ctl->tie_keys[0], m); return; }
+    const uint32_t D = ctl->live_keys;
+    const uint32_t zc = zig_cap_for(D);
+    if ((ctl->flags & F_FORCE_REPLAY) || s_ntied > (uint32_t)MAXTIE || D == zig_max_load(zc)) ctl->halt = H_REPLAY;
+    else if (zc != ctl->zcap) ctl->halt = H_ZCAP;
+    else ctl->need_tie = 1;
+}
+
 __global__ void heavy_ties_kernel(PairTable tbl, HeavyList hl, StepCtl* ctl) {
     const uint32_t m = ctl->max_count;
     if (m == 0) return;
@@ -198,11 +257,18 @@ __global__ void heavy_ties_kernel(PairTable tbl, HeavyList hl, StepCtl* ctl) {
 // the run of A that ends at the tile's left edge (run_local / run_full, chained by
 // run_chain_kernel so the cost stays linear on degenerate inputs such as "aaaa...").
 // =========================================================================================
-template <class TokT>
+// FROMCTL: the merge is read from the device control block (device-driven train loop) and the
+// kernel does nothing while the loop is halted; otherwise A / aeqb come from the arguments.
+template <class TokT, bool FROMCTL>
 __global__ void halo_kernel(const TokT* __restrict__ tok, size_t n_slots, uint32_t ntiles, TileHalo<TokT>* halo,
-                            uint32_t Au, int aeqb, uint32_t* run_local, uint8_t* run_full,
+                            const StepCtl* __restrict__ ctl, uint32_t Au, int aeqb, uint32_t* run_local, uint8_t* run_full,
                             TokT ext_l2, TokT ext_l1, TokT ext_r0, TokT ext_r1, TokT ext_r2) {
     const TokT H = (TokT)TokTraits<TokT>::hole;
+    if (FROMCTL) {
+        if (ctl->halt) return;
+        Au = ctl->A;
+        aeqb = (ctl->A == ctl->B) ? 1 : 0;
+    }
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles) return;
     TileHalo<TokT> h;
@@ -254,10 +320,11 @@ __global__ void halo_kernel(const TokT* __restrict__ tok, size_t n_slots, uint32
 }
 
 // sequential chain over tiles (A==B steps only): runA[t] = A's immediately before tile t
-template <class TokT>
+template <class TokT, bool FROMCTL>
 __global__ void run_chain_kernel(uint32_t ntiles, TileHalo<TokT>* halo, const uint32_t* run_local,
-                                 const uint8_t* run_full, uint32_t ext_run) {
+                                 const uint8_t* run_full, uint32_t ext_run, const StepCtl* __restrict__ ctl) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    if (FROMCTL && (ctl->halt || ctl->A != ctl->B)) return;
     uint32_t run = ext_run;
     halo[0].runA = run;
     for (uint32_t t = 1; t < ntiles; t++) {
@@ -337,11 +404,19 @@ template <> __device__ __forceinline__ bool vec_has<uint32_t>(const uint4& v, ui
 // consumed partner lies in the same tile, the hole over the partner. A partner that lies in the
 // next tile is blanked by that tile ("head duty": its left halo ends in an A that starts an
 // occurrence). So a tile without any A and without head duty is streamed and left untouched.
-template <class TokT, bool AEQB, bool DELTAS>
+// DELTAS: cntL / cntR / *nxx_out receive the neighbour-pair deltas (train); *nab_out always
+// receives the number of merged occurrences. FROMCTL as in halo_kernel.
+template <class TokT, bool DELTAS, bool FROMCTL>
 __global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, const TileHalo<TokT>* __restrict__ halo,
-                                                        StepCtl* ctl, uint32_t* __restrict__ cntL,
-                                                        uint32_t* __restrict__ cntR, uint32_t Au, uint32_t Bu, uint32_t Xu) {
+                                                        const StepCtl* __restrict__ ctl, uint32_t* __restrict__ cntL,
+                                                        uint32_t* __restrict__ cntR, uint32_t* nxx_out, uint32_t* nab_out,
+                                                        uint32_t Au, uint32_t Bu, uint32_t Xu) {
     __shared__ __align__(16) TokT ext[EXT];
+    if (FROMCTL) {
+        if (ctl->halt) return;
+        Au = ctl->A; Bu = ctl->B; Xu = ctl->X;
+    }
+    const bool AEQB = (Au == Bu);
     __shared__ uint32_t sh_runA;
     constexpr int VEC = 16 / (int)sizeof(TokT);   // slots per 16-byte vector
     constexpr int NV = TILE / VEC / THREADS;       // vectors per thread (interleaved for coalescing)
@@ -460,8 +535,8 @@ __global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, 
             }
         }
     }
-    if (nAB) atomicAdd(&ctl->cntAB, nAB);
-    if (DELTAS && nXX) atomicAdd(&ctl->cntXX, nXX);
+    if (nAB) atomicAdd(nab_out, nAB);
+    if (DELTAS && nXX) atomicAdd(nxx_out, nXX);
 }
 
 // =========================================================================================
@@ -519,37 +594,48 @@ __global__ void zig_rebuild_kernel(PairTable tbl, uint32_t* zcnt, uint32_t zmask
         if (tbl.counts[i] > 0) zcnt_add(zcnt, zmask, tbl.keys[i], +1, &ctl->err);
 }
 
-// one CTA (THREADS threads) per chunk of zchunk slots (zchunk = min(zcap, ZCHUNK))
-__global__ void zig_chunk_kernel(const uint32_t* __restrict__ zcnt, uint32_t zchunk, ChunkFn* __restrict__ fn) {
+// CTAs stride over chunks of zchunk = min(zcap, ZCHUNK) slots; no-op unless a tie is pending
+__global__ void zig_chunk_kernel(const uint32_t* __restrict__ zcnt, const StepCtl* __restrict__ ctl, ChunkFn* __restrict__ fn) {
     __shared__ ChunkFn sh[THREADS];
-    const uint32_t base = blockIdx.x * zchunk;
+    if (ctl->halt || !ctl->need_tie) return;
+    const uint32_t zcap = ctl->zcap;
+    const uint32_t zchunk = zcap < ZCHUNK ? zcap : ZCHUNK;
+    const uint32_t nchunks = zcap / zchunk;
     const uint32_t per = (zchunk + THREADS - 1) / THREADS;
-    ChunkFn f; f.add = 0; f.lo = 0;  // identity on o >= 0
-    for (uint32_t k = 0; k < per; k++) {
-        uint32_t x = threadIdx.x * per + k;
-        if (x < zchunk) {
-            ChunkFn g; g.add = (int32_t)zcnt_get(zcnt, base + x) - 1; g.lo = 0;
-            f = fn_compose(f, g);
+    for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const uint32_t base = c * zchunk;
+        ChunkFn f; f.add = 0; f.lo = 0;  // identity on o >= 0
+        for (uint32_t k = 0; k < per; k++) {
+            uint32_t x = threadIdx.x * per + k;
+            if (x < zchunk) {
+                ChunkFn g; g.add = (int32_t)zcnt_get(zcnt, base + x) - 1; g.lo = 0;
+                f = fn_compose(f, g);
+            }
         }
-    }
-    sh[threadIdx.x] = f;
-    __syncthreads();
-    for (int off = 1; off < THREADS; off <<= 1) {  // ordered tree reduction
-        int i = (int)threadIdx.x;
-        if ((i % (2 * off)) == 0 && i + off < THREADS) sh[i] = fn_compose(sh[i], sh[i + off]);
+        sh[threadIdx.x] = f;
+        __syncthreads();
+        for (int off = 1; off < THREADS; off <<= 1) {  // ordered tree reduction
+            int i = (int)threadIdx.x;
+            if ((i % (2 * off)) == 0 && i + off < THREADS) sh[i] = fn_compose(sh[i], sh[i + off]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) fn[c] = sh[0];
         __syncthreads();
     }
-    if (threadIdx.x == 0) fn[blockIdx.x] = sh[0];
 }
 
-// single CTA of MAXTIE threads
-__global__ void zig_resolve_kernel(const uint32_t* __restrict__ zcnt, uint32_t zcap, uint32_t zchunk,
-                                   const ChunkFn* __restrict__ fn, uint32_t nchunks, StepCtl* ctl) {
+// single CTA of MAXTIE threads; commits the merge or halts for the replay
+__global__ void zig_resolve_kernel(const uint32_t* __restrict__ zcnt, const ChunkFn* __restrict__ fn, StepCtl* ctl,
+                                   MergeRec* rec) {
     __shared__ ChunkFn agg[MAXTIE];
     __shared__ int32_t pre[MAXTIE];
     __shared__ uint32_t home[MAXTIE];
     __shared__ uint32_t efree[MAXTIE];
     __shared__ uint32_t bad;
+    if (ctl->halt || !ctl->need_tie) return;
+    const uint32_t zcap = ctl->zcap;
+    const uint32_t zchunk = zcap < ZCHUNK ? zcap : ZCHUNK;
+    const uint32_t nchunks = zcap / zchunk;
     const int t = (int)threadIdx.x;
     const uint32_t ntied = ctl->ntied;
     if (t == 0) bad = 0;
@@ -604,6 +690,50 @@ __global__ void zig_resolve_kernel(const uint32_t* __restrict__ zcnt, uint32_t z
         }
         ctl->tie_status = status;
         ctl->tie_winner = winner;
+        ctl->need_tie = 0;
+        if (status == TIE_FAST_OK && !(ctl->flags & F_CHECK_TIES)) { commit_merge(ctl, rec, winner, ctl->max_count); ctl->fast_ties += 1; }
+        else ctl->halt = H_REPLAY;
+    }
+}
+
+// =========================================================================================
+// apply_kernel: fold the merge deltas into the pair table (and the reference-home population on
+// births / deaths), one thread per token id, then advance the device-side step counter.
+// delta layout: [0,vcap) cntL, [vcap,2*vcap) cntR, [2*vcap] cntXX, [2*vcap+1] cntAB
+// =========================================================================================
+__global__ void apply_kernel(PairTable tbl, uint32_t* __restrict__ delta, uint32_t vcap, StepCtl* ctl,
+                             uint32_t* zcnt, uint32_t n_ids, HeavyList hl) {
+    if (ctl->halt) return;
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t A = ctl->A, B = ctl->B, X = ctl->X;
+    const uint32_t zmask = ctl->zcap - 1;
+    hl.theta = ctl->theta;
+    if (p < n_ids && p <= X) {
+        uint32_t c = delta[p];
+        if (c) {
+            delta[p] = 0;
+            tbl_sub(tbl, pair_key(p, A), c, ctl, zcnt, zmask);
+            tbl_add(tbl, pair_key(p, X), c, ctl, zcnt, zmask, hl);
+        }
+        c = delta[vcap + p];
+        if (c) {
+            delta[vcap + p] = 0;
+            tbl_sub(tbl, pair_key(B, p), c, ctl, zcnt, zmask);
+            tbl_add(tbl, pair_key(X, p), c, ctl, zcnt, zmask, hl);
+        }
+    }
+    if (p == 0) {
+        const uint32_t xx = delta[2 * vcap], ab = delta[2 * vcap + 1];
+        if (xx) {
+            tbl_sub(tbl, pair_key(B, A), xx, ctl, zcnt, zmask);
+            tbl_add(tbl, pair_key(X, X), xx, ctl, zcnt, zmask, hl);
+        }
+        if (ab) tbl_sub(tbl, pair_key(A, B), ab, ctl, zcnt, zmask);
+        delta[2 * vcap] = 0;
+        delta[2 * vcap + 1] = 0;
+        ctl->last_merged = ab;
+        ctl->live_tokens -= ab;
+        ctl->step += 1;
     }
 }
 
