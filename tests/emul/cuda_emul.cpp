@@ -6,6 +6,7 @@ dim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
 uint64_t g_launches = 0;
 int g_sync_or_acc[2] = {0, 0};
 int g_sync_or_phase = 0;
+uint32_t g_dyn_smem[64 * 1024];
 
 static ucontext_t g_sched;
 static std::vector<ucontext_t> g_ctx;

@@ -117,6 +117,8 @@ static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcp
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = 0) { memcpy(d, s, n); return 0; }
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return 0; }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = 0) { memset(d, v, n); return 0; }
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 static inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = 0; return 0; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
@@ -131,6 +133,10 @@ static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEve
 
 #define BPE_LAUNCH(kern, grid, block, stream, ...) \
     emul::launch(dim3(grid), dim3(block), [&]() { kern(__VA_ARGS__); }, true)
+#define BPE_LAUNCH_SMEM(kern, grid, block, smem, stream, ...) \
+    emul::launch(dim3(grid), dim3(block), [&]() { kern(__VA_ARGS__); }, true)
+namespace emul { extern uint32_t g_dyn_smem[64 * 1024]; }
+static inline uint32_t* bpe_dyn_smem() { return emul::g_dyn_smem; }  // up to 256 KB of "dynamic shared memory"
 // kernels that never call __syncthreads()/warp intrinsics: run threads as a plain loop
 #define BPE_LAUNCH_NS(kern, grid, block, stream, ...) \
     emul::launch(dim3(grid), dim3(block), [&]() { kern(__VA_ARGS__); }, false)

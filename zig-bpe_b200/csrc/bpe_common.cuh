@@ -22,6 +22,9 @@
 #include <cuda_runtime.h>
 #define BPE_LAUNCH(kern, grid, block, stream, ...) kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 #define BPE_LAUNCH_NS(kern, grid, block, stream, ...) kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define BPE_LAUNCH_SMEM(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+extern __shared__ uint32_t bpe_dyn_smem_[];
+__device__ __forceinline__ uint32_t* bpe_dyn_smem() { return bpe_dyn_smem_; }
 #endif
 
 namespace bpe {

@@ -331,7 +331,7 @@ static int launch_halo(bpe_ctx* ctx, Sequence<uint16_t>& sq, uint32_t A, bool ae
                   sq.run_full.as<uint8_t>(), H, H, H, H, H);
     ctx->launches++;
     if (aeqb) {
-        BPE_LAUNCH_NS((run_chain_kernel<uint16_t, false>), 1, 1, ctx->stream, nt, sq.halo.as<TileHalo<uint16_t>>(),
+        BPE_LAUNCH((run_chain_kernel<uint16_t, false>), 1, 1024, ctx->stream, nt, sq.halo.as<TileHalo<uint16_t>>(),
                       sq.run_local.as<uint32_t>(), sq.run_full.as<uint8_t>(), 0u, (const StepCtl*)nullptr);
         ctx->launches++;
     }
@@ -450,7 +450,7 @@ static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids) {
     BPE_LAUNCH_NS((halo_kernel<uint16_t, true>), grid_for(nt, 128, 1u << 30), 128, ctx->stream, R.sq.tok(), R.sq.n_slots, nt,
                   R.sq.halo.as<TileHalo<uint16_t>>(), (const StepCtl*)R.d_ctl(), 0u, 0, R.sq.run_local.as<uint32_t>(),
                   R.sq.run_full.as<uint8_t>(), H, H, H, H, H);
-    BPE_LAUNCH_NS((run_chain_kernel<uint16_t, true>), 1, 1, ctx->stream, nt, R.sq.halo.as<TileHalo<uint16_t>>(),
+    BPE_LAUNCH((run_chain_kernel<uint16_t, true>), 1, 1024, ctx->stream, nt, R.sq.halo.as<TileHalo<uint16_t>>(),
                   R.sq.run_local.as<uint32_t>(), R.sq.run_full.as<uint8_t>(), 0u, (const StepCtl*)R.d_ctl());
     R.prof.mark(K_MERGE);
     BPE_LAUNCH((merge_kernel<uint16_t, true, true>), nt, THREADS, ctx->stream, R.sq.tok(), R.sq.halo.as<TileHalo<uint16_t>>(),
@@ -503,7 +503,11 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     CU(cudaMemsetAsync(R.ctl.p, 0, sizeof(StepCtl), ctx->stream));
 
     // initial count (countCodePointPairs :257-278 on the byte sequence)
-    BPE_LAUNCH_NS(byte_pair_hist_kernel, grid_for(n, 256), 256, ctx->stream, d_text, n, -1, R.hist.as<uint32_t>());
+    {
+        CU(cudaFuncSetAttribute(byte_pair_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HIST_SMEM));
+        const unsigned hgrid = (unsigned)std::min<size_t>(148, (n + HIST_PASS - 1) / HIST_PASS);
+        BPE_LAUNCH_SMEM(byte_pair_hist_kernel, hgrid, HIST_THREADS, HIST_SMEM, ctx->stream, d_text, n, -1, R.hist.as<uint32_t>());
+    }
     BPE_LAUNCH_NS(hist_nonzero_kernel, 65536 / 256, 256, ctx->stream, R.hist.as<uint32_t>(), R.d_ctl());
     ctx->launches += 2;
     CU(cudaGetLastError());
@@ -703,7 +707,7 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
                       sq.run_local.template as<uint32_t>(), sq.run_full.template as<uint8_t>(), H, H, H, H, H);
         ctx->launches += 1;
         if (A == B) {
-            BPE_LAUNCH_NS((run_chain_kernel<TokT, false>), 1, 1, ctx->stream, nt, sq.halo.template as<TileHalo<TokT>>(),
+            BPE_LAUNCH((run_chain_kernel<TokT, false>), 1, 1024, ctx->stream, nt, sq.halo.template as<TileHalo<TokT>>(),
                           sq.run_local.template as<uint32_t>(), sq.run_full.template as<uint8_t>(), 0u, (const StepCtl*)nullptr);
             ctx->launches += 1;
         }

@@ -54,14 +54,58 @@ __global__ void fill_holes_kernel(TokT* tok, size_t from, size_t to) {
 // initial pair count over bytes: dense 256x256 histogram, hist[first | second << 8]
 // next_byte: first byte of the following shard (multi-GPU), -1 if none
 // =========================================================================================
-__global__ void byte_pair_hist_kernel(const uint8_t* __restrict__ text, size_t n, int next_byte,
-                                      uint32_t* __restrict__ hist) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) {
-        uint32_t a = text[i];
-        int b = (i + 1 < n) ? (int)text[i + 1] : next_byte;
-        if (b >= 0) atomicAdd(&hist[a | ((uint32_t)b << 8)], 1u);
+// Block-private bins in shared memory: 65,536 u16 counters (128 KB, two per word), flushed to the
+// global u32 histogram after every pass of HIST_PASS bytes so that no counter can overflow.
+constexpr int HIST_THREADS = 1024;
+constexpr int HIST_BPT = 32;                       // bytes per thread per pass
+constexpr int HIST_PASS = HIST_THREADS * HIST_BPT;  // 32,768 pairs per pass < 65,536
+constexpr size_t HIST_SMEM = 65536 * 2;
+
+__global__ void __launch_bounds__(HIST_THREADS, 1) byte_pair_hist_kernel(const uint8_t* __restrict__ text, size_t n,
+                                                                         int next_byte, uint32_t* __restrict__ hist) {
+    uint32_t* bins = bpe_dyn_smem();  // [32768] words
+    for (int i = (int)threadIdx.x; i < 32768; i += HIST_THREADS) bins[i] = 0;
+    __syncthreads();
+    const size_t npass = (n + HIST_PASS - 1) / HIST_PASS;
+    const bool aligned = ((size_t)text & 15) == 0;
+    for (size_t pass = blockIdx.x; pass < npass; pass += gridDim.x) {
+        const size_t base = pass * HIST_PASS + (size_t)threadIdx.x * HIST_BPT;
+        if (base < n) {
+            uint8_t b[HIST_BPT + 1];
+            const size_t avail = n - base;  // bytes from base to the end of the shard
+            if (aligned && avail >= HIST_BPT) {
+                const uint4* p = reinterpret_cast<const uint4*>(text + base);
+                uint4 v0 = p[0], v1 = p[1];
+                uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    b[4 * k + 0] = (uint8_t)(w[k]); b[4 * k + 1] = (uint8_t)(w[k] >> 8);
+                    b[4 * k + 2] = (uint8_t)(w[k] >> 16); b[4 * k + 3] = (uint8_t)(w[k] >> 24);
+                }
+            } else {
+                for (int k = 0; k < HIST_BPT; k++) b[k] = (size_t)k < avail ? text[base + k] : 0;
+            }
+            int cnt = avail >= HIST_BPT ? HIST_BPT : (int)avail;  // left tokens handled by this thread
+            int last = -1;                                        // successor of my last byte
+            if (avail > (size_t)cnt) last = text[base + cnt];
+            else last = next_byte;                                // end of shard: first byte of the next shard, or none
+            for (int k = 0; k < cnt; k++) {
+                int nb = (k + 1 < cnt) ? (int)b[k + 1] : last;
+                if (nb < 0) break;
+                uint32_t bin = (uint32_t)b[k] | ((uint32_t)nb << 8);
+                atomicAdd(&bins[bin >> 1], 1u << ((bin & 1u) * 16u));
+            }
+        }
+        __syncthreads();
+        for (int i = (int)threadIdx.x; i < 32768; i += HIST_THREADS) {
+            uint32_t wv = bins[i];
+            if (wv) {
+                bins[i] = 0;
+                if (wv & 0xFFFFu) atomicAdd(&hist[2 * i], wv & 0xFFFFu);
+                if (wv >> 16) atomicAdd(&hist[2 * i + 1], wv >> 16);
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -319,15 +363,42 @@ __global__ void halo_kernel(const TokT* __restrict__ tok, size_t n_slots, uint32
     }
 }
 
-// sequential chain over tiles (A==B steps only): runA[t] = A's immediately before tile t
+// chain over tiles (A==B steps only): runA[t] = live A's immediately before tile t
+//   run[t] = run_local[t] + (run_full[t] ? run[t-1] : 0), run[0] = ext_run
+// One CTA: each thread folds a contiguous range of tiles into (add, full), thread 0 chains the
+// ranges, then every thread replays its range from its carry-in.
 template <class TokT, bool FROMCTL>
 __global__ void run_chain_kernel(uint32_t ntiles, TileHalo<TokT>* halo, const uint32_t* run_local,
                                  const uint8_t* run_full, uint32_t ext_run, const StepCtl* __restrict__ ctl) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    __shared__ uint32_t s_add[1024];
+    __shared__ uint32_t s_full[1024];
     if (FROMCTL && (ctl->halt || ctl->A != ctl->B)) return;
-    uint32_t run = ext_run;
-    halo[0].runA = run;
-    for (uint32_t t = 1; t < ntiles; t++) {
+    const uint32_t nthr = blockDim.x;
+    const uint32_t q = (ntiles + nthr - 1) / nthr;
+    const uint32_t lo = threadIdx.x * q;
+    uint32_t hi = lo + q;
+    if (hi > ntiles) hi = ntiles;
+    // fold tiles [max(lo,1), hi): value after the range = add + (full ? carry_in : 0)
+    uint32_t add = 0, full = 1;
+    for (uint32_t t = (lo == 0 ? 1u : lo); t < hi; t++) {
+        if (run_full[t]) add += run_local[t];
+        else { add = run_local[t]; full = 0; }
+    }
+    s_add[threadIdx.x] = add;
+    s_full[threadIdx.x] = full;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t carry = ext_run;  // run entering tile 0
+        for (uint32_t i = 0; i < nthr; i++) {
+            uint32_t a = s_add[i], f = s_full[i];
+            s_add[i] = carry;  // carry-in of range i (= run[lo_i - 1], or ext_run for range 0)
+            carry = a + (f ? carry : 0u);
+        }
+    }
+    __syncthreads();
+    uint32_t run = s_add[threadIdx.x];
+    if (lo == 0 && lo < hi) halo[0].runA = run;
+    for (uint32_t t = (lo == 0 ? 1u : lo); t < hi; t++) {
         run = run_local[t] + (run_full[t] ? run : 0u);
         halo[t].runA = run;
     }
@@ -400,6 +471,21 @@ template <> __device__ __forceinline__ bool vec_has<uint32_t>(const uint4& v, ui
     return v.x == a || v.y == a || v.z == a || v.w == a;
 }
 
+// +1 for `key` in the block-private bins (open addressing, 8 probes), falling back to the global
+// arrays when the neighbourhood is too crowded
+template <int NBIN>
+__device__ __forceinline__ void bin_add(uint32_t* bin_key, uint32_t* bin_val, uint32_t key, uint32_t* cntL, uint32_t* cntR) {
+    uint32_t s = (key * 0x9E3779B1u) >> 23;  // 9 bits
+    s &= (uint32_t)(NBIN - 1);
+    for (int probe = 0; probe < 8; probe++) {
+        uint32_t k = ((volatile uint32_t*)bin_key)[s];
+        if (k == EMPTY_KEY) k = atomicCAS(&bin_key[s], EMPTY_KEY, key), k = (k == EMPTY_KEY) ? key : k;
+        if (k == key) { atomicAdd(&bin_val[s], 1u); return; }
+        s = (s + 1) & (uint32_t)(NBIN - 1);
+    }
+    atomicAdd((key & 0x10000u) ? &cntR[key & 0xFFFFu] : &cntL[key], 1u);
+}
+
 // Ownership of writes: the thread that holds the A of an occurrence writes X over it and, when the
 // consumed partner lies in the same tile, the hole over the partner. A partner that lies in the
 // next tile is blanked by that tile ("head duty": its left halo ends in an A that starts an
@@ -412,6 +498,10 @@ __global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, 
                                                         uint32_t* __restrict__ cntR, uint32_t* nxx_out, uint32_t* nab_out,
                                                         uint32_t Au, uint32_t Bu, uint32_t Xu) {
     __shared__ __align__(16) TokT ext[EXT];
+    // block-private bins for the neighbour deltas: key = token id (+ 0x10000 for the right side)
+    constexpr int NBIN = DELTAS ? 512 : 1;
+    __shared__ uint32_t bin_key[NBIN];
+    __shared__ uint32_t bin_val[NBIN];
     if (FROMCTL) {
         if (ctl->halt) return;
         Au = ctl->A; Bu = ctl->B; Xu = ctl->X;
@@ -429,16 +519,15 @@ __global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, 
     const uint4* src = reinterpret_cast<const uint4*>(tok + base);
     uint4 v[NV];
     bool any = false;
+    TileHalo<TokT> h;
+    if (threadIdx.x == 0) h = halo[blockIdx.x];  // issued first: its latency hides behind the tile loads
 #pragma unroll
     for (int k = 0; k < NV; k++) v[k] = src[k * THREADS + (int)threadIdx.x];
 #pragma unroll
     for (int k = 0; k < NV; k++) any |= vec_has<TokT>(v[k], Au);
-    TileHalo<TokT> h;
-    if (threadIdx.x == 0) {
-        h = halo[blockIdx.x];
-        if (h.l1 == A) any = true;  // possible head duty
-    }
+    if (threadIdx.x == 0 && h.l1 == A) any = true;  // possible head duty
     if (!__syncthreads_or(any ? 1 : 0)) return;
+    if (DELTAS) for (int i = (int)threadIdx.x; i < NBIN; i += THREADS) { bin_key[i] = EMPTY_KEY; bin_val[i] = 0; }
 
     // 2. stage the tile (+ halo) so that neighbours can be looked up across thread boundaries
     uint4* dst = reinterpret_cast<uint4*>(ext + OFF);
@@ -522,7 +611,7 @@ __global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, 
                         merged_second = false;
                         if (tp == B) { int pp = prev_live(ext, p); merged_second = (pp >= 0 && ext[pp] == A); }
                     }
-                    if (merged_second) nXX++; else atomicAdd(&cntL[tp], 1u);
+                    if (merged_second) nXX++; else bin_add<NBIN>(bin_key, bin_val, (uint32_t)tp, cntL, cntR);
                 }
                 // right side: owned only if the next live token does not start another occurrence
                 int n = next_live(ext, j);
@@ -530,13 +619,20 @@ __global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, 
                     const TokT tn = ext[n];
                     bool is_start = false;
                     if (tn == A) { int nn = next_live(ext, n); is_start = (nn >= 0 && ext[nn] == B); }
-                    if (!is_start) atomicAdd(&cntR[tn], 1u);
+                    if (!is_start) bin_add<NBIN>(bin_key, bin_val, 0x10000u | (uint32_t)tn, cntL, cntR);
                 }
             }
         }
     }
     if (nAB) atomicAdd(nab_out, nAB);
-    if (DELTAS && nXX) atomicAdd(nxx_out, nXX);
+    if (DELTAS) {
+        if (nXX) atomicAdd(nxx_out, nXX);
+        __syncthreads();
+        for (int i = (int)threadIdx.x; i < NBIN; i += THREADS) {
+            const uint32_t k = bin_key[i];
+            if (k != EMPTY_KEY) atomicAdd((k & 0x10000u) ? &cntR[k & 0xFFFFu] : &cntL[k], bin_val[i]);
+        }
+    }
 }
 
 // =========================================================================================
