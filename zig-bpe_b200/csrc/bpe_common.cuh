@@ -31,7 +31,7 @@ namespace bpe {
 
 // ---- geometry ----------------------------------------------------------------------------
 #ifndef BPE_TILE
-#define BPE_TILE 4096  // token slots per tile (one CTA pass)
+#define BPE_TILE 8192  // token slots per tile (one CTA pass): 16 KB of u16 ids, 4 x 16 B per thread
 #endif
 #ifndef BPE_THREADS
 #define BPE_THREADS 256
@@ -102,6 +102,8 @@ struct StepCtl {
     uint32_t verify_mismatch;
     uint32_t n_heavy;      // entries appended to the heavy-key list (may exceed its capacity)
     uint32_t hist_nonzero; // distinct byte pairs found by the initial count
+    uint32_t zpop_max;     // upper bound on the keys homed in any one chunk of the reference table
+    uint32_t pad0;
     // device-driven stepping
     uint32_t step;         // merges learned so far (= index of the merge being decided)
     uint32_t want_steps;
@@ -200,15 +202,20 @@ __host__ __device__ __forceinline__ uint32_t zig_cap_for(uint32_t d) {
 }
 __host__ __device__ __forceinline__ uint32_t zig_max_load(uint32_t cap) { return (uint32_t)((uint64_t)cap * 80 / 100); }
 
-// population of reference home slots, two u16 counters per u32 word
-__device__ __forceinline__ void zcnt_add(uint32_t* zcnt, uint32_t zmask, uint32_t key, int delta, uint32_t* err) {
-    uint32_t h = (uint32_t)zig_hash_pair(key) & zmask;
+// population of reference home slots: zcnt = two u16 counters per u32 word, zpop = keys homed in
+// each chunk of ZCHUNK slots (lets the tie resolver bound how far a probe run can reach)
+struct ZigPop { uint32_t* zcnt; uint32_t* zpop; uint32_t zmask; };
+__device__ __forceinline__ void zcnt_add(const ZigPop& z, uint32_t key, int delta, StepCtl* ctl) {
+    uint32_t h = (uint32_t)zig_hash_pair(key) & z.zmask;
     uint32_t sh = (h & 1u) * 16u;
     if (delta > 0) {
-        uint32_t old = atomicAdd(&zcnt[h >> 1], 1u << sh);
-        if (((old >> sh) & 0xFFFFu) == 0xFFFFu) atomicOr(err, (uint32_t)ERR_ZCNT_OVERFLOW);
+        uint32_t old = atomicAdd(&z.zcnt[h >> 1], 1u << sh);
+        if (((old >> sh) & 0xFFFFu) == 0xFFFFu) atomicOr(&ctl->err, (uint32_t)ERR_ZCNT_OVERFLOW);
+        uint32_t op = atomicAdd(&z.zpop[h / ZCHUNK], 1u);
+        if (op + 1 > ((volatile uint32_t*)&ctl->zpop_max)[0]) atomicMax(&ctl->zpop_max, op + 1);
     } else {
-        atomicSub(&zcnt[h >> 1], 1u << sh);
+        atomicSub(&z.zcnt[h >> 1], 1u << sh);
+        atomicSub(&z.zpop[h / ZCHUNK], 1u);
     }
 }
 __device__ __forceinline__ uint32_t zcnt_get(const uint32_t* zcnt, uint32_t h) {

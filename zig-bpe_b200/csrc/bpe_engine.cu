@@ -197,11 +197,13 @@ static int seq_compact(bpe_ctx* ctx, Sequence<TokT>& sq, uint64_t* new_live) {
 // pair table (+ reference-home population)
 // -----------------------------------------------------------------------------------------
 struct TableMem {
-    DevBuf keys, counts, zcnt, chunkfn;
+    DevBuf keys, counts, zcnt;  // zcnt: [cap words of u16 home counters][2*cap/ZCHUNK+1 words of chunk populations]
     uint32_t cap = 0;
     uint32_t zcap = 0;  // capacity of the reference's table that zcnt currently models (0 = stale)
     PairTable view() const { PairTable t; t.keys = keys.as<uint32_t>(); t.counts = counts.as<uint32_t>(); t.mask = cap - 1; return t; }
     uint32_t zmask() const { return zcap ? zcap - 1 : 0; }
+    size_t zpop_words() const { return (size_t)2 * cap / ZCHUNK + 1; }
+    ZigPop zig() const { ZigPop z; z.zcnt = zcnt.as<uint32_t>(); z.zpop = zcnt.as<uint32_t>() + cap; z.zmask = zmask(); return z; }
 };
 
 static int table_alloc(bpe_ctx* ctx, TableMem& tm, uint32_t cap) {
@@ -209,8 +211,7 @@ static int table_alloc(bpe_ctx* ctx, TableMem& tm, uint32_t cap) {
     tm.zcap = 0;
     CU(tm.keys.alloc((size_t)cap * 4));
     CU(tm.counts.alloc((size_t)cap * 4));
-    CU(tm.zcnt.alloc((size_t)cap * 4));  // 2*cap u16 home counters: enough for zig cap <= 2*cap
-    CU(tm.chunkfn.alloc(((size_t)2 * cap / ZCHUNK + 1) * sizeof(ChunkFn)));
+    CU(tm.zcnt.alloc(((size_t)cap + tm.zpop_words()) * 4));  // 2*cap u16 home counters: enough for zig cap <= 2*cap
     CU(cudaMemsetAsync(tm.keys.p, 0xFF, (size_t)cap * 4, ctx->stream));
     CU(cudaMemsetAsync(tm.counts.p, 0, (size_t)cap * 4, ctx->stream));
     return BPE_OK;
@@ -223,7 +224,9 @@ static int table_ensure_zcnt(bpe_ctx* ctx, TableMem& tm, StepCtl* d_ctl, uint32_
     if ((size_t)want > (size_t)2 * tm.cap) return fail(ctx, BPE_ERR_INTERNAL, "reference table capacity %u exceeds zcnt buffer", want);
     tm.zcap = want;
     CU(cudaMemsetAsync(tm.zcnt.p, 0, std::max<size_t>((size_t)want * 2, 4), ctx->stream));
-    BPE_LAUNCH_NS(zig_rebuild_kernel, grid_for(tm.cap, 256), 256, ctx->stream, tm.view(), tm.zcnt.as<uint32_t>(), tm.zmask(), d_ctl);
+    CU(cudaMemsetAsync(tm.zcnt.as<uint32_t>() + tm.cap, 0, tm.zpop_words() * 4, ctx->stream));
+    CU(cudaMemsetAsync(&d_ctl->zpop_max, 0, 4, ctx->stream));
+    BPE_LAUNCH_NS(zig_rebuild_kernel, grid_for(tm.cap, 256), 256, ctx->stream, tm.view(), tm.zig(), d_ctl);
     ctx->launches++;
     CU(cudaGetLastError());
     return BPE_OK;
@@ -425,7 +428,7 @@ static int grow_table(bpe_ctx* ctx, TrainRun& R, uint64_t need_free) {
     auto swap_buf = [](DevBuf& a, DevBuf& b) {
         std::swap(a.p, b.p); std::swap(a.bytes, b.bytes); std::swap(a.real, b.real); std::swap(a.from, b.from);
     };
-    swap_buf(R.tm.keys, nt.keys); swap_buf(R.tm.counts, nt.counts); swap_buf(R.tm.zcnt, nt.zcnt); swap_buf(R.tm.chunkfn, nt.chunkfn);
+    swap_buf(R.tm.keys, nt.keys); swap_buf(R.tm.counts, nt.counts); swap_buf(R.tm.zcnt, nt.zcnt);
     R.tm.cap = cap;
     R.tm.zcap = 0;
     R.hc()->n_inserted = live;
@@ -454,10 +457,10 @@ static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids) {
                   R.sq.run_local.as<uint32_t>(), R.sq.run_full.as<uint8_t>(), 0u, (const StepCtl*)R.d_ctl());
     R.prof.mark(K_MERGE);
     BPE_LAUNCH((merge_kernel<uint16_t, true, true>), nt, THREADS, ctx->stream, R.sq.tok(), R.sq.halo.as<TileHalo<uint16_t>>(),
-               (const StepCtl*)R.d_ctl(), R.cntL(), R.cntR(), R.nxx(), R.nab(), 0u, 0u, 0u);
+               (const StepCtl*)R.d_ctl(), R.cntL(), R.cntR(), R.nxx(), R.nab(), 0u, 0u, 0u, 4u * nt);
     R.prof.mark(K_APPLY);
     BPE_LAUNCH_NS(apply_kernel, (n_ids + 255) / 256, 256, ctx->stream, R.tm.view(), R.delta.as<uint32_t>(), R.vcap, R.d_ctl(),
-                  R.tm.zcnt.as<uint32_t>(), n_ids, R.hl());
+                  R.tm.zig(), n_ids, R.hl());
     ctx->launches += 4;
     CU(cudaGetLastError());
     return BPE_OK;
@@ -519,8 +522,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     while ((uint64_t)R.hc()->hist_nonzero * 4 > cap) cap <<= 1;  // the byte pairs alone must fit with room to spare
     rc = table_alloc(ctx, R.tm, cap);
     if (rc) return rc;
-    BPE_LAUNCH_NS(seed_table_kernel, 65536 / 256, 256, ctx->stream, R.hist.as<uint32_t>(), R.tm.view(), R.d_ctl(),
-                  (uint32_t*)nullptr, 0u);
+    BPE_LAUNCH_NS(seed_table_kernel, 65536 / 256, 256, ctx->stream, R.hist.as<uint32_t>(), R.tm.view(), R.d_ctl());
     ctx->launches += 1;
     CU(cudaGetLastError());
     {   // device-side loop state
@@ -561,17 +563,10 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
             R.st.compactions++;
         }
         // ---- one batch of device-driven steps ----
-        const uint32_t zch = R.tm.zcap < ZCHUNK ? 1u : R.tm.zcap / ZCHUNK;
-        const unsigned zgrid = zch < 592u ? zch : 592u;
         for (uint32_t k = 0; k < K; k++) {
             prof.mark(K_ARGMAX);
-            BPE_LAUNCH(select_kernel, 1, 1024, ctx->stream, R.tm.view(), R.hl(), R.d_ctl(), R.d_rec());
-            prof.mark(K_TIE);
-            BPE_LAUNCH(zig_chunk_kernel, zgrid, THREADS, ctx->stream, R.tm.zcnt.as<uint32_t>(), (const StepCtl*)R.d_ctl(),
-                       R.tm.chunkfn.as<ChunkFn>());
-            BPE_LAUNCH(zig_resolve_kernel, 1, MAXTIE, ctx->stream, R.tm.zcnt.as<uint32_t>(), R.tm.chunkfn.as<ChunkFn>(),
-                       R.d_ctl(), R.d_rec());
-            ctx->launches += 3;
+            BPE_LAUNCH(select_kernel, 1, 1024, ctx->stream, R.tm.view(), R.hl(), R.d_ctl(), R.d_rec(), R.tm.zig());
+            ctx->launches += 1;
             rc = enqueue_step_tail(ctx, R, 256 + steps_done + k + 1);
             if (rc) return rc;
         }
@@ -712,7 +707,7 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
             ctx->launches += 1;
         }
         BPE_LAUNCH((merge_kernel<TokT, false, false>), nt, THREADS, ctx->stream, sq.tok(), sq.halo.template as<TileHalo<TokT>>(),
-                   (const StepCtl*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, &d_ctl->cntAB, A, B, X);
+                   (const StepCtl*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, &d_ctl->cntAB, A, B, X, 0u);
         ctx->launches += 1;
         CU(cudaGetLastError());
         if (st) st->scanned_slots += sq.n_slots;

@@ -110,8 +110,7 @@ __global__ void __launch_bounds__(HIST_THREADS, 1) byte_pair_hist_kernel(const u
 }
 
 // hist (already summed over GPUs) -> pair table + reference-home population
-__global__ void seed_table_kernel(const uint32_t* __restrict__ hist, PairTable tbl, StepCtl* ctl,
-                                  uint32_t* zcnt, uint32_t zmask) {
+__global__ void seed_table_kernel(const uint32_t* __restrict__ hist, PairTable tbl, StepCtl* ctl) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 65536u) return;
     uint32_t c = hist[i];
@@ -121,7 +120,6 @@ __global__ void seed_table_kernel(const uint32_t* __restrict__ hist, PairTable t
     if (s == EMPTY_KEY) { atomicOr(&ctl->err, (uint32_t)ERR_TABLE_FULL); return; }
     atomicAdd(&tbl.counts[s], c);
     atomicAdd(&ctl->live_keys, 1u);
-    if (zcnt) zcnt_add(zcnt, zmask, key, +1, &ctl->err);
 }
 
 // =========================================================================================
@@ -232,12 +230,102 @@ __device__ __forceinline__ void commit_merge(StepCtl* ctl, MergeRec* rec, uint32
     rec[ctl->step].count = count;
 }
 
+// ---- tie fast path (device) -------------------------------------------------------------
+// The reference picks, among the pairs sharing the maximum count, the one in the lowest slot of its
+// hash table (Appendix A). For linear probing without deletions the *set* of occupied slots does not
+// depend on insertion order: with cnt[x] = keys whose home is x, the carry recurrence
+//     o[x] = max(0, o[x-1] + cnt[x] - 1)
+// says exactly which slots are free (slot x is free iff o[x-1] + cnt[x] == 0). If the tied key with
+// the smallest home h1 reaches a free slot before the next tied home, and no tied key's probe run
+// wraps past the end of the table, that key owns the lowest slot. Anything else goes to the replay.
+//
+// The carry entering a slot is computed locally: walking back over chunks of ZCHUNK slots, the carry
+// a chunk can pass on is at most its population, so once  ZCHUNK + sum(pop - ZCHUNK)  over the
+// chunks walked is <= 0 nothing further left can reach us (all chunk populations are <= ZCHUNK,
+// checked through zpop_max), and the recurrence restarted with o = 0 at that point is exact.
+struct ChunkFn { int32_t add; int32_t lo; };  // f(o) = max(lo, o + add)
+__device__ __forceinline__ ChunkFn fn_compose(ChunkFn f, ChunkFn g) {  // g after f
+    ChunkFn r;
+    r.add = f.add + g.add;
+    int32_t a = f.lo + g.add;
+    r.lo = g.lo > a ? g.lo : a;
+    return r;
+}
+__device__ __forceinline__ int32_t fn_eval(ChunkFn f, int32_t o) { int32_t a = o + f.add; return f.lo > a ? f.lo : a; }
+
+constexpr uint32_t TIE_MAX_BACK = 64;  // chunks walked back before giving up (-> replay)
+
+// one warp: first free slot at/after the home of `key`. returns false if it cannot be decided locally
+__device__ __forceinline__ bool zig_first_free(const ZigPop& z, uint32_t zcap, uint32_t key, uint32_t* home_out,
+                                               uint32_t* free_out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t zchunk = zcap < ZCHUNK ? zcap : ZCHUNK;
+    const uint32_t nchunks = zcap / zchunk;
+    const uint32_t h = (uint32_t)zig_hash_pair(key) & (zcap - 1);
+    const uint32_t c = h / zchunk;
+    // how many whole chunks to walk back (warp-uniform: every lane computes the same)
+    uint32_t K = 0;
+    bool full_lap = false;
+    {
+        int64_t P = 0;
+        while (true) {
+            K++;
+            if (K >= nchunks) { full_lap = true; break; }  // small table: take a whole lap (plus one more below)
+            if (K > TIE_MAX_BACK) return false;
+            const uint32_t cc = (c + nchunks - K) % nchunks;
+            P += (int64_t)z.zpop[cc] - (int64_t)zchunk;
+            if ((int64_t)zchunk + P <= 0) break;
+        }
+    }
+    // slots to evaluate before h: K chunks plus the part of chunk c before h; a full lap is taken
+    // twice (the first lap delivers the steady-state carry, load < 1 makes it a fixed point)
+    uint64_t len;
+    uint32_t start;
+    if (full_lap) { len = (uint64_t)2 * zcap; start = h; }  // start at h, go around twice, end at h
+    else { len = (uint64_t)K * zchunk + (h - c * zchunk); start = ((c + nchunks - K) % nchunks) * zchunk; }
+    // each lane folds a contiguous part, then an ordered shuffle reduction composes them
+    const uint64_t per = (len + 31) / 32;
+    uint64_t lo = per * lane, hi = lo + per;
+    if (lo > len) lo = len;
+    if (hi > len) hi = len;
+    ChunkFn f; f.add = 0; f.lo = 0;
+    for (uint64_t i = lo; i < hi; i++) {
+        const uint32_t x = (uint32_t)((start + i) & (uint64_t)(zcap - 1));
+        ChunkFn g; g.add = (int32_t)zcnt_get(z.zcnt, x) - 1; g.lo = 0;
+        f = fn_compose(f, g);
+    }
+    for (int off = 1; off < 32; off <<= 1) {
+        ChunkFn g;
+        g.add = (int32_t)__shfl_down_sync(0xffffffffu, (uint32_t)f.add, (unsigned)off);
+        g.lo = (int32_t)__shfl_down_sync(0xffffffffu, (uint32_t)f.lo, (unsigned)off);
+        if (lane + (uint32_t)off < 32u) f = fn_compose(f, g);
+    }
+    int32_t o = fn_eval(f, 0);  // lane 0: carry entering slot h
+    o = (int32_t)__shfl_sync(0xffffffffu, (uint32_t)o, 0);
+    uint32_t x = h;
+    bool ok = true;
+    while (true) {
+        int32_t occ = o + (int32_t)zcnt_get(z.zcnt, x);
+        if (occ == 0) break;  // free slot
+        o = occ - 1;
+        x++;
+        if (x == zcap) { ok = false; break; }  // the run wraps: order is not decided by homes alone
+    }
+    *home_out = h;
+    *free_out = x;
+    return ok;
+}
+
 // select_kernel (single CTA): the device-driven replacement of "sort, take [0]" (:186-193). Scans
-// the heavy list for the maximum and its ties, then either commits the merge (unique maximum),
-// hands the tie to the zig_* kernels (need_tie), or halts the loop for the host.
-__global__ void select_kernel(PairTable tbl, HeavyList hl, StepCtl* ctl, MergeRec* rec) {
+// the heavy list for the maximum and its ties, then commits the merge (unique maximum, or a tie
+// the occupancy test settles) or halts the loop for the host.
+__global__ void __launch_bounds__(1024) select_kernel(PairTable tbl, HeavyList hl, StepCtl* ctl, MergeRec* rec, ZigPop z) {
     __shared__ uint32_t sh[1024];
     __shared__ uint32_t s_ntied;
+    __shared__ uint32_t s_mode;  // 0 done, 1 settle the tie here
+    __shared__ uint32_t s_home[MAXTIE];
+    __shared__ uint32_t s_free[MAXTIE];
+    __shared__ uint32_t s_bad;
     if (ctl->halt) return;
     if (ctl->step >= ctl->want_steps) {
         if (threadIdx.x == 0) ctl->halt = H_DONE;
@@ -250,7 +338,7 @@ __global__ void select_kernel(PairTable tbl, HeavyList hl, StepCtl* ctl, MergeRe
         m = c > m ? c : m;
     }
     sh[threadIdx.x] = m;
-    if (threadIdx.x == 0) s_ntied = 0;
+    if (threadIdx.x == 0) { s_ntied = 0; s_mode = 0; s_bad = 0; }
     __syncthreads();
     for (int off = (int)blockDim.x / 2; off > 0; off >>= 1) {
         if ((int)threadIdx.x < off) { uint32_t o = sh[threadIdx.x + off]; if (o > sh[threadIdx.x]) sh[threadIdx.x] = o; }
@@ -268,18 +356,52 @@ __global__ void select_kernel(PairTable tbl, HeavyList hl, StepCtl* ctl, MergeRe
         }
     }
     __syncthreads();
+    const uint32_t ntied = s_ntied;
+    if (threadIdx.x == 0) {
+        ctl->max_count = m;
+        ctl->ntied = ntied;
+        ctl->tie_status = TIE_NONE;
+        ctl->need_tie = 0;
+        if (!list_ok) ctl->halt = H_HEAVY;
+        else if (ntied == 1) commit_merge(ctl, rec, ctl->tie_keys[0], m);
+        else {
+            const uint32_t D = ctl->live_keys;
+            const uint32_t zc = zig_cap_for(D);
+            if ((ctl->flags & F_FORCE_REPLAY) || ntied > (uint32_t)MAXTIE || D == zig_max_load(zc)) ctl->halt = H_REPLAY;
+            else if (zc != ctl->zcap) ctl->halt = H_ZCAP;
+            else if (ctl->zpop_max > (zc < ZCHUNK ? zc : ZCHUNK)) ctl->halt = H_REPLAY;  // a chunk could overflow into the next
+            else s_mode = 1;
+        }
+    }
+    __syncthreads();
+    if (s_mode != 1) return;
+    // settle the tie: one warp per tied key
+    const uint32_t zcap = ctl->zcap;
+    z.zmask = zcap - 1;
+    const uint32_t warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (uint32_t i = warp; i < ntied; i += nwarps) {
+        uint32_t hm = 0, fr = 0;
+        bool ok = zig_first_free(z, zcap, ctl->tie_keys[i], &hm, &fr);
+        if ((threadIdx.x & 31u) == 0) {
+            s_home[i] = hm;
+            s_free[i] = fr;
+            if (!ok) atomicOr(&s_bad, 1u);
+        }
+    }
+    __syncthreads();
     if (threadIdx.x != 0) return;
-    ctl->max_count = m;
-    ctl->ntied = s_ntied;
-    ctl->tie_status = TIE_NONE;
-    ctl->need_tie = 0;
-    if (!list_ok) { ctl->halt = H_HEAVY; return; }
-    if (s_ntied == 1) { commit_merge(ctl, rec, ctl->tie_keys[0], m); return; }
-    const uint32_t D = ctl->live_keys;
-    const uint32_t zc = zig_cap_for(D);
-    if ((ctl->flags & F_FORCE_REPLAY) || s_ntied > (uint32_t)MAXTIE || D == zig_max_load(zc)) ctl->halt = H_REPLAY;
-    else if (zc != ctl->zcap) ctl->halt = H_ZCAP;
-    else ctl->need_tie = 1;
+    uint32_t status = TIE_NEED_REPLAY, winner = 0;
+    if (!s_bad) {
+        uint32_t b = 0;
+        for (uint32_t i = 1; i < ntied; i++) if (s_home[i] < s_home[b]) b = i;
+        bool ok = true;
+        for (uint32_t i = 0; i < ntied; i++) if (i != b && s_home[i] < s_free[b]) { ok = false; break; }
+        if (ok) { status = TIE_FAST_OK; winner = ctl->tie_keys[b]; }
+    }
+    ctl->tie_status = status;
+    ctl->tie_winner = winner;
+    if (status == TIE_FAST_OK && !(ctl->flags & F_CHECK_TIES)) { commit_merge(ctl, rec, winner, m); ctl->fast_ties += 1; }
+    else ctl->halt = H_REPLAY;
 }
 
 __global__ void heavy_ties_kernel(PairTable tbl, HeavyList hl, StepCtl* ctl) {
@@ -496,15 +618,17 @@ template <class TokT, bool DELTAS, bool FROMCTL>
 __global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, const TileHalo<TokT>* __restrict__ halo,
                                                         const StepCtl* __restrict__ ctl, uint32_t* __restrict__ cntL,
                                                         uint32_t* __restrict__ cntR, uint32_t* nxx_out, uint32_t* nab_out,
-                                                        uint32_t Au, uint32_t Bu, uint32_t Xu) {
+                                                        uint32_t Au, uint32_t Bu, uint32_t Xu, uint32_t bins_min_count) {
     __shared__ __align__(16) TokT ext[EXT];
     // block-private bins for the neighbour deltas: key = token id (+ 0x10000 for the right side)
     constexpr int NBIN = DELTAS ? 512 : 1;
     __shared__ uint32_t bin_key[NBIN];
     __shared__ uint32_t bin_val[NBIN];
+    bool use_bins = false;  // dense steps privatise the deltas per CTA; sparse steps go straight to global
     if (FROMCTL) {
         if (ctl->halt) return;
         Au = ctl->A; Bu = ctl->B; Xu = ctl->X;
+        use_bins = DELTAS && ctl->max_count >= bins_min_count;
     }
     const bool AEQB = (Au == Bu);
     __shared__ uint32_t sh_runA;
@@ -527,7 +651,7 @@ __global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, 
     for (int k = 0; k < NV; k++) any |= vec_has<TokT>(v[k], Au);
     if (threadIdx.x == 0 && h.l1 == A) any = true;  // possible head duty
     if (!__syncthreads_or(any ? 1 : 0)) return;
-    if (DELTAS) for (int i = (int)threadIdx.x; i < NBIN; i += THREADS) { bin_key[i] = EMPTY_KEY; bin_val[i] = 0; }
+    if (use_bins) for (int i = (int)threadIdx.x; i < NBIN; i += THREADS) { bin_key[i] = EMPTY_KEY; bin_val[i] = 0; }
 
     // 2. stage the tile (+ halo) so that neighbours can be looked up across thread boundaries
     uint4* dst = reinterpret_cast<uint4*>(ext + OFF);
@@ -611,7 +735,9 @@ __global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, 
                         merged_second = false;
                         if (tp == B) { int pp = prev_live(ext, p); merged_second = (pp >= 0 && ext[pp] == A); }
                     }
-                    if (merged_second) nXX++; else bin_add<NBIN>(bin_key, bin_val, (uint32_t)tp, cntL, cntR);
+                    if (merged_second) nXX++;
+                    else if (use_bins) bin_add<NBIN>(bin_key, bin_val, (uint32_t)tp, cntL, cntR);
+                    else atomicAdd(&cntL[tp], 1u);
                 }
                 // right side: owned only if the next live token does not start another occurrence
                 int n = next_live(ext, j);
@@ -619,14 +745,17 @@ __global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, 
                     const TokT tn = ext[n];
                     bool is_start = false;
                     if (tn == A) { int nn = next_live(ext, n); is_start = (nn >= 0 && ext[nn] == B); }
-                    if (!is_start) bin_add<NBIN>(bin_key, bin_val, 0x10000u | (uint32_t)tn, cntL, cntR);
+                    if (!is_start) {
+                        if (use_bins) bin_add<NBIN>(bin_key, bin_val, 0x10000u | (uint32_t)tn, cntL, cntR);
+                        else atomicAdd(&cntR[tn], 1u);
+                    }
                 }
             }
         }
     }
     if (nAB) atomicAdd(nab_out, nAB);
-    if (DELTAS) {
-        if (nXX) atomicAdd(nxx_out, nXX);
+    if (DELTAS && nXX) atomicAdd(nxx_out, nXX);
+    if (use_bins) {
         __syncthreads();
         for (int i = (int)threadIdx.x; i < NBIN; i += THREADS) {
             const uint32_t k = bin_key[i];
@@ -639,19 +768,18 @@ __global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, 
 // apply_kernel: fold the per-neighbour merge deltas into the pair table (and into the
 // reference-home population on births / deaths). One thread per token id.
 // =========================================================================================
-__device__ __forceinline__ void tbl_sub(const PairTable& tbl, uint32_t key, uint32_t c, StepCtl* ctl,
-                                        uint32_t* zcnt, uint32_t zmask) {
+__device__ __forceinline__ void tbl_sub(const PairTable& tbl, uint32_t key, uint32_t c, StepCtl* ctl, const ZigPop& z) {
     uint32_t s = tbl_find(tbl, key);
     if (s == EMPTY_KEY) { atomicOr(&ctl->err, (uint32_t)ERR_KEY_MISSING); return; }
     uint32_t old = atomicSub(&tbl.counts[s], c);
     if (old < c) { atomicOr(&ctl->err, (uint32_t)ERR_COUNT_UNDERFLOW); return; }
     if (old == c) {  // death
         atomicSub(&ctl->live_keys, 1u);
-        if (zcnt) zcnt_add(zcnt, zmask, key, -1, &ctl->err);
+        zcnt_add(z, key, -1, ctl);
     }
 }
-__device__ __forceinline__ void tbl_add(const PairTable& tbl, uint32_t key, uint32_t c, StepCtl* ctl,
-                                        uint32_t* zcnt, uint32_t zmask, const HeavyList& hl) {
+__device__ __forceinline__ void tbl_add(const PairTable& tbl, uint32_t key, uint32_t c, StepCtl* ctl, const ZigPop& z,
+                                        const HeavyList& hl) {
     uint32_t s = tbl_find_or_insert(tbl, key, &ctl->n_inserted);
     if (s == EMPTY_KEY) { atomicOr(&ctl->err, (uint32_t)ERR_TABLE_FULL); return; }
     uint32_t old = atomicAdd(&tbl.counts[s], c);
@@ -661,135 +789,15 @@ __device__ __forceinline__ void tbl_add(const PairTable& tbl, uint32_t key, uint
     }
     if (old == 0) {  // birth
         atomicAdd(&ctl->live_keys, 1u);
-        if (zcnt) zcnt_add(zcnt, zmask, key, +1, &ctl->err);
+        zcnt_add(z, key, +1, ctl);
     }
 }
 
-// =========================================================================================
-// Tie fast path. The reference picks, among the pairs sharing the maximum count, the one in the
-// lowest slot of its hash table (Appendix A). For linear probing without deletions the *set* of
-// occupied slots does not depend on insertion order, so from the population of home slots
-// (zcnt) the carry recurrence  o[x] = max(0, o[x-1] + cnt[x] - 1)  gives exactly which slots are
-// free. If the tied key with the smallest home h1 reaches a free slot before the next tied home
-// and no tied key can wrap past the end of the table, that key owns the lowest slot. Otherwise
-// the step is handed to the full replay (TIE_NEED_REPLAY).
-// =========================================================================================
-struct ChunkFn { int32_t add; int32_t lo; };  // f(o) = max(lo, o + add)
-__device__ __forceinline__ ChunkFn fn_compose(ChunkFn f, ChunkFn g) {  // g after f
-    ChunkFn r;
-    r.add = f.add + g.add;
-    int32_t a = f.lo + g.add;
-    r.lo = g.lo > a ? g.lo : a;
-    return r;
-}
-__device__ __forceinline__ int32_t fn_eval(ChunkFn f, int32_t o) { int32_t a = o + f.add; return f.lo > a ? f.lo : a; }
-
-__global__ void zig_rebuild_kernel(PairTable tbl, uint32_t* zcnt, uint32_t zmask, StepCtl* ctl) {
+// rebuild the reference-home population from the table (capacity change / table rebuild)
+__global__ void zig_rebuild_kernel(PairTable tbl, ZigPop z, StepCtl* ctl) {
     size_t cap = (size_t)tbl.mask + 1;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x)
-        if (tbl.counts[i] > 0) zcnt_add(zcnt, zmask, tbl.keys[i], +1, &ctl->err);
-}
-
-// CTAs stride over chunks of zchunk = min(zcap, ZCHUNK) slots; no-op unless a tie is pending
-__global__ void zig_chunk_kernel(const uint32_t* __restrict__ zcnt, const StepCtl* __restrict__ ctl, ChunkFn* __restrict__ fn) {
-    __shared__ ChunkFn sh[THREADS];
-    if (ctl->halt || !ctl->need_tie) return;
-    const uint32_t zcap = ctl->zcap;
-    const uint32_t zchunk = zcap < ZCHUNK ? zcap : ZCHUNK;
-    const uint32_t nchunks = zcap / zchunk;
-    const uint32_t per = (zchunk + THREADS - 1) / THREADS;
-    for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
-        const uint32_t base = c * zchunk;
-        ChunkFn f; f.add = 0; f.lo = 0;  // identity on o >= 0
-        for (uint32_t k = 0; k < per; k++) {
-            uint32_t x = threadIdx.x * per + k;
-            if (x < zchunk) {
-                ChunkFn g; g.add = (int32_t)zcnt_get(zcnt, base + x) - 1; g.lo = 0;
-                f = fn_compose(f, g);
-            }
-        }
-        sh[threadIdx.x] = f;
-        __syncthreads();
-        for (int off = 1; off < THREADS; off <<= 1) {  // ordered tree reduction
-            int i = (int)threadIdx.x;
-            if ((i % (2 * off)) == 0 && i + off < THREADS) sh[i] = fn_compose(sh[i], sh[i + off]);
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) fn[c] = sh[0];
-        __syncthreads();
-    }
-}
-
-// single CTA of MAXTIE threads; commits the merge or halts for the replay
-__global__ void zig_resolve_kernel(const uint32_t* __restrict__ zcnt, const ChunkFn* __restrict__ fn, StepCtl* ctl,
-                                   MergeRec* rec) {
-    __shared__ ChunkFn agg[MAXTIE];
-    __shared__ int32_t pre[MAXTIE];
-    __shared__ uint32_t home[MAXTIE];
-    __shared__ uint32_t efree[MAXTIE];
-    __shared__ uint32_t bad;
-    if (ctl->halt || !ctl->need_tie) return;
-    const uint32_t zcap = ctl->zcap;
-    const uint32_t zchunk = zcap < ZCHUNK ? zcap : ZCHUNK;
-    const uint32_t nchunks = zcap / zchunk;
-    const int t = (int)threadIdx.x;
-    const uint32_t ntied = ctl->ntied;
-    if (t == 0) bad = 0;
-    // 1. carry into every range of chunks
-    const uint32_t q = (nchunks + MAXTIE - 1) / MAXTIE;  // chunks per thread range
-    ChunkFn f; f.add = 0; f.lo = 0;
-    for (uint32_t k = 0; k < q; k++) {
-        uint32_t c = (uint32_t)t * q + k;
-        if (c < nchunks) f = fn_compose(f, fn[c]);
-    }
-    agg[t] = f;
-    __syncthreads();
-    if (t == 0) {
-        ChunkFn all; all.add = 0; all.lo = 0;
-        for (int r = 0; r < MAXTIE; r++) all = fn_compose(all, agg[r]);
-        int32_t o = fn_eval(all, 0);  // steady-state carry entering slot 0 (load < 1 => fixed point)
-        for (int r = 0; r < MAXTIE; r++) { pre[r] = o; o = fn_eval(agg[r], o); }
-    }
-    __syncthreads();
-    // 2. per tied key: first free slot at/after its home
-    if ((uint32_t)t < ntied && ntied <= (uint32_t)MAXTIE) {
-        const uint32_t key = ctl->tie_keys[t];
-        const uint32_t h = (uint32_t)zig_hash_pair(key) & (zcap - 1);
-        const uint32_t c = h / zchunk;
-        const uint32_t r = c / q;
-        int32_t o = pre[r];
-        for (uint32_t cc = r * q; cc < c; cc++) o = fn_eval(fn[cc], o);
-        for (uint32_t x = c * zchunk; x < h; x++) { int32_t a = o + (int32_t)zcnt_get(zcnt, x) - 1; o = a > 0 ? a : 0; }
-        uint32_t x = h;
-        bool wrapped = false;
-        while (true) {
-            int32_t occ = o + (int32_t)zcnt_get(zcnt, x);
-            if (occ == 0) break;  // free slot
-            o = occ - 1;
-            x++;
-            if (x == zcap) { wrapped = true; break; }
-        }
-        home[t] = h;
-        efree[t] = x;
-        if (wrapped) atomicOr(&bad, 1u);
-    }
-    __syncthreads();
-    // 3. winner = smallest home, if its probe run ends before every other tied home
-    if (t == 0) {
-        uint32_t status = TIE_NEED_REPLAY, winner = 0;
-        if (ntied >= 2 && ntied <= (uint32_t)MAXTIE && !bad) {
-            uint32_t b = 0;
-            for (uint32_t i = 1; i < ntied; i++) if (home[i] < home[b]) b = i;
-            bool ok = true;
-            for (uint32_t i = 0; i < ntied; i++) if (i != b && home[i] < efree[b]) { ok = false; break; }
-            if (ok) { status = TIE_FAST_OK; winner = ctl->tie_keys[b]; }
-        }
-        ctl->tie_status = status;
-        ctl->tie_winner = winner;
-        ctl->need_tie = 0;
-        if (status == TIE_FAST_OK && !(ctl->flags & F_CHECK_TIES)) { commit_merge(ctl, rec, winner, ctl->max_count); ctl->fast_ties += 1; }
-        else ctl->halt = H_REPLAY;
-    }
+        if (tbl.counts[i] > 0) zcnt_add(z, tbl.keys[i], +1, ctl);
 }
 
 // =========================================================================================
@@ -798,33 +806,33 @@ __global__ void zig_resolve_kernel(const uint32_t* __restrict__ zcnt, const Chun
 // delta layout: [0,vcap) cntL, [vcap,2*vcap) cntR, [2*vcap] cntXX, [2*vcap+1] cntAB
 // =========================================================================================
 __global__ void apply_kernel(PairTable tbl, uint32_t* __restrict__ delta, uint32_t vcap, StepCtl* ctl,
-                             uint32_t* zcnt, uint32_t n_ids, HeavyList hl) {
+                             ZigPop z, uint32_t n_ids, HeavyList hl) {
     if (ctl->halt) return;
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t A = ctl->A, B = ctl->B, X = ctl->X;
-    const uint32_t zmask = ctl->zcap - 1;
+    z.zmask = ctl->zcap - 1;
     hl.theta = ctl->theta;
     if (p < n_ids && p <= X) {
         uint32_t c = delta[p];
         if (c) {
             delta[p] = 0;
-            tbl_sub(tbl, pair_key(p, A), c, ctl, zcnt, zmask);
-            tbl_add(tbl, pair_key(p, X), c, ctl, zcnt, zmask, hl);
+            tbl_sub(tbl, pair_key(p, A), c, ctl, z);
+            tbl_add(tbl, pair_key(p, X), c, ctl, z, hl);
         }
         c = delta[vcap + p];
         if (c) {
             delta[vcap + p] = 0;
-            tbl_sub(tbl, pair_key(B, p), c, ctl, zcnt, zmask);
-            tbl_add(tbl, pair_key(X, p), c, ctl, zcnt, zmask, hl);
+            tbl_sub(tbl, pair_key(B, p), c, ctl, z);
+            tbl_add(tbl, pair_key(X, p), c, ctl, z, hl);
         }
     }
     if (p == 0) {
         const uint32_t xx = delta[2 * vcap], ab = delta[2 * vcap + 1];
         if (xx) {
-            tbl_sub(tbl, pair_key(B, A), xx, ctl, zcnt, zmask);
-            tbl_add(tbl, pair_key(X, X), xx, ctl, zcnt, zmask, hl);
+            tbl_sub(tbl, pair_key(B, A), xx, ctl, z);
+            tbl_add(tbl, pair_key(X, X), xx, ctl, z, hl);
         }
-        if (ab) tbl_sub(tbl, pair_key(A, B), ab, ctl, zcnt, zmask);
+        if (ab) tbl_sub(tbl, pair_key(A, B), ab, ctl, z);
         delta[2 * vcap] = 0;
         delta[2 * vcap + 1] = 0;
         ctl->last_merged = ab;
