@@ -141,7 +141,7 @@ template <class TokT> struct Sequence {
     size_t cap_slots = 0;   // allocated slots per buffer (multiple of TILE)
     size_t n_slots = 0;     // slots in use (multiple of TILE)
     uint64_t live = 0;      // live tokens (host view; may lag the device by one step)
-    DevBuf halo, run_local, run_full, tile_live, tile_off, total;
+    DevBuf halo, run_local, run_full, tile_live, tile_off, total, done_counter;
     TokT* tok() const { return buf[cur].as<TokT>(); }
     TokT* other() const { return buf[cur ^ 1].as<TokT>(); }
     uint32_t ntiles() const { return (uint32_t)(n_slots / TILE); }
@@ -161,6 +161,8 @@ static int seq_init(bpe_ctx* ctx, Sequence<TokT>& sq, const uint8_t* d_text, siz
     CU(sq.tile_live.alloc(nt * sizeof(uint32_t)));
     CU(sq.tile_off.alloc(nt * sizeof(unsigned long long)));
     CU(sq.total.alloc(sizeof(unsigned long long)));
+    CU(sq.done_counter.alloc(4));
+    CU(cudaMemsetAsync(sq.done_counter.p, 0, 4, ctx->stream));
     BPE_LAUNCH_NS(widen_kernel<TokT>, grid_for(sq.cap_slots, 256), 256, ctx->stream, d_text, n, sq.tok(), sq.cap_slots);
     ctx->launches++;
     CU(cudaGetLastError());
@@ -329,15 +331,11 @@ static int read_ctl(bpe_ctx* ctx, TrainRun& R, bool with_ties) {
 static int launch_halo(bpe_ctx* ctx, Sequence<uint16_t>& sq, uint32_t A, bool aeqb) {
     const uint32_t nt = sq.ntiles();
     const uint16_t H = 0xFFFF;
-    BPE_LAUNCH_NS((halo_kernel<uint16_t, false>), grid_for(nt, 128, 1u << 30), 128, ctx->stream, sq.tok(), sq.n_slots, nt,
-                  sq.halo.as<TileHalo<uint16_t>>(), (const StepCtl*)nullptr, A, aeqb ? 1 : 0, sq.run_local.as<uint32_t>(),
-                  sq.run_full.as<uint8_t>(), H, H, H, H, H);
+    BPE_LAUNCH((halo_kernel<uint16_t, false>), (nt + HALO_THREADS - 1) / HALO_THREADS, HALO_THREADS, ctx->stream, sq.tok(),
+               sq.n_slots, nt, sq.halo.as<TileHalo<uint16_t>>(), (const StepCtl*)nullptr, A, aeqb ? 1 : 0,
+               sq.run_local.as<uint32_t>(), sq.run_full.as<uint8_t>(), sq.done_counter.as<uint32_t>(), (uint32_t*)nullptr, 0u,
+               H, H, H, H, H);
     ctx->launches++;
-    if (aeqb) {
-        BPE_LAUNCH((run_chain_kernel<uint16_t, false>), 1, 1024, ctx->stream, nt, sq.halo.as<TileHalo<uint16_t>>(),
-                      sq.run_local.as<uint32_t>(), sq.run_full.as<uint8_t>(), 0u, (const StepCtl*)nullptr);
-        ctx->launches++;
-    }
     CU(cudaGetLastError());
     return BPE_OK;
 }
@@ -450,18 +448,16 @@ static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids) {
     const uint32_t nt = R.sq.ntiles();
     const uint16_t H = 0xFFFF;
     R.prof.mark(K_HALO);
-    BPE_LAUNCH_NS((halo_kernel<uint16_t, true>), grid_for(nt, 128, 1u << 30), 128, ctx->stream, R.sq.tok(), R.sq.n_slots, nt,
-                  R.sq.halo.as<TileHalo<uint16_t>>(), (const StepCtl*)R.d_ctl(), 0u, 0, R.sq.run_local.as<uint32_t>(),
-                  R.sq.run_full.as<uint8_t>(), H, H, H, H, H);
-    BPE_LAUNCH((run_chain_kernel<uint16_t, true>), 1, 1024, ctx->stream, nt, R.sq.halo.as<TileHalo<uint16_t>>(),
-                  R.sq.run_local.as<uint32_t>(), R.sq.run_full.as<uint8_t>(), 0u, (const StepCtl*)R.d_ctl());
+    BPE_LAUNCH((halo_kernel<uint16_t, true>), (nt + HALO_THREADS - 1) / HALO_THREADS, HALO_THREADS, ctx->stream, R.sq.tok(),
+               R.sq.n_slots, nt, R.sq.halo.as<TileHalo<uint16_t>>(), (const StepCtl*)R.d_ctl(), 0u, 0, R.sq.run_local.as<uint32_t>(),
+               R.sq.run_full.as<uint8_t>(), R.sq.done_counter.as<uint32_t>(), R.nxx(), 0u, H, H, H, H, H);
     R.prof.mark(K_MERGE);
     BPE_LAUNCH((merge_kernel<uint16_t, true, true>), nt, THREADS, ctx->stream, R.sq.tok(), R.sq.halo.as<TileHalo<uint16_t>>(),
                (const StepCtl*)R.d_ctl(), R.cntL(), R.cntR(), R.nxx(), R.nab(), 0u, 0u, 0u, 4u * nt);
     R.prof.mark(K_APPLY);
-    BPE_LAUNCH_NS(apply_kernel, (n_ids + 255) / 256, 256, ctx->stream, R.tm.view(), R.delta.as<uint32_t>(), R.vcap, R.d_ctl(),
+    BPE_LAUNCH_NS(apply_kernel, (4 * n_ids + 3 + 255) / 256, 256, ctx->stream, R.tm.view(), R.delta.as<uint32_t>(), R.vcap, R.d_ctl(),
                   R.tm.zig(), n_ids, R.hl());
-    ctx->launches += 4;
+    ctx->launches += 3;
     CU(cudaGetLastError());
     return BPE_OK;
 }
@@ -697,15 +693,11 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
     };
     auto one_pass = [&](uint32_t A, uint32_t B, uint32_t X) -> int {
         const uint32_t nt = sq.ntiles();
-        BPE_LAUNCH_NS((halo_kernel<TokT, false>), grid_for(nt, 128, 1u << 30), 128, ctx->stream, sq.tok(), sq.n_slots, nt,
-                      sq.halo.template as<TileHalo<TokT>>(), (const StepCtl*)nullptr, A, A == B ? 1 : 0,
-                      sq.run_local.template as<uint32_t>(), sq.run_full.template as<uint8_t>(), H, H, H, H, H);
+        BPE_LAUNCH((halo_kernel<TokT, false>), (nt + HALO_THREADS - 1) / HALO_THREADS, HALO_THREADS, ctx->stream, sq.tok(), sq.n_slots,
+                   nt, sq.halo.template as<TileHalo<TokT>>(), (const StepCtl*)nullptr, A, A == B ? 1 : 0,
+                   sq.run_local.template as<uint32_t>(), sq.run_full.template as<uint8_t>(), sq.done_counter.template as<uint32_t>(),
+                   (uint32_t*)nullptr, 0u, H, H, H, H, H);
         ctx->launches += 1;
-        if (A == B) {
-            BPE_LAUNCH((run_chain_kernel<TokT, false>), 1, 1024, ctx->stream, nt, sq.halo.template as<TileHalo<TokT>>(),
-                          sq.run_local.template as<uint32_t>(), sq.run_full.template as<uint8_t>(), 0u, (const StepCtl*)nullptr);
-            ctx->launches += 1;
-        }
         BPE_LAUNCH((merge_kernel<TokT, false, false>), nt, THREADS, ctx->stream, sq.tok(), sq.halo.template as<TileHalo<TokT>>(),
                    (const StepCtl*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, &d_ctl->cntAB, A, B, X, 0u);
         ctx->launches += 1;

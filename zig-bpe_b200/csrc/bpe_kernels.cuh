@@ -333,7 +333,20 @@ __global__ void __launch_bounds__(1024) select_kernel(PairTable tbl, HeavyList h
     }
     const uint32_t n = ctl->n_heavy < hl.cap ? ctl->n_heavy : hl.cap;
     uint32_t m = 0;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    constexpr int SC = 16;  // list entries kept in registers per thread (covers lists up to 16K keys)
+    uint32_t cs[SC], cc[SC];
+#pragma unroll
+    for (int k = 0; k < SC; k++) {
+        const uint32_t i = threadIdx.x + (uint32_t)k * 1024u;
+        cs[k] = i < n ? hl.slots[i] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < SC; k++) {
+        const uint32_t i = threadIdx.x + (uint32_t)k * 1024u;
+        cc[k] = i < n ? tbl.counts[cs[k]] : 0u;
+        m = cc[k] > m ? cc[k] : m;
+    }
+    for (uint32_t i = threadIdx.x + (uint32_t)SC * 1024u; i < n; i += 1024u) {
         uint32_t c = tbl.counts[hl.slots[i]];
         m = c > m ? c : m;
     }
@@ -347,7 +360,14 @@ __global__ void __launch_bounds__(1024) select_kernel(PairTable tbl, HeavyList h
     m = sh[0];
     const bool list_ok = (ctl->theta != 0) && (ctl->n_heavy <= hl.cap) && (m >= ctl->theta);
     if (list_ok) {
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < SC; k++) {
+            if (cc[k] == m && threadIdx.x + (uint32_t)k * 1024u < n) {
+                uint32_t idx = atomicAdd(&s_ntied, 1u);
+                if (idx < (uint32_t)MAXTIE) ctl->tie_keys[idx] = tbl.keys[cs[k]];
+            }
+        }
+        for (uint32_t i = threadIdx.x + (uint32_t)SC * 1024u; i < n; i += 1024u) {
             uint32_t s = hl.slots[i];
             if (tbl.counts[s] == m) {
                 uint32_t idx = atomicAdd(&s_ntied, 1u);
@@ -425,86 +445,97 @@ __global__ void heavy_ties_kernel(PairTable tbl, HeavyList hl, StepCtl* ctl) {
 // =========================================================================================
 // FROMCTL: the merge is read from the device control block (device-driven train loop) and the
 // kernel does nothing while the loop is halted; otherwise A / aeqb come from the arguments.
+// For A==B steps the last CTA to finish chains the per-tile run lengths:
+//   runA[t] = run_local[t] + (run_full[t] ? runA[t-1] : 0), runA[0] = ext_run
+// (each thread folds a contiguous range of tiles into (add, full), thread 0 chains the ranges, then
+// every thread replays its range from its carry-in — linear work even on "aaaa..." inputs).
+// zero2 (nullable): the two scalar merge deltas (cntXX, cntAB) to clear before the merge pass.
+constexpr int HALO_THREADS = 128;
 template <class TokT, bool FROMCTL>
-__global__ void halo_kernel(const TokT* __restrict__ tok, size_t n_slots, uint32_t ntiles, TileHalo<TokT>* halo,
-                            const StepCtl* __restrict__ ctl, uint32_t Au, int aeqb, uint32_t* run_local, uint8_t* run_full,
+__global__ void __launch_bounds__(HALO_THREADS) halo_kernel(const TokT* __restrict__ tok, size_t n_slots, uint32_t ntiles,
+                            TileHalo<TokT>* halo, const StepCtl* __restrict__ ctl, uint32_t Au, int aeqb,
+                            uint32_t* run_local, uint8_t* run_full, uint32_t* done_counter, uint32_t* zero2, uint32_t ext_run,
                             TokT ext_l2, TokT ext_l1, TokT ext_r0, TokT ext_r1, TokT ext_r2) {
+    __shared__ uint32_t s_add[HALO_THREADS];
+    __shared__ uint32_t s_full[HALO_THREADS];
+    __shared__ uint32_t s_last;
     const TokT H = (TokT)TokTraits<TokT>::hole;
     if (FROMCTL) {
         if (ctl->halt) return;
         Au = ctl->A;
         aeqb = (ctl->A == ctl->B) ? 1 : 0;
     }
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ntiles) return;
-    TileHalo<TokT> h;
-    // left: last two live tokens before slot t*TILE
-    TokT l[2] = {H, H};
-    int nl = 0;
-    for (size_t i = (size_t)t * TILE; i > 0 && nl < 2;) {
-        --i;
-        TokT v = tok[i];
-        if (v != H) l[nl++] = v;
-    }
-    if (nl == 0) { l[0] = ext_l1; l[1] = ext_l2; }
-    else if (nl == 1) { l[1] = ext_l1; }
-    h.l1 = l[0];
-    h.l2 = (l[0] == H) ? H : l[1];
-    // right: first three live tokens at/after slot (t+1)*TILE
-    TokT r[3] = {H, H, H};
-    int nr = 0;
-    for (size_t i = (size_t)(t + 1) * TILE; i < n_slots && nr < 3; i++) {
-        TokT v = tok[i];
-        if (v != H) r[nr++] = v;
-    }
-    const TokT er[3] = {ext_r0, ext_r1, ext_r2};
-    for (int k = 0; nr < 3 && k < 3; k++) {
-        if (er[k] == H) break;
-        r[nr++] = er[k];
-    }
-    h.r0 = r[0]; h.r1 = r[1]; h.r2 = r[2];
-    h.runA = 0;
-    halo[t] = h;
-    if (aeqb) {
-        // live A's walking back from the tile's left edge, inside the previous tile only
-        const TokT A = (TokT)Au;
-        uint32_t cnt = 0;
-        uint8_t full = 1;
-        if (t == 0) { full = 0; }
-        else {
-            size_t lo = (size_t)(t - 1) * TILE;
-            for (size_t i = (size_t)t * TILE; i > lo;) {
-                --i;
-                TokT v = tok[i];
-                if (v == H) continue;
-                if (v == A) cnt++; else { full = 0; break; }
-            }
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0 && zero2) { zero2[0] = 0; zero2[1] = 0; }
+    if (t < ntiles) {
+        TileHalo<TokT> h;
+        // left: last two live tokens before slot t*TILE
+        TokT l[2] = {H, H};
+        int nl = 0;
+        for (size_t i = (size_t)t * TILE; i > 0 && nl < 2;) {
+            --i;
+            TokT v = tok[i];
+            if (v != H) l[nl++] = v;
         }
-        run_local[t] = cnt;
-        run_full[t] = full;
+        if (nl == 0) { l[0] = ext_l1; l[1] = ext_l2; }
+        else if (nl == 1) { l[1] = ext_l1; }
+        h.l1 = l[0];
+        h.l2 = (l[0] == H) ? H : l[1];
+        // right: first three live tokens at/after slot (t+1)*TILE
+        TokT r[3] = {H, H, H};
+        int nr = 0;
+        for (size_t i = (size_t)(t + 1) * TILE; i < n_slots && nr < 3; i++) {
+            TokT v = tok[i];
+            if (v != H) r[nr++] = v;
+        }
+        const TokT er[3] = {ext_r0, ext_r1, ext_r2};
+        for (int k = 0; nr < 3 && k < 3; k++) {
+            if (er[k] == H) break;
+            r[nr++] = er[k];
+        }
+        h.r0 = r[0]; h.r1 = r[1]; h.r2 = r[2];
+        h.runA = 0;
+        halo[t] = h;
+        if (aeqb) {
+            // live A's walking back from the tile's left edge, inside the previous tile only
+            const TokT A = (TokT)Au;
+            uint32_t cnt = 0;
+            uint8_t full = 1;
+            if (t == 0) { full = 0; }
+            else {
+                size_t lo = (size_t)(t - 1) * TILE;
+                for (size_t i = (size_t)t * TILE; i > lo;) {
+                    --i;
+                    TokT v = tok[i];
+                    if (v == H) continue;
+                    if (v == A) cnt++; else { full = 0; break; }
+                }
+            }
+            run_local[t] = cnt;
+            run_full[t] = full;
+        }
     }
-}
-
-// chain over tiles (A==B steps only): runA[t] = live A's immediately before tile t
-//   run[t] = run_local[t] + (run_full[t] ? run[t-1] : 0), run[0] = ext_run
-// One CTA: each thread folds a contiguous range of tiles into (add, full), thread 0 chains the
-// ranges, then every thread replays its range from its carry-in.
-template <class TokT, bool FROMCTL>
-__global__ void run_chain_kernel(uint32_t ntiles, TileHalo<TokT>* halo, const uint32_t* run_local,
-                                 const uint8_t* run_full, uint32_t ext_run, const StepCtl* __restrict__ ctl) {
-    __shared__ uint32_t s_add[1024];
-    __shared__ uint32_t s_full[1024];
-    if (FROMCTL && (ctl->halt || ctl->A != ctl->B)) return;
+    if (!aeqb) return;
+    // ---- the last CTA to get here chains the runs ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t prev = atomicAdd(done_counter, 1u);
+        s_last = (prev == gridDim.x - 1u) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
     const uint32_t nthr = blockDim.x;
     const uint32_t q = (ntiles + nthr - 1) / nthr;
     const uint32_t lo = threadIdx.x * q;
     uint32_t hi = lo + q;
     if (hi > ntiles) hi = ntiles;
-    // fold tiles [max(lo,1), hi): value after the range = add + (full ? carry_in : 0)
     uint32_t add = 0, full = 1;
-    for (uint32_t t = (lo == 0 ? 1u : lo); t < hi; t++) {
-        if (run_full[t]) add += run_local[t];
-        else { add = run_local[t]; full = 0; }
+    for (uint32_t i = (lo == 0 ? 1u : lo); i < hi; i++) {
+        const uint32_t rl = ((volatile uint32_t*)run_local)[i];
+        if (((volatile uint8_t*)run_full)[i]) add += rl;
+        else { add = rl; full = 0; }
     }
     s_add[threadIdx.x] = add;
     s_full[threadIdx.x] = full;
@@ -513,16 +544,17 @@ __global__ void run_chain_kernel(uint32_t ntiles, TileHalo<TokT>* halo, const ui
         uint32_t carry = ext_run;  // run entering tile 0
         for (uint32_t i = 0; i < nthr; i++) {
             uint32_t a = s_add[i], f = s_full[i];
-            s_add[i] = carry;  // carry-in of range i (= run[lo_i - 1], or ext_run for range 0)
+            s_add[i] = carry;
             carry = a + (f ? carry : 0u);
         }
+        *done_counter = 0;  // ready for the next launch
     }
     __syncthreads();
     uint32_t run = s_add[threadIdx.x];
     if (lo == 0 && lo < hi) halo[0].runA = run;
-    for (uint32_t t = (lo == 0 ? 1u : lo); t < hi; t++) {
-        run = run_local[t] + (run_full[t] ? run : 0u);
-        halo[t].runA = run;
+    for (uint32_t i = (lo == 0 ? 1u : lo); i < hi; i++) {
+        run = ((volatile uint32_t*)run_local)[i] + (((volatile uint8_t*)run_full)[i] ? run : 0u);
+        halo[i].runA = run;
     }
 }
 
@@ -637,14 +669,17 @@ __global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, 
     static_assert(NV >= 1 && NV * VEC * THREADS == TILE, "tile geometry");
     const TokT H = (TokT)TokTraits<TokT>::hole;
     const TokT A = (TokT)Au, B = (TokT)Bu, X = (TokT)Xu;
-    const size_t base = (size_t)blockIdx.x * TILE;
+    // odd steps walk the sequence backwards: the tiles the previous pass touched last are still in
+    // the 126 MB L2 when this pass starts with them
+    const uint32_t tile = (FROMCTL && (ctl->step & 1u)) ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
+    const size_t base = (size_t)tile * TILE;
 
     // 1. stream the tile through registers
     const uint4* src = reinterpret_cast<const uint4*>(tok + base);
     uint4 v[NV];
     bool any = false;
     TileHalo<TokT> h;
-    if (threadIdx.x == 0) h = halo[blockIdx.x];  // issued first: its latency hides behind the tile loads
+    if (threadIdx.x == 0) h = halo[tile];  // issued first: its latency hides behind the tile loads
 #pragma unroll
     for (int k = 0; k < NV; k++) v[k] = src[k * THREADS + (int)threadIdx.x];
 #pragma unroll
@@ -808,38 +843,40 @@ __global__ void zig_rebuild_kernel(PairTable tbl, ZigPop z, StepCtl* ctl) {
 __global__ void apply_kernel(PairTable tbl, uint32_t* __restrict__ delta, uint32_t vcap, StepCtl* ctl,
                              ZigPop z, uint32_t n_ids, HeavyList hl) {
     if (ctl->halt) return;
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    // thread t: token id p = t / 4, side = left/right neighbour, op = retire the old pair / credit the new one.
+    // The two ops of a (p, side) sit in adjacent lanes so the four table round trips overlap.
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t A = ctl->A, B = ctl->B, X = ctl->X;
     z.zmask = ctl->zcap - 1;
     hl.theta = ctl->theta;
+    const uint32_t p = t >> 2, side = (t >> 1) & 1u, op = t & 1u;
+    uint32_t c = 0;
+    uint32_t* cell = nullptr;
     if (p < n_ids && p <= X) {
-        uint32_t c = delta[p];
-        if (c) {
-            delta[p] = 0;
-            tbl_sub(tbl, pair_key(p, A), c, ctl, z);
-            tbl_add(tbl, pair_key(p, X), c, ctl, z, hl);
-        }
-        c = delta[vcap + p];
-        if (c) {
-            delta[vcap + p] = 0;
-            tbl_sub(tbl, pair_key(B, p), c, ctl, z);
-            tbl_add(tbl, pair_key(X, p), c, ctl, z, hl);
-        }
+        cell = &delta[side ? vcap + p : p];
+        c = *cell;
     }
-    if (p == 0) {
-        const uint32_t xx = delta[2 * vcap], ab = delta[2 * vcap + 1];
-        if (xx) {
-            tbl_sub(tbl, pair_key(B, A), xx, ctl, z);
-            tbl_add(tbl, pair_key(X, X), xx, ctl, z, hl);
-        }
+    __syncwarp();
+    if (c) {
+        if (op == 0) tbl_sub(tbl, side ? pair_key(B, p) : pair_key(p, A), c, ctl, z);
+        else { *cell = 0; tbl_add(tbl, side ? pair_key(X, p) : pair_key(p, X), c, ctl, z, hl); }
+    }
+    const uint32_t t0 = 4u * n_ids;  // three more threads: adjacent occurrences, the merged pair itself, bookkeeping
+    if (t == t0) {
+        const uint32_t xx = delta[2 * vcap];
+        if (xx) tbl_sub(tbl, pair_key(B, A), xx, ctl, z);
+    } else if (t == t0 + 1) {
+        const uint32_t xx = delta[2 * vcap];
+        if (xx) tbl_add(tbl, pair_key(X, X), xx, ctl, z, hl);
+    } else if (t == t0 + 2) {
+        const uint32_t ab = delta[2 * vcap + 1];
         if (ab) tbl_sub(tbl, pair_key(A, B), ab, ctl, z);
-        delta[2 * vcap] = 0;
-        delta[2 * vcap + 1] = 0;
         ctl->last_merged = ab;
         ctl->live_tokens -= ab;
         ctl->step += 1;
     }
 }
+
 
 // =========================================================================================
 // pair_visit_kernel: one CTA per tile, calls op(pos, key) for every live adjacent pair whose left
