@@ -616,14 +616,6 @@ template <> __device__ __forceinline__ uint32_t vec_mask<uint16_t>(const uint4& 
 template <> __device__ __forceinline__ uint32_t vec_mask<uint32_t>(const uint4& v, uint32_t a) {
     return (v.x == a ? 1u : 0u) | (v.y == a ? 2u : 0u) | (v.z == a ? 4u : 0u) | (v.w == a ? 8u : 0u);
 }
-template <class TokT> __device__ __forceinline__ void unpack_vec(const uint4& v, uint32_t* out);
-template <> __device__ __forceinline__ void unpack_vec<uint16_t>(const uint4& v, uint32_t* out) {
-    out[0] = v.x & 0xFFFFu; out[1] = v.x >> 16; out[2] = v.y & 0xFFFFu; out[3] = v.y >> 16;
-    out[4] = v.z & 0xFFFFu; out[5] = v.z >> 16; out[6] = v.w & 0xFFFFu; out[7] = v.w >> 16;
-}
-template <> __device__ __forceinline__ void unpack_vec<uint32_t>(const uint4& v, uint32_t* out) {
-    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
-}
 template <class TokT> __device__ __forceinline__ bool vec_has(const uint4& v, uint32_t a);
 template <> __device__ __forceinline__ bool vec_has<uint16_t>(const uint4& v, uint32_t a) {
     const uint32_t aa = a | (a << 16);
@@ -690,30 +682,8 @@ __global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, 
     if (threadIdx.x == 0) h = halo[tile];  // issued first: its latency hides behind the tile loads
 #pragma unroll
     for (int k = 0; k < NV; k++) v[k] = src[k * THREADS + (int)threadIdx.x];
-    // A tile needs the staged path only if some A may start an occurrence. Decided in registers: an
-    // A whose next live token (in this vector, or the first live token of the next lane's vector)
-    // is a live token other than B cannot; an A whose successor is B or lies out of reach might.
-    constexpr uint32_t UNK = 0x80000000u;
-    const uint32_t lane = threadIdx.x & 31u;
 #pragma unroll
-    for (int k = 0; k < NV; k++) {
-        const bool hasA = vec_has<TokT>(v[k], Au);
-        if (!__any_sync(0xffffffffu, hasA ? 1 : 0)) continue;
-        uint32_t tv[VEC];
-        unpack_vec<TokT>(v[k], tv);
-        uint32_t fl = (uint32_t)H;
-#pragma unroll
-        for (int i = VEC - 1; i >= 0; i--) fl = (tv[i] != (uint32_t)H) ? tv[i] : fl;
-        uint32_t nl = __shfl_down_sync(0xffffffffu, fl, 1);
-        if (lane == 31u || nl == (uint32_t)H) nl = UNK;
-        if (hasA) {
-#pragma unroll
-            for (int i = VEC - 1; i >= 0; i--) {
-                if (tv[i] == Au && (nl == Bu || nl == UNK)) any = true;
-                if (tv[i] != (uint32_t)H) nl = tv[i];
-            }
-        }
-    }
+    for (int k = 0; k < NV; k++) any |= vec_has<TokT>(v[k], Au);
     if (threadIdx.x == 0 && h.l1 == A) any = true;  // possible head duty
     if (!__syncthreads_or(any ? 1 : 0)) return;
     if (use_bins) for (int i = (int)threadIdx.x; i < NBIN; i += THREADS) { bin_key[i] = EMPTY_KEY; bin_val[i] = 0; }
