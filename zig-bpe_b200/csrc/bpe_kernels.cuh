@@ -656,6 +656,9 @@ __global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, 
     constexpr int NBIN = DELTAS ? 512 : 1;
     __shared__ uint32_t bin_key[NBIN];
     __shared__ uint32_t bin_val[NBIN];
+    constexpr int QCAP = 2048;  // queued A positions per tile (denser tiles overflow to in-place handling)
+    __shared__ uint16_t q_pos[QCAP];
+    __shared__ uint32_t q_n;
     bool use_bins = false;  // dense steps privatise the deltas per CTA; sparse steps go straight to global
     if (FROMCTL) {
         if (ctl->halt) return;
@@ -701,32 +704,79 @@ __global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, 
         ext[OFF + TILE + 2] = h.r2;
         for (int i = OFF + TILE + 3; i < EXT; i++) ext[i] = H;
         sh_runA = h.runA;
+        q_n = 0;
     }
     __syncthreads();
 
     uint32_t nAB = 0, nXX = 0;
-    if (!AEQB && threadIdx.x == 0 && ext[OFF - 1] == A) {
-        // head duty: the A just before this tile starts an occurrence iff our first live token is B
-        int f = next_live(ext, OFF - 1);
-        if (f >= 0 && f < OFF + TILE && ext[f] == B) tok[base + (size_t)(f - OFF)] = H;
-    }
+    // one occurrence candidate: the A at ext index s (A != B). Writes X / hole, emits the deltas.
+    auto process_ab = [&](int s) {
+        const int j = next_live(ext, s);
+        if (j < 0 || ext[j] != B) return;
+        tok[base + (size_t)(s - OFF)] = X;
+        if (j < OFF + TILE) tok[base + (size_t)(j - OFF)] = H;
+        nAB++;
+        if (DELTAS) {
+            // left side: always owned by this occurrence
+            const int p = prev_live(ext, s);
+            if (p >= 0) {
+                const TokT tp = ext[p];
+                bool merged_second = false;
+                if (tp == B) { int pp = prev_live(ext, p); merged_second = (pp >= 0 && ext[pp] == A); }
+                if (merged_second) nXX++;
+                else if (use_bins) bin_add<NBIN>(bin_key, bin_val, (uint32_t)tp, cntL, cntR);
+                else atomicAdd(&cntL[tp], 1u);
+            }
+            // right side: owned only if the next live token does not start another occurrence
+            const int n = next_live(ext, j);
+            if (n >= 0) {
+                const TokT tn = ext[n];
+                bool is_start = false;
+                if (tn == A) { int nn = next_live(ext, n); is_start = (nn >= 0 && ext[nn] == B); }
+                if (!is_start) {
+                    if (use_bins) bin_add<NBIN>(bin_key, bin_val, 0x10000u | (uint32_t)tn, cntL, cntR);
+                    else atomicAdd(&cntR[tn], 1u);
+                }
+            }
+        }
+    };
+    if (!AEQB) {
+        if (threadIdx.x == 0 && ext[OFF - 1] == A) {
+            // head duty: the A just before this tile starts an occurrence iff our first live token is B
+            int f = next_live(ext, OFF - 1);
+            if (f >= 0 && f < OFF + TILE && ext[f] == B) tok[base + (size_t)(f - OFF)] = H;
+        }
+        // The A's are sparse and unevenly spread over the lanes, so each thread only queues the
+        // positions of its A's; the CTA then works through the queue with all lanes busy.
 #pragma unroll
-    for (int k = 0; k < NV; k++) {
-        uint32_t mask = vec_mask<TokT>(v[k], Au);
-        if (!mask) continue;
-        const int s0 = OFF + (k * THREADS + (int)threadIdx.x) * VEC;
-        uint32_t run = 0;       // AEQB: consecutive live A's immediately before the current slot
-        bool run_known = false;
-        while (mask) {
-            const int bit = __ffs((int)mask) - 1;
-            mask &= mask - 1;
-            const int s = s0 + bit;
-            bool start = false;
-            int j = -1;
-            if (!AEQB) {
-                j = next_live(ext, s);
-                start = (j >= 0 && ext[j] == B);
-            } else {
+        for (int k = 0; k < NV; k++) {
+            uint32_t mask = vec_mask<TokT>(v[k], Au);
+            if (!mask) continue;
+            const int s0 = OFF + (k * THREADS + (int)threadIdx.x) * VEC;
+            uint32_t at = atomicAdd(&q_n, (uint32_t)__popc(mask));
+            while (mask) {
+                const int bit = __ffs((int)mask) - 1;
+                mask &= mask - 1;
+                if (at < (uint32_t)QCAP) q_pos[at] = (uint16_t)(s0 + bit);
+                else process_ab(s0 + bit);  // queue full (very dense step): handle in place
+                at++;
+            }
+        }
+        __syncthreads();
+        const uint32_t nq = q_n < (uint32_t)QCAP ? q_n : (uint32_t)QCAP;
+        for (uint32_t i = threadIdx.x; i < nq; i += THREADS) process_ab((int)q_pos[i]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            uint32_t mask = vec_mask<TokT>(v[k], Au);
+            if (!mask) continue;
+            const int s0 = OFF + (k * THREADS + (int)threadIdx.x) * VEC;
+            uint32_t run = 0;       // consecutive live A's immediately before the current slot
+            bool run_known = false;
+            while (mask) {
+                const int bit = __ffs((int)mask) - 1;
+                mask &= mask - 1;
+                const int s = s0 + bit;
                 if (!run_known) {
                     // live A's immediately before s inside the tile; if the tile start is reached
                     // the run continues into earlier tiles (runA)
@@ -741,48 +791,38 @@ __global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, 
                     run_known = true;
                 }
                 const uint32_t off = run;
-                // next A of this vector continues the run only if nothing but holes lies between
+                // the next A of this vector continues the run only if nothing but holes lies between
                 if (mask) {
                     const int nb = __ffs((int)mask) - 1;
                     bool contiguous = true;
                     for (int q = s + 1; q < s0 + nb; q++) if (ext[q] != H) { contiguous = false; break; }
-                    if (contiguous) run = off + 1; else { run = 0; }
+                    run = contiguous ? off + 1 : 0;
                 }
                 if (off & 1u) {
                     tok[base + (size_t)(s - OFF)] = H;  // second element of the occurrence at off-1
-                } else {
-                    j = next_live(ext, s);
-                    start = (j >= 0 && ext[j] == A);
+                    continue;
                 }
-            }
-            if (!start) continue;
-            tok[base + (size_t)(s - OFF)] = X;
-            if (!AEQB && j < OFF + TILE) tok[base + (size_t)(j - OFF)] = H;
-            nAB++;
-            if (DELTAS) {
-                // left side: always owned by this occurrence
-                int p = prev_live(ext, s);
-                if (p >= 0) {
-                    const TokT tp = ext[p];
-                    bool merged_second;
-                    if (AEQB) merged_second = (tp == A);  // same run, odd offset
-                    else {
-                        merged_second = false;
-                        if (tp == B) { int pp = prev_live(ext, p); merged_second = (pp >= 0 && ext[pp] == A); }
+                const int j = next_live(ext, s);
+                if (j < 0 || ext[j] != A) continue;
+                tok[base + (size_t)(s - OFF)] = X;
+                nAB++;
+                if (DELTAS) {
+                    const int p = prev_live(ext, s);
+                    if (p >= 0) {
+                        const TokT tp = ext[p];
+                        if (tp == A) nXX++;  // same run, odd offset: second element of the previous occurrence
+                        else if (use_bins) bin_add<NBIN>(bin_key, bin_val, (uint32_t)tp, cntL, cntR);
+                        else atomicAdd(&cntL[tp], 1u);
                     }
-                    if (merged_second) nXX++;
-                    else if (use_bins) bin_add<NBIN>(bin_key, bin_val, (uint32_t)tp, cntL, cntR);
-                    else atomicAdd(&cntL[tp], 1u);
-                }
-                // right side: owned only if the next live token does not start another occurrence
-                int n = next_live(ext, j);
-                if (n >= 0) {
-                    const TokT tn = ext[n];
-                    bool is_start = false;
-                    if (tn == A) { int nn = next_live(ext, n); is_start = (nn >= 0 && ext[nn] == B); }
-                    if (!is_start) {
-                        if (use_bins) bin_add<NBIN>(bin_key, bin_val, 0x10000u | (uint32_t)tn, cntL, cntR);
-                        else atomicAdd(&cntR[tn], 1u);
+                    const int n = next_live(ext, j);
+                    if (n >= 0) {
+                        const TokT tn = ext[n];
+                        bool is_start = false;
+                        if (tn == A) { int nn = next_live(ext, n); is_start = (nn >= 0 && ext[nn] == A); }
+                        if (!is_start) {
+                            if (use_bins) bin_add<NBIN>(bin_key, bin_val, 0x10000u | (uint32_t)tn, cntL, cntR);
+                            else atomicAdd(&cntR[tn], 1u);
+                        }
                     }
                 }
             }
