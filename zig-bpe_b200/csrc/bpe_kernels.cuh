@@ -646,8 +646,11 @@ __device__ __forceinline__ void bin_add(uint32_t* bin_key, uint32_t* bin_val, ui
 // occurrence). So a tile without any A and without head duty is streamed and left untouched.
 // DELTAS: cntL / cntR / *nxx_out receive the neighbour-pair deltas (train); *nab_out always
 // receives the number of merged occurrences. FROMCTL as in halo_kernel.
+#ifndef BPE_MERGE_MINBLOCKS
+#define BPE_MERGE_MINBLOCKS 6
+#endif
 template <class TokT, bool DELTAS, bool FROMCTL>
-__global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, const TileHalo<TokT>* __restrict__ halo,
+__global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(TokT* __restrict__ tok, const TileHalo<TokT>* __restrict__ halo,
                                                         const StepCtl* __restrict__ ctl, uint32_t* __restrict__ cntL,
                                                         uint32_t* __restrict__ cntR, uint32_t* nxx_out, uint32_t* nab_out,
                                                         uint32_t Au, uint32_t Bu, uint32_t Xu, uint32_t bins_min_count) {
@@ -696,15 +699,17 @@ __global__ void __launch_bounds__(THREADS) merge_kernel(TokT* __restrict__ tok, 
 #pragma unroll
     for (int k = 0; k < NV; k++) dst[k * THREADS + (int)threadIdx.x] = v[k];
     if (threadIdx.x == 0) {
-        for (int i = 0; i < OFF - 2; i++) ext[i] = H;
         ext[OFF - 2] = h.l2;
         ext[OFF - 1] = h.l1;
         ext[OFF + TILE + 0] = h.r0;
         ext[OFF + TILE + 1] = h.r1;
         ext[OFF + TILE + 2] = h.r2;
-        for (int i = OFF + TILE + 3; i < EXT; i++) ext[i] = H;
         sh_runA = h.runA;
         q_n = 0;
+    } else if (threadIdx.x < 32) {
+        const int i = (int)threadIdx.x - 1;  // the remaining margin slots are holes
+        if (i < OFF - 2) ext[i] = H;
+        else if (OFF + TILE + 3 + (i - (OFF - 2)) < EXT) ext[OFF + TILE + 3 + (i - (OFF - 2))] = H;
     }
     __syncthreads();
 
