@@ -1,0 +1,100 @@
+"""tests/dist_worker.py — one rank of the world_size-N CPU test of sharded training.
+
+The kernels run in the CPU emulation build (tests/emul); the per-step exchange that NCCL performs on
+GPUs is delegated to a callback which all-reduces the buffer over torch.distributed/gloo. Every rank
+trains on its contiguous shard and must obtain the merges the oracle learns from the whole corpus."""
+import ctypes
+import importlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    case, vocab, out_path = sys.argv[1], int(sys.argv[2]), sys.argv[3]
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    zb = importlib.import_module("zig-bpe_b200")
+    lib = zb.load_library(os.path.join(ROOT, "tests", "emul", "libbpe_emul.so"))
+
+    CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int)
+
+    def allreduce(buf, count, kind):
+        try:
+            if kind == 0:
+                a = np.ctypeslib.as_array(ctypes.cast(buf, ctypes.POINTER(ctypes.c_uint32)), shape=(count,))
+                t = torch.from_numpy(a.astype(np.int64))  # exact: sums stay far below 2^63
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                a[:] = (t.numpy() & 0xFFFFFFFF).astype(np.uint32)
+            else:
+                a = np.ctypeslib.as_array(ctypes.cast(buf, ctypes.POINTER(ctypes.c_uint64)), shape=(count,))
+                # order-preserving map of u64 onto i64 so that gloo's signed min/max are exact
+                t = torch.from_numpy((a ^ np.uint64(1 << 63)).view(np.int64).copy())
+                dist.all_reduce(t, op=dist.ReduceOp.MIN if kind == 1 else dist.ReduceOp.MAX)
+                a[:] = t.numpy().view(np.uint64) ^ np.uint64(1 << 63)
+            return 0
+        except Exception as e:  # pragma: no cover
+            print("allreduce callback failed:", e, file=sys.stderr)
+            return 1
+
+    cb = CB(allreduce)
+    lib.bpe_ctx_create_dist_cb.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, CB]
+    ctx = ctypes.c_void_p()
+    assert lib.bpe_ctx_create_dist_cb(ctypes.byref(ctx), rank, world, cb) == 0
+    eng = zb.Engine.__new__(zb.Engine)
+    eng.lib, eng._ctx, eng.rank, eng.world, eng.last_stats = lib, ctx, rank, world, {}
+    eng.set_option("table_log2", 13)
+    for opt in sys.argv[4:]:
+        k, v = opt.split("=")
+        eng.set_option(k, int(v))
+
+    data = make_case(case)
+    bounds = shard_bounds(case, len(data), world)
+    shard = data[bounds[rank]:bounds[rank + 1]]
+    merges, counts = eng.train(shard, vocab)
+    got = np.stack([merges["first"], merges["second"], merges["new_token"]], axis=1) if len(merges) else np.zeros((0, 3), np.uint16)
+    np.savez(f"{out_path}.{rank}.npz", merges=got, counts=counts, tie_steps=eng.last_stats["tie_steps"],
+             tie_slow=eng.last_stats["tie_slow_steps"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def make_case(case):
+    rng = np.random.default_rng(1234)
+    if case == "taylor":
+        return open(os.path.join(ROOT, "tests", "golden", "taylorswift.txt"), "rb").read()[:30000]
+    if case == "aaaa":
+        return b"a" * 3001
+    if case == "abab":
+        return b"ab" * 1500 + b"a"
+    if case == "runs":
+        return b"xyz" + b"a" * 700 + b"b" + b"a" * 513 + b"cc" + b"a" * 1024 + b"q"
+    if case == "rand4":
+        return bytes(rng.integers(97, 101, size=6000, dtype=np.uint8))
+    if case == "rand256":
+        return bytes(rng.integers(0, 256, size=6000, dtype=np.uint8))
+    if case == "tiny":
+        return b"abcabcabc"
+    raise ValueError(case)
+
+
+def shard_bounds(case, n, world):
+    if case == "tiny":  # some ranks get one byte or nothing
+        b = [0, 1] + [n] * (world - 1)
+        return b[: world + 1] if world >= 2 else [0, n]
+    if case == "runs":  # cut inside the runs of 'a', at odd offsets
+        cuts = sorted({0, n} | {min(n, 3 + 351 + 700 * i) for i in range(world - 1)})
+        while len(cuts) < world + 1:
+            cuts.insert(-1, cuts[-2])
+        return cuts
+    return [n * r // world for r in range(world + 1)]
+
+
+if __name__ == "__main__":
+    main()

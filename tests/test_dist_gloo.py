@@ -1,0 +1,62 @@
+"""Multi-GPU host logic on the CPU: world_size-2 (and 3) runs of the sharded training path over gloo.
+Kernels run in the emulation build; see tests/dist_worker.py. All ranks must return the merges the
+oracle learns from the unsharded corpus (so sharding is invisible in the result)."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import dist_worker  # noqa: E402
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _run(case, vocab, world, tmp_path, *opts):
+    out = str(tmp_path / f"{case}_{world}")
+    port = _free_port()
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_worker.py"), case, str(vocab), out, *opts],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    logs = [p.communicate(timeout=600)[0] for p in procs]
+    for r, p in enumerate(procs):
+        assert p.returncode == 0, f"rank {r} failed:\n{logs[r][-3000:]}"
+    return [np.load(f"{out}.{r}.npz") for r in range(world)]
+
+
+@pytest.mark.parametrize("case,vocab,world", [
+    ("taylor", 290, 2), ("aaaa", 266, 2), ("abab", 268, 2), ("runs", 280, 2), ("runs", 280, 3),
+    ("rand4", 290, 2), ("rand256", 300, 3), ("tiny", 270, 2),
+])
+def test_sharded_train_matches_oracle(ora, tmp_path, case, vocab, world):
+    res = _run(case, vocab, world, tmp_path)
+    om, oc = ora.train(dist_worker.make_case(case), vocab, fast=True)
+    for r in range(world):
+        assert np.array_equal(res[r]["merges"], om), f"rank {r}"
+        assert np.array_equal(res[r]["counts"], oc), f"rank {r}"
+
+
+def test_sharded_train_forced_replay(ora, tmp_path):
+    """Every tie through the cross-rank replay (first-occurrence positions min-reduced in key order)."""
+    res = _run("rand4", 285, 2, tmp_path, "force_slow_tiebreak=1")
+    om, oc = ora.train(dist_worker.make_case("rand4"), 285, fast=True)
+    for r in range(2):
+        assert np.array_equal(res[r]["merges"], om) and np.array_equal(res[r]["counts"], oc)
+        assert res[r]["tie_slow"] == res[r]["tie_steps"] > 0
+    res = _run("taylor", 280, 2, tmp_path, "check_tiebreak=1")
+    om, _ = ora.train(dist_worker.make_case("taylor"), 280, fast=True)
+    assert np.array_equal(res[0]["merges"], om)

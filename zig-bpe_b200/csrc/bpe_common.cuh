@@ -114,9 +114,24 @@ struct StepCtl {
     uint32_t flags;        // F_*
     uint32_t last_merged;  // occurrences merged by the last applied step
     unsigned long long live_tokens;
-    unsigned long long fast_ties;   // tie steps settled by the zig_* kernels
+    unsigned long long fast_ties;   // tie steps settled on the device
+    unsigned long long local_live;  // live tokens of this GPU's shard (multi-GPU; live_tokens is the global count)
     uint32_t tie_keys[MAXTIE];
 };
+
+// Multi-GPU: what one shard tells the others about its ends, exchanged once per merge step (it rides
+// in the same all-reduce as the merge deltas: every rank fills only its own slot, the rest are 0).
+struct EdgeInfo {
+    uint32_t first[3];  // first live tokens of the shard
+    uint32_t nfirst;    // how many of them exist (0..3)
+    uint32_t last[2];   // last live tokens, nearest the end first
+    uint32_t nlast;     // 0..2
+    uint32_t run_tok;   // the last live token ...
+    uint32_t run_len;   // ... and how many consecutive live copies of it end the shard
+    uint32_t all_same;  // the whole shard consists of that token only
+    uint32_t pad[6];
+};
+static_assert(sizeof(EdgeInfo) == 64, "EdgeInfo is 16 words");
 
 // Per-tile neighbourhood, produced by halo_kernel before each merge pass: what a tile needs to
 // know about live tokens outside itself. hole value = "no such token" (sequence start/end).

@@ -318,6 +318,10 @@ struct TrainRun {
     uint32_t* cntR() const { return delta.as<uint32_t>() + vcap; }
     uint32_t* nxx() const { return delta.as<uint32_t>() + 2 * (size_t)vcap; }
     uint32_t* nab() const { return delta.as<uint32_t>() + 2 * (size_t)vcap + 1; }
+    // multi-GPU: the exchange buffer is [deltas | pad | one EdgeInfo per rank]; one all-reduce per step sums it
+    size_t edge_off = 0;  // word offset of the EdgeInfo slots inside `delta`
+    EdgeInfo* edges() const { return ctx->dist.world > 1 ? reinterpret_cast<EdgeInfo*>(delta.as<uint32_t>() + edge_off) : nullptr; }
+    size_t exchange_words() const { return edge_off + (size_t)ctx->dist.world * 16; }
 };
 
 static int read_ctl(bpe_ctx* ctx, TrainRun& R, bool with_ties) {
@@ -328,13 +332,12 @@ static int read_ctl(bpe_ctx* ctx, TrainRun& R, bool with_ties) {
 }
 
 // halo (+ run chain) for a host-chosen A (replay / verify passes)
-static int launch_halo(bpe_ctx* ctx, Sequence<uint16_t>& sq, uint32_t A, bool aeqb) {
+static int launch_halo(bpe_ctx* ctx, Sequence<uint16_t>& sq, uint32_t A, bool aeqb, const EdgeInfo* edges) {
     const uint32_t nt = sq.ntiles();
-    const uint16_t H = 0xFFFF;
     BPE_LAUNCH((halo_kernel<uint16_t, false>), (nt + HALO_THREADS - 1) / HALO_THREADS, HALO_THREADS, ctx->stream, sq.tok(),
                sq.n_slots, nt, sq.halo.as<TileHalo<uint16_t>>(), (const StepCtl*)nullptr, A, aeqb ? 1 : 0,
-               sq.run_local.as<uint32_t>(), sq.run_full.as<uint8_t>(), sq.done_counter.as<uint32_t>(), (uint32_t*)nullptr, 0u,
-               H, H, H, H, H);
+               sq.run_local.as<uint32_t>(), sq.run_full.as<uint8_t>(), sq.done_counter.as<uint32_t>(), (uint32_t*)nullptr,
+               edges, ctx->dist.rank, ctx->dist.world);
     ctx->launches++;
     CU(cudaGetLastError());
     return BPE_OK;
@@ -342,7 +345,7 @@ static int launch_halo(bpe_ctx* ctx, Sequence<uint16_t>& sq, uint32_t A, bool ae
 
 // full table replay for one tie step (see tiebreak_host.hpp)
 static int replay_winner(bpe_ctx* ctx, TrainRun& R, uint32_t max_count, uint32_t* winner) {
-    int rc = launch_halo(ctx, R.sq, 0, false);
+    int rc = launch_halo(ctx, R.sq, 0, false, R.edges());
     if (rc) return rc;
     const uint32_t cap = R.tm.cap;
     if (R.firstpos.bytes < (size_t)cap * 4) CU(R.firstpos.alloc((size_t)cap * 4));
@@ -362,15 +365,42 @@ static int replay_winner(bpe_ctx* ctx, TrainRun& R, uint32_t max_count, uint32_t
     if (R.hc()->err) return fail(ctx, BPE_ERR_INTERNAL, "device error flags 0x%x during replay", R.hc()->err);
     std::vector<ReplayKey> rk;
     std::vector<uint32_t> tied;
+    const uint64_t rank_hi = (uint64_t)ctx->dist.rank << 32;
+    const bool multi = ctx->dist.world > 1;
     for (uint32_t i = 0; i < cap; i++) {
         if (keys[i] == EMPTY_KEY || counts[i] == 0) continue;
-        if (fpos[i] == 0xFFFFFFFFu) return fail(ctx, BPE_ERR_INTERNAL, "live pair without occurrence");
-        ReplayKey k; k.key = keys[i]; k.home_hash = (uint32_t)zig_hash_pair(keys[i]); k.first_pos = fpos[i];
+        if (!multi && fpos[i] == 0xFFFFFFFFu) return fail(ctx, BPE_ERR_INTERNAL, "live pair without occurrence");
+        ReplayKey k; k.key = keys[i]; k.home_hash = (uint32_t)zig_hash_pair(keys[i]);
+        k.first_pos = fpos[i] == 0xFFFFFFFFu ? ~0ull : (rank_hi | fpos[i]);  // (shard, slot) orders positions globally
         rk.push_back(k);
         if (counts[i] == max_count) tied.push_back(keys[i]);
     }
+    uint64_t last_pair = rank_hi | R.hc()->last_pair_pos;
+    if (multi) {
+        // The replicated tables hold the same keys in different slots, so positions are exchanged in
+        // key order: min over ranks of each key's first occurrence, max of the last pair position.
+        std::sort(rk.begin(), rk.end(), [](const ReplayKey& a, const ReplayKey& b) { return a.key < b.key; });
+        std::vector<uint64_t> pos(rk.size() + 1);
+        for (size_t i = 0; i < rk.size(); i++) pos[i] = rk[i].first_pos;
+        bool any_pair = false;
+        for (size_t i = 0; i < rk.size(); i++) if (rk[i].first_pos != ~0ull) { any_pair = true; break; }
+        DevBuf dpos;
+        CU(dpos.alloc(pos.size() * 8));
+        CU(cudaMemcpyAsync(dpos.p, pos.data(), rk.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (!ctx->dist.allreduce(dpos.p, rk.size(), DIST_U64_MIN)) return fail(ctx, BPE_ERR_CUDA, "all-reduce (min) failed");
+        uint64_t lp = any_pair ? last_pair : 0;
+        CU(cudaMemcpyAsync(dpos.as<uint64_t>() + rk.size(), &lp, 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (!ctx->dist.allreduce(dpos.as<uint64_t>() + rk.size(), 1, DIST_U64_MAX)) return fail(ctx, BPE_ERR_CUDA, "all-reduce (max) failed");
+        CU(cudaMemcpyAsync(pos.data(), dpos.p, pos.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (size_t i = 0; i < rk.size(); i++) {
+            if (pos[i] == ~0ull) return fail(ctx, BPE_ERR_INTERNAL, "live pair without occurrence on any rank");
+            rk[i].first_pos = pos[i];
+        }
+        last_pair = pos[rk.size()];
+    }
     ZigTableReplay rep;
-    rep.run(rk, R.hc()->last_pair_pos);
+    rep.run(rk, last_pair);
     uint32_t w = rep.winner(rk, tied);
     if (w == ZigTableReplay::NONE) return fail(ctx, BPE_ERR_INTERNAL, "replay found no tied key");
     *winner = w;
@@ -378,7 +408,7 @@ static int replay_winner(bpe_ctx* ctx, TrainRun& R, uint32_t max_count, uint32_t
 }
 
 static int verify_state(bpe_ctx* ctx, TrainRun& R, uint32_t step) {
-    int rc = launch_halo(ctx, R.sq, 0, false);
+    int rc = launch_halo(ctx, R.sq, 0, false, R.edges());
     if (rc) return rc;
     const uint32_t cap = R.tm.cap;
     if (R.recount.bytes < (size_t)cap * 4) CU(R.recount.alloc((size_t)cap * 4));
@@ -446,15 +476,21 @@ static int sync_zcap(bpe_ctx* ctx, TrainRun& R, uint32_t d) {
 // the part of a step after the merge has been chosen: halo, merge, apply (all read the merge from ctl)
 static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids) {
     const uint32_t nt = R.sq.ntiles();
-    const uint16_t H = 0xFFFF;
     R.prof.mark(K_HALO);
     BPE_LAUNCH((halo_kernel<uint16_t, true>), (nt + HALO_THREADS - 1) / HALO_THREADS, HALO_THREADS, ctx->stream, R.sq.tok(),
                R.sq.n_slots, nt, R.sq.halo.as<TileHalo<uint16_t>>(), (const StepCtl*)R.d_ctl(), 0u, 0, R.sq.run_local.as<uint32_t>(),
-               R.sq.run_full.as<uint8_t>(), R.sq.done_counter.as<uint32_t>(), R.nxx(), 0u, H, H, H, H, H);
+               R.sq.run_full.as<uint8_t>(), R.sq.done_counter.as<uint32_t>(), R.nxx(), R.edges(), ctx->dist.rank, ctx->dist.world);
     R.prof.mark(K_MERGE);
     BPE_LAUNCH((merge_kernel<uint16_t, true, true>), nt, THREADS, ctx->stream, R.sq.tok(), R.sq.halo.as<TileHalo<uint16_t>>(),
                (const StepCtl*)R.d_ctl(), R.cntL(), R.cntR(), R.nxx(), R.nab(), 0u, 0u, 0u, 4u * nt);
     R.prof.mark(K_APPLY);
+    if (ctx->dist.world > 1) {
+        // describe this shard's (post-merge) ends, then one all-reduce sums the deltas and gathers the edges
+        BPE_LAUNCH_NS(edge_kernel<uint16_t>, 1, 32, ctx->stream, R.sq.tok(), R.sq.n_slots, R.edges(), ctx->dist.rank, ctx->dist.world,
+                      R.d_ctl(), R.nab(), 1);
+        ctx->launches++;
+        if (!ctx->dist.allreduce(R.delta.p, R.exchange_words(), DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-reduce of the merge deltas failed");
+    }
     BPE_LAUNCH_NS(apply_kernel, (4 * n_ids + 3 + 255) / 256, 256, ctx->stream, R.tm.view(), R.delta.as<uint32_t>(), R.vcap, R.d_ctl(),
                   R.tm.zig(), n_ids, R.hl());
     ctx->launches += 3;
@@ -476,7 +512,8 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     TrainRun R;
     R.ctx = ctx;
     memset(&R.st, 0, sizeof R.st);
-    if (want == 0 || n < 2) {  // no pairs (:188-191; n == 0 underflows in the reference, defined as no pairs)
+    const bool multi = ctx->dist.world > 1;
+    if (want == 0 || (!multi && n < 2)) {  // no pairs (:188-191; n == 0 underflows in the reference, defined as no pairs)
         if (stats_out) { *stats_out = R.st; stats_out->total_ms = now_ms() - t_host0; }
         return BPE_OK;
     }
@@ -485,7 +522,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     CU(cudaEventCreate(&ev0));
     CU(cudaEventCreate(&ev1));
     CU(cudaEventRecord(ev0, ctx->stream));
-    const bool debug_sync = ctx->verify_recount != 0;  // per-step host checks: batches of one step
+    const bool debug_sync = ctx->verify_recount != 0 && !multi;  // per-step host checks: batches of one step
     EvProfile& prof = R.prof;
     prof.init(ctx->time_phases ? 1 : (int)ctx->profile, ctx->stream, &ctx->ev_pool, R.st.kernel_ms, R.st.kernel_calls);
     prof.mark(K_INIT);
@@ -493,19 +530,28 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     int rc = seq_init(ctx, R.sq, d_text, n);
     if (rc) return rc;
     R.vcap = (uint32_t)vocab_size + 1;
-    CU(R.delta.alloc(((size_t)2 * R.vcap + 2) * 4)); CU(R.hist.alloc(65536 * 4));
+    R.edge_off = ((size_t)2 * R.vcap + 2 + 15) / 16 * 16;
+    CU(R.delta.alloc(R.exchange_words() * 4)); CU(R.hist.alloc(65536 * 4));
     CU(R.ctl.alloc(sizeof(StepCtl))); CU(R.rec.alloc(want * sizeof(MergeRec)));
     CU(R.heavy.alloc((size_t)(1u << 20) * 4));
     CU(R.h_ctl.alloc(sizeof(StepCtl)));
-    CU(cudaMemsetAsync(R.delta.p, 0, ((size_t)2 * R.vcap + 2) * 4, ctx->stream));
+    CU(cudaMemsetAsync(R.delta.p, 0, R.exchange_words() * 4, ctx->stream));
     CU(cudaMemsetAsync(R.hist.p, 0, 65536 * 4, ctx->stream));
     CU(cudaMemsetAsync(R.ctl.p, 0, sizeof(StepCtl), ctx->stream));
 
     // initial count (countCodePointPairs :257-278 on the byte sequence)
     {
         CU(cudaFuncSetAttribute(byte_pair_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HIST_SMEM));
-        const unsigned hgrid = (unsigned)std::min<size_t>(148, (n + HIST_PASS - 1) / HIST_PASS);
-        BPE_LAUNCH_SMEM(byte_pair_hist_kernel, hgrid, HIST_THREADS, HIST_SMEM, ctx->stream, d_text, n, -1, R.hist.as<uint32_t>());
+        if (multi) {  // the pair that straddles two shards belongs to the left one: it needs the next shard's first byte
+            BPE_LAUNCH_NS(edge_kernel<uint16_t>, 1, 32, ctx->stream, R.sq.tok(), R.sq.n_slots, R.edges(), ctx->dist.rank, ctx->dist.world,
+                          R.d_ctl(), R.nab(), 0);
+            ctx->launches++;
+            if (!ctx->dist.allreduce(R.edges(), (size_t)ctx->dist.world * 16, DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-reduce of the shard edges failed");
+        }
+        const unsigned hgrid = (unsigned)std::max<size_t>(1, std::min<size_t>(148, (n + HIST_PASS - 1) / HIST_PASS));
+        BPE_LAUNCH_SMEM(byte_pair_hist_kernel, hgrid, HIST_THREADS, HIST_SMEM, ctx->stream, d_text, n, (const EdgeInfo*)R.edges(),
+                        ctx->dist.rank, ctx->dist.world, R.hist.as<uint32_t>());
+        if (multi && !ctx->dist.allreduce(R.hist.p, 65536, DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-reduce of the byte-pair histogram failed");
     }
     BPE_LAUNCH_NS(hist_nonzero_kernel, 65536 / 256, 256, ctx->stream, R.hist.as<uint32_t>(), R.d_ctl());
     ctx->launches += 2;
@@ -525,7 +571,8 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
         StepCtl init;
         memset(&init, 0, sizeof init);
         init.want_steps = (uint32_t)want;
-        init.live_tokens = n;
+        init.live_tokens = n;  // multi-GPU: only local_live is meaningful
+        init.local_live = n;
         init.flags = (ctx->force_slow_tiebreak ? F_FORCE_REPLAY : 0u) | (ctx->check_tiebreak ? F_CHECK_TIES : 0u);
         CU(cudaMemcpyAsync(&R.d_ctl()->step, &init.step, offsetof(StepCtl, tie_keys) - offsetof(StepCtl, step),
                            cudaMemcpyHostToDevice, ctx->stream));
@@ -573,7 +620,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
         if (hc->err) return fail(ctx, BPE_ERR_INTERNAL, "device error flags 0x%x near step %u", hc->err, hc->step);
         R.st.scanned_slots += (uint64_t)(hc->step - steps_done) * R.sq.n_slots;
         steps_done = hc->step;
-        R.sq.live = hc->live_tokens;
+        R.sq.live = multi ? hc->local_live : hc->live_tokens;
         if (debug_sync && hc->halt == H_NONE) { rc = verify_state(ctx, R, steps_done); if (rc) return rc; hc = R.hc(); }
         switch (hc->halt) {
             case H_NONE: break;
@@ -626,7 +673,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
                 if (hc->err) return fail(ctx, BPE_ERR_INTERNAL, "device error flags 0x%x near step %u", hc->err, hc->step);
                 R.st.scanned_slots += R.sq.n_slots;
                 steps_done = hc->step;
-                R.sq.live = hc->live_tokens;
+                R.sq.live = multi ? hc->local_live : hc->live_tokens;
                 if (debug_sync) { rc = verify_state(ctx, R, steps_done); if (rc) return rc; }
                 break;
             }
@@ -696,7 +743,7 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
         BPE_LAUNCH((halo_kernel<TokT, false>), (nt + HALO_THREADS - 1) / HALO_THREADS, HALO_THREADS, ctx->stream, sq.tok(), sq.n_slots,
                    nt, sq.halo.template as<TileHalo<TokT>>(), (const StepCtl*)nullptr, A, A == B ? 1 : 0,
                    sq.run_local.template as<uint32_t>(), sq.run_full.template as<uint8_t>(), sq.done_counter.template as<uint32_t>(),
-                   (uint32_t*)nullptr, 0u, H, H, H, H, H);
+                   (uint32_t*)nullptr, (const EdgeInfo*)nullptr, 0, 1);
         ctx->launches += 1;
         BPE_LAUNCH((merge_kernel<TokT, false, false>), nt, THREADS, ctx->stream, sq.tok(), sq.halo.template as<TileHalo<TokT>>(),
                    (const StepCtl*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, &d_ctl->cntAB, A, B, X, 0u);
@@ -983,6 +1030,18 @@ int bpe_ctx_create_dist(bpe_ctx** out, int device, int rank, int world, const vo
     }
     return BPE_OK;
 }
+
+#ifdef BPE_EMUL
+// emulation build only (tests): a "multi-GPU" context whose exchange is a caller-supplied callback
+int bpe_ctx_create_dist_cb(bpe_ctx** out, int rank, int world, dist_allreduce_cb cb) {
+    int rc = bpe_ctx_create(out, 0);
+    if (rc) return rc;
+    (*out)->dist.rank = rank;
+    (*out)->dist.world = world;
+    (*out)->dist.cb = cb;
+    return BPE_OK;
+}
+#endif
 
 void bpe_ctx_destroy(bpe_ctx* ctx) {
     if (!ctx) return;

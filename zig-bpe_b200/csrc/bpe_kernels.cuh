@@ -62,8 +62,11 @@ constexpr int HIST_PASS = HIST_THREADS * HIST_BPT;  // 32,768 pairs per pass < 6
 constexpr size_t HIST_SMEM = 65536 * 2;
 
 __global__ void __launch_bounds__(HIST_THREADS, 1) byte_pair_hist_kernel(const uint8_t* __restrict__ text, size_t n,
-                                                                         int next_byte, uint32_t* __restrict__ hist) {
+                                                                         const EdgeInfo* __restrict__ edges, int rank, int world,
+                                                                         uint32_t* __restrict__ hist) {
     uint32_t* bins = bpe_dyn_smem();  // [32768] words
+    int next_byte = -1;  // first byte of the following shards (multi-GPU), none otherwise
+    if (edges) for (int q = rank + 1; q < world; q++) if (edges[q].nfirst) { next_byte = (int)edges[q].first[0]; break; }
     for (int i = (int)threadIdx.x; i < 32768; i += HIST_THREADS) bins[i] = 0;
     __syncthreads();
     const size_t npass = (n + HIST_PASS - 1) / HIST_PASS;
@@ -454,8 +457,8 @@ constexpr int HALO_THREADS = 128;
 template <class TokT, bool FROMCTL>
 __global__ void __launch_bounds__(HALO_THREADS) halo_kernel(const TokT* __restrict__ tok, size_t n_slots, uint32_t ntiles,
                             TileHalo<TokT>* halo, const StepCtl* __restrict__ ctl, uint32_t Au, int aeqb,
-                            uint32_t* run_local, uint8_t* run_full, uint32_t* done_counter, uint32_t* zero2, uint32_t ext_run,
-                            TokT ext_l2, TokT ext_l1, TokT ext_r0, TokT ext_r1, TokT ext_r2) {
+                            uint32_t* run_local, uint8_t* run_full, uint32_t* done_counter, uint32_t* zero2,
+                            const EdgeInfo* __restrict__ edges, int rank, int world) {
     __shared__ uint32_t s_add[HALO_THREADS];
     __shared__ uint32_t s_full[HALO_THREADS];
     __shared__ uint32_t s_last;
@@ -477,8 +480,10 @@ __global__ void __launch_bounds__(HALO_THREADS) halo_kernel(const TokT* __restri
             TokT v = tok[i];
             if (v != H) l[nl++] = v;
         }
-        if (nl == 0) { l[0] = ext_l1; l[1] = ext_l2; }
-        else if (nl == 1) { l[1] = ext_l1; }
+        if (nl < 2 && edges) {  // fell off the shard: continue in the shards before this one
+            for (int r = rank - 1; r >= 0 && nl < 2; r--)
+                for (uint32_t k = 0; k < edges[r].nlast && nl < 2; k++) l[nl++] = (TokT)edges[r].last[k];
+        }
         h.l1 = l[0];
         h.l2 = (l[0] == H) ? H : l[1];
         // right: first three live tokens at/after slot (t+1)*TILE
@@ -488,10 +493,9 @@ __global__ void __launch_bounds__(HALO_THREADS) halo_kernel(const TokT* __restri
             TokT v = tok[i];
             if (v != H) r[nr++] = v;
         }
-        const TokT er[3] = {ext_r0, ext_r1, ext_r2};
-        for (int k = 0; nr < 3 && k < 3; k++) {
-            if (er[k] == H) break;
-            r[nr++] = er[k];
+        if (nr < 3 && edges) {  // continue in the shards after this one
+            for (int q = rank + 1; q < world && nr < 3; q++)
+                for (uint32_t k = 0; k < edges[q].nfirst && nr < 3; k++) r[nr++] = (TokT)edges[q].first[k];
         }
         h.r0 = r[0]; h.r1 = r[1]; h.r2 = r[2];
         h.runA = 0;
@@ -541,7 +545,15 @@ __global__ void __launch_bounds__(HALO_THREADS) halo_kernel(const TokT* __restri
     s_full[threadIdx.x] = full;
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t carry = ext_run;  // run entering tile 0
+        uint32_t carry = 0;  // run of A entering tile 0: it may continue through the shards before this one
+        if (edges) {
+            for (int r = rank - 1; r >= 0; r--) {
+                if (edges[r].nlast == 0) continue;           // empty shard
+                if (edges[r].run_tok != Au) break;
+                carry += edges[r].run_len;
+                if (!edges[r].all_same) break;
+            }
+        }
         for (uint32_t i = 0; i < nthr; i++) {
             uint32_t a = s_add[i], f = s_full[i];
             s_add[i] = carry;
@@ -555,6 +567,52 @@ __global__ void __launch_bounds__(HALO_THREADS) halo_kernel(const TokT* __restri
     for (uint32_t i = (lo == 0 ? 1u : lo); i < hi; i++) {
         run = ((volatile uint32_t*)run_local)[i] + (((volatile uint8_t*)run_full)[i] ? run : 0u);
         halo[i].runA = run;
+    }
+}
+
+// =========================================================================================
+// edge_kernel (multi-GPU, one warp): describe this shard's ends in its EdgeInfo slot of the exchange
+// buffer and zero the other ranks' slots (the buffer is summed by the all-reduce). It also keeps the
+// shard's own live-token count, because after the all-reduce only the global merged count is left.
+// =========================================================================================
+template <class TokT>
+__global__ void edge_kernel(const TokT* __restrict__ tok, size_t n_slots, EdgeInfo* all, int rank, int world,
+                            StepCtl* ctl, const uint32_t* nab_local, int account) {
+    const TokT H = (TokT)TokTraits<TokT>::hole;
+    const uint32_t lane = threadIdx.x;
+    if (blockIdx.x != 0) return;
+    // zero every other slot
+    uint32_t* words = reinterpret_cast<uint32_t*>(all);
+    for (uint32_t w = lane; w < (uint32_t)world * 16u; w += blockDim.x)
+        if ((int)(w / 16u) != rank) words[w] = 0;
+    EdgeInfo* e = &all[rank];
+    if (lane == 0) {
+        uint32_t n = 0;
+        for (size_t i = 0; i < n_slots && n < 3; i++) { TokT v = tok[i]; if (v != H) e->first[n++] = v; }
+        for (uint32_t k = n; k < 3; k++) e->first[k] = 0;
+        e->nfirst = n;
+        for (int k = 0; k < 6; k++) e->pad[k] = 0;
+        if (account && !ctl->halt) ctl->local_live -= *nab_local;
+    } else if (lane == 1) {
+        uint32_t n = 0, run = 0, all_same = 1;
+        TokT lastv = H;
+        uint32_t lasts[2] = {0, 0};
+        for (size_t i = n_slots; i > 0;) {
+            --i;
+            TokT v = tok[i];
+            if (v == H) continue;
+            if (n < 2) lasts[n] = v;
+            if (n == 0) lastv = v;
+            n++;
+            if (v == lastv && run + 1 == n) run++;      // still inside the trailing run
+            else { all_same = 0; if (n >= 2) break; }   // run ended and both last tokens are known
+        }
+        if (n == 0) all_same = 0;
+        e->last[0] = lasts[0]; e->last[1] = lasts[1];
+        e->nlast = n < 2 ? n : 2;
+        e->run_tok = (n ? (uint32_t)lastv : 0u);
+        e->run_len = run;
+        e->all_same = all_same;
     }
 }
 

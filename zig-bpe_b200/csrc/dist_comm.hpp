@@ -59,6 +59,7 @@ inline bool dist_unique_id(void* out128, std::string* err) {
     return true;
 }
 
+enum { DIST_U32_SUM = 0, DIST_U64_MIN = 1, DIST_U64_MAX = 2 };
 struct DistComm {
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
@@ -74,17 +75,29 @@ struct DistComm {
         return true;
     }
     void destroy() { if (comm) { nccl_api().CommDestroy(comm); comm = nullptr; } }
-    bool allreduce_u32_sum(uint32_t* buf, size_t n) { return nccl_api().AllReduce(buf, buf, n, ncclUint32, ncclSum, comm, stream) == ncclSuccess; }
-    bool allreduce_u64_sum(uint64_t* buf, size_t n) { return nccl_api().AllReduce(buf, buf, n, ncclUint64, ncclSum, comm, stream) == ncclSuccess; }
-    bool allreduce_u64_min(uint64_t* buf, size_t n) { return nccl_api().AllReduce(buf, buf, n, ncclUint64, ncclMin, comm, stream) == ncclSuccess; }
-    bool allgather_bytes(const void* src, void* dst, size_t bytes_per_rank) { return nccl_api().AllGather(src, dst, bytes_per_rank, ncclUint8, comm, stream) == ncclSuccess; }
+    // in-place all-reduce of a device buffer, enqueued on the context's stream
+    bool allreduce(void* buf, size_t count, int kind) {
+        if (world == 1) return true;
+        int dt = kind == DIST_U32_SUM ? ncclUint32 : ncclUint64;
+        int op = kind == DIST_U32_SUM ? ncclSum : (kind == DIST_U64_MIN ? ncclMin : ncclMax);
+        return nccl_api().AllReduce(buf, buf, count, dt, op, comm, stream) == ncclSuccess;
+    }
 };
 #else
+// emulation build (tests only): the exchange is delegated to a callback so that a world_size-2
+// gloo test on the CPU can drive the same host logic
+enum { DIST_U32_SUM = 0, DIST_U64_MIN = 1, DIST_U64_MAX = 2 };
+typedef int (*dist_allreduce_cb)(void* buf, size_t count, int kind);
 inline bool dist_unique_id(void* out128, std::string*) { memset(out128, 0, 128); return true; }
 struct DistComm {
     int rank = 0, world = 1;
+    dist_allreduce_cb cb = nullptr;
     bool init(int, int, const void*, int, std::string* err) { if (err) *err = "no NCCL in the emulation build"; return false; }
     void destroy() {}
+    bool allreduce(void* buf, size_t count, int kind) {
+        if (world == 1) return true;
+        return cb && cb(buf, count, kind) == 0;
+    }
 };
 #endif
 
