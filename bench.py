@@ -218,6 +218,9 @@ def main():
         assert np.array_equal(m2, merges), "host-buffer and device-resident runs disagree"
 
     if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     peak, peak_src = peaks()
     alg_bytes = scanned * 2  # u16 slots
@@ -254,6 +257,7 @@ def main():
                                 "host_cores_available": os.cpu_count(), "matches_gpu_merges": ok}
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -486,7 +486,7 @@ static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids) {
     R.prof.mark(K_APPLY);
     if (ctx->dist.world > 1) {
         // describe this shard's (post-merge) ends, then one all-reduce sums the deltas and gathers the edges
-        BPE_LAUNCH_NS(edge_kernel<uint16_t>, 1, 32, ctx->stream, R.sq.tok(), R.sq.n_slots, R.edges(), ctx->dist.rank, ctx->dist.world,
+        BPE_LAUNCH(edge_kernel<uint16_t>, 1, 32, ctx->stream, R.sq.tok(), R.sq.n_slots, R.edges(), ctx->dist.rank, ctx->dist.world,
                       R.d_ctl(), R.nab(), 1);
         ctx->launches++;
         if (!ctx->dist.allreduce(R.delta.p, R.exchange_words(), DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-reduce of the merge deltas failed");
@@ -543,7 +543,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     {
         CU(cudaFuncSetAttribute(byte_pair_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HIST_SMEM));
         if (multi) {  // the pair that straddles two shards belongs to the left one: it needs the next shard's first byte
-            BPE_LAUNCH_NS(edge_kernel<uint16_t>, 1, 32, ctx->stream, R.sq.tok(), R.sq.n_slots, R.edges(), ctx->dist.rank, ctx->dist.world,
+            BPE_LAUNCH(edge_kernel<uint16_t>, 1, 32, ctx->stream, R.sq.tok(), R.sq.n_slots, R.edges(), ctx->dist.rank, ctx->dist.world,
                           R.d_ctl(), R.nab(), 0);
             ctx->launches++;
             if (!ctx->dist.allreduce(R.edges(), (size_t)ctx->dist.world * 16, DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-reduce of the shard edges failed");

@@ -579,40 +579,61 @@ template <class TokT>
 __global__ void edge_kernel(const TokT* __restrict__ tok, size_t n_slots, EdgeInfo* all, int rank, int world,
                             StepCtl* ctl, const uint32_t* nab_local, int account) {
     const TokT H = (TokT)TokTraits<TokT>::hole;
-    const uint32_t lane = threadIdx.x;
-    if (blockIdx.x != 0) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
     // zero every other slot
     uint32_t* words = reinterpret_cast<uint32_t*>(all);
-    for (uint32_t w = lane; w < (uint32_t)world * 16u; w += blockDim.x)
+    for (uint32_t w = lane; w < (uint32_t)world * 16u; w += 32u)
         if ((int)(w / 16u) != rank) words[w] = 0;
     EdgeInfo* e = &all[rank];
-    if (lane == 0) {
-        uint32_t n = 0;
-        for (size_t i = 0; i < n_slots && n < 3; i++) { TokT v = tok[i]; if (v != H) e->first[n++] = v; }
-        for (uint32_t k = n; k < 3; k++) e->first[k] = 0;
-        e->nfirst = n;
-        for (int k = 0; k < 6; k++) e->pad[k] = 0;
-        if (account && !ctl->halt) ctl->local_live -= *nab_local;
-    } else if (lane == 1) {
-        uint32_t n = 0, run = 0, all_same = 1;
-        TokT lastv = H;
-        uint32_t lasts[2] = {0, 0};
-        for (size_t i = n_slots; i > 0;) {
-            --i;
-            TokT v = tok[i];
-            if (v == H) continue;
-            if (n < 2) lasts[n] = v;
-            if (n == 0) lastv = v;
-            n++;
-            if (v == lastv && run + 1 == n) run++;      // still inside the trailing run
-            else { all_same = 0; if (n >= 2) break; }   // run ended and both last tokens are known
+    // ---- first three live tokens: the warp scans 32 slots at a time ----
+    uint32_t nf = 0, fv[3] = {0, 0, 0};
+    for (size_t base = 0; base < n_slots && nf < 3; base += 32) {
+        const size_t i = base + lane;
+        const uint32_t v = i < n_slots ? (uint32_t)tok[i] : (uint32_t)H;
+        uint32_t live = __ballot_sync(0xffffffffu, v != (uint32_t)H);
+        while (live && nf < 3) {
+            const int src = __ffs((int)live) - 1;
+            live &= live - 1;
+            fv[nf++] = __shfl_sync(0xffffffffu, v, src);
         }
-        if (n == 0) all_same = 0;
+    }
+    // ---- last two live tokens and the run of equal tokens that ends the shard ----
+    uint32_t n = 0, run = 0, all_same = 1, lastv = 0, lasts[2] = {0, 0};
+    bool stop = false;
+    for (size_t top = n_slots; top > 0 && !stop;) {
+        const size_t base = top >= 32 ? top - 32 : 0;
+        const size_t i = base + lane;
+        const uint32_t v = i < top ? (uint32_t)tok[i] : (uint32_t)H;
+        uint32_t live = __ballot_sync(0xffffffffu, v != (uint32_t)H);
+        // fast path for long runs: every live token of this chunk continues the run
+        if (live && n >= 2 && run == n) {
+            const uint32_t same = __ballot_sync(0xffffffffu, v == lastv);
+            if (same == live) { const uint32_t c = (uint32_t)__popc(live); n += c; run += c; top = base; continue; }
+        }
+        while (live) {
+            const int src = 31 - __clz((int)live);
+            live &= ~(1u << src);
+            const uint32_t tv = __shfl_sync(0xffffffffu, v, src);
+            if (n < 2) lasts[n] = tv;
+            if (n == 0) lastv = tv;
+            n++;
+            if (tv == lastv && run + 1 == n) run++;
+            else { all_same = 0; if (n >= 2) { stop = true; break; } }
+        }
+        top = base;
+    }
+    if (n == 0) all_same = 0;
+    if (lane == 0) {
+        for (uint32_t k = 0; k < 3; k++) e->first[k] = fv[k];
+        e->nfirst = nf;
         e->last[0] = lasts[0]; e->last[1] = lasts[1];
         e->nlast = n < 2 ? n : 2;
-        e->run_tok = (n ? (uint32_t)lastv : 0u);
+        e->run_tok = n ? lastv : 0u;
         e->run_len = run;
         e->all_same = all_same;
+        for (int k = 0; k < 6; k++) e->pad[k] = 0;
+        if (account && !ctl->halt) ctl->local_live -= *nab_local;
     }
 }
 
