@@ -168,6 +168,8 @@ def main():
         m, c = eng.train(host, args.vocab)
         return m, c, dict(eng.last_stats)
 
+    if os.environ.get("BPE_DEBUG"):
+        eng.set_option("debug", int(os.environ["BPE_DEBUG"]))
     eng.set_option("profile", 2)  # event marks around the merge kernel only (2 records per merge step)
     for _ in range(args.warmup):
         merges, counts, st = step_device()

@@ -219,3 +219,21 @@ def test_c2_full_size_properties(gpu, ora, synth):
     sl = slice(12_345_678, 12_345_678 + 200_000)
     assert np.array_equal(gpu.encode(data[sl], m), ora.encode(data[sl], ma, linear=True))
     assert st["tie_slow_steps"] <= st["tie_steps"]
+
+
+def test_cpp_host_mirror_runs_main_zig_workload(zb, taylor, tmp_path):
+    """The C++ host mirror (zig-bpe_b200/host) binds the same C symbols the Zig shim declares; its main.cpp is
+    the reference's main.zig workload: train to vocab 300, write merges.txt, encode + decode the sample."""
+    import subprocess
+    from conftest import ROOT
+    exe = tmp_path / "zig-bpe-cpp"
+    lib_dir = os.path.dirname(zb.LIB_PATH)
+    subprocess.run(["g++", "-O2", "-std=c++17", f"-I{ROOT}/include", f"{ROOT}/zig-bpe_b200/host/main.cpp", f"-L{lib_dir}",
+                    "-lbpe_b200", f"-Wl,-rpath,{lib_dir}", "-o", str(exe)], check=True)
+    out = tmp_path / "merges.txt"
+    r = subprocess.run([str(exe), os.path.join(GOLDEN, "taylorswift.txt"), str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert out.read_bytes() == open(os.path.join(GOLDEN, "merges_300.txt"), "rb").read()
+    assert " ".join(str(t) for t in MAIN_ZIG_TOKENS) in r.stderr
+    assert MAIN_ZIG_STRING.decode() in r.stderr
+    assert "Training completed in" in r.stderr and "Time statistics:" in r.stderr

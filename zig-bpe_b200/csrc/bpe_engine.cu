@@ -55,7 +55,7 @@ struct bpe_ctx {
     std::string err;
     // options
     long verify_recount = 0, force_slow_tiebreak = 0, check_tiebreak = 0, compact_pct = 85, table_log2 = 0,
-         max_steps = 0, time_phases = 0, profile = 0;
+         max_steps = 0, time_phases = 0, profile = 0, debug = 0;
     DistComm dist;  // world == 1 when single GPU
     uint64_t launches = 0;
     BufCache cache;
@@ -622,6 +622,10 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
         steps_done = hc->step;
         R.sq.live = multi ? hc->local_live : hc->live_tokens;
         if (debug_sync && hc->halt == H_NONE) { rc = verify_state(ctx, R, steps_done); if (rc) return rc; hc = R.hc(); }
+        if (ctx->debug && (hc->halt != H_NONE || ctx->debug > 1))
+            fprintf(stderr, "[bpe r%d] step %u halt %u max %u ntied %u live_keys %u inserted %u cap %u n_heavy %u theta %u zcap %u slots %zu live %llu\n",
+                    ctx->dist.rank, hc->step, hc->halt, hc->max_count, hc->ntied, hc->live_keys, hc->n_inserted, R.tm.cap, hc->n_heavy,
+                    R.theta, R.tm.zcap, R.sq.n_slots, (unsigned long long)R.sq.live);
         switch (hc->halt) {
             case H_NONE: break;
             case H_DONE: finished = true; break;
@@ -1064,6 +1068,7 @@ int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value) {
     else if (s == "max_steps") ctx->max_steps = value;
     else if (s == "time_phases") ctx->time_phases = value;
     else if (s == "profile") ctx->profile = value;
+    else if (s == "debug") ctx->debug = value;
     else return fail(ctx, BPE_ERR_INVALID_ARG, "unknown option '%s'", name);
     return BPE_OK;
 }
