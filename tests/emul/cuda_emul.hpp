@@ -137,6 +137,13 @@ static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEve
     emul::launch(dim3(grid), dim3(block), [&]() { kern(__VA_ARGS__); }, true)
 namespace emul { extern uint32_t g_dyn_smem[64 * 1024]; }
 static inline uint32_t* bpe_dyn_smem() { return emul::g_dyn_smem; }  // up to 256 KB of "dynamic shared memory"
+// TMA bulk copy + mbarrier: the copy happens at issue time, so waiting is a no-op
+static inline void mbar_init(uint64_t* bar, uint32_t) { *bar = 0; }
+static inline void mbar_fence_init() {}
+static inline void fence_proxy_async() {}
+static inline void mbar_arrive_expect_tx(uint64_t*, uint32_t) {}
+static inline void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t*) { memcpy(dst, src, bytes); }
+static inline void mbar_wait(uint64_t*, uint32_t) {}
 // kernels that never call __syncthreads()/warp intrinsics: run threads as a plain loop
 #define BPE_LAUNCH_NS(kern, grid, block, stream, ...) \
     emul::launch(dim3(grid), dim3(block), [&]() { kern(__VA_ARGS__); }, false)

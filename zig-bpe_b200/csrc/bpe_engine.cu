@@ -55,7 +55,8 @@ struct bpe_ctx {
     std::string err;
     // options
     long verify_recount = 0, force_slow_tiebreak = 0, check_tiebreak = 0, compact_pct = 85, table_log2 = 0,
-         max_steps = 0, time_phases = 0, profile = 0, debug = 0;
+         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0;
+    int num_sms = 148;
     DistComm dist;  // world == 1 when single GPU
     uint64_t launches = 0;
     BufCache cache;
@@ -473,6 +474,23 @@ static int sync_zcap(bpe_ctx* ctx, TrainRun& R, uint32_t d) {
     return BPE_OK;
 }
 
+// one merge pass over the sequence: the TMA-ring kernel (default) or the register-streaming kernel
+template <class TokT, bool DELTAS, bool FROMCTL>
+static int launch_merge(bpe_ctx* ctx, TokT* tok, const TileHalo<TokT>* halo, uint32_t nt, const StepCtl* d_ctl, uint32_t* cntL,
+                        uint32_t* cntR, uint32_t* nxx, uint32_t* nab, uint32_t A, uint32_t B, uint32_t X, uint32_t bins_min) {
+    if (ctx->merge_impl == 0) {
+        auto kern = merge_tma_kernel<TokT, DELTAS, FROMCTL>;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem_bytes<TokT>()));
+        const unsigned grid = (unsigned)std::min<uint32_t>(nt, 2u * (uint32_t)ctx->num_sms);
+        BPE_LAUNCH_SMEM(kern, grid, THREADS, ring_smem_bytes<TokT>(), ctx->stream, tok, halo, d_ctl, cntL, cntR, nxx, nab, A, B, X,
+                        bins_min, nt);
+    } else {
+        BPE_LAUNCH((merge_kernel<TokT, DELTAS, FROMCTL>), nt, THREADS, ctx->stream, tok, halo, d_ctl, cntL, cntR, nxx, nab, A, B, X, bins_min);
+    }
+    ctx->launches++;
+    return BPE_OK;
+}
+
 // the part of a step after the merge has been chosen: halo, merge, apply (all read the merge from ctl)
 static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids) {
     const uint32_t nt = R.sq.ntiles();
@@ -481,8 +499,11 @@ static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids) {
                R.sq.n_slots, nt, R.sq.halo.as<TileHalo<uint16_t>>(), (const StepCtl*)R.d_ctl(), 0u, 0, R.sq.run_local.as<uint32_t>(),
                R.sq.run_full.as<uint8_t>(), R.sq.done_counter.as<uint32_t>(), R.nxx(), R.edges(), ctx->dist.rank, ctx->dist.world);
     R.prof.mark(K_MERGE);
-    BPE_LAUNCH((merge_kernel<uint16_t, true, true>), nt, THREADS, ctx->stream, R.sq.tok(), R.sq.halo.as<TileHalo<uint16_t>>(),
-               (const StepCtl*)R.d_ctl(), R.cntL(), R.cntR(), R.nxx(), R.nab(), 0u, 0u, 0u, 4u * nt);
+    {
+        int rcm = launch_merge<uint16_t, true, true>(ctx, R.sq.tok(), R.sq.halo.as<TileHalo<uint16_t>>(), nt, (const StepCtl*)R.d_ctl(),
+                                                     R.cntL(), R.cntR(), R.nxx(), R.nab(), 0u, 0u, 0u, 4u * nt);
+        if (rcm) return rcm;
+    }
     R.prof.mark(K_APPLY);
     if (ctx->dist.world > 1) {
         // describe this shard's (post-merge) ends, then one all-reduce sums the deltas and gathers the edges
@@ -493,7 +514,7 @@ static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids) {
     }
     BPE_LAUNCH_NS(apply_kernel, (4 * n_ids + 3 + 255) / 256, 256, ctx->stream, R.tm.view(), R.delta.as<uint32_t>(), R.vcap, R.d_ctl(),
                   R.tm.zig(), n_ids, R.hl());
-    ctx->launches += 3;
+    ctx->launches += 2;
     CU(cudaGetLastError());
     return BPE_OK;
 }
@@ -749,9 +770,11 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
                    sq.run_local.template as<uint32_t>(), sq.run_full.template as<uint8_t>(), sq.done_counter.template as<uint32_t>(),
                    (uint32_t*)nullptr, (const EdgeInfo*)nullptr, 0, 1);
         ctx->launches += 1;
-        BPE_LAUNCH((merge_kernel<TokT, false, false>), nt, THREADS, ctx->stream, sq.tok(), sq.halo.template as<TileHalo<TokT>>(),
-                   (const StepCtl*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, &d_ctl->cntAB, A, B, X, 0u);
-        ctx->launches += 1;
+        {
+            int rcm = launch_merge<TokT, false, false>(ctx, sq.tok(), sq.halo.template as<TileHalo<TokT>>(), nt, (const StepCtl*)nullptr,
+                                                       (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, &d_ctl->cntAB, A, B, X, 0u);
+            if (rcm) return rcm;
+        }
         CU(cudaGetLastError());
         if (st) st->scanned_slots += sq.n_slots;
         return BPE_OK;
@@ -1014,6 +1037,7 @@ int bpe_ctx_create(bpe_ctx** out, int device) {
     if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, BPE_ERR_CUDA, "cudaSetDevice(%d) failed", device);
     ctx = new bpe_ctx();
     ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
     if (cudaStreamCreate(&ctx->stream) != cudaSuccess) { delete ctx; return fail(nullptr, BPE_ERR_CUDA, "cudaStreamCreate failed"); }
     *out = ctx;
     return BPE_OK;
@@ -1069,6 +1093,7 @@ int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value) {
     else if (s == "time_phases") ctx->time_phases = value;
     else if (s == "profile") ctx->profile = value;
     else if (s == "debug") ctx->debug = value;
+    else if (s == "merge_impl") ctx->merge_impl = value;
     else return fail(ctx, BPE_ERR_INVALID_ARG, "unknown option '%s'", name);
     return BPE_OK;
 }

@@ -725,66 +725,39 @@ __device__ __forceinline__ void bin_add(uint32_t* bin_key, uint32_t* bin_val, ui
 // occurrence). So a tile without any A and without head duty is streamed and left untouched.
 // DELTAS: cntL / cntR / *nxx_out receive the neighbour-pair deltas (train); *nab_out always
 // receives the number of merged occurrences. FROMCTL as in halo_kernel.
-#ifndef BPE_MERGE_MINBLOCKS
-#define BPE_MERGE_MINBLOCKS 6
-#endif
-template <class TokT, bool DELTAS, bool FROMCTL>
-__global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(TokT* __restrict__ tok, const TileHalo<TokT>* __restrict__ halo,
-                                                        const StepCtl* __restrict__ ctl, uint32_t* __restrict__ cntL,
-                                                        uint32_t* __restrict__ cntR, uint32_t* nxx_out, uint32_t* nab_out,
-                                                        uint32_t Au, uint32_t Bu, uint32_t Xu, uint32_t bins_min_count) {
-    __shared__ __align__(16) TokT ext[EXT];
-    // block-private bins for the neighbour deltas: key = token id (+ 0x10000 for the right side)
-    constexpr int NBIN = DELTAS ? 512 : 1;
-    __shared__ uint32_t bin_key[NBIN];
-    __shared__ uint32_t bin_val[NBIN];
-    constexpr int QCAP = 2048;  // queued A positions per tile (denser tiles overflow to in-place handling)
-    __shared__ uint16_t q_pos[QCAP];
-    __shared__ uint32_t q_n;
-    bool use_bins = false;  // dense steps privatise the deltas per CTA; sparse steps go straight to global
-    if (FROMCTL) {
-        if (ctl->halt) return;
-        Au = ctl->A; Bu = ctl->B; Xu = ctl->X;
-        use_bins = DELTAS && ctl->max_count >= bins_min_count;
-    }
-    const bool AEQB = (Au == Bu);
-    __shared__ uint32_t sh_runA;
-    constexpr int VEC = 16 / (int)sizeof(TokT);   // slots per 16-byte vector
-    constexpr int NV = TILE / VEC / THREADS;       // vectors per thread (interleaved for coalescing)
-    static_assert(NV >= 1 && NV * VEC * THREADS == TILE, "tile geometry");
+constexpr int MERGE_NBIN = 512;   // block-private delta bins (train)
+constexpr int MERGE_QCAP = 2048;  // queued A positions per tile (denser tiles overflow to in-place handling)
+
+// The staged path of one tile, shared by the register-streaming and the TMA-ring kernels: write the
+// halo margins, queue the A positions, resolve occurrences, write X / holes, emit the deltas.
+// h is valid in thread 0 only. Ends with all threads past their last read of ext.
+template <class TokT, bool DELTAS, bool STAGE_FROM_REGS, int NV>
+__device__ __forceinline__ void tile_staged_path(TokT* ext, const uint4 (&v)[NV], TokT* __restrict__ tok, size_t base,
+                                                 const TileHalo<TokT>& h, uint32_t Au, uint32_t Bu, uint32_t Xu, bool use_bins,
+                                                 uint32_t* bin_key, uint32_t* bin_val, uint16_t* q_pos, uint32_t* q_n,
+                                                 uint32_t* sh_runA, uint32_t* __restrict__ cntL, uint32_t* __restrict__ cntR,
+                                                 uint32_t& nAB, uint32_t& nXX) {
+    constexpr int VEC = 16 / (int)sizeof(TokT);
+    constexpr int NBIN = MERGE_NBIN;
+    constexpr int QCAP = MERGE_QCAP;
     const TokT H = (TokT)TokTraits<TokT>::hole;
     const TokT A = (TokT)Au, B = (TokT)Bu, X = (TokT)Xu;
-    // odd steps walk the sequence backwards: the tiles the previous pass touched last are still in
-    // the 126 MB L2 when this pass starts with them
-    const uint32_t tile = (FROMCTL && (ctl->step & 1u)) ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
-    const size_t base = (size_t)tile * TILE;
-
-    // 1. stream the tile through registers
-    const uint4* src = reinterpret_cast<const uint4*>(tok + base);
-    uint4 v[NV];
-    bool any = false;
-    TileHalo<TokT> h;
-    if (threadIdx.x == 0) h = halo[tile];  // issued first: its latency hides behind the tile loads
-#pragma unroll
-    for (int k = 0; k < NV; k++) v[k] = src[k * THREADS + (int)threadIdx.x];
-#pragma unroll
-    for (int k = 0; k < NV; k++) any |= vec_has<TokT>(v[k], Au);
-    if (threadIdx.x == 0 && h.l1 == A) any = true;  // possible head duty
-    if (!__syncthreads_or(any ? 1 : 0)) return;
+    const bool AEQB = (Au == Bu);
     if (use_bins) for (int i = (int)threadIdx.x; i < NBIN; i += THREADS) { bin_key[i] = EMPTY_KEY; bin_val[i] = 0; }
-
-    // 2. stage the tile (+ halo) so that neighbours can be looked up across thread boundaries
-    uint4* dst = reinterpret_cast<uint4*>(ext + OFF);
+    // stage the tile (+ halo) so that neighbours can be looked up across thread boundaries
+    if (STAGE_FROM_REGS) {
+        uint4* dst = reinterpret_cast<uint4*>(ext + OFF);
 #pragma unroll
-    for (int k = 0; k < NV; k++) dst[k * THREADS + (int)threadIdx.x] = v[k];
+        for (int k = 0; k < NV; k++) dst[k * THREADS + (int)threadIdx.x] = v[k];
+    }
     if (threadIdx.x == 0) {
         ext[OFF - 2] = h.l2;
         ext[OFF - 1] = h.l1;
         ext[OFF + TILE + 0] = h.r0;
         ext[OFF + TILE + 1] = h.r1;
         ext[OFF + TILE + 2] = h.r2;
-        sh_runA = h.runA;
-        q_n = 0;
+        *sh_runA = h.runA;
+        *q_n = 0;
     } else if (threadIdx.x < 32) {
         const int i = (int)threadIdx.x - 1;  // the remaining margin slots are holes
         if (i < OFF - 2) ext[i] = H;
@@ -792,7 +765,6 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(Tok
     }
     __syncthreads();
 
-    uint32_t nAB = 0, nXX = 0;
     // one occurrence candidate: the A at ext index s (A != B). Writes X / hole, emits the deltas.
     auto process_ab = [&](int s) {
         const int j = next_live(ext, s);
@@ -837,7 +809,7 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(Tok
             uint32_t mask = vec_mask<TokT>(v[k], Au);
             if (!mask) continue;
             const int s0 = OFF + (k * THREADS + (int)threadIdx.x) * VEC;
-            uint32_t at = atomicAdd(&q_n, (uint32_t)__popc(mask));
+            uint32_t at = atomicAdd(q_n, (uint32_t)__popc(mask));
             while (mask) {
                 const int bit = __ffs((int)mask) - 1;
                 mask &= mask - 1;
@@ -847,7 +819,7 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(Tok
             }
         }
         __syncthreads();
-        const uint32_t nq = q_n < (uint32_t)QCAP ? q_n : (uint32_t)QCAP;
+        const uint32_t nq = *q_n < (uint32_t)QCAP ? *q_n : (uint32_t)QCAP;
         for (uint32_t i = threadIdx.x; i < nq; i += THREADS) process_ab((int)q_pos[i]);
     } else {
 #pragma unroll
@@ -871,7 +843,7 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(Tok
                         if (u == H) continue;
                         if (u == A) c++; else { stop = true; break; }
                     }
-                    run = stop ? c : c + sh_runA;
+                    run = stop ? c : c + *sh_runA;
                     run_known = true;
                 }
                 const uint32_t off = run;
@@ -912,8 +884,6 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(Tok
             }
         }
     }
-    if (nAB) atomicAdd(nab_out, nAB);
-    if (DELTAS && nXX) atomicAdd(nxx_out, nXX);
     if (use_bins) {
         __syncthreads();
         for (int i = (int)threadIdx.x; i < NBIN; i += THREADS) {
@@ -921,6 +891,57 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(Tok
             if (k != EMPTY_KEY) atomicAdd((k & 0x10000u) ? &cntR[k & 0xFFFFu] : &cntL[k], bin_val[i]);
         }
     }
+}
+
+#ifndef BPE_MERGE_MINBLOCKS
+#define BPE_MERGE_MINBLOCKS 6
+#endif
+template <class TokT, bool DELTAS, bool FROMCTL>
+__global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(TokT* __restrict__ tok, const TileHalo<TokT>* __restrict__ halo,
+                                                        const StepCtl* __restrict__ ctl, uint32_t* __restrict__ cntL,
+                                                        uint32_t* __restrict__ cntR, uint32_t* nxx_out, uint32_t* nab_out,
+                                                        uint32_t Au, uint32_t Bu, uint32_t Xu, uint32_t bins_min_count) {
+    __shared__ __align__(16) TokT ext[EXT];
+    // block-private bins for the neighbour deltas: key = token id (+ 0x10000 for the right side)
+    __shared__ uint32_t bin_key[DELTAS ? MERGE_NBIN : 1];
+    __shared__ uint32_t bin_val[DELTAS ? MERGE_NBIN : 1];
+    __shared__ uint16_t q_pos[MERGE_QCAP];
+    __shared__ uint32_t q_n;
+    bool use_bins = false;  // dense steps privatise the deltas per CTA; sparse steps go straight to global
+    if (FROMCTL) {
+        if (ctl->halt) return;
+        Au = ctl->A; Bu = ctl->B; Xu = ctl->X;
+        use_bins = DELTAS && ctl->max_count >= bins_min_count;
+    }
+    const bool AEQB = (Au == Bu);
+    __shared__ uint32_t sh_runA;
+    constexpr int VEC = 16 / (int)sizeof(TokT);   // slots per 16-byte vector
+    constexpr int NV = TILE / VEC / THREADS;       // vectors per thread (interleaved for coalescing)
+    static_assert(NV >= 1 && NV * VEC * THREADS == TILE, "tile geometry");
+    const TokT H = (TokT)TokTraits<TokT>::hole;
+    const TokT A = (TokT)Au, B = (TokT)Bu, X = (TokT)Xu;
+    // odd steps walk the sequence backwards: the tiles the previous pass touched last are still in
+    // the 126 MB L2 when this pass starts with them
+    const uint32_t tile = (FROMCTL && (ctl->step & 1u)) ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
+    const size_t base = (size_t)tile * TILE;
+
+    // 1. stream the tile through registers
+    const uint4* src = reinterpret_cast<const uint4*>(tok + base);
+    uint4 v[NV];
+    bool any = false;
+    TileHalo<TokT> h;
+    if (threadIdx.x == 0) h = halo[tile];  // issued first: its latency hides behind the tile loads
+#pragma unroll
+    for (int k = 0; k < NV; k++) v[k] = src[k * THREADS + (int)threadIdx.x];
+#pragma unroll
+    for (int k = 0; k < NV; k++) any |= vec_has<TokT>(v[k], Au);
+    if (threadIdx.x == 0 && h.l1 == A) any = true;  // possible head duty
+    if (!__syncthreads_or(any ? 1 : 0)) return;
+    uint32_t nAB = 0, nXX = 0;
+    tile_staged_path<TokT, DELTAS, true, NV>(ext, v, tok, base, h, Au, Bu, Xu, use_bins, bin_key, bin_val, q_pos, &q_n, &sh_runA,
+                                             cntL, cntR, nAB, nXX);
+    if (nAB) atomicAdd(nab_out, nAB);
+    if (DELTAS && nXX) atomicAdd(nxx_out, nXX);
 }
 
 // =========================================================================================
@@ -957,6 +978,90 @@ __global__ void zig_rebuild_kernel(PairTable tbl, ZigPop z, StepCtl* ctl) {
     size_t cap = (size_t)tbl.mask + 1;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x)
         if (tbl.counts[i] > 0) zcnt_add(z, tbl.keys[i], +1, ctl);
+}
+
+// =========================================================================================
+// merge_tma_kernel: the same pass as merge_kernel, fed by a TMA ring. A persistent CTA owns every
+// gridDim.x-th tile; one thread keeps RING_STAGES bulk copies (cp.async.bulk, 16 KB each) in flight
+// into shared memory, each completing on its own mbarrier. The tile therefore arrives already
+// staged: the streaming test reads it from shared memory, and a tile that needs work pays no extra
+// copy and no extra load latency (the next tiles are already on their way). In-flight data per SM
+// = 2 CTAs x RING_STAGES x 16 KB, independent of the register budget.
+// =========================================================================================
+constexpr int RING_STAGES = 5;
+template <class TokT> constexpr size_t ring_stage_bytes() { return (size_t)EXT * sizeof(TokT); }
+template <class TokT> constexpr size_t ring_smem_bytes() { return RING_STAGES * ring_stage_bytes<TokT>(); }
+
+template <class TokT, bool DELTAS, bool FROMCTL>
+__global__ void __launch_bounds__(THREADS, 2) merge_tma_kernel(TokT* __restrict__ tok, const TileHalo<TokT>* __restrict__ halo,
+                                                               const StepCtl* __restrict__ ctl, uint32_t* __restrict__ cntL,
+                                                               uint32_t* __restrict__ cntR, uint32_t* nxx_out, uint32_t* nab_out,
+                                                               uint32_t Au, uint32_t Bu, uint32_t Xu, uint32_t bins_min_count,
+                                                               uint32_t ntiles) {
+    __shared__ uint32_t bin_key[DELTAS ? MERGE_NBIN : 1];
+    __shared__ uint32_t bin_val[DELTAS ? MERGE_NBIN : 1];
+    __shared__ uint16_t q_pos[MERGE_QCAP];
+    __shared__ uint32_t q_n;
+    __shared__ uint32_t sh_runA;
+    __shared__ __align__(8) uint64_t bar[RING_STAGES];
+    constexpr int VEC = 16 / (int)sizeof(TokT);
+    constexpr int NV = TILE / VEC / THREADS;
+    constexpr uint32_t TILE_BYTES = (uint32_t)(TILE * sizeof(TokT));
+    bool use_bins = false;
+    bool backwards = false;
+    if (FROMCTL) {
+        if (ctl->halt) return;
+        Au = ctl->A; Bu = ctl->B; Xu = ctl->X;
+        use_bins = DELTAS && ctl->max_count >= bins_min_count;
+        backwards = (ctl->step & 1u) != 0;  // odd steps walk backwards: the previous pass's tail is still in L2
+    }
+    const TokT A = (TokT)Au;
+    unsigned char* ring = reinterpret_cast<unsigned char*>(bpe_dyn_smem());
+    const uint32_t first = blockIdx.x, stride = gridDim.x;
+    const uint32_t n_my = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
+    auto tile_of = [&](uint32_t j) { uint32_t t = first + j * stride; return backwards ? ntiles - 1u - t : t; };
+    auto stage_ptr = [&](uint32_t s) { return reinterpret_cast<TokT*>(ring + (size_t)s * ring_stage_bytes<TokT>()); };
+    auto issue = [&](uint32_t j) {  // thread 0 only
+        const uint32_t s = j % RING_STAGES;
+        mbar_arrive_expect_tx(&bar[s], TILE_BYTES);
+        tma_load_1d(stage_ptr(s) + OFF, tok + (size_t)tile_of(j) * TILE, TILE_BYTES, &bar[s]);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < RING_STAGES; s++) mbar_init(&bar[s], 1);
+        mbar_fence_init();
+        fence_proxy_async();
+        for (uint32_t j = 0; j < n_my && j < (uint32_t)RING_STAGES; j++) issue(j);
+    }
+    __syncthreads();
+
+    uint32_t nAB = 0, nXX = 0;
+    for (uint32_t j = 0; j < n_my; j++) {
+        const uint32_t s = j % RING_STAGES;
+        const uint32_t tile = tile_of(j);
+        TileHalo<TokT> h;
+        if (threadIdx.x == 0) h = halo[tile];  // its latency hides behind the wait
+        mbar_wait(&bar[s], (j / RING_STAGES) & 1u);
+        TokT* ext = stage_ptr(s);
+        const uint4* src = reinterpret_cast<const uint4*>(ext + OFF);
+        uint4 v[NV];
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < NV; k++) v[k] = src[k * THREADS + (int)threadIdx.x];
+#pragma unroll
+        for (int k = 0; k < NV; k++) any |= vec_has<TokT>(v[k], Au);
+        if (threadIdx.x == 0 && h.l1 == A) any = true;  // possible head duty
+        if (__syncthreads_or(any ? 1 : 0)) {
+            tile_staged_path<TokT, DELTAS, false, NV>(ext, v, tok, (size_t)tile * TILE, h, Au, Bu, Xu, use_bins, bin_key, bin_val,
+                                                      q_pos, &q_n, &sh_runA, cntL, cntR, nAB, nXX);
+            __syncthreads();  // every thread is done with this stage
+        }
+        if (threadIdx.x == 0 && j + RING_STAGES < n_my) {
+            fence_proxy_async();  // order the generic-proxy accesses to the stage before the async refill
+            issue(j + RING_STAGES);
+        }
+    }
+    if (nAB) atomicAdd(nab_out, nAB);
+    if (DELTAS && nXX) atomicAdd(nxx_out, nXX);
 }
 
 // =========================================================================================
