@@ -989,8 +989,8 @@ __global__ void zig_rebuild_kernel(PairTable tbl, ZigPop z, StepCtl* ctl) {
 // = 2 CTAs x RING_STAGES x 16 KB, independent of the register budget.
 // =========================================================================================
 constexpr int RING_STAGES = 5;
-template <class TokT> constexpr size_t ring_stage_bytes() { return (size_t)EXT * sizeof(TokT); }
-template <class TokT> constexpr size_t ring_smem_bytes() { return RING_STAGES * ring_stage_bytes<TokT>(); }
+template <class TokT> __host__ __device__ constexpr size_t ring_stage_bytes() { return (size_t)EXT * sizeof(TokT); }
+template <class TokT> __host__ __device__ constexpr size_t ring_smem_bytes() { return RING_STAGES * ring_stage_bytes<TokT>(); }
 
 template <class TokT, bool DELTAS, bool FROMCTL>
 __global__ void __launch_bounds__(THREADS, 2) merge_tma_kernel(TokT* __restrict__ tok, const TileHalo<TokT>* __restrict__ halo,
