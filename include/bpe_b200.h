@@ -93,8 +93,9 @@ const char* bpe_last_error(const bpe_ctx* ctx);
  *   "compact_pct"         live/slots percentage below which the sequence is compacted (default 85)
  *   "table_log2"          log2 of the initial pair-table capacity (default: sized from n)
  *   "max_steps"           stop training after this many merges (0 = no limit)
- *   "merge_impl"          0 (default): merge pass fed by a TMA ring (cp.async.bulk + mbarrier, persistent CTAs);
- *                         1: register-streaming kernel, one CTA per tile
+ *   "merge_impl"          0 (default): register-streaming merge kernel, one CTA per tile;
+ *                         1: merge pass fed by a TMA ring (cp.async.bulk + mbarrier, persistent CTAs) —
+ *                            measured slower on B200 for this access pattern, kept for comparison
  *   "time_phases"         1: fill the reference's TimeStats buckets (synchronises per phase)
  *   "profile"             1: fill bpe_stats_t.kernel_ms / kernel_calls for every kernel class;
  *                         2: only the merge kernel (two event records per merge step)

@@ -474,14 +474,14 @@ static int sync_zcap(bpe_ctx* ctx, TrainRun& R, uint32_t d) {
     return BPE_OK;
 }
 
-// one merge pass over the sequence: the TMA-ring kernel (default) or the register-streaming kernel
+// one merge pass over the sequence: the register-streaming kernel (default) or the TMA-ring kernel (merge_impl = 1)
 template <class TokT, bool DELTAS, bool FROMCTL>
 static int launch_merge(bpe_ctx* ctx, TokT* tok, const TileHalo<TokT>* halo, uint32_t nt, const StepCtl* d_ctl, uint32_t* cntL,
                         uint32_t* cntR, uint32_t* nxx, uint32_t* nab, uint32_t A, uint32_t B, uint32_t X, uint32_t bins_min) {
-    if (ctx->merge_impl == 0) {
+    if (ctx->merge_impl == 1) {
         auto kern = merge_tma_kernel<TokT, DELTAS, FROMCTL>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem_bytes<TokT>()));
-        const unsigned grid = (unsigned)std::min<uint32_t>(nt, 2u * (uint32_t)ctx->num_sms);
+        const unsigned grid = (unsigned)std::min<uint32_t>(nt, (uint32_t)RING_CTAS_PER_SM * (uint32_t)ctx->num_sms);
         BPE_LAUNCH_SMEM(kern, grid, THREADS, ring_smem_bytes<TokT>(), ctx->stream, tok, halo, d_ctl, cntL, cntR, nxx, nab, A, B, X,
                         bins_min, nt);
     } else {

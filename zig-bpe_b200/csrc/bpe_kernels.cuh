@@ -685,13 +685,15 @@ template <class TokT> __device__ __forceinline__ int prev_live(const TokT* ext, 
 // bit i of the result is set when slot i of the 16-byte vector equals `a`
 template <class TokT> __device__ __forceinline__ uint32_t vec_mask(const uint4& v, uint32_t a);
 template <> __device__ __forceinline__ uint32_t vec_mask<uint16_t>(const uint4& v, uint32_t a) {
+    // bit (i + 16*half) <-> slot 2*i + half: one AND per word instead of a per-slot shuffle of bits
     const uint32_t aa = a | (a << 16);
-    const uint32_t w[4] = {__vcmpeq2(v.x, aa), __vcmpeq2(v.y, aa), __vcmpeq2(v.z, aa), __vcmpeq2(v.w, aa)};
-    uint32_t m = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) m |= ((w[i] & 1u) | ((w[i] >> 15) & 2u)) << (2 * i);
-    return m;
+    return (__vcmpeq2(v.x, aa) & 0x00010001u) | ((__vcmpeq2(v.y, aa) & 0x00010001u) << 1) |
+           ((__vcmpeq2(v.z, aa) & 0x00010001u) << 2) | ((__vcmpeq2(v.w, aa) & 0x00010001u) << 3);
 }
+// slot index of a set bit of vec_mask
+template <class TokT> __device__ __forceinline__ int mask_bit_to_slot(int bit);
+template <> __device__ __forceinline__ int mask_bit_to_slot<uint16_t>(int bit) { return ((bit & 15) << 1) | (bit >> 4); }
+template <> __device__ __forceinline__ int mask_bit_to_slot<uint32_t>(int bit) { return bit; }
 template <> __device__ __forceinline__ uint32_t vec_mask<uint32_t>(const uint4& v, uint32_t a) {
     return (v.x == a ? 1u : 0u) | (v.y == a ? 2u : 0u) | (v.z == a ? 4u : 0u) | (v.w == a ? 8u : 0u);
 }
@@ -733,7 +735,8 @@ constexpr int MERGE_QCAP = 2048;  // queued A positions per tile (denser tiles o
 // h is valid in thread 0 only. Ends with all threads past their last read of ext.
 template <class TokT, bool DELTAS, bool STAGE_FROM_REGS, int NV>
 __device__ __forceinline__ void tile_staged_path(TokT* ext, const uint4 (&v)[NV], TokT* __restrict__ tok, size_t base,
-                                                 const TileHalo<TokT>& h, uint32_t Au, uint32_t Bu, uint32_t Xu, bool use_bins,
+                                                 const TileHalo<TokT>& h, uint32_t hitbits, uint32_t Au, uint32_t Bu, uint32_t Xu,
+                                                 bool use_bins,
                                                  uint32_t* bin_key, uint32_t* bin_val, uint16_t* q_pos, uint32_t* q_n,
                                                  uint32_t* sh_runA, uint32_t* __restrict__ cntL, uint32_t* __restrict__ cntR,
                                                  uint32_t& nAB, uint32_t& nXX) {
@@ -806,15 +809,16 @@ __device__ __forceinline__ void tile_staged_path(TokT* ext, const uint4 (&v)[NV]
         // positions of its A's; the CTA then works through the queue with all lanes busy.
 #pragma unroll
         for (int k = 0; k < NV; k++) {
+            if (!((hitbits >> k) & 1u)) continue;
             uint32_t mask = vec_mask<TokT>(v[k], Au);
-            if (!mask) continue;
             const int s0 = OFF + (k * THREADS + (int)threadIdx.x) * VEC;
             uint32_t at = atomicAdd(q_n, (uint32_t)__popc(mask));
             while (mask) {
                 const int bit = __ffs((int)mask) - 1;
                 mask &= mask - 1;
-                if (at < (uint32_t)QCAP) q_pos[at] = (uint16_t)(s0 + bit);
-                else process_ab(s0 + bit);  // queue full (very dense step): handle in place
+                const int s = s0 + mask_bit_to_slot<TokT>(bit);
+                if (at < (uint32_t)QCAP) q_pos[at] = (uint16_t)s;
+                else process_ab(s);  // queue full (very dense step): handle in place
                 at++;
             }
         }
@@ -824,8 +828,12 @@ __device__ __forceinline__ void tile_staged_path(TokT* ext, const uint4 (&v)[NV]
     } else {
 #pragma unroll
         for (int k = 0; k < NV; k++) {
-            uint32_t mask = vec_mask<TokT>(v[k], Au);
-            if (!mask) continue;
+            if (!((hitbits >> k) & 1u)) continue;
+            uint32_t mask = 0;  // A==B needs the slots in ascending order: bit = slot
+            {
+                uint32_t m = vec_mask<TokT>(v[k], Au);
+                while (m) { const int bit = __ffs((int)m) - 1; m &= m - 1; mask |= 1u << mask_bit_to_slot<TokT>(bit); }
+            }
             const int s0 = OFF + (k * THREADS + (int)threadIdx.x) * VEC;
             uint32_t run = 0;       // consecutive live A's immediately before the current slot
             bool run_known = false;
@@ -933,12 +941,14 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(Tok
     if (threadIdx.x == 0) h = halo[tile];  // issued first: its latency hides behind the tile loads
 #pragma unroll
     for (int k = 0; k < NV; k++) v[k] = src[k * THREADS + (int)threadIdx.x];
+    uint32_t hitbits = 0;  // which of my vectors hold an A
 #pragma unroll
-    for (int k = 0; k < NV; k++) any |= vec_has<TokT>(v[k], Au);
+    for (int k = 0; k < NV; k++) hitbits |= vec_has<TokT>(v[k], Au) ? (1u << k) : 0u;
+    any = hitbits != 0;
     if (threadIdx.x == 0 && h.l1 == A) any = true;  // possible head duty
     if (!__syncthreads_or(any ? 1 : 0)) return;
     uint32_t nAB = 0, nXX = 0;
-    tile_staged_path<TokT, DELTAS, true, NV>(ext, v, tok, base, h, Au, Bu, Xu, use_bins, bin_key, bin_val, q_pos, &q_n, &sh_runA,
+    tile_staged_path<TokT, DELTAS, true, NV>(ext, v, tok, base, h, hitbits, Au, Bu, Xu, use_bins, bin_key, bin_val, q_pos, &q_n, &sh_runA,
                                              cntL, cntR, nAB, nXX);
     if (nAB) atomicAdd(nab_out, nAB);
     if (DELTAS && nXX) atomicAdd(nxx_out, nXX);
@@ -988,12 +998,19 @@ __global__ void zig_rebuild_kernel(PairTable tbl, ZigPop z, StepCtl* ctl) {
 // copy and no extra load latency (the next tiles are already on their way). In-flight data per SM
 // = 2 CTAs x RING_STAGES x 16 KB, independent of the register budget.
 // =========================================================================================
-constexpr int RING_STAGES = 5;
+#ifndef BPE_RING_STAGES
+#define BPE_RING_STAGES 3
+#endif
+#ifndef BPE_RING_CTAS
+#define BPE_RING_CTAS 4
+#endif
+constexpr int RING_STAGES = BPE_RING_STAGES;  // bulk copies in flight per CTA
+constexpr int RING_CTAS_PER_SM = BPE_RING_CTAS;
 template <class TokT> __host__ __device__ constexpr size_t ring_stage_bytes() { return (size_t)EXT * sizeof(TokT); }
 template <class TokT> __host__ __device__ constexpr size_t ring_smem_bytes() { return RING_STAGES * ring_stage_bytes<TokT>(); }
 
 template <class TokT, bool DELTAS, bool FROMCTL>
-__global__ void __launch_bounds__(THREADS, 2) merge_tma_kernel(TokT* __restrict__ tok, const TileHalo<TokT>* __restrict__ halo,
+__global__ void __launch_bounds__(THREADS, RING_CTAS_PER_SM) merge_tma_kernel(TokT* __restrict__ tok, const TileHalo<TokT>* __restrict__ halo,
                                                                const StepCtl* __restrict__ ctl, uint32_t* __restrict__ cntL,
                                                                uint32_t* __restrict__ cntR, uint32_t* nxx_out, uint32_t* nab_out,
                                                                uint32_t Au, uint32_t Bu, uint32_t Xu, uint32_t bins_min_count,
@@ -1047,11 +1064,13 @@ __global__ void __launch_bounds__(THREADS, 2) merge_tma_kernel(TokT* __restrict_
         bool any = false;
 #pragma unroll
         for (int k = 0; k < NV; k++) v[k] = src[k * THREADS + (int)threadIdx.x];
+        uint32_t hitbits = 0;
 #pragma unroll
-        for (int k = 0; k < NV; k++) any |= vec_has<TokT>(v[k], Au);
+        for (int k = 0; k < NV; k++) hitbits |= vec_has<TokT>(v[k], Au) ? (1u << k) : 0u;
+        any = hitbits != 0;
         if (threadIdx.x == 0 && h.l1 == A) any = true;  // possible head duty
         if (__syncthreads_or(any ? 1 : 0)) {
-            tile_staged_path<TokT, DELTAS, false, NV>(ext, v, tok, (size_t)tile * TILE, h, Au, Bu, Xu, use_bins, bin_key, bin_val,
+            tile_staged_path<TokT, DELTAS, false, NV>(ext, v, tok, (size_t)tile * TILE, h, hitbits, Au, Bu, Xu, use_bins, bin_key, bin_val,
                                                       q_pos, &q_n, &sh_runA, cntL, cntR, nAB, nXX);
             __syncthreads();  // every thread is done with this stage
         }
