@@ -686,9 +686,11 @@ template <class TokT> __device__ __forceinline__ int prev_live(const TokT* ext, 
 template <class TokT> __device__ __forceinline__ uint32_t vec_mask(const uint4& v, uint32_t a);
 template <> __device__ __forceinline__ uint32_t vec_mask<uint16_t>(const uint4& v, uint32_t a) {
     // bit (i + 16*half) <-> slot 2*i + half: one AND per word instead of a per-slot shuffle of bits
+    // exact zero-halfword test without cross-lane carries: z = ~(((x & 0x7FFF7FFF) + 0x7FFF7FFF) | x) & 0x80008000
+    // (sm_100 has no SIMD video compare: __vcmpeq2 expands to ~6 instructions per word)
     const uint32_t aa = a | (a << 16);
-    return (__vcmpeq2(v.x, aa) & 0x00010001u) | ((__vcmpeq2(v.y, aa) & 0x00010001u) << 1) |
-           ((__vcmpeq2(v.z, aa) & 0x00010001u) << 2) | ((__vcmpeq2(v.w, aa) & 0x00010001u) << 3);
+    auto z = [&](uint32_t w) { const uint32_t x = w ^ aa; return ~(((x & 0x7FFF7FFFu) + 0x7FFF7FFFu) | x) & 0x80008000u; };
+    return (z(v.x) >> 15) | (z(v.y) >> 14) | (z(v.z) >> 13) | (z(v.w) >> 12);
 }
 // slot index of a set bit of vec_mask
 template <class TokT> __device__ __forceinline__ int mask_bit_to_slot(int bit);
@@ -699,8 +701,11 @@ template <> __device__ __forceinline__ uint32_t vec_mask<uint32_t>(const uint4& 
 }
 template <class TokT> __device__ __forceinline__ bool vec_has(const uint4& v, uint32_t a);
 template <> __device__ __forceinline__ bool vec_has<uint16_t>(const uint4& v, uint32_t a) {
+    // "has a zero halfword" of w ^ aa: (x - 0x00010001) & ~x & 0x80008000. A borrow can only flag a
+    // neighbouring lane falsely when a lower lane really is zero, so the any-test is exact.
     const uint32_t aa = a | (a << 16);
-    return (__vcmpeq2(v.x, aa) | __vcmpeq2(v.y, aa) | __vcmpeq2(v.z, aa) | __vcmpeq2(v.w, aa)) != 0u;
+    auto t = [&](uint32_t w) { const uint32_t x = w ^ aa; return (x - 0x00010001u) & ~x; };
+    return ((t(v.x) | t(v.y) | t(v.z) | t(v.w)) & 0x80008000u) != 0u;
 }
 template <> __device__ __forceinline__ bool vec_has<uint32_t>(const uint4& v, uint32_t a) {
     return v.x == a || v.y == a || v.z == a || v.w == a;
