@@ -477,7 +477,8 @@ static int sync_zcap(bpe_ctx* ctx, TrainRun& R, uint32_t d) {
 // one merge pass over the sequence: the register-streaming kernel (default) or the TMA-ring kernel (merge_impl = 1)
 template <class TokT, bool DELTAS, bool FROMCTL>
 static int launch_merge(bpe_ctx* ctx, TokT* tok, const TileHalo<TokT>* halo, uint32_t nt, const StepCtl* d_ctl, uint32_t* cntL,
-                        uint32_t* cntR, uint32_t* nxx, uint32_t* nab, uint32_t A, uint32_t B, uint32_t X, uint32_t bins_min) {
+                        uint32_t* cntR, uint32_t* nxx, uint32_t* nab, uint32_t A, uint32_t B, uint32_t X, uint32_t bins_min,
+                        int backwards) {
     if (ctx->merge_impl == 1) {
         auto kern = merge_tma_kernel<TokT, DELTAS, FROMCTL>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem_bytes<TokT>()));
@@ -485,14 +486,15 @@ static int launch_merge(bpe_ctx* ctx, TokT* tok, const TileHalo<TokT>* halo, uin
         BPE_LAUNCH_SMEM(kern, grid, THREADS, ring_smem_bytes<TokT>(), ctx->stream, tok, halo, d_ctl, cntL, cntR, nxx, nab, A, B, X,
                         bins_min, nt);
     } else {
-        BPE_LAUNCH((merge_kernel<TokT, DELTAS, FROMCTL>), nt, THREADS, ctx->stream, tok, halo, d_ctl, cntL, cntR, nxx, nab, A, B, X, bins_min);
+        BPE_LAUNCH((merge_kernel<TokT, DELTAS, FROMCTL>), nt, THREADS, ctx->stream, tok, halo, d_ctl, cntL, cntR, nxx, nab, A, B, X, bins_min,
+                   backwards);
     }
     ctx->launches++;
     return BPE_OK;
 }
 
 // the part of a step after the merge has been chosen: halo, merge, apply (all read the merge from ctl)
-static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids) {
+static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uint32_t step_index) {
     const uint32_t nt = R.sq.ntiles();
     R.prof.mark(K_HALO);
     BPE_LAUNCH((halo_kernel<uint16_t, true>), (nt + HALO_THREADS - 1) / HALO_THREADS, HALO_THREADS, ctx->stream, R.sq.tok(),
@@ -501,7 +503,7 @@ static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids) {
     R.prof.mark(K_MERGE);
     {
         int rcm = launch_merge<uint16_t, true, true>(ctx, R.sq.tok(), R.sq.halo.as<TileHalo<uint16_t>>(), nt, (const StepCtl*)R.d_ctl(),
-                                                     R.cntL(), R.cntR(), R.nxx(), R.nab(), 0u, 0u, 0u, 4u * nt);
+                                                     R.cntL(), R.cntR(), R.nxx(), R.nab(), 0u, 0u, 0u, 4u * nt, (int)(step_index & 1u));
         if (rcm) return rcm;
     }
     R.prof.mark(K_APPLY);
@@ -631,7 +633,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
             prof.mark(K_ARGMAX);
             BPE_LAUNCH(select_kernel, 1, 1024, ctx->stream, R.tm.view(), R.hl(), R.d_ctl(), R.d_rec(), R.tm.zig());
             ctx->launches += 1;
-            rc = enqueue_step_tail(ctx, R, 256 + steps_done + k + 1);
+            rc = enqueue_step_tail(ctx, R, 256 + steps_done + k + 1, steps_done + k);
             if (rc) return rc;
         }
         prof.mark(K_HOSTGAP);
@@ -690,7 +692,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
                 if (!had_fast) R.st.tie_slow_steps++;
                 BPE_LAUNCH_NS(ctl_set_kernel, 1, 1, ctx->stream, R.d_ctl(), R.d_rec(), 0, 0u, 0, 0u, 1, 1, w, maxc);
                 ctx->launches++;
-                rc = enqueue_step_tail(ctx, R, 256 + steps_done + 1);
+                rc = enqueue_step_tail(ctx, R, 256 + steps_done + 1, steps_done);
                 if (rc) return rc;
                 rc = read_ctl(ctx, R, false);
                 if (rc) return rc;
@@ -754,6 +756,7 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
     StepCtl* d_ctl = ctl.as<StepCtl>();
     const TokT H = (TokT)TokTraits<TokT>::hole;
     uint32_t merged_seen = 0;  // device cntAB accumulates over passes; host subtracts what it has seen
+    uint32_t pass_index = 0;   // alternate the scan direction so consecutive passes reuse the L2
     auto read_merged = [&](uint32_t* fresh) -> int {
         uint32_t acc = 0;
         CU(cudaMemcpyAsync(&acc, &d_ctl->cntAB, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -772,7 +775,8 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
         ctx->launches += 1;
         {
             int rcm = launch_merge<TokT, false, false>(ctx, sq.tok(), sq.halo.template as<TileHalo<TokT>>(), nt, (const StepCtl*)nullptr,
-                                                       (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, &d_ctl->cntAB, A, B, X, 0u);
+                                                       (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, &d_ctl->cntAB, A, B, X, 0u,
+                                                       (int)(pass_index++ & 1u));
             if (rcm) return rcm;
         }
         CU(cudaGetLastError());

@@ -913,39 +913,40 @@ template <class TokT, bool DELTAS, bool FROMCTL>
 __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(TokT* __restrict__ tok, const TileHalo<TokT>* __restrict__ halo,
                                                         const StepCtl* __restrict__ ctl, uint32_t* __restrict__ cntL,
                                                         uint32_t* __restrict__ cntR, uint32_t* nxx_out, uint32_t* nab_out,
-                                                        uint32_t Au, uint32_t Bu, uint32_t Xu, uint32_t bins_min_count) {
+                                                        uint32_t Au, uint32_t Bu, uint32_t Xu, uint32_t bins_min_count,
+                                                        int backwards) {
     __shared__ __align__(16) TokT ext[EXT];
     // block-private bins for the neighbour deltas: key = token id (+ 0x10000 for the right side)
     __shared__ uint32_t bin_key[DELTAS ? MERGE_NBIN : 1];
     __shared__ uint32_t bin_val[DELTAS ? MERGE_NBIN : 1];
     __shared__ uint16_t q_pos[MERGE_QCAP];
     __shared__ uint32_t q_n;
+    __shared__ uint32_t sh_runA;
+    constexpr int VEC = 16 / (int)sizeof(TokT);   // slots per 16-byte vector
+    constexpr int NV = TILE / VEC / THREADS;       // vectors per thread (interleaved for coalescing)
+    static_assert(NV >= 1 && NV * VEC * THREADS == TILE, "tile geometry");
+    const TokT H = (TokT)TokTraits<TokT>::hole;
+    // odd steps walk the sequence backwards (`backwards`, chosen by the host from the step parity): the
+    // tiles the previous pass touched last are still in the 126 MB L2 when this pass starts with them
+    const uint32_t tile = backwards ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
+    const size_t base = (size_t)tile * TILE;
+
+    // 1. stream the tile through registers. The loads are issued before the control block is read so
+    // that the two latencies overlap.
+    const uint4* src = reinterpret_cast<const uint4*>(tok + base);
+    uint4 v[NV];
+    bool any = false;
+    TileHalo<TokT> h;
+    if (threadIdx.x == 0) h = halo[tile];
+#pragma unroll
+    for (int k = 0; k < NV; k++) v[k] = src[k * THREADS + (int)threadIdx.x];
     bool use_bins = false;  // dense steps privatise the deltas per CTA; sparse steps go straight to global
     if (FROMCTL) {
         if (ctl->halt) return;
         Au = ctl->A; Bu = ctl->B; Xu = ctl->X;
         use_bins = DELTAS && ctl->max_count >= bins_min_count;
     }
-    const bool AEQB = (Au == Bu);
-    __shared__ uint32_t sh_runA;
-    constexpr int VEC = 16 / (int)sizeof(TokT);   // slots per 16-byte vector
-    constexpr int NV = TILE / VEC / THREADS;       // vectors per thread (interleaved for coalescing)
-    static_assert(NV >= 1 && NV * VEC * THREADS == TILE, "tile geometry");
-    const TokT H = (TokT)TokTraits<TokT>::hole;
-    const TokT A = (TokT)Au, B = (TokT)Bu, X = (TokT)Xu;
-    // odd steps walk the sequence backwards: the tiles the previous pass touched last are still in
-    // the 126 MB L2 when this pass starts with them
-    const uint32_t tile = (FROMCTL && (ctl->step & 1u)) ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
-    const size_t base = (size_t)tile * TILE;
-
-    // 1. stream the tile through registers
-    const uint4* src = reinterpret_cast<const uint4*>(tok + base);
-    uint4 v[NV];
-    bool any = false;
-    TileHalo<TokT> h;
-    if (threadIdx.x == 0) h = halo[tile];  // issued first: its latency hides behind the tile loads
-#pragma unroll
-    for (int k = 0; k < NV; k++) v[k] = src[k * THREADS + (int)threadIdx.x];
+    const TokT A = (TokT)Au;
     uint32_t hitbits = 0;  // which of my vectors hold an A
 #pragma unroll
     for (int k = 0; k < NV; k++) hitbits |= vec_has<TokT>(v[k], Au) ? (1u << k) : 0u;
