@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=2, help="merge steps timed for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-encode", action="store_true")
+    ap.add_argument("--max-steps", type=int, default=0, help="profiling aid: stop every training run after this many merges")
     return ap.parse_args()
 
 
@@ -168,6 +170,8 @@ def main():
         m, c = eng.train(host, args.vocab)
         return m, c, dict(eng.last_stats)
 
+    if args.max_steps:
+        eng.set_option("max_steps", args.max_steps)
     if os.environ.get("BPE_DEBUG"):
         eng.set_option("debug", int(os.environ["BPE_DEBUG"]))
     eng.set_option("profile", 2)  # event marks around the merge kernel only (2 records per merge step)
@@ -219,6 +223,26 @@ def main():
                "d2h_bytes_per_step": int(len(m2)) * (6 + 8), "steps": ksteps}
         assert np.array_equal(m2, merges), "host-buffer and device-resident runs disagree"
 
+    # encode (the other half of BASELINE.json's metric): every GPU encodes its own shard with the merges just learned
+    enc = None
+    if not args.no_encode:
+        eng.set_option("profile", 0)
+        d_out = torch.empty(n, dtype=torch.int16, device=dev)
+        n_ids = eng.encode_device(d_text.data_ptr(), n, merges, d_out.data_ptr())  # warm-up
+        barrier()
+        t3 = time.perf_counter()
+        n_ids = eng.encode_device(d_text.data_ptr(), n, merges, d_out.data_ptr())
+        est = dict(eng.last_stats)
+        barrier()
+        enc_ms = (time.perf_counter() - t3) * 1000
+        te = torch.tensor([enc_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        enc = {"metric": "encode_input_GB_per_sec", "value": n * world / 1e9 / (float(te[0]) / 1000.0), "unit": "GB/s", "merges": int(len(merges)),
+               "bytes_per_gpu": n, "ids_out_rank0": int(n_ids), "passes": int(len(merges)), "gpu_launches": int(est["kernel_launches"]),
+               "scan_GBps_per_gpu": est["scanned_slots"] * 2 / 1e9 / (est["device_ms"] / 1000.0),
+               "note": "reference semantics: one pass per merge in list order (exact for any list); algorithmic bytes n + 2*n_out"}
+        del d_out
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -245,6 +269,7 @@ def main():
                      "kernel_share_of_step": merge_ms / dev_ms if dev_ms else None,
                      "whole_step_scan_GBps": alg_bytes / 1e9 / (dev_ms / 1000.0) if dev_ms else None},
         "tie_steps": int(st["tie_steps"]), "tie_slow_steps": int(st["tie_slow_steps"]), "compactions": int(st["compactions"]),
+        "encode": enc,
     }
     if not args.no_cpu_baseline and world == 1:
         from oracle import oracle_py as ora
