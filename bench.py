@@ -250,6 +250,10 @@ def main():
         return
     peak, peak_src = peaks()
     alg_bytes = scanned * 2  # u16 slots
+    traffic = None  # DRAM bytes per launch from the committed ncu --set full capture (ratio to algorithmic bytes)
+    tp = os.path.join(ROOT, "profiles", "r01_merge_traffic.json")
+    if os.path.exists(tp) and merge_calls:
+        traffic = json.load(open(tp))["traffic_over_algorithmic"] * alg_bytes / merge_calls
     achieved = alg_bytes / 1e9 / (merge_ms / 1000.0) if merge_ms > 0 else None
     line = {
         "metric": "train_merges_per_sec", "value": value, "unit": "merges/s", "n_gpus": world, "steps": args.steps,
@@ -264,7 +268,7 @@ def main():
         "clocks": clk,
         "e2e": e2e,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                     "traffic": None, "kernel": "merge_kernel<u16>", "peak_source": peak_src,
+                     "traffic": traffic, "kernel": "merge_kernel<u16>", "peak_source": peak_src,
                      "bytes_per_launch": alg_bytes / max(merge_calls, 1), "avg_launch_ms": merge_ms / max(merge_calls, 1),
                      "kernel_share_of_step": merge_ms / dev_ms if dev_ms else None,
                      "whole_step_scan_GBps": alg_bytes / 1e9 / (dev_ms / 1000.0) if dev_ms else None},
