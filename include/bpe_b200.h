@@ -117,8 +117,10 @@ int bpe_train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t voc
 
 /* ---- encode (src/basic_tokenizer.zig:71-88) ----------------------------------------------
  * Applies merges[0..m) in list order, one left-to-right greedy pass each, exactly as the
- * reference does. out: capacity n ids. In a dist context each rank encodes its own shard;
- * shards are independent byte ranges, so shard boundaries are token boundaries. */
+ * reference does. out: capacity n ids. In a dist context every rank passes its contiguous shard
+ * and receives the ids of its shard; the shards exchange their end tokens before every pass, so the
+ * concatenation of the ranks' outputs equals the single-GPU encoding of the whole text (a token that
+ * straddles two shards is emitted by the left one). */
 int bpe_encode(bpe_ctx* ctx, const uint8_t* text, size_t n, const bpe_merge_t* merges, size_t m,
                uint16_t* out, size_t* out_n, bpe_stats_t* stats);
 /* d_text and d_out (capacity n ids) are device pointers. */

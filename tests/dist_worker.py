@@ -57,12 +57,29 @@ def main():
     data = make_case(case)
     bounds = shard_bounds(case, len(data), world)
     shard = data[bounds[rank]:bounds[rank + 1]]
+    if os.environ.get("DIST_MODE") == "encode":
+        # sharded encode with a fixed merge list: the concatenation of the ranks' ids must equal the
+        # single-process encoding of the whole text
+        ids = eng.encode(shard, ENCODE_MERGES[case])
+        np.savez(f"{out_path}.{rank}.npz", ids=ids)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     merges, counts = eng.train(shard, vocab)
     got = np.stack([merges["first"], merges["second"], merges["new_token"]], axis=1) if len(merges) else np.zeros((0, 3), np.uint16)
     np.savez(f"{out_path}.{rank}.npz", merges=got, counts=counts, tie_steps=eng.last_stats["tie_steps"],
              tie_slow=eng.last_stats["tie_slow_steps"])
     dist.barrier()
     dist.destroy_process_group()
+
+
+ENCODE_MERGES = {
+    "aaaa": [(97, 97, 256), (256, 256, 257), (257, 97, 258)],
+    "abab": [(97, 98, 256), (256, 256, 257), (98, 97, 258), (257, 97, 259)],
+    "runs": [(97, 97, 256), (256, 256, 257), (257, 257, 258), (98, 258, 259), (99, 99, 260)],
+    "cascade": [(ord("X"), ord("b"), ord("X")), (ord("a"), ord("a"), ord("a"))],
+    "tiny": [(97, 98, 256), (256, 99, 257), (257, 257, 258)],
+}
 
 
 def make_case(case):
@@ -79,6 +96,8 @@ def make_case(case):
         return bytes(rng.integers(97, 101, size=6000, dtype=np.uint8))
     if case == "rand256":
         return bytes(rng.integers(0, 256, size=6000, dtype=np.uint8))
+    if case == "cascade":
+        return b"Xbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbbb c" + b"a" * 777 + b"Xbb"
     if case == "tiny":
         return b"abcabcabc"
     raise ValueError(case)

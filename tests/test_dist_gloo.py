@@ -23,13 +23,13 @@ def _free_port():
     return p
 
 
-def _run(case, vocab, world, tmp_path, *opts):
-    out = str(tmp_path / f"{case}_{world}")
+def _run(case, vocab, world, tmp_path, *opts, mode="train"):
+    out = str(tmp_path / f"{case}_{world}_{mode}")
     port = _free_port()
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
-                   OMP_NUM_THREADS="1")
+                   OMP_NUM_THREADS="1", DIST_MODE=mode)
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_worker.py"), case, str(vocab), out, *opts],
                                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     logs = [p.communicate(timeout=600)[0] for p in procs]
@@ -60,3 +60,13 @@ def test_sharded_train_forced_replay(ora, tmp_path):
     res = _run("taylor", 280, 2, tmp_path, "check_tiebreak=1")
     om, _ = ora.train(dist_worker.make_case("taylor"), 280, fast=True)
     assert np.array_equal(res[0]["merges"], om)
+
+
+@pytest.mark.parametrize("case,world", [("aaaa", 2), ("abab", 3), ("runs", 2), ("runs", 3), ("cascade", 2), ("tiny", 2)])
+def test_sharded_encode_matches_single_process(ora, tmp_path, case, world):
+    """Sharded encode: tokens that straddle shard boundaries (also runs cut at odd offsets, shards of one byte,
+    the cascade rule) must come out exactly as in the reference's single-sequence encode."""
+    res = _run(case, 300, world, tmp_path, mode="encode")
+    got = np.concatenate([res[r]["ids"] for r in range(world)])
+    want = ora.encode(dist_worker.make_case(case), dist_worker.ENCODE_MERGES[case], linear=False)
+    assert np.array_equal(got, want)

@@ -25,13 +25,26 @@ for rep in range(2):
     torch.cuda.synchronize(); dist.barrier()
     dt = time.time() - t
 st = eng.last_stats
+# sharded encode: the concatenation over ranks must equal the single-GPU encoding
+ids = eng.encode(shard, m)
+sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+dist.all_gather(sizes, torch.tensor([len(ids)], dtype=torch.int64, device="cuda"))
+sizes = [int(x) for x in sizes]
+pad = torch.zeros(max(sizes), dtype=torch.int32, device="cuda")
+pad[: len(ids)] = torch.from_numpy(ids.astype(np.int32)).cuda()
+allids = [torch.zeros(max(sizes), dtype=torch.int32, device="cuda") for _ in range(world)]
+dist.all_gather(allids, pad)
 ok = None
 if rank == 0:
     single = zb.Engine(device=lr)
     full = sc.generate(n_total, sc.SEED_C3, sc.BYTE)
     t = time.time(); ms, cs = single.train(full, vocab); dt1 = time.time() - t
     ok = bool(np.array_equal(m, ms) and np.array_equal(c, cs))
-    print(json.dumps({"world": world, "bytes": n_total, "vocab": vocab, "merges": len(m), "sharded_s": round(dt, 3), "single_gpu_s": round(dt1, 3),
+    ids_single = single.encode(full, ms)
+    cat = np.concatenate([allids[r][: sizes[r]].cpu().numpy().astype(np.uint16) for r in range(world)])
+    enc_ok = bool(np.array_equal(cat, ids_single))
+    ok = ok and enc_ok
+    print(json.dumps({"world": world, "encode_identical": enc_ok, "bytes": n_total, "vocab": vocab, "merges": len(m), "sharded_s": round(dt, 3), "single_gpu_s": round(dt1, 3),
                       "identical_to_single_gpu": ok, "tie_steps": st["tie_steps"], "tie_slow": st["tie_slow_steps"], "launches": st["kernel_launches"]}), flush=True)
 flag = torch.tensor([1 if (ok is None or ok) else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -754,7 +754,17 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
     CU(ctl.alloc(sizeof(StepCtl)));
     CU(cudaMemsetAsync(ctl.p, 0, sizeof(StepCtl), ctx->stream));
     StepCtl* d_ctl = ctl.as<StepCtl>();
-    const TokT H = (TokT)TokTraits<TokT>::hole;
+    // multi-GPU: shards exchange their end tokens before every pass (one small all-reduce), so a pair
+    // that straddles two shards is merged exactly as on one GPU (X stays left, the hole goes right)
+    const bool multi = ctx->dist.world > 1;
+    DevBuf edges_buf, flag_buf;
+    EdgeInfo* edges = nullptr;
+    if (multi) {
+        CU(edges_buf.alloc((size_t)ctx->dist.world * sizeof(EdgeInfo)));
+        CU(flag_buf.alloc(4));
+        CU(cudaMemsetAsync(edges_buf.p, 0, (size_t)ctx->dist.world * sizeof(EdgeInfo), ctx->stream));
+        edges = edges_buf.as<EdgeInfo>();
+    }
     uint32_t merged_seen = 0;  // device cntAB accumulates over passes; host subtracts what it has seen
     uint32_t pass_index = 0;   // alternate the scan direction so consecutive passes reuse the L2
     auto read_merged = [&](uint32_t* fresh) -> int {
@@ -768,10 +778,16 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
     };
     auto one_pass = [&](uint32_t A, uint32_t B, uint32_t X) -> int {
         const uint32_t nt = sq.ntiles();
+        if (multi) {
+            BPE_LAUNCH(edge_kernel<TokT>, 1, 32, ctx->stream, sq.tok(), sq.n_slots, edges, ctx->dist.rank, ctx->dist.world, d_ctl,
+                       &d_ctl->cntAB, 0);
+            ctx->launches += 1;
+            if (!ctx->dist.allreduce(edges, (size_t)ctx->dist.world * 16, DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-reduce of the shard edges failed");
+        }
         BPE_LAUNCH((halo_kernel<TokT, false>), (nt + HALO_THREADS - 1) / HALO_THREADS, HALO_THREADS, ctx->stream, sq.tok(), sq.n_slots,
                    nt, sq.halo.template as<TileHalo<TokT>>(), (const StepCtl*)nullptr, A, A == B ? 1 : 0,
                    sq.run_local.template as<uint32_t>(), sq.run_full.template as<uint8_t>(), sq.done_counter.template as<uint32_t>(),
-                   (uint32_t*)nullptr, (const EdgeInfo*)nullptr, 0, 1);
+                   (uint32_t*)nullptr, (const EdgeInfo*)edges, ctx->dist.rank, ctx->dist.world);
         ctx->launches += 1;
         {
             int rcm = launch_merge<TokT, false, false>(ctx, sq.tok(), sq.halo.template as<TileHalo<TokT>>(), nt, (const StepCtl*)nullptr,
@@ -784,7 +800,7 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
         return BPE_OK;
     };
     size_t since_check = 0;
-    for (size_t i = 0; i < m && n > 1; i++) {
+    for (size_t i = 0; i < m && (n > 1 || multi); i++) {
         const uint32_t A = merges[i].first, B = merges[i].second, X = merges[i].new_token;
         rc = one_pass(A, B, X);
         if (rc) return rc;
@@ -796,6 +812,12 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
                 uint32_t fresh = 0;
                 rc = read_merged(&fresh);
                 if (rc) return rc;
+                if (multi) {  // "nothing changed" must hold on every shard
+                    CU(cudaMemcpyAsync(flag_buf.p, &fresh, 4, cudaMemcpyHostToDevice, ctx->stream));
+                    if (!ctx->dist.allreduce(flag_buf.p, 1, DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-reduce failed");
+                    CU(cudaMemcpyAsync(&fresh, flag_buf.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+                    CU(cudaStreamSynchronize(ctx->stream));
+                }
                 if (!fresh) break;
                 rc = one_pass(A, B, X);
                 if (rc) return rc;
@@ -839,8 +861,8 @@ static int encode_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
     memset(&st, 0, sizeof st);
     const double t0 = now_ms();
     const uint64_t l0 = ctx->launches;
-    if (n == 0) { if (stats_out) *stats_out = st; return BPE_OK; }
-    if (!d_out) return fail(ctx, BPE_ERR_INVALID_ARG, "out is null");
+    if (n == 0 && ctx->dist.world == 1) { if (stats_out) *stats_out = st; return BPE_OK; }
+    if (n && !d_out) return fail(ctx, BPE_ERR_INVALID_ARG, "out is null");
     if (n >= 0xFFFFFFF0ull) return fail(ctx, BPE_ERR_INVALID_ARG, "input of %zu bytes exceeds the 32-bit position range", n);
     CU(cudaSetDevice(ctx->device));
     cudaEvent_t ev0, ev1;
@@ -1137,13 +1159,13 @@ int bpe_encode(bpe_ctx* ctx, const uint8_t* text, size_t n, const bpe_merge_t* m
     CacheScope cache_scope(ctx);
     if (!out_n) return fail(ctx, BPE_ERR_INVALID_ARG, "out_n is null");
     *out_n = 0;
-    if (n == 0) { if (stats) memset(stats, 0, sizeof *stats); return BPE_OK; }
-    if (!text || !out) return fail(ctx, BPE_ERR_INVALID_ARG, "text/out is null");
+    if (n == 0 && ctx->dist.world == 1) { if (stats) memset(stats, 0, sizeof *stats); return BPE_OK; }
+    if (n && (!text || !out)) return fail(ctx, BPE_ERR_INVALID_ARG, "text/out is null");
     const double t0 = now_ms();
     CU(cudaSetDevice(ctx->device));
     DevBuf d_in, d_out;
-    if (cudaMalloc(&d_in.p, n) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", n);
-    if (cudaMalloc(&d_out.p, n * 2) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", n * 2);
+    if (cudaMalloc(&d_in.p, n ? n : 1) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", n);
+    if (cudaMalloc(&d_out.p, n ? n * 2 : 2) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", n * 2);
     CU(cudaMemcpyAsync(d_in.p, text, n, cudaMemcpyHostToDevice, ctx->stream));
     int rc = encode_device(ctx, d_in.as<uint8_t>(), n, merges, m, d_out.as<uint16_t>(), out_n, stats);
     if (rc) return rc;
