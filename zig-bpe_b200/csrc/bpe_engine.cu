@@ -142,6 +142,7 @@ template <class TokT> struct Sequence {
     size_t cap_slots = 0;   // allocated slots per buffer (multiple of TILE)
     size_t n_slots = 0;     // slots in use (multiple of TILE)
     uint64_t live = 0;      // live tokens (host view; may lag the device by one step)
+    size_t dense_end = 0;   // slots at/after this index are padding holes (set by the load and by every compaction)
     DevBuf halo, run_local, run_full, tile_live, tile_off, total, done_counter;
     TokT* tok() const { return buf[cur].as<TokT>(); }
     TokT* other() const { return buf[cur ^ 1].as<TokT>(); }
@@ -153,6 +154,7 @@ static int seq_init(bpe_ctx* ctx, Sequence<TokT>& sq, const uint8_t* d_text, siz
     sq.cap_slots = round_up(n ? n : 1, TILE);
     sq.n_slots = sq.cap_slots;
     sq.live = n;
+    sq.dense_end = n;
     CU(sq.buf[0].alloc(sq.cap_slots * sizeof(TokT)));
     CU(sq.buf[1].alloc(sq.cap_slots * sizeof(TokT)));
     size_t nt = sq.cap_slots / TILE;
@@ -192,6 +194,7 @@ static int seq_compact(bpe_ctx* ctx, Sequence<TokT>& sq, uint64_t* new_live) {
     sq.cur ^= 1;
     sq.n_slots = ns;
     sq.live = total;
+    sq.dense_end = (size_t)total;
     if (new_live) *new_live = total;
     return BPE_OK;
 }
@@ -509,7 +512,7 @@ static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uint32_t
     R.prof.mark(K_APPLY);
     if (ctx->dist.world > 1) {
         // describe this shard's (post-merge) ends, then one all-reduce sums the deltas and gathers the edges
-        BPE_LAUNCH(edge_kernel<uint16_t>, 1, 32, ctx->stream, R.sq.tok(), R.sq.n_slots, R.edges(), ctx->dist.rank, ctx->dist.world,
+        BPE_LAUNCH(edge_kernel<uint16_t>, 1, 32, ctx->stream, R.sq.tok(), R.sq.n_slots, R.sq.dense_end, R.edges(), ctx->dist.rank, ctx->dist.world,
                       R.d_ctl(), R.nab(), 1);
         ctx->launches++;
         if (!ctx->dist.allreduce(R.delta.p, R.exchange_words(), DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-reduce of the merge deltas failed");
@@ -566,7 +569,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     {
         CU(cudaFuncSetAttribute(byte_pair_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HIST_SMEM));
         if (multi) {  // the pair that straddles two shards belongs to the left one: it needs the next shard's first byte
-            BPE_LAUNCH(edge_kernel<uint16_t>, 1, 32, ctx->stream, R.sq.tok(), R.sq.n_slots, R.edges(), ctx->dist.rank, ctx->dist.world,
+            BPE_LAUNCH(edge_kernel<uint16_t>, 1, 32, ctx->stream, R.sq.tok(), R.sq.n_slots, R.sq.dense_end, R.edges(), ctx->dist.rank, ctx->dist.world,
                           R.d_ctl(), R.nab(), 0);
             ctx->launches++;
             if (!ctx->dist.allreduce(R.edges(), (size_t)ctx->dist.world * 16, DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-reduce of the shard edges failed");
@@ -779,7 +782,7 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
     auto one_pass = [&](uint32_t A, uint32_t B, uint32_t X) -> int {
         const uint32_t nt = sq.ntiles();
         if (multi) {
-            BPE_LAUNCH(edge_kernel<TokT>, 1, 32, ctx->stream, sq.tok(), sq.n_slots, edges, ctx->dist.rank, ctx->dist.world, d_ctl,
+            BPE_LAUNCH(edge_kernel<TokT>, 1, 32, ctx->stream, sq.tok(), sq.n_slots, sq.dense_end, edges, ctx->dist.rank, ctx->dist.world, d_ctl,
                        &d_ctl->cntAB, 0);
             ctx->launches += 1;
             if (!ctx->dist.allreduce(edges, (size_t)ctx->dist.world * 16, DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-reduce of the shard edges failed");

@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(HALO_THREADS) halo_kernel(const TokT* __restri
 // shard's own live-token count, because after the all-reduce only the global merged count is left.
 // =========================================================================================
 template <class TokT>
-__global__ void edge_kernel(const TokT* __restrict__ tok, size_t n_slots, EdgeInfo* all, int rank, int world,
+__global__ void edge_kernel(const TokT* __restrict__ tok, size_t n_slots, size_t tail_hint, EdgeInfo* all, int rank, int world,
                             StepCtl* ctl, const uint32_t* nab_local, int account) {
     const TokT H = (TokT)TokTraits<TokT>::hole;
     const uint32_t lane = threadIdx.x & 31u;
@@ -601,7 +601,8 @@ __global__ void edge_kernel(const TokT* __restrict__ tok, size_t n_slots, EdgeIn
     // ---- last two live tokens and the run of equal tokens that ends the shard ----
     uint32_t n = 0, run = 0, all_same = 1, lastv = 0, lasts[2] = {0, 0};
     bool stop = false;
-    for (size_t top = n_slots; top > 0 && !stop;) {
+    // everything at or beyond tail_hint is padding (holes written by the load / the last compaction)
+    for (size_t top = tail_hint < n_slots ? tail_hint : n_slots; top > 0 && !stop;) {
         const size_t base = top >= 32 ? top - 32 : 0;
         const size_t i = base + lane;
         const uint32_t v = i < top ? (uint32_t)tok[i] : (uint32_t)H;
