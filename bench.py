@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--bytes", type=int, default=GB, help="corpus bytes PER JOB at N=1; per GPU the shard is bytes (weak scaling)")
+    ap.add_argument("--bytes", type=int, default=GB, help="corpus bytes of the whole job (BASELINE config 3: 1 GB); N GPUs hold contiguous shards of bytes/N")
     ap.add_argument("--vocab", type=int, default=8192)
     ap.add_argument("--cpu-steps", type=int, default=2, help="merge steps timed for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -115,7 +115,7 @@ def run_reference(args, rank, world):
     sample = f"first {ksteps} merge steps (full recount each, as the reference does) of the {n}-byte corpus per step"
     line = {"impl": "reference", "metric": "train_merges_per_sec", "value": val, "unit": "merges/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic (synthcorpus-v1 byte variant, seed 0x5EED0003)",
+            "scaling": "strong", "vs_baseline": None, "dtype": "u16", "data": "synthetic (synthcorpus-v1 byte variant, seed 0x5EED0003)",
             "config": {"workload": f"C3: {n}-byte synthetic byte corpus, vocab {args.vocab} (train)", "bytes": n, "vocab": args.vocab},
             "cpu_baseline": {"value": val, "unit": "merges/s", "cores": 1, "kind": "port", "sample": sample,
                              "host_cores_available": os.cpu_count()},
@@ -142,17 +142,21 @@ def main():
     dev = torch.device("cuda", local_rank)
     uid = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
         box = [zb.Engine.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         uid = box[0]
     eng = zb.Engine(device=local_rank, rank=rank, world=world, nccl_unique_id=uid)
 
-    # weak scaling: every GPU holds `bytes` of the corpus (rank r = bytes [r*n, (r+1)*n) of one stream)
-    n = args.bytes
+    # strong scaling (BASELINE config 3: the same 1 GB corpus on 1/2/4/8 GPUs): rank r holds the r-th contiguous shard
+    total_bytes = args.bytes
+    lo, hi = total_bytes * rank // world, total_bytes * (rank + 1) // world
+    n = hi - lo
     pinned = torch.empty(n, dtype=torch.uint8, pin_memory=True)
     host = pinned.numpy()
-    sc.generate(n, sc.SEED_C3, sc.BYTE, offset=rank * n, out=host)
+    sc.generate(n, sc.SEED_C3, sc.BYTE, offset=lo, out=host)
     d_text = pinned.to(dev, non_blocking=False)
     n_merges_target = args.vocab - 256
 
@@ -219,7 +223,7 @@ def main():
         te = torch.tensor([e_ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": got_e / (float(te[0]) / 1000.0), "unit": "merges/s", "h2d_bytes_per_step": n * world,
+        e2e = {"value": got_e / (float(te[0]) / 1000.0), "unit": "merges/s", "h2d_bytes_per_step": total_bytes,
                "d2h_bytes_per_step": int(len(m2)) * (6 + 8), "steps": ksteps}
         assert np.array_equal(m2, merges), "host-buffer and device-resident runs disagree"
 
@@ -238,8 +242,8 @@ def main():
         te = torch.tensor([enc_ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        enc = {"metric": "encode_input_GB_per_sec", "value": n * world / 1e9 / (float(te[0]) / 1000.0), "unit": "GB/s", "merges": int(len(merges)),
-               "bytes_per_gpu": n, "ids_out_rank0": int(n_ids), "passes": int(len(merges)), "gpu_launches": int(est["kernel_launches"]),
+        enc = {"metric": "encode_input_GB_per_sec", "value": total_bytes / 1e9 / (float(te[0]) / 1000.0), "unit": "GB/s", "merges": int(len(merges)),
+               "bytes_rank0": n, "ids_out_rank0": int(n_ids), "passes": int(len(merges)), "gpu_launches": int(est["kernel_launches"]),
                "scan_GBps_per_gpu": est["scanned_slots"] * 2 / 1e9 / (est["device_ms"] / 1000.0),
                "note": "reference semantics: one pass per merge in list order (exact for any list); algorithmic bytes n + 2*n_out"}
         del d_out
@@ -257,11 +261,13 @@ def main():
     achieved = alg_bytes / 1e9 / (merge_ms / 1000.0) if merge_ms > 0 else None
     line = {
         "metric": "train_merges_per_sec", "value": value, "unit": "merges/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": timed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": timed_ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u16", "data": "synthetic (synthcorpus-v1 byte variant, seed 0x5EED0003)",
-        "config": {"workload": f"C3: {n}-byte synthetic byte corpus per GPU, vocab {args.vocab} (train, {n_merges_target} merges/step)",
-                   "bytes_per_gpu": n, "vocab": args.vocab, "merges_per_step": int(len(merges)),
-                   "l2": "inputs (>= 2 GB of u16 token slots per scan) are larger than the 126 MB L2; no explicit flush",
+        "config": {"workload": f"C3: {total_bytes}-byte synthetic byte corpus, vocab {args.vocab} (train, {n_merges_target} merges/step), "
+                               f"contiguous shards over {world} GPU(s)",
+                   "bytes": total_bytes, "bytes_rank0": n, "vocab": args.vocab, "merges_per_step": int(len(merges)),
+                   "l2": "the resident sequence (2 B x token slots) is larger than the 126 MB L2 for all but the last steps at N>=4; consecutive "
+                         "passes alternate direction so the tail of one pass is reused from L2 by the next; no explicit flush",
                    "timing": "host clock between barrier+synchronize pairs, max over ranks; the library's CUDA-event device_ms is reported beside it"},
         "device_ms_per_step": dev_ms_max / args.steps,
         "gpu_launches": int(launches),

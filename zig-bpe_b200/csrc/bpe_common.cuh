@@ -129,7 +129,7 @@ struct StepCtl {
     uint32_t n_heavy;      // entries appended to the heavy-key list (may exceed its capacity)
     uint32_t hist_nonzero; // distinct byte pairs found by the initial count
     uint32_t zpop_max;     // upper bound on the keys homed in any one chunk of the reference table
-    uint32_t pad0;
+    uint32_t apply_done;   // CTAs of apply_kernel that have finished (last one runs the next selection)
     // device-driven stepping
     uint32_t step;         // merges learned so far (= index of the merge being decided)
     uint32_t want_steps;

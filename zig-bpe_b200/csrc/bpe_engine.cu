@@ -497,7 +497,7 @@ static int launch_merge(bpe_ctx* ctx, TokT* tok, const TileHalo<TokT>* halo, uin
 }
 
 // the part of a step after the merge has been chosen: halo, merge, apply (all read the merge from ctl)
-static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uint32_t step_index) {
+static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uint32_t step_index, bool fuse_select) {
     const uint32_t nt = R.sq.ntiles();
     R.prof.mark(K_HALO);
     BPE_LAUNCH((halo_kernel<uint16_t, true>), (nt + HALO_THREADS - 1) / HALO_THREADS, HALO_THREADS, ctx->stream, R.sq.tok(),
@@ -517,8 +517,8 @@ static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uint32_t
         ctx->launches++;
         if (!ctx->dist.allreduce(R.delta.p, R.exchange_words(), DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-reduce of the merge deltas failed");
     }
-    BPE_LAUNCH_NS(apply_kernel, (4 * n_ids + 3 + 255) / 256, 256, ctx->stream, R.tm.view(), R.delta.as<uint32_t>(), R.vcap, R.d_ctl(),
-                  R.tm.zig(), n_ids, R.hl());
+    BPE_LAUNCH(apply_kernel, (4 * n_ids + 3 + 255) / 256, 256, ctx->stream, R.tm.view(), R.delta.as<uint32_t>(), R.vcap, R.d_ctl(),
+                  R.tm.zig(), n_ids, R.hl(), R.d_rec(), fuse_select ? 1 : 0);
     ctx->launches += 2;
     CU(cudaGetLastError());
     return BPE_OK;
@@ -611,6 +611,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
 
     uint32_t steps_done = 0;
     bool finished = false;
+    bool selection_pending = false;  // the last enqueued apply_kernel also selects the following merge
     while (!finished) {
         StepCtl* hc = R.hc();
         // ---- housekeeping between batches (the table and the sequence are quiescent here) ----
@@ -633,10 +634,13 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
         }
         // ---- one batch of device-driven steps ----
         for (uint32_t k = 0; k < K; k++) {
-            prof.mark(K_ARGMAX);
-            BPE_LAUNCH(select_kernel, 1, 1024, ctx->stream, R.tm.view(), R.hl(), R.d_ctl(), R.d_rec(), R.tm.zig());
-            ctx->launches += 1;
-            rc = enqueue_step_tail(ctx, R, 256 + steps_done + k + 1, steps_done + k);
+            if (!selection_pending) {  // otherwise the previous apply_kernel already chose this step's merge
+                prof.mark(K_ARGMAX);
+                BPE_LAUNCH(select_kernel, 1, 1024, ctx->stream, R.tm.view(), R.hl(), R.d_ctl(), R.d_rec(), R.tm.zig());
+                ctx->launches += 1;
+            }
+            selection_pending = !debug_sync;
+            rc = enqueue_step_tail(ctx, R, 256 + steps_done + k + 1, steps_done + k, selection_pending);
             if (rc) return rc;
         }
         prof.mark(K_HOSTGAP);
@@ -652,6 +656,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
             fprintf(stderr, "[bpe r%d] step %u halt %u max %u ntied %u live_keys %u inserted %u cap %u n_heavy %u theta %u zcap %u slots %zu live %llu\n",
                     ctx->dist.rank, hc->step, hc->halt, hc->max_count, hc->ntied, hc->live_keys, hc->n_inserted, R.tm.cap, hc->n_heavy,
                     R.theta, R.tm.zcap, R.sq.n_slots, (unsigned long long)R.sq.live);
+        if (hc->halt != H_NONE) selection_pending = false;  // the host intervenes: start the next batch with a select_kernel
         switch (hc->halt) {
             case H_NONE: break;
             case H_DONE: finished = true; break;
@@ -695,7 +700,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
                 if (!had_fast) R.st.tie_slow_steps++;
                 BPE_LAUNCH_NS(ctl_set_kernel, 1, 1, ctx->stream, R.d_ctl(), R.d_rec(), 0, 0u, 0, 0u, 1, 1, w, maxc);
                 ctx->launches++;
-                rc = enqueue_step_tail(ctx, R, 256 + steps_done + 1, steps_done);
+                rc = enqueue_step_tail(ctx, R, 256 + steps_done + 1, steps_done, false);
                 if (rc) return rc;
                 rc = read_ctl(ctx, R, false);
                 if (rc) return rc;

@@ -322,7 +322,7 @@ __device__ __forceinline__ bool zig_first_free(const ZigPop& z, uint32_t zcap, u
 // select_kernel (single CTA): the device-driven replacement of "sort, take [0]" (:186-193). Scans
 // the heavy list for the maximum and its ties, then commits the merge (unique maximum, or a tie
 // the occupancy test settles) or halts the loop for the host.
-__global__ void __launch_bounds__(1024) select_kernel(PairTable tbl, HeavyList hl, StepCtl* ctl, MergeRec* rec, ZigPop z) {
+__device__ __forceinline__ void select_body(const PairTable& tbl, HeavyList hl, StepCtl* ctl, MergeRec* rec, ZigPop z) {
     __shared__ uint32_t sh[1024];
     __shared__ uint32_t s_ntied;
     __shared__ uint32_t s_mode;  // 0 done, 1 settle the tie here
@@ -334,22 +334,24 @@ __global__ void __launch_bounds__(1024) select_kernel(PairTable tbl, HeavyList h
         if (threadIdx.x == 0) ctl->halt = H_DONE;
         return;
     }
+    const uint32_t nthr = blockDim.x;
+    hl.theta = ctl->theta;
     const uint32_t n = ctl->n_heavy < hl.cap ? ctl->n_heavy : hl.cap;
     uint32_t m = 0;
     constexpr int SC = 16;  // list entries kept in registers per thread (covers lists up to 16K keys)
     uint32_t cs[SC], cc[SC];
 #pragma unroll
     for (int k = 0; k < SC; k++) {
-        const uint32_t i = threadIdx.x + (uint32_t)k * 1024u;
+        const uint32_t i = threadIdx.x + (uint32_t)k * nthr;
         cs[k] = i < n ? hl.slots[i] : 0u;
     }
 #pragma unroll
     for (int k = 0; k < SC; k++) {
-        const uint32_t i = threadIdx.x + (uint32_t)k * 1024u;
+        const uint32_t i = threadIdx.x + (uint32_t)k * nthr;
         cc[k] = i < n ? tbl.counts[cs[k]] : 0u;
         m = cc[k] > m ? cc[k] : m;
     }
-    for (uint32_t i = threadIdx.x + (uint32_t)SC * 1024u; i < n; i += 1024u) {
+    for (uint32_t i = threadIdx.x + (uint32_t)SC * nthr; i < n; i += nthr) {
         uint32_t c = tbl.counts[hl.slots[i]];
         m = c > m ? c : m;
     }
@@ -365,12 +367,12 @@ __global__ void __launch_bounds__(1024) select_kernel(PairTable tbl, HeavyList h
     if (list_ok) {
 #pragma unroll
         for (int k = 0; k < SC; k++) {
-            if (cc[k] == m && threadIdx.x + (uint32_t)k * 1024u < n) {
+            if (cc[k] == m && threadIdx.x + (uint32_t)k * nthr < n) {
                 uint32_t idx = atomicAdd(&s_ntied, 1u);
                 if (idx < (uint32_t)MAXTIE) ctl->tie_keys[idx] = tbl.keys[cs[k]];
             }
         }
-        for (uint32_t i = threadIdx.x + (uint32_t)SC * 1024u; i < n; i += 1024u) {
+        for (uint32_t i = threadIdx.x + (uint32_t)SC * nthr; i < n; i += nthr) {
             uint32_t s = hl.slots[i];
             if (tbl.counts[s] == m) {
                 uint32_t idx = atomicAdd(&s_ntied, 1u);
@@ -425,6 +427,10 @@ __global__ void __launch_bounds__(1024) select_kernel(PairTable tbl, HeavyList h
     ctl->tie_winner = winner;
     if (status == TIE_FAST_OK && !(ctl->flags & F_CHECK_TIES)) { commit_merge(ctl, rec, winner, m); ctl->fast_ties += 1; }
     else ctl->halt = H_REPLAY;
+}
+
+__global__ void __launch_bounds__(1024) select_kernel(PairTable tbl, HeavyList hl, StepCtl* ctl, MergeRec* rec, ZigPop z) {
+    select_body(tbl, hl, ctl, rec, z);
 }
 
 __global__ void heavy_ties_kernel(PairTable tbl, HeavyList hl, StepCtl* ctl) {
@@ -1095,8 +1101,8 @@ __global__ void __launch_bounds__(THREADS, RING_CTAS_PER_SM) merge_tma_kernel(To
 // births / deaths), one thread per token id, then advance the device-side step counter.
 // delta layout: [0,vcap) cntL, [vcap,2*vcap) cntR, [2*vcap] cntXX, [2*vcap+1] cntAB
 // =========================================================================================
-__global__ void apply_kernel(PairTable tbl, uint32_t* __restrict__ delta, uint32_t vcap, StepCtl* ctl,
-                             ZigPop z, uint32_t n_ids, HeavyList hl) {
+__global__ void __launch_bounds__(256) apply_kernel(PairTable tbl, uint32_t* __restrict__ delta, uint32_t vcap, StepCtl* ctl,
+                             ZigPop z, uint32_t n_ids, HeavyList hl, MergeRec* rec, int fuse_select) {
     if (ctl->halt) return;
     // thread t: token id p = t / 4, side = left/right neighbour, op = retire the old pair / credit the new one.
     // The two ops of a (p, side) sit in adjacent lanes so the four table round trips overlap.
@@ -1130,6 +1136,20 @@ __global__ void apply_kernel(PairTable tbl, uint32_t* __restrict__ delta, uint32
         ctl->live_tokens -= ab;
         ctl->step += 1;
     }
+    if (!fuse_select) return;
+    // the last CTA to finish chooses the next merge (saves a launch and its gap on every step)
+    __shared__ uint32_t s_is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(&ctl->apply_done, 1u);
+        s_is_last = (prev == gridDim.x - 1u) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_is_last) return;
+    if (threadIdx.x == 0) ctl->apply_done = 0;
+    __threadfence();
+    select_body(tbl, hl, ctl, rec, z);
 }
 
 
