@@ -120,11 +120,29 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": val, "unit": "merges/s", "cores": 1, "kind": "port", "sample": sample,
                              "host_cores_available": os.cpu_count()},
             "e2e": {"value": val, "unit": "merges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """Print the one JSON line on the real stdout (libraries such as NCCL write banners to fd 1, which is
+    pointed at stderr for the duration of the run)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
 
 
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -142,8 +160,6 @@ def main():
     dev = torch.device("cuda", local_rank)
     uid = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
         box = [zb.Engine.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
@@ -292,7 +308,7 @@ def main():
         line["cpu_baseline"] = {"value": k / cpu_s, "unit": "merges/s", "cores": 1, "kind": "port",
                                 "sample": f"first {k} merge steps (verbatim per-step recount) of the same {n}-byte corpus, {cpu_s:.1f} s",
                                 "host_cores_available": os.cpu_count(), "matches_gpu_merges": ok}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
