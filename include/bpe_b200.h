@@ -96,6 +96,9 @@ const char* bpe_last_error(const bpe_ctx* ctx);
  *   "merge_impl"          0 (default): register-streaming merge kernel, one CTA per tile;
  *                         1: merge pass fed by a TMA ring (cp.async.bulk + mbarrier, persistent CTAs) —
  *                            measured slower on B200 for this access pattern, kept for comparison
+ *   "xchg_impl"           multi-GPU per-step exchange. 0 (default): peer-memory mailboxes over NVLink (each rank
+ *                         writes its deltas into every peer's mailbox and raises a flag; falls back to 1 when
+ *                         peer access is unavailable); 1: NCCL all-reduce
  *   "time_phases"         1: fill the reference's TimeStats buckets (synchronises per phase)
  *   "profile"             1: fill bpe_stats_t.kernel_ms / kernel_calls for every kernel class;
  *                         2: only the merge kernel (two event records per merge step)

@@ -62,6 +62,8 @@ static inline int __syncthreads_or(int pred) {
 }
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
 static inline void __threadfence() {}
+static inline void __threadfence_system() {}
+template <class T> static inline T __ldcg(const T* p) { return *p; }
 
 // ---- atomics (single OS thread: plain read-modify-write) --------------------------------
 template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = (T)(o + v); return o; }

@@ -87,6 +87,7 @@ enum : uint32_t {
     ERR_COUNT_UNDERFLOW = 1u << 2,
     ERR_VERIFY_MISMATCH = 1u << 3,
     ERR_ZCNT_OVERFLOW = 1u << 4,
+    ERR_PEER_TIMEOUT = 1u << 5,   // a peer's deltas did not arrive (multi-GPU peer exchange)
 };
 
 // tie-resolution verdicts (StepCtl::tie_status)
@@ -158,6 +159,16 @@ struct EdgeInfo {
     uint32_t pad[6];
 };
 static_assert(sizeof(EdgeInfo) == 64, "EdgeInfo is 16 words");
+
+// Multi-GPU peer exchange (NVLink peer memory instead of an NCCL all-reduce): every rank owns a mailbox
+// [2 parities][world slots][xw words] + one arrival flag per sender; peers write their deltas straight
+// into it and raise their flag, the consumer sums the slots while it applies them.
+constexpr int MAX_PEERS = 8;
+struct PeerSet {
+    uint32_t* mbox[MAX_PEERS];   // mailbox base of every rank (own entry = local pointer)
+    uint32_t* flags[MAX_PEERS];  // flags[p][sender] on rank p
+    uint32_t slot_words;         // capacity of one mailbox slot in words
+};
 
 // Per-tile neighbourhood, produced by halo_kernel before each merge pass: what a tile needs to
 // know about live tokens outside itself. hole value = "no such token" (sequence start/end).

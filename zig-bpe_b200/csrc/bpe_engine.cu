@@ -55,7 +55,7 @@ struct bpe_ctx {
     std::string err;
     // options
     long verify_recount = 0, force_slow_tiebreak = 0, check_tiebreak = 0, compact_pct = 85, table_log2 = 0,
-         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0;
+         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0;
     int num_sms = 148;
     DistComm dist;  // world == 1 when single GPU
     uint64_t launches = 0;
@@ -510,7 +510,15 @@ static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uint32_t
         if (rcm) return rcm;
     }
     R.prof.mark(K_APPLY);
-    if (ctx->dist.world > 1) {
+    const bool peer = ctx->dist.world > 1 && ctx->dist.peer_ok && ctx->xchg_impl == 0 && R.exchange_words() <= ctx->dist.peers.slot_words;
+    const uint32_t parity = step_index & 1u, epoch = ctx->dist.epoch_base + step_index + 1u;
+    if (peer) {
+        // push this rank's deltas + shard ends into every peer's mailbox over NVLink and raise the arrival flag
+        BPE_LAUNCH(xchg_kernel<uint16_t>, 32, 256, ctx->stream, R.sq.tok(), R.sq.n_slots, R.sq.dense_end, R.delta.as<uint32_t>(),
+                   (uint32_t)R.edge_off, (uint32_t)(2 * R.vcap / 4), R.nab(), ctx->dist.peers, ctx->dist.rank, ctx->dist.world, parity, epoch,
+                   R.d_ctl(), R.sq.done_counter.as<uint32_t>());
+        ctx->launches++;
+    } else if (ctx->dist.world > 1) {
         // describe this shard's (post-merge) ends, then one all-reduce sums the deltas and gathers the edges
         BPE_LAUNCH(edge_kernel<uint16_t>, 1, 32, ctx->stream, R.sq.tok(), R.sq.n_slots, R.sq.dense_end, R.edges(), ctx->dist.rank, ctx->dist.world,
                       R.d_ctl(), R.nab(), 1);
@@ -518,7 +526,8 @@ static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uint32_t
         if (!ctx->dist.allreduce(R.delta.p, R.exchange_words(), DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-reduce of the merge deltas failed");
     }
     BPE_LAUNCH(apply_kernel, (4 * n_ids + 3 + 255) / 256, 256, ctx->stream, R.tm.view(), R.delta.as<uint32_t>(), R.vcap, R.d_ctl(),
-                  R.tm.zig(), n_ids, R.hl(), R.d_rec(), fuse_select ? 1 : 0);
+                  R.tm.zig(), n_ids, R.hl(), R.d_rec(), fuse_select ? 1 : 0, peer ? 1 : 0, ctx->dist.peers, ctx->dist.rank, ctx->dist.world,
+                  parity, epoch, (uint32_t)R.edge_off);
     ctx->launches += 2;
     CU(cudaGetLastError());
     return BPE_OK;
@@ -555,7 +564,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
 
     int rc = seq_init(ctx, R.sq, d_text, n);
     if (rc) return rc;
-    R.vcap = (uint32_t)vocab_size + 1;
+    R.vcap = ((uint32_t)vocab_size + 2u) & ~1u;  // even, so the cntL|cntR block is a whole number of 16-byte vectors
     R.edge_off = ((size_t)2 * R.vcap + 2 + 15) / 16 * 16;
     CU(R.delta.alloc(R.exchange_words() * 4)); CU(R.hist.alloc(65536 * 4));
     CU(R.ctl.alloc(sizeof(StepCtl))); CU(R.rec.alloc(want * sizeof(MergeRec)));
@@ -717,6 +726,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
         CU(cudaGetLastError());
         if (steps_done >= want) finished = true;
     }
+    ctx->dist.epoch_base += (uint32_t)want + 8u;  // arrival flags of the peer exchange never go backwards
     // merge list back to the host
     std::vector<MergeRec> recs(steps_done);
     if (steps_done) CU(cudaMemcpyAsync(recs.data(), R.rec.p, steps_done * sizeof(MergeRec), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1089,6 +1099,10 @@ int bpe_ctx_create_dist(bpe_ctx** out, int device, int rank, int world, const vo
             *out = nullptr;
             return fail(nullptr, BPE_ERR_CUDA, "NCCL init failed: %s", err.c_str());
         }
+#ifndef BPE_EMUL
+        // NVLink peer mailboxes for the per-step exchange; if peer access is unavailable the NCCL all-reduce is used
+        if (!(*out)->dist.init_peers(&err)) g_create_err = "peer exchange disabled: " + err;
+#endif
     }
     return BPE_OK;
 }
@@ -1108,6 +1122,7 @@ int bpe_ctx_create_dist_cb(bpe_ctx** out, int rank, int world, dist_allreduce_cb
 void bpe_ctx_destroy(bpe_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    ctx->dist.destroy_peers();
     ctx->dist.destroy();
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     ctx->cache.clear();
@@ -1128,6 +1143,7 @@ int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value) {
     else if (s == "profile") ctx->profile = value;
     else if (s == "debug") ctx->debug = value;
     else if (s == "merge_impl") ctx->merge_impl = value;
+    else if (s == "xchg_impl") ctx->xchg_impl = value;
     else return fail(ctx, BPE_ERR_INVALID_ARG, "unknown option '%s'", name);
     return BPE_OK;
 }

@@ -581,16 +581,17 @@ __global__ void __launch_bounds__(HALO_THREADS) halo_kernel(const TokT* __restri
 // buffer and zero the other ranks' slots (the buffer is summed by the all-reduce). It also keeps the
 // shard's own live-token count, because after the all-reduce only the global merged count is left.
 // =========================================================================================
+// one warp; zero_others: clear the other ranks' slots (all-reduce path: the buffer is summed)
 template <class TokT>
-__global__ void edge_kernel(const TokT* __restrict__ tok, size_t n_slots, size_t tail_hint, EdgeInfo* all, int rank, int world,
-                            StepCtl* ctl, const uint32_t* nab_local, int account) {
+__device__ __forceinline__ void edge_body(const TokT* __restrict__ tok, size_t n_slots, size_t tail_hint, EdgeInfo* all, int rank,
+                                          int world, StepCtl* ctl, const uint32_t* nab_local, int account, bool zero_others) {
     const TokT H = (TokT)TokTraits<TokT>::hole;
     const uint32_t lane = threadIdx.x & 31u;
-    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
-    // zero every other slot
-    uint32_t* words = reinterpret_cast<uint32_t*>(all);
-    for (uint32_t w = lane; w < (uint32_t)world * 16u; w += 32u)
-        if ((int)(w / 16u) != rank) words[w] = 0;
+    if (zero_others) {
+        uint32_t* words = reinterpret_cast<uint32_t*>(all);
+        for (uint32_t w = lane; w < (uint32_t)world * 16u; w += 32u)
+            if ((int)(w / 16u) != rank) words[w] = 0;
+    }
     EdgeInfo* e = &all[rank];
     // ---- first three live tokens: the warp scans 32 slots at a time ----
     uint32_t nf = 0, fv[3] = {0, 0, 0};
@@ -642,6 +643,57 @@ __global__ void edge_kernel(const TokT* __restrict__ tok, size_t n_slots, size_t
         for (int k = 0; k < 6; k++) e->pad[k] = 0;
         if (account && !ctl->halt) ctl->local_live -= *nab_local;
     }
+}
+
+template <class TokT>
+__global__ void edge_kernel(const TokT* __restrict__ tok, size_t n_slots, size_t tail_hint, EdgeInfo* all, int rank, int world,
+                            StepCtl* ctl, const uint32_t* nab_local, int account) {
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    edge_body<TokT>(tok, n_slots, tail_hint, all, rank, world, ctl, nab_local, account, true);
+}
+
+// xchg_kernel (multi-GPU, peer-memory path): block 0 describes the shard's ends, then all blocks push
+// this rank's deltas (+ its EdgeInfo) into slot `rank` of every peer's mailbox over NVLink, clear the
+// local deltas, and the last block to finish raises this rank's arrival flag on every peer.
+template <class TokT>
+__global__ void __launch_bounds__(256) xchg_kernel(const TokT* __restrict__ tok, size_t n_slots, size_t tail_hint,
+                                                   uint32_t* __restrict__ delta, uint32_t edge_off, uint32_t zero_vecs,
+                                                   const uint32_t* nab_local, PeerSet ps, int rank, int world,
+                                                   uint32_t parity, uint32_t epoch, StepCtl* ctl, uint32_t* done_counter) {
+    __shared__ uint32_t s_last;
+    if (ctl->halt) return;
+    EdgeInfo* edges = reinterpret_cast<EdgeInfo*>(delta + edge_off);
+    const size_t slot = ((size_t)parity * (size_t)world + (size_t)rank) * ps.slot_words;
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < 32) edge_body<TokT>(tok, n_slots, tail_hint, edges, rank, world, ctl, nab_local, 1, false);
+        __syncthreads();
+        // my EdgeInfo slot (16 words) to every peer
+        for (uint32_t i = threadIdx.x; i < 16u * (uint32_t)world; i += blockDim.x) {
+            const uint32_t p = i / 16u, w = i % 16u;
+            ps.mbox[p][slot + edge_off + (uint32_t)rank * 16u + w] = delta[edge_off + (uint32_t)rank * 16u + w];
+        }
+    }
+    // deltas: 16-byte stores to every peer, then clear the local copy for the next merge pass
+    const uint32_t nvec = edge_off / 4u;
+    uint4* dl = reinterpret_cast<uint4*>(delta);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
+        const uint4 v = dl[i];
+        for (int p = 0; p < world; p++) reinterpret_cast<uint4*>(ps.mbox[p] + slot)[i] = v;
+        // (the vector holding cntXX / cntAB is left alone: block 0 still reads it, the next halo pass clears it)
+        if (i < zero_vecs && (v.x | v.y | v.z | v.w)) dl[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(done_counter, 1u);
+        s_last = (prev == gridDim.x - 1u) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    if ((int)threadIdx.x < world) *((volatile uint32_t*)&ps.flags[threadIdx.x][rank]) = epoch;
+    if (threadIdx.x == 0) *done_counter = 0;
+    __threadfence_system();
 }
 
 // =========================================================================================
@@ -1101,9 +1153,37 @@ __global__ void __launch_bounds__(THREADS, RING_CTAS_PER_SM) merge_tma_kernel(To
 // births / deaths), one thread per token id, then advance the device-side step counter.
 // delta layout: [0,vcap) cntL, [vcap,2*vcap) cntR, [2*vcap] cntXX, [2*vcap+1] cntAB
 // =========================================================================================
+// Peer mode (ps_on): the deltas are the sum over the mailbox slots the peers filled; wait for their
+// arrival flags first, and copy the gathered EdgeInfo slots to where the next halo pass reads them.
 __global__ void __launch_bounds__(256) apply_kernel(PairTable tbl, uint32_t* __restrict__ delta, uint32_t vcap, StepCtl* ctl,
-                             ZigPop z, uint32_t n_ids, HeavyList hl, MergeRec* rec, int fuse_select) {
+                             ZigPop z, uint32_t n_ids, HeavyList hl, MergeRec* rec, int fuse_select,
+                             int ps_on, PeerSet ps, int rank, int world, uint32_t parity, uint32_t epoch, uint32_t edge_off) {
     if (ctl->halt) return;
+    const uint32_t* mb = nullptr;
+    if (ps_on) {
+        if (threadIdx.x == 0) {
+            const volatile uint32_t* fl = ps.flags[rank];
+            for (int r = 0; r < world; r++) {
+                uint32_t spins = 0;
+                while ((int32_t)(fl[r] - epoch) < 0) {
+                    if (++spins > (1u << 28)) { atomicOr(&ctl->err, (uint32_t)ERR_PEER_TIMEOUT); break; }
+                }
+            }
+        }
+        __syncthreads();
+        __threadfence();
+        mb = ps.mbox[rank] + (size_t)parity * (size_t)world * ps.slot_words;
+        if (blockIdx.x == 0 && threadIdx.x < 16u * (uint32_t)world) {  // gathered shard ends for the next halo pass
+            const uint32_t r = threadIdx.x / 16u, w = threadIdx.x % 16u;
+            delta[edge_off + r * 16u + w] = __ldcg(mb + (size_t)r * ps.slot_words + edge_off + r * 16u + w);
+        }
+    }
+    auto cell_value = [&](uint32_t idx) -> uint32_t {
+        if (!ps_on) return delta[idx];
+        uint32_t sum = 0;
+        for (int r = 0; r < world; r++) sum += __ldcg(mb + (size_t)r * ps.slot_words + idx);
+        return sum;
+    };
     // thread t: token id p = t / 4, side = left/right neighbour, op = retire the old pair / credit the new one.
     // The two ops of a (p, side) sit in adjacent lanes so the four table round trips overlap.
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1112,25 +1192,25 @@ __global__ void __launch_bounds__(256) apply_kernel(PairTable tbl, uint32_t* __r
     hl.theta = ctl->theta;
     const uint32_t p = t >> 2, side = (t >> 1) & 1u, op = t & 1u;
     uint32_t c = 0;
-    uint32_t* cell = nullptr;
+    uint32_t cell = 0;
     if (p < n_ids && p <= X) {
-        cell = &delta[side ? vcap + p : p];
-        c = *cell;
+        cell = side ? vcap + p : p;
+        c = cell_value(cell);
     }
     __syncwarp();
     if (c) {
         if (op == 0) tbl_sub(tbl, side ? pair_key(B, p) : pair_key(p, A), c, ctl, z);
-        else { *cell = 0; tbl_add(tbl, side ? pair_key(X, p) : pair_key(p, X), c, ctl, z, hl); }
+        else { if (!ps_on) delta[cell] = 0; tbl_add(tbl, side ? pair_key(X, p) : pair_key(p, X), c, ctl, z, hl); }
     }
     const uint32_t t0 = 4u * n_ids;  // three more threads: adjacent occurrences, the merged pair itself, bookkeeping
     if (t == t0) {
-        const uint32_t xx = delta[2 * vcap];
+        const uint32_t xx = cell_value(2 * vcap);
         if (xx) tbl_sub(tbl, pair_key(B, A), xx, ctl, z);
     } else if (t == t0 + 1) {
-        const uint32_t xx = delta[2 * vcap];
+        const uint32_t xx = cell_value(2 * vcap);
         if (xx) tbl_add(tbl, pair_key(X, X), xx, ctl, z, hl);
     } else if (t == t0 + 2) {
-        const uint32_t ab = delta[2 * vcap + 1];
+        const uint32_t ab = cell_value(2 * vcap + 1);
         if (ab) tbl_sub(tbl, pair_key(A, B), ab, ctl, z);
         ctl->last_merged = ab;
         ctl->live_tokens -= ab;

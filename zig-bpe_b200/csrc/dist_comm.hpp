@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #ifndef BPE_EMUL
 #include <cuda_runtime.h>
@@ -82,6 +83,57 @@ struct DistComm {
         int op = kind == DIST_U32_SUM ? ncclSum : (kind == DIST_U64_MIN ? ncclMin : ncclMax);
         return nccl_api().AllReduce(buf, buf, count, dt, op, comm, stream) == ncclSuccess;
     }
+    bool allgather_bytes(const void* src, void* dst, size_t bytes_per_rank) {
+        return nccl_api().AllGather(src, dst, bytes_per_rank, ncclUint8, comm, stream) == ncclSuccess;
+    }
+
+    // ---- peer-memory mailboxes (NVLink): the per-step exchange of sharded training without NCCL ----
+    PeerSet peers;             // valid when peer_ok
+    bool peer_ok = false;
+    void* mbox_local = nullptr;
+    void* peer_mapped[MAX_PEERS] = {nullptr};
+    uint32_t epoch_base = 0;   // arrival flags only ever grow, across training calls
+    static size_t mbox_slot_words() { return (size_t)2 * 65552 + 16 + 16 * MAX_PEERS; }
+    // allocate this rank's mailbox, exchange IPC handles through NCCL, map every peer's mailbox
+    bool init_peers(std::string* err) {
+        if (world < 2 || world > MAX_PEERS) { if (err) *err = "peer exchange supports 2..8 ranks"; return false; }
+        const size_t slot = mbox_slot_words();
+        const size_t words = (size_t)2 * world * slot + 64;
+        if (cudaMalloc(&mbox_local, words * 4) != cudaSuccess) { if (err) *err = "mailbox allocation failed"; cudaGetLastError(); return false; }
+        cudaMemset(mbox_local, 0, words * 4);
+        cudaIpcMemHandle_t mine;
+        if (cudaIpcGetMemHandle(&mine, mbox_local) != cudaSuccess) { if (err) *err = "cudaIpcGetMemHandle failed"; cudaGetLastError(); return false; }
+        void* d_h = nullptr;
+        if (cudaMalloc(&d_h, sizeof(mine) * (size_t)(world + 1)) != cudaSuccess) { cudaGetLastError(); return false; }
+        cudaMemcpy((char*)d_h + sizeof(mine) * world, &mine, sizeof(mine), cudaMemcpyHostToDevice);
+        bool ok = allgather_bytes((char*)d_h + sizeof(mine) * world, d_h, sizeof(mine));
+        cudaStreamSynchronize(stream);
+        std::vector<cudaIpcMemHandle_t> all((size_t)world);
+        cudaMemcpy(all.data(), d_h, sizeof(mine) * world, cudaMemcpyDeviceToHost);
+        cudaFree(d_h);
+        if (!ok) { if (err) *err = "all-gather of IPC handles failed"; return false; }
+        for (int p = 0; p < world; p++) {
+            void* base = mbox_local;
+            if (p != rank) {
+                if (cudaIpcOpenMemHandle(&base, all[(size_t)p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    if (err) *err = "cudaIpcOpenMemHandle failed (no peer access?)";
+                    cudaGetLastError();
+                    return false;
+                }
+                peer_mapped[p] = base;
+            }
+            peers.mbox[p] = (uint32_t*)base;
+            peers.flags[p] = (uint32_t*)base + (size_t)2 * world * slot;
+        }
+        peers.slot_words = (uint32_t)slot;
+        peer_ok = true;
+        return true;
+    }
+    void destroy_peers() {
+        for (int p = 0; p < MAX_PEERS; p++) if (peer_mapped[p]) { cudaIpcCloseMemHandle(peer_mapped[p]); peer_mapped[p] = nullptr; }
+        if (mbox_local) { cudaFree(mbox_local); mbox_local = nullptr; }
+        peer_ok = false;
+    }
 };
 #else
 // emulation build (tests only): the exchange is delegated to a callback so that a world_size-2
@@ -92,6 +144,10 @@ inline bool dist_unique_id(void* out128, std::string*) { memset(out128, 0, 128);
 struct DistComm {
     int rank = 0, world = 1;
     dist_allreduce_cb cb = nullptr;
+    PeerSet peers;
+    bool peer_ok = false;
+    uint32_t epoch_base = 0;
+    void destroy_peers() {}
     bool init(int, int, const void*, int, std::string* err) { if (err) *err = "no NCCL in the emulation build"; return false; }
     void destroy() {}
     bool allreduce(void* buf, size_t count, int kind) {
