@@ -12,9 +12,15 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 box = [zb.Engine.nccl_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(box, src=0)
 eng = zb.Engine(device=lr, rank=rank, world=world, nccl_unique_id=box[0])
-shard = sc.generate(n, sc.SEED_C3, sc.BYTE, offset=rank * n)
+lo, hi = n * rank // world, n * (rank + 1) // world  # strong scaling: n is the whole corpus
+shard = sc.generate(hi - lo, sc.SEED_C3, sc.BYTE, offset=lo)
+n = hi - lo
 d = torch.from_numpy(shard).cuda()
 eng.set_option("profile", prof)
+if len(sys.argv) > 4:
+    eng.set_option("xchg_impl", int(sys.argv[4]))
+if rank == 0:
+    print("create note:", eng.lib.bpe_last_error(None).decode() or "(peer exchange ready)", flush=True)
 for rep in range(2):
     torch.cuda.synchronize(); dist.barrier()
     m, c = eng.train(None, vocab, device_ptr=d.data_ptr(), n=n)

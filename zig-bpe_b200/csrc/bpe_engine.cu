@@ -677,7 +677,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
                 ctx->launches++;
                 break;
             case H_HEAVY: {
-                // the list no longer covers the maximum: one full pass, then rebuild it at half the maximum
+                // the list no longer covers the maximum: one full pass, then rebuild it
                 prof.mark(K_ARGMAX);
                 BPE_LAUNCH_NS(reset_argmax_kernel, 1, 1, ctx->stream, R.d_ctl());
                 BPE_LAUNCH(argmax_kernel, grid_for(R.tm.cap, THREADS), THREADS, ctx->stream, R.tm.view(), R.d_ctl());
@@ -687,7 +687,9 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
                 if (rc) return rc;
                 hc = R.hc();
                 if (hc->max_count == 0) { finished = true; break; }  // "No more pairs to merge" (:188-191)
-                R.theta = hc->max_count / 2 > 1 ? hc->max_count / 2 : 1;
+                // theta = 3/4 of the maximum: a short list (the per-step select scans it) at the price of a few more rebuilds
+                R.theta = hc->max_count - hc->max_count / 4;
+                if (R.theta < 1) R.theta = 1;
                 rc = collect_heavy(ctx, R);
                 if (rc) return rc;
                 BPE_LAUNCH_NS(ctl_set_kernel, 1, 1, ctx->stream, R.d_ctl(), R.d_rec(), 1, R.theta, 0, 0u, 1, 0, 0u, 0u);
