@@ -920,6 +920,7 @@ struct Vocab {
 };
 static const uint32_t VOC_TOO_BIG = 0xFFFFFFFFu;
 static const uint32_t VOC_MAX_LEN = 1u << 19;
+static const size_t VOC_MAX_TOTAL = (size_t)1 << 28;  // all expansions together (host memory guard against doubling chains)
 
 // findMerge (:109-116) returns the FIRST merge whose new_token matches; decodeMerge (:118-138)
 // expands first then second, recursively. Ids whose expansion is undefined (unknown component or
@@ -934,6 +935,7 @@ static void build_vocab(const bpe_merge_t* merges, size_t m, Vocab& v) {
     v.len.assign(NID, 0);
     for (uint32_t b = 0; b < 256; b++) { exp[b].assign(1, (uint8_t)b); state[b] = 2; v.len[b] = 1; }
     std::vector<uint32_t> stack;
+    size_t total_exp = 256;
     for (uint32_t id = 256; id < NID; id++) {
         if (state[id] || def[id] < 0) continue;
         stack.push_back(id);
@@ -954,8 +956,10 @@ static void build_vocab(const bpe_merge_t* merges, size_t m, Vocab& v) {
             }
             if (wait) continue;
             if (bad) v.len[t] = 0;
-            else if (big || (uint64_t)v.len[parts[0]] + v.len[parts[1]] > VOC_MAX_LEN) v.len[t] = VOC_TOO_BIG;
+            else if (big || (uint64_t)v.len[parts[0]] + v.len[parts[1]] > VOC_MAX_LEN ||
+                     total_exp + v.len[parts[0]] + v.len[parts[1]] > VOC_MAX_TOTAL) v.len[t] = VOC_TOO_BIG;
             else {
+                total_exp += (size_t)v.len[parts[0]] + v.len[parts[1]];
                 exp[t] = exp[parts[0]];
                 exp[t].insert(exp[t].end(), exp[parts[1]].begin(), exp[parts[1]].end());
                 v.len[t] = (uint32_t)exp[t].size();
