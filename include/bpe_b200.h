@@ -57,7 +57,8 @@ typedef struct bpe_stats_t {
      * the context's stream between launches, resolved after the run; no extra synchronisation):
      * [0] load+initial count  [1] argmax+ties  [2] tie occupancy kernels  [3] table replay
      * [4] halo  [5] merge  [6] apply deltas  [7] compaction  [8] table rebuild / zcnt rebuild
-     * [9] host gap (status read-back until the next launch)  [10..11] reserved */
+     * [9] host gap (status read-back until the next launch)  [10] profile 3: slots scanned by the sampled
+     * merge launches  [11] reserved */
     double kernel_ms[12];
     uint64_t kernel_calls[12];
 } bpe_stats_t;
@@ -102,6 +103,8 @@ const char* bpe_last_error(const bpe_ctx* ctx);
  *   "time_phases"         1: fill the reference's TimeStats buckets (synchronises per phase)
  *   "profile"             1: fill bpe_stats_t.kernel_ms / kernel_calls for every kernel class;
  *                         2: only the merge kernel (two event records per merge step)
+ *                         3: the merge kernel of every 8th step only; kernel_ms[10] then holds the token slots
+ *                            those sampled launches scanned (lowest overhead; what bench.py uses)
  */
 int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value);
 

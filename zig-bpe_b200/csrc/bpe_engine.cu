@@ -245,11 +245,12 @@ static int table_ensure_zcnt(bpe_ctx* ctx, TableMem& tm, StepCtl* d_ctl, uint32_
 // of the earlier one. Nothing synchronises until the pool is exhausted or finish().
 enum { K_INIT = 0, K_ARGMAX, K_TIE, K_REPLAY, K_HALO, K_MERGE, K_APPLY, K_COMPACT, K_TABLE, K_HOSTGAP, K_NB = 12 };
 struct EvProfile {
-    int level = 0;  // 0 off, 1 all buckets, 2 merge kernel only (2 records per step)
+    int level = 0;  // 0 off, 1 all buckets, 2 merge kernel only (2 records per step), 3 merge kernel of every 8th step
     cudaStream_t st = 0;
     std::vector<cudaEvent_t>* ev = nullptr;  // pool owned by the context (reused across calls)
     std::vector<int> bucket;
     size_t used = 0;
+    bool sample_now = true;  // level 3: set per step by the caller
     double* ms = nullptr;
     uint64_t* calls = nullptr;
     void init(int lvl, cudaStream_t s, std::vector<cudaEvent_t>* pool, double* ms_out, uint64_t* calls_out) {
@@ -263,7 +264,7 @@ struct EvProfile {
         if (used == 0) return;
         cudaEventSynchronize((*ev)[used - 1]);
         for (size_t i = 0; i + 1 < used; i++) {
-            if (bucket[i] < 0 || (level == 2 && bucket[i] != K_MERGE)) continue;
+            if (bucket[i] < 0 || (level >= 2 && bucket[i] != K_MERGE)) continue;
             float t = 0;
             cudaEventElapsedTime(&t, (*ev)[i], (*ev)[i + 1]);
             ms[bucket[i]] += t;
@@ -274,7 +275,8 @@ struct EvProfile {
     }
     void mark(int b) {
         if (!level) return;
-        if (level == 2 && b != K_MERGE && b != K_APPLY) return;
+        if (level >= 2 && b != K_MERGE && b != K_APPLY) return;
+        if (level == 3 && !sample_now) return;
         if (used == ev->size()) drain(true);
         cudaEventRecord((*ev)[used], st);
         bucket[used] = b;
@@ -499,6 +501,8 @@ static int launch_merge(bpe_ctx* ctx, TokT* tok, const TileHalo<TokT>* halo, uin
 // the part of a step after the merge has been chosen: halo, merge, apply (all read the merge from ctl)
 static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uint32_t step_index, bool fuse_select) {
     const uint32_t nt = R.sq.ntiles();
+    R.prof.sample_now = (step_index % 8u) == 0;
+    if (R.prof.level == 3 && R.prof.sample_now) R.st.kernel_ms[10] += (double)R.sq.n_slots;  // slots of the sampled launches
     R.prof.mark(K_HALO);
     BPE_LAUNCH((halo_kernel<uint16_t, true>), (nt + HALO_THREADS - 1) / HALO_THREADS, HALO_THREADS, ctx->stream, R.sq.tok(),
                R.sq.n_slots, nt, R.sq.halo.as<TileHalo<uint16_t>>(), (const StepCtl*)R.d_ctl(), 0u, 0, R.sq.run_local.as<uint32_t>(),
