@@ -317,6 +317,8 @@ struct TrainRun {
     HostBuf h_ctl;
     bpe_stats_t st;
     EvProfile prof;
+    std::vector<uint32_t> pending_samples;  // profile 3: sampled steps enqueued in the current batch
+    uint64_t sampled_noop = 0;              // sampled launches that turned out to be no-ops (batch halted earlier)
     StepCtl* d_ctl() const { return ctl.as<StepCtl>(); }
     StepCtl* hc() const { return h_ctl.as<StepCtl>(); }
     MergeRec* d_rec() const { return rec.as<MergeRec>(); }
@@ -502,7 +504,7 @@ static int launch_merge(bpe_ctx* ctx, TokT* tok, const TileHalo<TokT>* halo, uin
 static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uint32_t step_index, bool fuse_select) {
     const uint32_t nt = R.sq.ntiles();
     R.prof.sample_now = (step_index % 8u) == 0;
-    if (R.prof.level == 3 && R.prof.sample_now) R.st.kernel_ms[10] += (double)R.sq.n_slots;  // slots of the sampled launches
+    if (R.prof.level == 3 && R.prof.sample_now) R.pending_samples.push_back(step_index);  // credited once the step is known to have run
     R.prof.mark(K_HALO);
     BPE_LAUNCH((halo_kernel<uint16_t, true>), (nt + HALO_THREADS - 1) / HALO_THREADS, HALO_THREADS, ctx->stream, R.sq.tok(),
                R.sq.n_slots, nt, R.sq.halo.as<TileHalo<uint16_t>>(), (const StepCtl*)R.d_ctl(), 0u, 0, R.sq.run_local.as<uint32_t>(),
@@ -662,6 +664,10 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
         hc = R.hc();
         if (hc->err) return fail(ctx, BPE_ERR_INTERNAL, "device error flags 0x%x near step %u", hc->err, hc->step);
         R.st.scanned_slots += (uint64_t)(hc->step - steps_done) * R.sq.n_slots;
+        for (uint32_t sidx : R.pending_samples) {
+            if (sidx < hc->step) R.st.kernel_ms[10] += (double)R.sq.n_slots; else R.sampled_noop++;
+        }
+        R.pending_samples.clear();
         steps_done = hc->step;
         R.sq.live = multi ? hc->local_live : hc->live_tokens;
         if (debug_sync && hc->halt == H_NONE) { rc = verify_state(ctx, R, steps_done); if (rc) return rc; hc = R.hc(); }
@@ -722,6 +728,10 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
                 hc = R.hc();
                 if (hc->err) return fail(ctx, BPE_ERR_INTERNAL, "device error flags 0x%x near step %u", hc->err, hc->step);
                 R.st.scanned_slots += R.sq.n_slots;
+                for (uint32_t sidx : R.pending_samples) {
+                    if (sidx < hc->step) R.st.kernel_ms[10] += (double)R.sq.n_slots; else R.sampled_noop++;
+                }
+                R.pending_samples.clear();
                 steps_done = hc->step;
                 R.sq.live = multi ? hc->local_live : hc->live_tokens;
                 if (debug_sync) { rc = verify_state(ctx, R, steps_done); if (rc) return rc; }
@@ -739,6 +749,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     CU(cudaEventRecord(ev1, ctx->stream));
     CU(cudaEventSynchronize(ev1));
     prof.finish();
+    if (prof.level == 3 && R.st.kernel_calls[K_MERGE] >= R.sampled_noop) R.st.kernel_calls[K_MERGE] -= R.sampled_noop;
     float dev_ms = 0;
     CU(cudaEventElapsedTime(&dev_ms, ev0, ev1));
     cudaEventDestroy(ev0);
