@@ -9,7 +9,7 @@ from test_oracle import MAIN_ZIG_STRING, MAIN_ZIG_TOKENS, REF_TEST_MERGES
 
 
 def _train_check(emu, ora, data, vocab, **opts):
-    for k, v in {"verify_recount": 0, "check_tiebreak": 1, "force_slow_tiebreak": 0, "compact_pct": 85, **opts}.items():
+    for k, v in {"verify_recount": 0, "check_tiebreak": 1, "force_slow_tiebreak": 0, "compact_pct": 85, "merge_impl": 0, **opts}.items():
         emu.set_option(k, v)
     m, c = emu.train(data, vocab)
     om, oc = ora.train(data, vocab, fast=True)
@@ -87,3 +87,26 @@ def test_decode_errors(emu, zb):
         emu.decode([256], [(256, 97, 256)])
     assert emu.decode([257], [(97, 98, 257), (99, 99, 257)]) == b"ab"  # first matching merge wins (:109-116)
     assert emu.decode([], REF_TEST_MERGES) == b""
+
+
+@pytest.mark.parametrize("data,vocab", [
+    (b"hello world hello", 300), (b"ab" * 700 + b"a", 270), (b"aaab" * 300 + b"aa", 280), (b"a" * 1000, 266),
+])
+def test_train_candidate_scan_path(emu, ora, data, vocab):
+    """merge_impl = 2: scan / resolve / write kernels instead of halo + tiled merge (A == B and dense steps
+    fall back to the tiled pass through H_CLASSIC)."""
+    try:
+        _train_check(emu, ora, data, vocab, verify_recount=1, merge_impl=2)
+        _train_check(emu, ora, data, vocab, merge_impl=2)
+    finally:
+        emu.set_option("merge_impl", 0)
+
+
+def test_train_candidate_scan_path_random(emu, ora, taylor):
+    rng = np.random.default_rng(9)
+    try:
+        _train_check(emu, ora, bytes(rng.integers(97, 101, size=3000, dtype=np.uint8)), 290, verify_recount=1, merge_impl=2)
+        _train_check(emu, ora, bytes(rng.integers(0, 256, size=4000, dtype=np.uint8)), 330, merge_impl=2)
+        _train_check(emu, ora, taylor[:30000], 300, merge_impl=2)
+    finally:
+        emu.set_option("merge_impl", 0)

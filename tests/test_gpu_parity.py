@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 def _opts(eng, **opts):
     for k, v in {"verify_recount": 0, "check_tiebreak": 0, "force_slow_tiebreak": 0, "compact_pct": 85, "table_log2": 0,
-                 "max_steps": 0, **opts}.items():
+                 "max_steps": 0, "merge_impl": 0, **opts}.items():
         eng.set_option(k, v)
 
 
@@ -261,3 +261,14 @@ def test_c3_full_size_properties(gpu, ora, synth):
     out = gpu.decode(ids, m)
     assert len(out) == n and hashlib.sha256(out).digest() == hashlib.sha256(data.tobytes()).digest()
     assert st["tie_steps"] > 0 and st["scanned_slots"] > 0
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+def test_train_alternative_merge_paths(gpu, ora, synth, taylor, impl):
+    """merge_impl = 1 (TMA ring) and 2 (candidate scan) must learn exactly what the default path learns."""
+    rng = np.random.default_rng(31)
+    _train_check(gpu, ora, taylor, 400, merge_impl=impl, check_tiebreak=1)
+    _train_check(gpu, ora, bytes(rng.integers(97, 101, size=200000, dtype=np.uint8)), 350, merge_impl=impl, verify_recount=1)
+    _train_check(gpu, ora, b"xyz" + b"a" * 40961 + b"b" + b"a" * 8192 + b"cc" + b"a" * 12287 + b"q", 300, merge_impl=impl, verify_recount=1)
+    data = bytes(synth.generate(3_000_000, synth.SEED_C3, synth.BYTE))
+    _train_check(gpu, ora, data, 256 + 300, merge_impl=impl)

@@ -100,6 +100,7 @@ enum : uint32_t {
     H_HEAVY = 2,     // heavy-key list no longer covers the maximum (or overflowed): host rebuilds it
     H_ZCAP = 3,      // zcnt models another capacity of the reference's table: host rebuilds it
     H_REPLAY = 4,    // tie that needs the full table replay on the host
+    H_CLASSIC = 5,   // candidate-scan merge path cannot take this step (A == B, or too many candidates): host runs the tiled pass
 };
 // StepCtl::flags
 enum : uint32_t { F_FORCE_REPLAY = 1u << 0, F_CHECK_TIES = 1u << 1 };
@@ -140,6 +141,8 @@ struct StepCtl {
     uint32_t need_tie;     // the current step's tie is being settled by the zig_* kernels
     uint32_t flags;        // F_*
     uint32_t last_merged;  // occurrences merged by the last applied step
+    uint32_t cand_n;       // candidate-scan merge path: queued A positions ...
+    uint32_t w_n;          // ... and token writes decided for them
     unsigned long long live_tokens;
     unsigned long long fast_ties;   // tie steps settled on the device
     unsigned long long local_live;  // live tokens of this GPU's shard (multi-GPU; live_tokens is the global count)

@@ -303,14 +303,15 @@ __global__ void ctl_set_kernel(StepCtl* ctl, MergeRec* rec, int set_theta, uint3
     if (set_theta) ctl->theta = theta;
     if (set_zcap) ctl->zcap = zcap;
     if (commit) { commit_merge(ctl, rec, key, count); ctl->need_tie = 0; }
-    if (clear_halt) ctl->halt = H_NONE;
+    if (clear_halt) { ctl->halt = H_NONE; ctl->cand_n = 0; ctl->w_n = 0; }
 }
 
 struct TrainRun {
     bpe_ctx* ctx;
     Sequence<uint16_t> sq;
     TableMem tm;
-    DevBuf delta, hist, ctl, rec, firstpos, recount, live_chk, heavy;
+    DevBuf delta, hist, ctl, rec, firstpos, recount, live_chk, heavy, cand, wr;
+    uint32_t cand_cap = 0;  // candidate-scan merge path: queue capacity
     uint32_t vcap = 0;   // stride of the cntL / cntR halves of `delta`
     uint32_t theta = 0;  // heavy-list threshold (0 = list invalid)
     HeavyList hl() const { HeavyList h; h.slots = heavy.as<uint32_t>(); h.cap = (uint32_t)(heavy.bytes / 4); h.theta = theta; return h; }
@@ -500,6 +501,27 @@ static int launch_merge(bpe_ctx* ctx, TokT* tok, const TileHalo<TokT>* halo, uin
     return BPE_OK;
 }
 
+// candidate-scan variant of the step tail (single GPU, A != B): scan, resolve, write, apply
+static int enqueue_step_tail_scan(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uint32_t step_index, bool fuse_select) {
+    const uint32_t nt = R.sq.ntiles();
+    R.prof.sample_now = (step_index % 8u) == 0;
+    if (R.prof.level == 3 && R.prof.sample_now) R.pending_samples.push_back(step_index);
+    R.prof.mark(K_MERGE);
+    BPE_LAUNCH_NS(scan_kernel<uint16_t>, nt, THREADS, ctx->stream, R.sq.tok(), R.d_ctl(), R.cand.as<uint32_t>(), R.cand_cap,
+                  (int)(step_index & 1u));
+    BPE_LAUNCH_NS(resolve_kernel<uint16_t>, 148 * 4, 256, ctx->stream, R.sq.tok(), R.sq.n_slots, R.d_ctl(), R.cand.as<uint32_t>(), R.cand_cap,
+                  R.wr.as<TokWrite>(), R.cntL(), R.cntR(), R.nxx(), R.nab());
+    BPE_LAUNCH_NS(write_kernel<uint16_t>, 148 * 4, 256, ctx->stream, R.sq.tok(), R.d_ctl(), R.wr.as<TokWrite>());
+    R.prof.mark(K_APPLY);
+    PeerSet none;
+    memset(&none, 0, sizeof none);
+    BPE_LAUNCH(apply_kernel, (4 * n_ids + 3 + 255) / 256, 256, ctx->stream, R.tm.view(), R.delta.as<uint32_t>(), R.vcap, R.d_ctl(),
+               R.tm.zig(), n_ids, R.hl(), R.d_rec(), fuse_select ? 1 : 0, 0, none, 0, 1, 0u, 0u, (uint32_t)R.edge_off);
+    ctx->launches += 4;
+    CU(cudaGetLastError());
+    return BPE_OK;
+}
+
 // the part of a step after the merge has been chosen: halo, merge, apply (all read the merge from ctl)
 static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uint32_t step_index, bool fuse_select) {
     const uint32_t nt = R.sq.ntiles();
@@ -575,6 +597,13 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     CU(R.delta.alloc(R.exchange_words() * 4)); CU(R.hist.alloc(65536 * 4));
     CU(R.ctl.alloc(sizeof(StepCtl))); CU(R.rec.alloc(want * sizeof(MergeRec)));
     CU(R.heavy.alloc((size_t)(1u << 20) * 4));
+    const bool scan_path = ctx->merge_impl == 2 && !multi;
+    if (scan_path) {
+        R.cand_cap = (uint32_t)std::max<size_t>(1u << 16, n / 32);
+        CU(R.cand.alloc((size_t)R.cand_cap * 4));
+        CU(R.wr.alloc((size_t)R.cand_cap * 2 * sizeof(TokWrite)));
+    }
+    uint32_t scan_not_before = 0;  // first step that may use the candidate-scan path again (set after a dense step)
     CU(R.h_ctl.alloc(sizeof(StepCtl)));
     CU(cudaMemsetAsync(R.delta.p, 0, R.exchange_words() * 4, ctx->stream));
     CU(cudaMemsetAsync(R.hist.p, 0, 65536 * 4, ctx->stream));
@@ -655,7 +684,9 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
                 ctx->launches += 1;
             }
             selection_pending = !debug_sync;
-            rc = enqueue_step_tail(ctx, R, 256 + steps_done + k + 1, steps_done + k, selection_pending);
+            const bool use_scan = scan_path && steps_done >= scan_not_before && (uint64_t)hc->max_count * 4 < R.cand_cap;
+            rc = use_scan ? enqueue_step_tail_scan(ctx, R, 256 + steps_done + k + 1, steps_done + k, selection_pending)
+                          : enqueue_step_tail(ctx, R, 256 + steps_done + k + 1, steps_done + k, selection_pending);
             if (rc) return rc;
         }
         prof.mark(K_HOSTGAP);
@@ -704,6 +735,28 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
                 if (rc) return rc;
                 BPE_LAUNCH_NS(ctl_set_kernel, 1, 1, ctx->stream, R.d_ctl(), R.d_rec(), 1, R.theta, 0, 0u, 1, 0, 0u, 0u);
                 ctx->launches++;
+                break;
+            }
+            case H_CLASSIC: {
+                // the candidate-scan path declined this step (A == B or too many candidates); nothing was modified:
+                // run the tiled pass for the merge already chosen
+                if (hc->A != hc->B) scan_not_before = steps_done + 64;
+                BPE_LAUNCH_NS(ctl_set_kernel, 1, 1, ctx->stream, R.d_ctl(), R.d_rec(), 0, 0u, 0, 0u, 1, 0, 0u, 0u);
+                ctx->launches++;
+                rc = enqueue_step_tail(ctx, R, 256 + steps_done + 1, steps_done, false);
+                if (rc) return rc;
+                rc = read_ctl(ctx, R, false);
+                if (rc) return rc;
+                hc = R.hc();
+                if (hc->err) return fail(ctx, BPE_ERR_INTERNAL, "device error flags 0x%x near step %u", hc->err, hc->step);
+                R.st.scanned_slots += R.sq.n_slots;
+                for (uint32_t sidx : R.pending_samples) {
+                    if (sidx < hc->step) R.st.kernel_ms[10] += (double)R.sq.n_slots; else R.sampled_noop++;
+                }
+                R.pending_samples.clear();
+                steps_done = hc->step;
+                R.sq.live = hc->live_tokens;
+                if (debug_sync) { rc = verify_state(ctx, R, steps_done); if (rc) return rc; }
                 break;
             }
             case H_REPLAY: {

@@ -758,6 +758,14 @@ template <> __device__ __forceinline__ int mask_bit_to_slot<uint32_t>(int bit) {
 template <> __device__ __forceinline__ uint32_t vec_mask<uint32_t>(const uint4& v, uint32_t a) {
     return (v.x == a ? 1u : 0u) | (v.y == a ? 2u : 0u) | (v.z == a ? 4u : 0u) | (v.w == a ? 8u : 0u);
 }
+template <class TokT> __device__ __forceinline__ void unpack_vec(const uint4& v, uint32_t* out);
+template <> __device__ __forceinline__ void unpack_vec<uint16_t>(const uint4& v, uint32_t* out) {
+    out[0] = v.x & 0xFFFFu; out[1] = v.x >> 16; out[2] = v.y & 0xFFFFu; out[3] = v.y >> 16;
+    out[4] = v.z & 0xFFFFu; out[5] = v.z >> 16; out[6] = v.w & 0xFFFFu; out[7] = v.w >> 16;
+}
+template <> __device__ __forceinline__ void unpack_vec<uint32_t>(const uint4& v, uint32_t* out) {
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+}
 template <class TokT> __device__ __forceinline__ bool vec_has(const uint4& v, uint32_t a);
 template <> __device__ __forceinline__ bool vec_has<uint16_t>(const uint4& v, uint32_t a) {
     // "has a zero halfword" of w ^ aa: (x - 0x00010001) & ~x & 0x80008000. A borrow can only flag a
@@ -1149,6 +1157,108 @@ __global__ void __launch_bounds__(THREADS, RING_CTAS_PER_SM) merge_tma_kernel(To
 }
 
 // =========================================================================================
+// Candidate-scan merge path (A != B, single GPU): three small steps instead of halo + tiled merge.
+//   scan_kernel    streams the sequence once through registers (no shared memory, no barrier). An A
+//                  whose successor inside the same 16-byte vector is a live token other than B can never
+//                  start an occurrence and is dropped on the spot; only the others (successor is B, a
+//                  hole, or lies in the next vector) are queued by position.
+//   resolve_kernel one thread per queued A walks the (still unmodified) sequence in global memory,
+//                  decides the occurrence, emits the neighbour deltas and the token writes.
+//   write_kernel   applies the writes (X over A, hole over the consumed B).
+// Nothing is modified before every decision has been taken, so no tiles, halos or staging are needed.
+// =========================================================================================
+struct TokWrite { uint32_t pos; uint32_t val; };
+
+template <class TokT>
+__global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) scan_kernel(const TokT* __restrict__ tok, StepCtl* ctl,
+                                                                           uint32_t* __restrict__ cand, uint32_t cand_cap, int backwards) {
+    constexpr int VEC = 16 / (int)sizeof(TokT);
+    constexpr int NV = TILE / VEC / THREADS;
+    const uint32_t H = TokTraits<TokT>::hole;
+    const uint32_t tile = backwards ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
+    const size_t base = (size_t)tile * TILE;
+    const uint4* src = reinterpret_cast<const uint4*>(tok + base);
+    uint4 v[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) v[k] = src[k * THREADS + (int)threadIdx.x];
+    if (ctl->halt) return;
+    const uint32_t Au = ctl->A, Bu = ctl->B;
+    if (Au == Bu) {  // runs need parity from the run start: the tiled pass handles them
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctl->halt = H_CLASSIC;
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        if (!vec_has<TokT>(v[k], Au)) continue;
+        uint32_t tv[VEC];
+        unpack_vec<TokT>(v[k], tv);
+        const uint32_t p0 = (uint32_t)(base + (size_t)(k * THREADS + (int)threadIdx.x) * VEC);
+#pragma unroll
+        for (int i = 0; i < VEC; i++) {
+            if (tv[i] != Au) continue;
+            bool c = true;  // last slot of the vector: the successor is out of reach
+            if (i + 1 < VEC) c = (tv[i + 1] == Bu) || (tv[i + 1] == H);
+            if (c) {
+                const uint32_t at = atomicAdd(&ctl->cand_n, 1u);
+                if (at < cand_cap) cand[at] = p0 + (uint32_t)i;
+            }
+        }
+    }
+}
+
+template <class TokT>
+__global__ void resolve_kernel(const TokT* __restrict__ tok, size_t n_slots, StepCtl* ctl, const uint32_t* __restrict__ cand,
+                               uint32_t cand_cap, TokWrite* __restrict__ wr, uint32_t* __restrict__ cntL, uint32_t* __restrict__ cntR,
+                               uint32_t* nxx_out, uint32_t* nab_out) {
+    const TokT H = (TokT)TokTraits<TokT>::hole;
+    if (ctl->halt) return;
+    const uint32_t n = ctl->cand_n;
+    if (n > cand_cap) {  // too dense for the queue: nothing has been modified yet, the tiled pass redoes the step
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctl->halt = H_CLASSIC;
+        return;
+    }
+    const TokT A = (TokT)ctl->A, B = (TokT)ctl->B;
+    const uint32_t X = ctl->X;
+    auto next_of = [&](size_t i) -> long long { for (size_t j = i + 1; j < n_slots; j++) if (tok[j] != H) return (long long)j; return -1; };
+    auto prev_of = [&](size_t i) -> long long { for (size_t j = i; j > 0;) { --j; if (tok[j] != H) return (long long)j; } return -1; };
+    uint32_t nAB = 0, nXX = 0;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        const size_t s = cand[c];
+        const long long j = next_of(s);
+        if (j < 0 || tok[j] != B) continue;
+        const uint32_t w = atomicAdd(&ctl->w_n, 2u);
+        wr[w].pos = (uint32_t)s; wr[w].val = X;
+        wr[w + 1].pos = (uint32_t)j; wr[w + 1].val = (uint32_t)H;
+        nAB++;
+        // left side: always owned by this occurrence
+        const long long p = prev_of(s);
+        if (p >= 0) {
+            const TokT tp = tok[p];
+            bool merged_second = false;
+            if (tp == B) { const long long pp = prev_of((size_t)p); merged_second = (pp >= 0 && tok[pp] == A); }
+            if (merged_second) nXX++; else atomicAdd(&cntL[tp], 1u);
+        }
+        // right side: owned only if the next live token does not start another occurrence
+        const long long nx = next_of((size_t)j);
+        if (nx >= 0) {
+            const TokT tn = tok[nx];
+            bool is_start = false;
+            if (tn == A) { const long long nn = next_of((size_t)nx); is_start = (nn >= 0 && tok[nn] == B); }
+            if (!is_start) atomicAdd(&cntR[tn], 1u);
+        }
+    }
+    if (nAB) atomicAdd(nab_out, nAB);
+    if (nXX) atomicAdd(nxx_out, nXX);
+}
+
+template <class TokT>
+__global__ void write_kernel(TokT* __restrict__ tok, StepCtl* ctl, const TokWrite* __restrict__ wr) {
+    if (ctl->halt) return;
+    const uint32_t n = ctl->w_n;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) tok[wr[i].pos] = (TokT)wr[i].val;
+}
+
+// =========================================================================================
 // apply_kernel: fold the merge deltas into the pair table (and the reference-home population on
 // births / deaths), one thread per token id, then advance the device-side step counter.
 // delta layout: [0,vcap) cntL, [vcap,2*vcap) cntR, [2*vcap] cntXX, [2*vcap+1] cntAB
@@ -1203,17 +1313,23 @@ __global__ void __launch_bounds__(256) apply_kernel(PairTable tbl, uint32_t* __r
         else { if (!ps_on) delta[cell] = 0; tbl_add(tbl, side ? pair_key(X, p) : pair_key(p, X), c, ctl, z, hl); }
     }
     const uint32_t t0 = 4u * n_ids;  // three more threads: adjacent occurrences, the merged pair itself, bookkeeping
+    // (t0 is a multiple of 4, so these three threads share a warp: all read the scalars, then one clears them)
+    uint32_t scalar = 0;
+    if (t == t0 || t == t0 + 1) scalar = cell_value(2 * vcap);
+    else if (t == t0 + 2) scalar = cell_value(2 * vcap + 1);
+    __syncwarp();
     if (t == t0) {
-        const uint32_t xx = cell_value(2 * vcap);
-        if (xx) tbl_sub(tbl, pair_key(B, A), xx, ctl, z);
+        if (scalar) tbl_sub(tbl, pair_key(B, A), scalar, ctl, z);
     } else if (t == t0 + 1) {
-        const uint32_t xx = cell_value(2 * vcap);
-        if (xx) tbl_add(tbl, pair_key(X, X), xx, ctl, z, hl);
+        if (scalar) tbl_add(tbl, pair_key(X, X), scalar, ctl, z, hl);
     } else if (t == t0 + 2) {
-        const uint32_t ab = cell_value(2 * vcap + 1);
-        if (ab) tbl_sub(tbl, pair_key(A, B), ab, ctl, z);
-        ctl->last_merged = ab;
-        ctl->live_tokens -= ab;
+        delta[2 * vcap] = 0;      // local scalars ready for the next merge pass
+        delta[2 * vcap + 1] = 0;
+        ctl->cand_n = 0;          // candidate-scan path: queues ready for the next step
+        ctl->w_n = 0;
+        if (scalar) tbl_sub(tbl, pair_key(A, B), scalar, ctl, z);
+        ctl->last_merged = scalar;
+        ctl->live_tokens -= scalar;
         ctl->step += 1;
     }
     if (!fuse_select) return;
