@@ -97,8 +97,9 @@ const char* bpe_last_error(const bpe_ctx* ctx);
  *   "merge_impl"          0 (default): register-streaming merge kernel, one CTA per tile;
  *                         1: merge pass fed by a TMA ring (cp.async.bulk + mbarrier, persistent CTAs) —
  *                            measured slower on B200 for this access pattern, kept for comparison
- *                         2: candidate-scan path (single GPU): one barrier-free streaming scan queues the A's that can
- *                            start an occurrence, a resolve + a write kernel finish the step (no tiles / halos)
+ *                         2: candidate-scan path (single GPU, experimental, currently slower): one barrier-free
+ *                            streaming scan queues the A's that can start an occurrence, a resolve + a write kernel
+ *                            finish the step (no tiles / halos)
  *   "xchg_impl"           multi-GPU per-step exchange. 0 (default): peer-memory mailboxes over NVLink (each rank
  *                         writes its deltas into every peer's mailbox and raises a flag; falls back to 1 when
  *                         peer access is unavailable); 1: NCCL all-reduce
