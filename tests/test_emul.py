@@ -110,3 +110,12 @@ def test_train_candidate_scan_path_random(emu, ora, taylor):
         _train_check(emu, ora, taylor[:30000], 300, merge_impl=2)
     finally:
         emu.set_option("merge_impl", 0)
+
+
+def test_train_until_everything_ties(emu, ora):
+    """Late phase of a long training: the maximum count drops to 1 and every remaining pair ties (the heavy
+    list then holds the whole table and the tie goes to the replay)."""
+    rng = np.random.default_rng(17)
+    data = bytes(rng.integers(0, 256, size=1200, dtype=np.uint8))
+    st = _train_check(emu, ora, data, 256 + 120, check_tiebreak=0)
+    assert st["tie_steps"] > 100 and st["tie_slow_steps"] > 0  # > 1,024 tied pairs go to the replay

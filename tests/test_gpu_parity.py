@@ -272,3 +272,12 @@ def test_train_alternative_merge_paths(gpu, ora, synth, taylor, impl):
     _train_check(gpu, ora, b"xyz" + b"a" * 40961 + b"b" + b"a" * 8192 + b"cc" + b"a" * 12287 + b"q", 300, merge_impl=impl, verify_recount=1)
     data = bytes(synth.generate(3_000_000, synth.SEED_C3, synth.BYTE))
     _train_check(gpu, ora, data, 256 + 300, merge_impl=impl)
+
+
+def test_train_long_run_on_random_bytes(gpu, ora):
+    """A long training on random bytes ends in the regime where the maximum is 1-2 and (hundreds of) thousands of
+    pairs tie: the heavy list holds the whole table there and ties beyond 1,024 keys go to the replay."""
+    rng = np.random.default_rng(41)
+    data = bytes(rng.integers(0, 256, size=40000, dtype=np.uint8))
+    st = _train_check(gpu, ora, data, 256 + 1500)
+    assert st["tie_steps"] > 500

@@ -596,7 +596,6 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     R.edge_off = ((size_t)2 * R.vcap + 2 + 15) / 16 * 16;
     CU(R.delta.alloc(R.exchange_words() * 4)); CU(R.hist.alloc(65536 * 4));
     CU(R.ctl.alloc(sizeof(StepCtl))); CU(R.rec.alloc(want * sizeof(MergeRec)));
-    CU(R.heavy.alloc((size_t)(1u << 20) * 4));
     const bool scan_path = ctx->merge_impl == 2 && !multi;
     if (scan_path) {
         R.cand_cap = (uint32_t)std::max<size_t>(1u << 16, n / 32);
@@ -634,6 +633,9 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     while ((uint64_t)R.hc()->hist_nonzero * 4 > cap) cap <<= 1;  // the byte pairs alone must fit with room to spare
     rc = table_alloc(ctx, R.tm, cap);
     if (rc) return rc;
+    // the heavy list can hold every key of the table, so it cannot overflow even when the whole table ties
+    // (e.g. the late phase of a long training on random bytes, where every pair occurs once)
+    CU(R.heavy.alloc((size_t)cap * 4));
     BPE_LAUNCH_NS(seed_table_kernel, 65536 / 256, 256, ctx->stream, R.hist.as<uint32_t>(), R.tm.view(), R.d_ctl());
     ctx->launches += 1;
     CU(cudaGetLastError());
@@ -668,6 +670,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
             if (rc) return rc;
             rc = sync_zcap(ctx, R, hc->live_keys);
             if (rc) return rc;
+            if (R.heavy.bytes < (size_t)R.tm.cap * 4) CU(R.heavy.alloc((size_t)R.tm.cap * 4));
             if (R.theta) { rc = collect_heavy(ctx, R); if (rc) return rc; }  // slot indices changed
         }
         if (R.sq.n_slots > (size_t)TILE && R.sq.live * 100 < (uint64_t)R.sq.n_slots * (uint64_t)ctx->compact_pct) {
