@@ -509,8 +509,10 @@ static int enqueue_step_tail_scan(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uin
     R.prof.mark(K_MERGE);
     BPE_LAUNCH_NS(scan_kernel<uint16_t>, nt, THREADS, ctx->stream, R.sq.tok(), R.d_ctl(), R.cand.as<uint32_t>(), R.cand_cap,
                   (int)(step_index & 1u));
+    R.prof.mark(K_TIE);    // profile 1: the resolve kernel is booked under "tie", the write kernel under bucket 11
     BPE_LAUNCH_NS(resolve_kernel<uint16_t>, 148 * 4, 256, ctx->stream, R.sq.tok(), R.sq.n_slots, R.d_ctl(), R.cand.as<uint32_t>(), R.cand_cap,
                   R.wr.as<TokWrite>(), R.cntL(), R.cntR(), R.nxx(), R.nab());
+    R.prof.mark(11);
     BPE_LAUNCH_NS(write_kernel<uint16_t>, 148 * 4, 256, ctx->stream, R.sq.tok(), R.d_ctl(), R.wr.as<TokWrite>());
     R.prof.mark(K_APPLY);
     PeerSet none;
