@@ -94,6 +94,9 @@ const char* bpe_last_error(const bpe_ctx* ctx);
  *   "compact_pct"         live/slots percentage below which the sequence is compacted (default 85)
  *   "table_log2"          log2 of the initial pair-table capacity (default: sized from n)
  *   "max_steps"           stop training after this many merges (0 = no limit)
+ *   "encode_impl"         0 (default): level-scheduled encode — merges that commute (no shared produced token, no
+ *                         token that is second of one pair and first of another) are applied in one pass per
+ *                         level; 1: one pass per merge, in list order. Both give the reference's result.
  *   "merge_impl"          0 (default): register-streaming merge kernel, one CTA per tile;
  *                         1: merge pass fed by a TMA ring (cp.async.bulk + mbarrier, persistent CTAs) —
  *                            measured slower on B200 for this access pattern, kept for comparison

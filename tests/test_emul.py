@@ -119,3 +119,85 @@ def test_train_until_everything_ties(emu, ora):
     data = bytes(rng.integers(0, 256, size=1200, dtype=np.uint8))
     st = _train_check(emu, ora, data, 256 + 120, check_tiebreak=0)
     assert st["tie_steps"] > 100 and st["tie_slow_steps"] > 0  # > 1,024 tied pairs go to the replay
+
+
+def _encode_both(emu, ora, data, merges):
+    """level-scheduled encode (default) and one-pass-per-merge encode against the oracle's verbatim loop"""
+    want = ora.encode(data, merges, linear=False)
+    try:
+        for impl in (0, 1):
+            emu.set_option("encode_impl", impl)
+            got = emu.encode(data, merges)
+            assert np.array_equal(got, want), (impl, merges[:8])
+    finally:
+        emu.set_option("encode_impl", 0)
+    return want
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_encode_levels_trained_lists(emu, ora, seed):
+    """merge lists as training produces them, on other text than they were trained on (tiles of 256 slots:
+    pairs straddle tile ends, levels are split by compactions)"""
+    rng = np.random.default_rng(100 + seed)
+    alpha = [2, 3, 5, 26, 64, 256][seed]
+    train = bytes(rng.integers(0, alpha, size=3000, dtype=np.uint8))
+    merges, _ = ora.train(train, 256 + [40, 60, 90, 120, 80, 40][seed])
+    merges = [tuple(int(x) for x in r) for r in merges]
+    text = bytes(rng.integers(0, alpha, size=2500, dtype=np.uint8)) + train[:700]
+    ids = _encode_both(emu, ora, text, merges)
+    assert emu.decode(ids, merges) == text
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_encode_levels_arbitrary_lists(emu, ora, seed):
+    """lists no training run would write: repeated pairs, new ids that are bytes, that equal a component or that were
+    used before, runs of equal tokens — the schedule must keep exactly the reference's sequential meaning"""
+    rng = np.random.default_rng(500 + seed)
+    nsym = int(rng.integers(2, 7))
+    pool = list(range(97, 97 + nsym))
+    merges = []
+    for k in range(int(rng.integers(4, 40))):
+        a, b = int(rng.choice(pool)), int(rng.choice(pool))
+        mode = rng.random()
+        if mode < 0.75:
+            z = 256 + k
+        elif mode < 0.85:
+            z = int(rng.choice(pool))           # reuses an id (maybe a byte, maybe a or b)
+        elif mode < 0.95:
+            z = 256 + int(rng.integers(0, k + 1))  # an id an earlier merge may have produced
+        else:
+            z = 65535 if rng.random() < 0.5 else a
+        merges.append((a, b, z))
+        if z not in pool and rng.random() < 0.8:
+            pool.append(z)
+    data = bytes(rng.integers(97, 97 + nsym, size=int(rng.integers(300, 1500)), dtype=np.uint8))
+    _encode_both(emu, ora, data, merges)
+
+
+def test_encode_levels_large_level(emu, ora):
+    """more pairs in one level than one pass holds (LVL_MAX = 1024): the level is split"""
+    merges = [(a, b, 256 + i) for i, (a, b) in enumerate((a, b) for a in range(0, 40) for b in range(100, 130))]
+    rng = np.random.default_rng(3)
+    data = bytes(rng.choice(np.array(list(range(0, 40)) + list(range(100, 130)), dtype=np.uint8), size=3000))
+    _encode_both(emu, ora, data, merges)
+
+
+def test_encode_levels_id_65535_pair(emu, ora):
+    """(65535,65535) packs to the hash's empty marker: it must never look like a hit"""
+    merges = [(97, 98, 65535), (65535, 99, 300), (99, 99, 301), (65535, 97, 302)]
+    data = b"ababc" * 40 + b"abab" * 30 + b"abc" * 20
+    _encode_both(emu, ora, data, merges)
+
+
+def test_encode_levels_round_robin_tiles(emu, ora):
+    """fewer CTAs than tiles (encode_grid < 0: absolute CTA count): each CTA stages several tiles in turn"""
+    rng = np.random.default_rng(77)
+    train = bytes(rng.integers(97, 103, size=3000, dtype=np.uint8))
+    merges = [tuple(int(x) for x in r) for r in ora.train(train, 256 + 70)[0]]
+    text = bytes(rng.integers(97, 103, size=4000, dtype=np.uint8))
+    try:
+        for g in (-1, -2, -3):
+            emu.set_option("encode_grid", g)
+            assert np.array_equal(emu.encode(text, merges), ora.encode(text, merges, linear=False))
+    finally:
+        emu.set_option("encode_grid", 6)

@@ -186,6 +186,46 @@ def test_encode_edge_cases(gpu, ora, data, merges):
         assert rc == 0 and gpu.decode(ids, merges) == want
 
 
+def test_encode_levels_vs_single_passes(gpu, ora, synth):
+    """the level-scheduled encode (default) against one pass per merge (encode_impl = 1) and the oracle, on
+    a list long enough for ~50 levels, text with and without the training corpus"""
+    data = bytes(synth.generate(3_000_000, synth.SEED_C3, synth.BYTE))
+    m, _ = gpu.train(data, 256 + 1500)
+    other = bytes(synth.generate(2_000_000, synth.SEED_C4, synth.BYTE)) + data[:100_000]
+    want = ora.encode(other, merges_array(m), linear=True)
+    try:
+        for impl in (0, 1):
+            gpu.set_option("encode_impl", impl)
+            ids = gpu.encode(other, m)
+            launches = gpu.last_stats["kernel_launches"]
+            assert np.array_equal(ids, want), impl
+            if impl == 0:
+                lvl_launches = launches
+        assert lvl_launches * 4 < launches  # far fewer passes
+    finally:
+        gpu.set_option("encode_impl", 0)
+    assert gpu.decode(ids, m) == other
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_encode_arbitrary_lists(gpu, ora, seed):
+    """merge lists no training run writes (repeated pairs, ids reused, id 65535, new id equal to a component)"""
+    rng = np.random.default_rng(900 + seed)
+    nsym = int(rng.integers(2, 7))
+    pool = list(range(97, 97 + nsym))
+    merges = []
+    for k in range(int(rng.integers(4, 60))):
+        a, b = int(rng.choice(pool)), int(rng.choice(pool))
+        mode = rng.random()
+        z = 256 + k if mode < 0.75 else int(rng.choice(pool)) if mode < 0.85 else 256 + int(rng.integers(0, k + 1)) if mode < 0.95 \
+            else (65535 if rng.random() < 0.5 else a)
+        merges.append((a, b, z))
+        if z not in pool and rng.random() < 0.8:
+            pool.append(z)
+    data = bytes(rng.integers(97, 97 + nsym, size=int(rng.integers(20_000, 60_000)), dtype=np.uint8))
+    assert np.array_equal(gpu.encode(data, merges), ora.encode(data, merges, linear=False))
+
+
 def test_decode_semantics(gpu, zb):
     with pytest.raises(zb.InvalidToken):
         gpu.decode([256], [(256, 97, 256)])  # cyclic definition (stack overflow in the reference)

@@ -1,0 +1,36 @@
+"""tools/encode_gpu.py <bytes> <vocab> [variants] — train on the synthetic corpus, then time encode (device-resident text and ids)
+with the level schedule (encode_impl = 0) and with one pass per merge (encode_impl = 1); both must give the same ids."""
+import importlib, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+zb = importlib.import_module("zig-bpe_b200")
+from tools import synthcorpus as sc
+n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1_000_000_000
+vocab = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
+# variants: impl[:grid] — encode_impl and, for the level schedule, encode_grid (CTAs per SM; 0 = one CTA per tile)
+variants = sys.argv[3].split(",") if len(sys.argv) > 3 else ["0:6", "0:0", "1"]
+eng = zb.Engine(device=0)
+d_text = torch.from_numpy(sc.generate(n, sc.SEED_C3, sc.BYTE)).cuda()
+m, _ = eng.train(None, vocab, device_ptr=d_text.data_ptr(), n=n)
+out = {"bytes": n, "merges": int(len(m)), "train_ms": round(eng.last_stats["device_ms"], 1)}
+ref = None
+for var in variants:
+    impl = int(var.split(":")[0])
+    eng.set_option("encode_impl", impl)
+    if ":" in var:
+        eng.set_option("encode_grid", int(var.split(":")[1]))
+    d_ids = torch.empty(n, dtype=torch.int16, device="cuda")
+    best = None
+    for rep in range(2):
+        torch.cuda.synchronize(); t = time.time()
+        k = eng.encode_device(d_text.data_ptr(), n, m, d_ids.data_ptr())
+        torch.cuda.synchronize(); dt = time.time() - t
+        best = dt if best is None else min(best, dt)
+    st = eng.last_stats
+    out[f"impl{var}"] = {"s": round(best, 4), "GBps": round(n / 1e9 / best, 2), "launches": int(st["kernel_launches"]), "compactions": int(st["compactions"]), "ids": int(k)}
+    if ref is None:
+        ref = d_ids[:k].clone()
+    else:
+        out["same_ids"] = bool(k == ref.numel() and torch.equal(ref, d_ids[:k]))
+print(json.dumps(out))

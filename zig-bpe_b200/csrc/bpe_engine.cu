@@ -11,6 +11,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <unordered_set>
 
 #include "../../include/bpe_b200.h"
 #include "bpe_kernels.cuh"
@@ -55,7 +56,7 @@ struct bpe_ctx {
     std::string err;
     // options
     long verify_recount = 0, force_slow_tiebreak = 0, check_tiebreak = 0, compact_pct = 85, table_log2 = 0,
-         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0;
+         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 6;
     int num_sms = 148;
     DistComm dist;  // world == 1 when single GPU
     uint64_t launches = 0;
@@ -837,6 +838,69 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
 // -----------------------------------------------------------------------------------------
 // encode (src/basic_tokenizer.zig:71-88): one merge pass per list entry, in list order
 // -----------------------------------------------------------------------------------------
+// Encode schedule. The reference applies the merges one at a time in list order (:71-88). Two merges q < r
+// commute on every token sequence when neither uses the token the other produces and no token is the second
+// component of one pair and the first component of the other (their occurrences then never overlap and
+// neither pass creates or destroys an occurrence of the other). Giving every merge the level
+// 1 + max(level of the earlier merges it does NOT commute with) and running the levels in order is
+// therefore a reordering of the list by swaps of adjacent commuting merges, i.e. the same function.
+// All pairs of a level with first != second go through ONE level_kernel pass; pairs with first == second
+// (greedy runs) keep their own merge pass inside their level. Lists a trained tokenizer cannot produce
+// (new id below 256, equal to a component, already mentioned earlier, or a repeated pair) act as barriers
+// and run alone, in list position.
+struct EncStep { int single; uint32_t off, cnt; };  // single >= 0: merges[single] as one merge pass; else a level pass over ents[off, off+cnt)
+static void build_encode_schedule(const bpe_merge_t* merges, size_t m, bool levels, std::vector<EncStep>& steps,
+                                  std::vector<LevelEntry>& ents) {
+    steps.clear();
+    ents.clear();
+    if (!levels) {
+        for (size_t i = 0; i < m; i++) steps.push_back(EncStep{(int)i, 0u, 0u});
+        return;
+    }
+    std::vector<uint32_t> lastZ(65536, 0), lastF(65536, 0), lastS(65536, 0), lvl(m, 0);
+    std::vector<uint8_t> used(65536, 0), alone(m, 0);
+    std::unordered_set<uint32_t> seen;
+    seen.reserve(m * 2 + 16);
+    uint32_t floor_lvl = 0, max_lvl = 0;
+    for (size_t i = 0; i < m; i++) {
+        const uint32_t a = merges[i].first, b = merges[i].second, z = merges[i].new_token, key = pair_key(a, b);
+        const bool regular = z >= 256 && z != a && z != b && !used[z] && !seen.count(key);
+        uint32_t l;
+        if (regular) {
+            l = 1 + std::max(std::max(floor_lvl, lastZ[a]), std::max(lastZ[b], std::max(lastS[a], lastF[b])));
+            alone[i] = (a == b) ? 1 : 0;
+        } else {
+            l = max_lvl + 1;
+            floor_lvl = l;
+            alone[i] = 1;
+        }
+        lvl[i] = l;
+        lastF[a] = std::max(lastF[a], l); lastS[b] = std::max(lastS[b], l); lastZ[z] = std::max(lastZ[z], l);
+        used[a] = used[b] = used[z] = 1;
+        seen.insert(key);
+        max_lvl = std::max(max_lvl, l);
+    }
+    std::vector<uint32_t> order(m);
+    for (size_t i = 0; i < m; i++) order[i] = (uint32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return lvl[x] < lvl[y]; });
+    size_t i = 0;
+    while (i < m) {
+        size_t j = i;
+        while (j < m && lvl[order[j]] == lvl[order[i]]) j++;
+        uint32_t off = (uint32_t)ents.size(), cnt = 0;
+        for (size_t k = i; k < j; k++) {
+            const bpe_merge_t& mg = merges[order[k]];
+            if (alone[order[k]]) continue;
+            ents.push_back(LevelEntry{pair_key(mg.first, mg.second), mg.new_token});
+            if (++cnt == (uint32_t)LVL_MAX) { steps.push_back(EncStep{-1, off, cnt}); off = (uint32_t)ents.size(); cnt = 0; }
+        }
+        if (cnt) steps.push_back(EncStep{-1, off, cnt});
+        for (size_t k = i; k < j; k++)
+            if (alone[order[k]]) steps.push_back(EncStep{(int)order[k], 0u, 0u});
+        i = j;
+    }
+}
+
 template <class TokT>
 static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bpe_merge_t* merges, size_t m,
                          uint16_t* d_out, size_t* out_n, bpe_stats_t* st) {
@@ -869,8 +933,19 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
         sq.live -= *fresh;
         return BPE_OK;
     };
-    auto one_pass = [&](uint32_t A, uint32_t B, uint32_t X) -> int {
+    std::vector<EncStep> steps;
+    std::vector<LevelEntry> ents;
+    build_encode_schedule(merges, m, ctx->encode_impl == 0, steps, ents);
+    DevBuf ents_buf;
+    if (!ents.empty()) {
+        CU(ents_buf.alloc(ents.size() * sizeof(LevelEntry)));
+        CU(cudaMemcpyAsync(ents_buf.p, ents.data(), ents.size() * sizeof(LevelEntry), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaFuncSetAttribute(level_kernel<TokT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)level_smem_bytes<TokT>(LVL_HASH_MAX)));
+    }
+    // ent_cnt == 0: one merge pass for (A,B) -> X; else one level pass over ents[ent_off, ent_off + ent_cnt)
+    auto one_pass = [&](uint32_t A, uint32_t B, uint32_t X, uint32_t ent_off = 0, uint32_t ent_cnt = 0) -> int {
         const uint32_t nt = sq.ntiles();
+        if (ent_cnt) { A = 1; B = X = 0; }  // the halo of a level pass carries no run of equal tokens
         if (multi) {
             BPE_LAUNCH(edge_kernel<TokT>, 1, 32, ctx->stream, sq.tok(), sq.n_slots, sq.dense_end, edges, ctx->dist.rank, ctx->dist.world, d_ctl,
                        &d_ctl->cntAB, 0);
@@ -882,7 +957,19 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
                    sq.run_local.template as<uint32_t>(), sq.run_full.template as<uint8_t>(), sq.done_counter.template as<uint32_t>(),
                    (uint32_t*)nullptr, (const EdgeInfo*)edges, ctx->dist.rank, ctx->dist.world);
         ctx->launches += 1;
-        {
+        if (ent_cnt) {
+            const int backwards = (int)(pass_index++ & 1u);
+            uint32_t hash_log2 = 6;
+            while ((1u << hash_log2) < 2u * ent_cnt) hash_log2++;
+            // encode_grid CTAs per SM take the tiles round-robin (the level's tables are built once per CTA); 0: one CTA per tile
+            const uint32_t grid = ctx->encode_grid > 0   ? std::min<uint32_t>(nt, (uint32_t)ctx->encode_grid * (uint32_t)ctx->num_sms)
+                                  : ctx->encode_grid < 0 ? std::min<uint32_t>(nt, (uint32_t)(-ctx->encode_grid))  // absolute CTA count (tests)
+                                                         : nt;
+            BPE_LAUNCH_SMEM(level_kernel<TokT>, grid, THREADS, level_smem_bytes<TokT>((int)(1u << hash_log2)), ctx->stream, sq.tok(),
+                            (const TileHalo<TokT>*)sq.halo.template as<TileHalo<TokT>>(), (const LevelEntry*)ents_buf.template as<LevelEntry>() + ent_off,
+                            ent_cnt, &d_ctl->cntAB, backwards, nt, hash_log2);
+            ctx->launches++;
+        } else {
             int rcm = launch_merge<TokT, false, false>(ctx, sq.tok(), sq.halo.template as<TileHalo<TokT>>(), nt, (const StepCtl*)nullptr,
                                                        (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, &d_ctl->cntAB, A, B, X, 0u,
                                                        (int)(pass_index++ & 1u));
@@ -893,12 +980,23 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
         return BPE_OK;
     };
     size_t since_check = 0;
-    for (size_t i = 0; i < m && (n > 1 || multi); i++) {
-        const uint32_t A = merges[i].first, B = merges[i].second, X = merges[i].new_token;
-        rc = one_pass(A, B, X);
-        if (rc) return rc;
-        since_check++;
-        if (X == A) {
+    for (size_t si = 0; si < steps.size() && (n > 1 || multi); si++) {
+        const EncStep& es = steps[si];
+        const bool last_step = si + 1 == steps.size();
+        if (es.single < 0) {
+            // a level pass can remove a large share of the tokens: look at the live count after each one
+            rc = one_pass(0, 0, 0, es.off, es.cnt);
+            if (rc) return rc;
+            since_check += 32;
+        }
+        const uint32_t A = es.single < 0 ? 1u : merges[es.single].first, B = es.single < 0 ? 0u : merges[es.single].second,
+                       X = es.single < 0 ? 0u : merges[es.single].new_token;
+        if (es.single >= 0) {
+            rc = one_pass(A, B, X);
+            if (rc) return rc;
+            since_check++;
+        }
+        if (es.single >= 0 && X == A) {
             // the reference does not advance `i` after a hit (:78-81), so a merge whose new token
             // equals its own first component keeps absorbing: repeat until a pass changes nothing
             while (true) {
@@ -917,12 +1015,12 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
             }
             since_check = 0;
         }
-        if (since_check >= 32 || i + 1 == m) {
+        if (since_check >= 32 || last_step) {
             uint32_t fresh = 0;
             rc = read_merged(&fresh);
             if (rc) return rc;
             since_check = 0;
-            if (sq.n_slots > (size_t)TILE && sq.live * 100 < (uint64_t)sq.n_slots * (uint64_t)ctx->compact_pct && i + 1 < m) {
+            if (sq.n_slots > (size_t)TILE && sq.live * 100 < (uint64_t)sq.n_slots * (uint64_t)ctx->compact_pct && !last_step) {
                 rc = seq_compact(ctx, sq, nullptr);
                 if (rc) return rc;
                 if (st) st->compactions++;
@@ -1223,6 +1321,8 @@ int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value) {
     else if (s == "debug") ctx->debug = value;
     else if (s == "merge_impl") ctx->merge_impl = value;
     else if (s == "xchg_impl") ctx->xchg_impl = value;
+    else if (s == "encode_impl") ctx->encode_impl = value;
+    else if (s == "encode_grid") ctx->encode_grid = value;
     else return fail(ctx, BPE_ERR_INVALID_ARG, "unknown option '%s'", name);
     return BPE_OK;
 }

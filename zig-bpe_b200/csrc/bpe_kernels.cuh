@@ -1405,6 +1405,143 @@ __global__ void verify_counts_kernel(PairTable tbl, const uint32_t* __restrict__
 }
 
 // =========================================================================================
+// level_kernel (encode): apply a whole set of mutually independent merges in ONE pass. The host
+// (build_encode_schedule) groups the merge list into levels such that, inside a level, no merge uses
+// a token another one produces and no token is the second component of one pair and the first of
+// another. Occurrences of different pairs of a level therefore never overlap and never create or
+// destroy each other, so every slot can decide on its own: a live token that is the first component
+// of a level pair and whose next live token completes it becomes the new id; a live token that is the
+// second component of a level pair whose previous live token completes it becomes a hole. The result
+// is the same as running the level's merges one after the other (src/basic_tokenizer.zig:71-88).
+// One CTA per tile; the level's pairs live in shared memory (2-bit role map per id + open-addressing
+// hash pair -> new id).
+// =========================================================================================
+struct LevelEntry { uint32_t key; uint32_t z; };
+constexpr int LVL_MAX = 1024;        // pairs per pass (larger levels are split; any subset of a level is a level)
+constexpr int LVL_HASH_MAX = 2048;   // hash slots for LVL_MAX pairs; smaller levels use fewer (power of two >= 2 * pairs)
+constexpr int LVL_ROLE_WORDS = 65536 / 32;  // 1 bit per id: "first component of a pair of this level"
+template <class TokT> __host__ __device__ constexpr size_t level_smem_bytes(int hash_slots) {
+    return (size_t)EXT * sizeof(TokT) + (size_t)LVL_ROLE_WORDS * 4 + (size_t)hash_slots * 4 + (size_t)hash_slots * 2;
+}
+__device__ __forceinline__ uint32_t lvl_find(const uint32_t* hkey, const uint16_t* hval, uint32_t key, uint32_t hash_shift,
+                                             uint32_t hash_mask) {
+    if (key == EMPTY_KEY) return EMPTY_KEY;  // (65535,65535): first == second pairs are never part of a level pass
+    uint32_t s = (key * 0x9E3779B1u) >> hash_shift;
+    for (uint32_t probe = 0; probe <= hash_mask; probe++) {
+        const uint32_t k = hkey[s];
+        if (k == key) return (uint32_t)hval[s];
+        if (k == EMPTY_KEY) return EMPTY_KEY;
+        s = (s + 1) & hash_mask;
+    }
+    return EMPTY_KEY;
+}
+
+// Work split: (1) every thread tests its 32 slots against the role bitmap (uniform, no divergence) and keeps a
+// 32-bit candidate mask; (2) it walks its candidates with ONE copy of the look-up code, working in place on the
+// staged tile: the slot of the first component becomes the new id and, if the second component lies in the same
+// tile, that slot becomes a hole. In-place is safe inside a level: a slot is written only by the owner of the
+// occurrence it belongs to, and whatever a concurrent reader can see instead of the original token (a new id, which
+// no pair of the level mentions) leads to the same decision. A second component that lies in the NEXT tile is
+// turned into a hole by that tile (its first live token against the previous tile's last one, from the halo
+// snapshot). (3) the threads write their vectors back if they changed. CTAs take tiles round-robin so the level's
+// tables are built once per CTA.
+template <class TokT>
+__global__ void __launch_bounds__(THREADS, sizeof(TokT) == 2 ? 6 : 4) level_kernel(TokT* __restrict__ tok, const TileHalo<TokT>* __restrict__ halo,
+                                                        const LevelEntry* __restrict__ ents, uint32_t n_ent, uint32_t* nab_out,
+                                                        int backwards, uint32_t ntiles, uint32_t hash_log2) {
+    unsigned char* raw = reinterpret_cast<unsigned char*>(bpe_dyn_smem());
+    TokT* ext = reinterpret_cast<TokT*>(raw);
+    uint32_t* role = reinterpret_cast<uint32_t*>(raw + (size_t)EXT * sizeof(TokT));
+    uint32_t* hkey = role + LVL_ROLE_WORDS;
+    const uint32_t hash_slots = 1u << hash_log2, hash_mask = hash_slots - 1u, hash_shift = 32u - hash_log2;
+    uint16_t* hval = reinterpret_cast<uint16_t*>(hkey + hash_slots);
+    __shared__ uint32_t sh_n;
+    constexpr int VEC = 16 / (int)sizeof(TokT);
+    constexpr int NV = TILE / VEC / THREADS;
+    static_assert(NV * VEC <= 32, "candidate mask is 32 bits");
+    const uint32_t H = TokTraits<TokT>::hole;
+    for (int i = threadIdx.x; i < LVL_ROLE_WORDS; i += THREADS) role[i] = 0u;
+    for (uint32_t i = threadIdx.x; i < hash_slots; i += THREADS) hkey[i] = EMPTY_KEY;
+    if (threadIdx.x == 0) sh_n = 0u;
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < n_ent; e += THREADS) {
+        const uint32_t key = ents[e].key, a = key & 0xFFFFu;
+        atomicOr(&role[a >> 5], 1u << (a & 31u));
+        uint32_t s = (key * 0x9E3779B1u) >> hash_shift;
+        while (true) {
+            const uint32_t old = atomicCAS(&hkey[s], EMPTY_KEY, key);
+            if (old == EMPTY_KEY) { hval[s] = (uint16_t)ents[e].z; break; }
+            s = (s + 1) & hash_mask;
+        }
+    }
+    uint32_t merged = 0;
+    for (uint32_t it = blockIdx.x; it < ntiles; it += gridDim.x) {
+        const uint32_t tile = backwards ? ntiles - 1u - it : it;
+        uint4* gv = reinterpret_cast<uint4*>(tok + (size_t)tile * TILE);
+        uint4 v[NV];
+#pragma unroll
+        for (int k = 0; k < NV; k++) v[k] = gv[k * THREADS + (int)threadIdx.x];
+        uint4* xv = reinterpret_cast<uint4*>(ext + OFF);
+        __syncthreads();  // the previous tile's write-back has read the stage (first round: the tables are complete)
+#pragma unroll
+        for (int k = 0; k < NV; k++) xv[k * THREADS + (int)threadIdx.x] = v[k];
+        if (threadIdx.x == 0) {
+            const TileHalo<TokT> h = halo[tile];
+            for (int i = 0; i < OFF - 2; i++) ext[i] = (TokT)H;
+            ext[OFF - 2] = h.l2; ext[OFF - 1] = h.l1;
+            ext[OFF + TILE + 0] = h.r0; ext[OFF + TILE + 1] = h.r1; ext[OFF + TILE + 2] = h.r2;
+            for (int i = OFF + TILE + 3; i < EXT; i++) ext[i] = (TokT)H;
+        }
+        // (1) candidates: my slots whose token is the first component of some pair of the level
+        uint32_t cand = 0;
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            uint32_t tv[VEC];
+            unpack_vec<TokT>(v[k], tv);
+#pragma unroll
+            for (int i = 0; i < VEC; i++) {
+                const uint32_t t = tv[i] & 0xFFFFu;  // a hole maps to id 65535, whose bit is only set on u32 slots
+                const uint32_t bit = (role[t >> 5] >> (t & 31u)) & 1u;
+                cand |= ((sizeof(TokT) == 4 && tv[i] == H) ? 0u : bit) << (k * VEC + i);
+            }
+        }
+        if (sizeof(TokT) == 2) {
+            // u16 slots never hold id 65535 as a token, so its role bit is never set and holes drop out by themselves
+        }
+        __syncthreads();
+        // (2) the tile's first live token may be the second component of a pair that starts in the previous tile
+        if (threadIdx.x == 0) {
+            const uint32_t p = (uint32_t)ext[OFF - 1];
+            const int f = next_live(ext, OFF - 1);
+            if (p != H && f >= 0 && f < OFF + TILE && lvl_find(hkey, hval, pair_key(p, (uint32_t)ext[f]), hash_shift, hash_mask) != EMPTY_KEY)
+                ext[f] = (TokT)H;
+        }
+        while (cand) {
+            const int c = __ffs((int)cand) - 1;
+            cand &= cand - 1u;
+            const int s = OFF + ((c / VEC) * THREADS + (int)threadIdx.x) * VEC + (c % VEC);
+            const int j = next_live(ext, s);
+            if (j < 0) continue;
+            const uint32_t z = lvl_find(hkey, hval, pair_key((uint32_t)ext[s], (uint32_t)ext[j]), hash_shift, hash_mask);
+            if (z == EMPTY_KEY) continue;
+            ext[s] = (TokT)z;
+            if (j < OFF + TILE) ext[j] = (TokT)H;
+            merged++;
+        }
+        __syncthreads();
+        // (3) write back what changed
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            const uint4 o = xv[k * THREADS + (int)threadIdx.x];
+            if (o.x != v[k].x || o.y != v[k].y || o.z != v[k].z || o.w != v[k].w) gv[k * THREADS + (int)threadIdx.x] = o;
+        }
+    }
+    if (merged) atomicAdd(&sh_n, merged);
+    __syncthreads();
+    if (threadIdx.x == 0 && sh_n) atomicAdd(nab_out, sh_n);
+}
+
+// =========================================================================================
 // compaction: squeeze the holes out (ballot-free v1: per-tile counts, scan, scatter)
 // =========================================================================================
 template <class TokT>
