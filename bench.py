@@ -259,9 +259,9 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         enc = {"metric": "encode_input_GB_per_sec", "value": total_bytes / 1e9 / (float(te[0]) / 1000.0), "unit": "GB/s", "merges": int(len(merges)),
-               "bytes_rank0": n, "ids_out_rank0": int(n_ids), "passes": int(len(merges)), "gpu_launches": int(est["kernel_launches"]),
+               "bytes_rank0": n, "ids_out_rank0": int(n_ids), "gpu_launches": int(est["kernel_launches"]),
                "scan_GBps_per_gpu": est["scanned_slots"] * 2 / 1e9 / (est["device_ms"] / 1000.0),
-               "note": "reference semantics: one pass per merge in list order (exact for any list); algorithmic bytes n + 2*n_out"}
+               "note": "level-scheduled passes: merges that commute share one pass (exact for any list, same ids as one pass per merge); algorithmic bytes n + 2*n_out"}
         del d_out
     if rank != 0:
         if world > 1:
