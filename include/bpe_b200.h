@@ -97,6 +97,8 @@ const char* bpe_last_error(const bpe_ctx* ctx);
  *   "encode_impl"         0 (default): level-scheduled encode — merges that commute (no shared produced token, no
  *                         token that is second of one pair and first of another) are applied in one pass per
  *                         level; 1: one pass per merge, in list order. Both give the reference's result.
+ *   "encode_grid"         CTAs per SM of a level pass (default 6; they take the tiles round-robin); 0: one CTA per
+ *                         tile; negative: absolute CTA count (tests).
  *   "merge_impl"          0 (default): register-streaming merge kernel, one CTA per tile;
  *                         1: merge pass fed by a TMA ring (cp.async.bulk + mbarrier, persistent CTAs) —
  *                            measured slower on B200 for this access pattern, kept for comparison

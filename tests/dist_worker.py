@@ -79,6 +79,9 @@ ENCODE_MERGES = {
     "runs": [(97, 97, 256), (256, 256, 257), (257, 257, 258), (98, 258, 259), (99, 99, 260)],
     "cascade": [(ord("X"), ord("b"), ord("X")), (ord("a"), ord("a"), ord("a"))],
     "tiny": [(97, 98, 256), (256, 99, 257), (257, 257, 258)],
+    # several commuting pairs per level (one level pass each), pairs that straddle the shard ends
+    "rand4": [(97, 98, 256), (99, 100, 257), (100, 97, 258), (256, 257, 259), (98, 99, 260), (259, 258, 261), (97, 97, 262),
+              (256, 99, 263), (100, 100, 264), (263, 264, 265), (99, 97, 266), (98, 98, 267), (266, 267, 268)],
 }
 
 

@@ -62,7 +62,8 @@ def test_sharded_train_forced_replay(ora, tmp_path):
     assert np.array_equal(res[0]["merges"], om)
 
 
-@pytest.mark.parametrize("case,world", [("aaaa", 2), ("abab", 3), ("runs", 2), ("runs", 3), ("cascade", 2), ("tiny", 2)])
+@pytest.mark.parametrize("case,world", [("aaaa", 2), ("abab", 3), ("runs", 2), ("runs", 3), ("cascade", 2), ("tiny", 2), ("rand4", 2),
+                                        ("rand4", 3)])
 def test_sharded_encode_matches_single_process(ora, tmp_path, case, world):
     """Sharded encode: tokens that straddle shard boundaries (also runs cut at odd offsets, shards of one byte,
     the cascade rule) must come out exactly as in the reference's single-sequence encode."""

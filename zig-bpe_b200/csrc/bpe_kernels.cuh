@@ -1505,9 +1505,7 @@ __global__ void __launch_bounds__(THREADS, sizeof(TokT) == 2 ? 6 : 4) level_kern
                 cand |= ((sizeof(TokT) == 4 && tv[i] == H) ? 0u : bit) << (k * VEC + i);
             }
         }
-        if (sizeof(TokT) == 2) {
-            // u16 slots never hold id 65535 as a token, so its role bit is never set and holes drop out by themselves
-        }
+        // (u16 slots never hold id 65535 as a token, so its role bit is never set and holes drop out by themselves)
         __syncthreads();
         // (2) the tile's first live token may be the second component of a pair that starts in the previous tile
         if (threadIdx.x == 0) {
