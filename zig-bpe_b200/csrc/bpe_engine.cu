@@ -836,7 +836,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
 }
 
 // -----------------------------------------------------------------------------------------
-// encode (src/basic_tokenizer.zig:71-88): one merge pass per list entry, in list order
+// encode (src/basic_tokenizer.zig:71-88): the list in order, commuting merges grouped into level passes (build_encode_schedule)
 // -----------------------------------------------------------------------------------------
 // Encode schedule. The reference applies the merges one at a time in list order (:71-88). Two merges q < r
 // commute on every token sequence when neither uses the token the other produces and no token is the second
