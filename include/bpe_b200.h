@@ -99,6 +99,8 @@ const char* bpe_last_error(const bpe_ctx* ctx);
  *                         level; 1: one pass per merge, in list order. Both give the reference's result.
  *   "encode_grid"         CTAs per SM of a level pass (default 6; they take the tiles round-robin); 0: one CTA per
  *                         tile; negative: absolute CTA count (tests).
+ *   "encode_filter"       1: level pass with one role byte per id and an in-register successor filter (used when
+ *                         every id of the list is below 16384); 0 (default): 1-bit role map over all ids.
  *   "merge_impl"          0 (default): register-streaming merge kernel, one CTA per tile;
  *                         1: merge pass fed by a TMA ring (cp.async.bulk + mbarrier, persistent CTAs) —
  *                            measured slower on B200 for this access pattern, kept for comparison

@@ -321,3 +321,18 @@ def test_train_long_run_on_random_bytes(gpu, ora):
     data = bytes(rng.integers(0, 256, size=40000, dtype=np.uint8))
     st = _train_check(gpu, ora, data, 256 + 1500)
     assert st["tie_steps"] > 500
+
+
+def test_encode_filter_variant(gpu, ora, synth):
+    """encode_filter = 1 (byte role map + in-register successor filter in the level pass) gives the same ids"""
+    data = bytes(synth.generate(2_000_000, synth.SEED_C3, synth.BYTE))
+    m, _ = gpu.train(data, 256 + 1200)
+    other = bytes(synth.generate(1_500_000, synth.SEED_C5, synth.BYTE)) + data[:50_000]
+    want = ora.encode(other, merges_array(m), linear=True)
+    try:
+        gpu.set_option("encode_filter", 1)
+        assert np.array_equal(gpu.encode(other, m), want)
+        assert np.array_equal(gpu.encode(b"ab" * 5000 + b"a", [(97, 98, 256), (256, 256, 257), (98, 97, 258), (257, 97, 259)]),
+                              ora.encode(b"ab" * 5000 + b"a", [(97, 98, 256), (256, 256, 257), (98, 97, 258), (257, 97, 259)], linear=False))
+    finally:
+        gpu.set_option("encode_filter", 0)

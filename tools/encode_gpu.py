@@ -8,7 +8,8 @@ zb = importlib.import_module("zig-bpe_b200")
 from tools import synthcorpus as sc
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1_000_000_000
 vocab = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
-# variants: impl[:grid] — encode_impl and, for the level schedule, encode_grid (CTAs per SM; 0 = one CTA per tile)
+# variants: impl[:grid[:filter]] — encode_impl and, for the level schedule, encode_grid (CTAs per SM; 0 = one CTA per
+# tile) and encode_filter
 variants = sys.argv[3].split(",") if len(sys.argv) > 3 else ["0:6", "0:0", "1"]
 eng = zb.Engine(device=0)
 d_text = torch.from_numpy(sc.generate(n, sc.SEED_C3, sc.BYTE)).cuda()
@@ -18,8 +19,10 @@ ref = None
 for var in variants:
     impl = int(var.split(":")[0])
     eng.set_option("encode_impl", impl)
-    if ":" in var:
-        eng.set_option("encode_grid", int(var.split(":")[1]))
+    parts = var.split(":")
+    if len(parts) > 1:
+        eng.set_option("encode_grid", int(parts[1]))
+    eng.set_option("encode_filter", int(parts[2]) if len(parts) > 2 else 0)
     d_ids = torch.empty(n, dtype=torch.int16, device="cuda")
     best = None
     for rep in range(2):

@@ -56,7 +56,7 @@ struct bpe_ctx {
     std::string err;
     // options
     long verify_recount = 0, force_slow_tiebreak = 0, check_tiebreak = 0, compact_pct = 85, table_log2 = 0,
-         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 6;
+         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 6, encode_filter = 0;
     int num_sms = 148;
     DistComm dist;  // world == 1 when single GPU
     uint64_t launches = 0;
@@ -940,8 +940,15 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
     if (!ents.empty()) {
         CU(ents_buf.alloc(ents.size() * sizeof(LevelEntry)));
         CU(cudaMemcpyAsync(ents_buf.p, ents.data(), ents.size() * sizeof(LevelEntry), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaFuncSetAttribute(level_kernel<TokT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)level_smem_bytes<TokT>(LVL_HASH_MAX)));
+        CU(cudaFuncSetAttribute(level_kernel<TokT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)level_smem_bytes<TokT>(LVL_HASH_MAX)));
+        CU(cudaFuncSetAttribute(level_kernel<TokT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)level_smem_bytes<TokT>(LVL_HASH_MAX, LVL_BYTE_IDS_MAX / 4)));
     }
+    // encode_filter = 1: byte role map + successor filter (level_kernel MODE 1) when every id fits the byte map
+    uint32_t max_id = 255;
+    for (size_t i = 0; i < m; i++) max_id = std::max(max_id, (uint32_t)std::max(merges[i].first, std::max(merges[i].second, merges[i].new_token)));
+    const bool byte_roles = ctx->encode_filter == 1 && max_id < (uint32_t)LVL_BYTE_IDS_MAX;
+    const uint32_t role_words = byte_roles ? ((max_id + 1u + 15u) / 16u) * 4u : (uint32_t)LVL_ROLE_WORDS;
     // ent_cnt == 0: one merge pass for (A,B) -> X; else one level pass over ents[ent_off, ent_off + ent_cnt)
     auto one_pass = [&](uint32_t A, uint32_t B, uint32_t X, uint32_t ent_off = 0, uint32_t ent_cnt = 0) -> int {
         const uint32_t nt = sq.ntiles();
@@ -965,9 +972,15 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
             const uint32_t grid = ctx->encode_grid > 0   ? std::min<uint32_t>(nt, (uint32_t)ctx->encode_grid * (uint32_t)ctx->num_sms)
                                   : ctx->encode_grid < 0 ? std::min<uint32_t>(nt, (uint32_t)(-ctx->encode_grid))  // absolute CTA count (tests)
                                                          : nt;
-            BPE_LAUNCH_SMEM(level_kernel<TokT>, grid, THREADS, level_smem_bytes<TokT>((int)(1u << hash_log2)), ctx->stream, sq.tok(),
-                            (const TileHalo<TokT>*)sq.halo.template as<TileHalo<TokT>>(), (const LevelEntry*)ents_buf.template as<LevelEntry>() + ent_off,
-                            ent_cnt, &d_ctl->cntAB, backwards, nt, hash_log2);
+            const size_t smem = level_smem_bytes<TokT>((int)(1u << hash_log2), (int)role_words);
+            const TileHalo<TokT>* halo_p = sq.halo.template as<TileHalo<TokT>>();
+            const LevelEntry* ents_p = (const LevelEntry*)ents_buf.template as<LevelEntry>() + ent_off;
+            if (byte_roles)
+                BPE_LAUNCH_SMEM((level_kernel<TokT, 1>), grid, THREADS, smem, ctx->stream, sq.tok(), halo_p, ents_p, ent_cnt, &d_ctl->cntAB, backwards,
+                                nt, hash_log2, role_words);
+            else
+                BPE_LAUNCH_SMEM((level_kernel<TokT, 0>), grid, THREADS, smem, ctx->stream, sq.tok(), halo_p, ents_p, ent_cnt, &d_ctl->cntAB, backwards,
+                                nt, hash_log2, role_words);
             ctx->launches++;
         } else {
             int rcm = launch_merge<TokT, false, false>(ctx, sq.tok(), sq.halo.template as<TileHalo<TokT>>(), nt, (const StepCtl*)nullptr,
@@ -1323,6 +1336,7 @@ int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value) {
     else if (s == "xchg_impl") ctx->xchg_impl = value;
     else if (s == "encode_impl") ctx->encode_impl = value;
     else if (s == "encode_grid") ctx->encode_grid = value;
+    else if (s == "encode_filter") ctx->encode_filter = value;
     else return fail(ctx, BPE_ERR_INVALID_ARG, "unknown option '%s'", name);
     return BPE_OK;
 }

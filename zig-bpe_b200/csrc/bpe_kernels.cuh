@@ -1420,8 +1420,10 @@ struct LevelEntry { uint32_t key; uint32_t z; };
 constexpr int LVL_MAX = 1024;        // pairs per pass (larger levels are split; any subset of a level is a level)
 constexpr int LVL_HASH_MAX = 2048;   // hash slots for LVL_MAX pairs; smaller levels use fewer (power of two >= 2 * pairs)
 constexpr int LVL_ROLE_WORDS = 65536 / 32;  // 1 bit per id: "first component of a pair of this level"
-template <class TokT> __host__ __device__ constexpr size_t level_smem_bytes(int hash_slots) {
-    return (size_t)EXT * sizeof(TokT) + (size_t)LVL_ROLE_WORDS * 4 + (size_t)hash_slots * 4 + (size_t)hash_slots * 2;
+constexpr int LVL_BYTE_IDS_MAX = 16384;     // MODE 1 keeps one role byte per id (ids below this bound)
+// MODE 0: role_words = LVL_ROLE_WORDS (bitmap over all ids); MODE 1: role_words = ids / 4 (one byte per id)
+template <class TokT> __host__ __device__ constexpr size_t level_smem_bytes(int hash_slots, int role_words = LVL_ROLE_WORDS) {
+    return (size_t)EXT * sizeof(TokT) + (size_t)role_words * 4 + (size_t)hash_slots * 4 + (size_t)hash_slots * 2;
 }
 __device__ __forceinline__ uint32_t lvl_find(const uint32_t* hkey, const uint16_t* hval, uint32_t key, uint32_t hash_shift,
                                              uint32_t hash_mask) {
@@ -1445,14 +1447,20 @@ __device__ __forceinline__ uint32_t lvl_find(const uint32_t* hkey, const uint16_
 // turned into a hole by that tile (its first live token against the previous tile's last one, from the halo
 // snapshot). (3) the threads write their vectors back if they changed. CTAs take tiles round-robin so the level's
 // tables are built once per CTA.
-template <class TokT>
+// MODE 1 (encode_filter = 1, not yet measured on a GPU): one role BYTE per id (bit 0 first, bit 1 second component;
+// ids < role_words * 4 <= LVL_BYTE_IDS_MAX) and a register-level filter — a slot stays a candidate only if its
+// in-vector successor is a second component of the level, a hole, or out of the vector — so that far fewer slots reach
+// the hash look-up.
+template <class TokT, int MODE>
 __global__ void __launch_bounds__(THREADS, sizeof(TokT) == 2 ? 6 : 4) level_kernel(TokT* __restrict__ tok, const TileHalo<TokT>* __restrict__ halo,
                                                         const LevelEntry* __restrict__ ents, uint32_t n_ent, uint32_t* nab_out,
-                                                        int backwards, uint32_t ntiles, uint32_t hash_log2) {
+                                                        int backwards, uint32_t ntiles, uint32_t hash_log2, uint32_t role_words) {
     unsigned char* raw = reinterpret_cast<unsigned char*>(bpe_dyn_smem());
     TokT* ext = reinterpret_cast<TokT*>(raw);
     uint32_t* role = reinterpret_cast<uint32_t*>(raw + (size_t)EXT * sizeof(TokT));
-    uint32_t* hkey = role + LVL_ROLE_WORDS;
+    if (MODE == 0) role_words = LVL_ROLE_WORDS;
+    const unsigned char* role8 = reinterpret_cast<const unsigned char*>(role);
+    uint32_t* hkey = role + role_words;
     const uint32_t hash_slots = 1u << hash_log2, hash_mask = hash_slots - 1u, hash_shift = 32u - hash_log2;
     uint16_t* hval = reinterpret_cast<uint16_t*>(hkey + hash_slots);
     __shared__ uint32_t sh_n;
@@ -1460,13 +1468,19 @@ __global__ void __launch_bounds__(THREADS, sizeof(TokT) == 2 ? 6 : 4) level_kern
     constexpr int NV = TILE / VEC / THREADS;
     static_assert(NV * VEC <= 32, "candidate mask is 32 bits");
     const uint32_t H = TokTraits<TokT>::hole;
-    for (int i = threadIdx.x; i < LVL_ROLE_WORDS; i += THREADS) role[i] = 0u;
+    for (uint32_t i = threadIdx.x; i < role_words; i += THREADS) role[i] = 0u;
     for (uint32_t i = threadIdx.x; i < hash_slots; i += THREADS) hkey[i] = EMPTY_KEY;
     if (threadIdx.x == 0) sh_n = 0u;
     __syncthreads();
     for (uint32_t e = threadIdx.x; e < n_ent; e += THREADS) {
         const uint32_t key = ents[e].key, a = key & 0xFFFFu;
-        atomicOr(&role[a >> 5], 1u << (a & 31u));
+        if (MODE == 0) {
+            atomicOr(&role[a >> 5], 1u << (a & 31u));
+        } else {
+            const uint32_t b = key >> 16;
+            atomicOr(&role[a >> 2], 1u << ((a & 3u) * 8u));
+            atomicOr(&role[b >> 2], 2u << ((b & 3u) * 8u));
+        }
         uint32_t s = (key * 0x9E3779B1u) >> hash_shift;
         while (true) {
             const uint32_t old = atomicCAS(&hkey[s], EMPTY_KEY, key);
@@ -1498,11 +1512,23 @@ __global__ void __launch_bounds__(THREADS, sizeof(TokT) == 2 ? 6 : 4) level_kern
         for (int k = 0; k < NV; k++) {
             uint32_t tv[VEC];
             unpack_vec<TokT>(v[k], tv);
+            if (MODE == 0) {
 #pragma unroll
-            for (int i = 0; i < VEC; i++) {
-                const uint32_t t = tv[i] & 0xFFFFu;  // a hole maps to id 65535, whose bit is only set on u32 slots
-                const uint32_t bit = (role[t >> 5] >> (t & 31u)) & 1u;
-                cand |= ((sizeof(TokT) == 4 && tv[i] == H) ? 0u : bit) << (k * VEC + i);
+                for (int i = 0; i < VEC; i++) {
+                    const uint32_t t = tv[i] & 0xFFFFu;  // a hole maps to id 65535, whose bit is only set on u32 slots
+                    const uint32_t bit = (role[t >> 5] >> (t & 31u)) & 1u;
+                    cand |= ((sizeof(TokT) == 4 && tv[i] == H) ? 0u : bit) << (k * VEC + i);
+                }
+            } else {
+                uint32_t fm = 0, sm = 0;  // first-component slots; slots that are a second component or a hole
+#pragma unroll
+                for (int i = 0; i < VEC; i++) {
+                    const bool hole = tv[i] == H;
+                    const uint32_t r = hole ? 2u : (uint32_t)role8[tv[i]];
+                    fm |= (r & 1u) << i;
+                    sm |= (r >> 1) << i;
+                }
+                cand |= (fm & ((sm >> 1) | (1u << (VEC - 1)))) << (k * VEC);
             }
         }
         // (u16 slots never hold id 65535 as a token, so its role bit is never set and holes drop out by themselves)
