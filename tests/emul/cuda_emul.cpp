@@ -19,6 +19,29 @@ static bool g_in_fiber = false;
 static int g_cur = 0;
 static const size_t STACK = 128 * 1024;
 
+// EMUL_ORDER=reverse|random permutes the order in which the threads of a block (and the blocks of a grid) run
+// between barriers: results must not depend on it (a cheap stand-in for the concurrency of a real GPU)
+static int order_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("EMUL_ORDER");
+        mode = !e ? 0 : (!strncmp(e, "reverse", 7) ? 1 : (!strncmp(e, "random", 6) ? 2 : 0));
+        if (e && strstr(e, "_blocks")) mode |= 16;   // permute only the blocks
+        if (e && strstr(e, "_threads")) mode |= 32;  // permute only the threads
+    }
+    return mode;
+}
+static uint64_t g_rng = 0x9E3779B97F4A7C15ull;
+static uint32_t rnd() { g_rng ^= g_rng << 13; g_rng ^= g_rng >> 7; g_rng ^= g_rng << 17; return (uint32_t)(g_rng >> 32); }
+static void make_order(std::vector<int>& ord, int n, bool blocks) {
+    ord.resize((size_t)n);
+    for (int i = 0; i < n; i++) ord[(size_t)i] = i;
+    const int m = order_mode();
+    if ((blocks && (m & 32)) || (!blocks && (m & 16))) return;
+    if ((m & 3) == 1) std::reverse(ord.begin(), ord.end());
+    else if ((m & 3) == 2) for (int i = n - 1; i > 0; i--) std::swap(ord[(size_t)i], ord[(size_t)(rnd() % (uint32_t)(i + 1))]);
+}
+
 static void fiber_entry() {
     (*g_body)();
     g_state[g_cur] = 2;
@@ -79,12 +102,15 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& body, bool uses_
     g_gridDim = grid;
     g_blockDim = block;
     const int n = (int)block.x;
+    std::vector<int> border, torder;
+    make_order(border, (int)grid.x, true);
     if (!uses_sync) {
         g_in_fiber = false;
-        for (unsigned b = 0; b < grid.x; b++) {
-            g_blockIdx = dim3(b);
-            for (int t = 0; t < n; t++) {
-                g_threadIdx = dim3((unsigned)t);
+        for (unsigned bi = 0; bi < grid.x; bi++) {
+            g_blockIdx = dim3((unsigned)border[bi]);
+            make_order(torder, n, false);
+            for (int ti = 0; ti < n; ti++) {
+                g_threadIdx = dim3((unsigned)torder[(size_t)ti]);
                 body();
             }
         }
@@ -100,7 +126,8 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& body, bool uses_
     g_wval.assign((size_t)n, 0); g_wres.assign((size_t)n, 0); g_warg.assign((size_t)n, 0); g_wop.assign((size_t)n, 0);
     g_body = &body;
     g_in_fiber = true;
-    for (unsigned b = 0; b < grid.x; b++) {
+    for (unsigned bi = 0; bi < grid.x; bi++) {
+        const unsigned b = (unsigned)border[bi];
         g_blockIdx = dim3(b);
         for (int t = 0; t < n; t++) {
             getcontext(&g_ctx[t]);
@@ -115,7 +142,9 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& body, bool uses_
         int done = 0;
         while (done < n) {
             bool progressed = false;
-            for (int t = 0; t < n; t++) {
+            make_order(torder, n, false);
+            for (int ti = 0; ti < n; ti++) {
+                const int t = torder[(size_t)ti];
                 if (g_state[t] != 0) continue;
                 g_cur = t;
                 g_threadIdx = dim3((unsigned)t);

@@ -17,6 +17,7 @@
 #include <cstring>
 #include <functional>
 #include <vector>
+#include <algorithm>
 
 #define __global__
 #define __device__
@@ -60,7 +61,8 @@ static inline int __syncthreads_or(int pred) {
     emul::sync_threads();
     return r;
 }
-static inline void __syncwarp(unsigned = 0xffffffffu) {}
+// a warp-wide rendezvous (only meaningful in fiber kernels; plain-loop kernels never call it)
+static inline void __syncwarp(unsigned = 0xffffffffu) { (void)emul::warp_exchange(0u, 5 /* EMUL_ANY */, 0); }
 static inline void __threadfence() {}
 static inline void __threadfence_system() {}
 template <class T> static inline T __ldcg(const T* p) { return *p; }
