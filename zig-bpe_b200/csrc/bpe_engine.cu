@@ -1001,21 +1001,18 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
             rc = one_pass(0, 0, 0, es.off, es.cnt);
             if (rc) return rc;
             since_check += 32;
-        }
-        const uint32_t A = es.single < 0 ? 1u : merges[es.single].first, B = es.single < 0 ? 0u : merges[es.single].second,
-                       X = es.single < 0 ? 0u : merges[es.single].new_token;
-        if (es.single >= 0) {
+        } else {
+            const uint32_t A = merges[es.single].first, B = merges[es.single].second, X = merges[es.single].new_token;
             rc = one_pass(A, B, X);
             if (rc) return rc;
             since_check++;
-        }
-        if (es.single >= 0 && X == A) {
             // the reference does not advance `i` after a hit (:78-81), so a merge whose new token
             // equals its own first component keeps absorbing: repeat until a pass changes nothing
-            while (true) {
+            while (X == A) {
                 uint32_t fresh = 0;
                 rc = read_merged(&fresh);
                 if (rc) return rc;
+                since_check = 0;
                 if (multi) {  // "nothing changed" must hold on every shard
                     CU(cudaMemcpyAsync(flag_buf.p, &fresh, 4, cudaMemcpyHostToDevice, ctx->stream));
                     if (!ctx->dist.allreduce(flag_buf.p, 1, DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-reduce failed");
@@ -1026,7 +1023,6 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
                 rc = one_pass(A, B, X);
                 if (rc) return rc;
             }
-            since_check = 0;
         }
         if (since_check >= 32 || last_step) {
             uint32_t fresh = 0;
