@@ -323,6 +323,21 @@ def test_train_long_run_on_random_bytes(gpu, ora):
     assert st["tie_steps"] > 500
 
 
+def test_encode_levels_repeatable_at_size(gpu, synth):
+    """50 MB, 2,000 merges: the in-place level pass gives the same ids on every run (a race would show up as run-to-run
+    differences) and the same ids as one pass per merge"""
+    data = synth.generate(50_000_000, synth.SEED_C3, synth.BYTE)
+    m, _ = gpu.train(data, 256 + 2000)
+    runs = [gpu.encode(data, m) for _ in range(3)]
+    assert np.array_equal(runs[0], runs[1]) and np.array_equal(runs[0], runs[2])
+    try:
+        gpu.set_option("encode_impl", 1)
+        assert np.array_equal(gpu.encode(data, m), runs[0])
+    finally:
+        gpu.set_option("encode_impl", 0)
+    assert gpu.decode(runs[0], m) == data.tobytes()
+
+
 def test_encode_filter_variant(gpu, ora, synth):
     """encode_filter = 1 (byte role map + in-register successor filter in the level pass) gives the same ids"""
     data = bytes(synth.generate(2_000_000, synth.SEED_C3, synth.BYTE))
