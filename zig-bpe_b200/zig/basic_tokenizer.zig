@@ -154,12 +154,15 @@ pub const BasicTokenizer = struct {
         const rc = bpe_train(self.ctx, text.ptr, text.len, vocabSize, out.ptr, counts.ptr, &n, &st);
         if (rc == BPE_ERR_INVALID_VOCAB) return TrainError.InvalidVocabSize;
         if (rc != BPE_OK) return TrainError.OutOfMemory;
-        self.timeStats.sort_pairs_time += @intFromFloat(st.sort_pairs_ms);
-        self.timeStats.sort_pairs_calls += st.sort_pairs_calls;
-        self.timeStats.replace_pair_time += @intFromFloat(st.replace_pair_ms);
-        self.timeStats.replace_pair_calls += st.replace_pair_calls;
-        self.timeStats.just_count_pairs_time += @intFromFloat(st.just_count_pairs_ms);
-        self.timeStats.just_count_pairs_calls += st.just_count_pairs_calls;
+        // (explicit @as: compound assignment gives the cast builtins no result type)
+        self.timeStats.sort_pairs_time += @as(i64, @intFromFloat(st.sort_pairs_ms));
+        self.timeStats.sort_pairs_calls += @as(usize, @intCast(st.sort_pairs_calls));
+        self.timeStats.replace_pair_time += @as(i64, @intFromFloat(st.replace_pair_ms));
+        self.timeStats.replace_pair_calls += @as(usize, @intCast(st.replace_pair_calls));
+        self.timeStats.generate_pairs_time += @as(i64, @intFromFloat(st.generate_pairs_ms));
+        self.timeStats.generate_pairs_calls += @as(usize, @intCast(st.generate_pairs_calls));
+        self.timeStats.just_count_pairs_time += @as(i64, @intFromFloat(st.just_count_pairs_ms));
+        self.timeStats.just_count_pairs_calls += @as(usize, @intCast(st.just_count_pairs_calls));
         for (out[0..n], 0..) |m, i| {
             if (verbose) {
                 std.debug.print("merge {d}/{d}: ({d},{d}) -> {d} had {d} occurrences\n", .{ i + 1, vocabSize - vocabStart, m.first, m.second, m.new_token, counts[i] });
