@@ -4,36 +4,34 @@
 //        -o zig-out/lib/libbpe_b200.so <b200-bpe>/zig-bpe_b200/csrc/bpe_engine.cu -ldl
 const std = @import("std");
 
+const EngineDirs = struct { bpe: []const u8, cuda: []const u8 };
+
+/// link a compile step (the executable or the test binary) against the CUDA engine
+fn linkEngine(step: *std.Build.Step.Compile, dirs: EngineDirs) void {
+    for ([_][]const u8{ dirs.bpe, dirs.cuda }) |dir| step.addLibraryPath(.{ .cwd_relative = dir });
+    step.addRPath(.{ .cwd_relative = dirs.bpe });
+    step.linkSystemLibrary("bpe_b200");
+    step.linkSystemLibrary("cudart");
+    step.linkLibC();
+}
+
 pub fn build(b: *std.Build) void {
-    const target = b.standardTargetOptions(.{});
-    const optimize = b.standardOptimizeOption(.{});
-    const bpe_lib_dir = b.option([]const u8, "bpe-lib-dir", "directory holding libbpe_b200.so") orelse "zig-out/lib";
-    const cuda_lib_dir = b.option([]const u8, "cuda-lib-dir", "CUDA runtime library directory") orelse "/usr/local/cuda/lib64";
+    const dirs = EngineDirs{
+        .bpe = b.option([]const u8, "bpe-lib-dir", "directory holding libbpe_b200.so") orelse "zig-out/lib",
+        .cuda = b.option([]const u8, "cuda-lib-dir", "CUDA runtime library directory") orelse "/usr/local/cuda/lib64",
+    };
+    const opts = .{ .target = b.standardTargetOptions(.{}), .optimize = b.standardOptimizeOption(.{}) };
 
-    const exe = b.addExecutable(.{
-        .name = "zig-bpe",
-        .root_source_file = b.path("src/main.zig"),
-        .target = target,
-        .optimize = optimize,
-    });
-    exe.addLibraryPath(.{ .cwd_relative = bpe_lib_dir });
-    exe.addLibraryPath(.{ .cwd_relative = cuda_lib_dir });
-    exe.addRPath(.{ .cwd_relative = bpe_lib_dir });
-    exe.linkSystemLibrary("bpe_b200");
-    exe.linkSystemLibrary("cudart");
-    exe.linkLibC();
-    b.installArtifact(exe);
+    // `zig build run`: the main.zig workload (train 300, serialize, encode, decode)
+    const app = b.addExecutable(.{ .name = "zig-bpe", .root_source_file = b.path("src/main.zig"), .target = opts.target, .optimize = opts.optimize });
+    linkEngine(app, dirs);
+    b.installArtifact(app);
+    const launch = b.addRunArtifact(app);
+    launch.step.dependOn(b.getInstallStep());
+    b.step("run", "Train, serialize, encode and decode through the CUDA engine").dependOn(&launch.step);
 
-    const run_cmd = b.addRunArtifact(exe);
-    run_cmd.step.dependOn(b.getInstallStep());
-    const run_step = b.step("run", "Run the app");
-    run_step.dependOn(&run_cmd.step);
-
-    const tests = b.addTest(.{ .root_source_file = b.path("src/basic_tokenizer.zig"), .target = target, .optimize = optimize });
-    tests.addLibraryPath(.{ .cwd_relative = bpe_lib_dir });
-    tests.addRPath(.{ .cwd_relative = bpe_lib_dir });
-    tests.linkSystemLibrary("bpe_b200");
-    tests.linkLibC();
-    const test_step = b.step("test", "Run the reference's in-file tests against the CUDA engine");
-    test_step.dependOn(&b.addRunArtifact(tests).step);
+    // `zig build test`: the reference's in-file tests against the CUDA engine
+    const unit = b.addTest(.{ .root_source_file = b.path("src/basic_tokenizer.zig"), .target = opts.target, .optimize = opts.optimize });
+    linkEngine(unit, dirs);
+    b.step("test", "Run the reference's in-file tests against the CUDA engine").dependOn(&b.addRunArtifact(unit).step);
 }
