@@ -598,7 +598,9 @@ uint32_t oracle_zigmap_slots(const uint16_t* pairs, size_t n_pairs, uint32_t* sl
 
 #ifdef ORACLE_MAIN
 // CLI used for quick checks and CPU-baseline timing:
-//   bpe_oracle train <text-file> <vocab> <merges-out> [max_steps] [fast]
+//   bpe_oracle train <text-file> <vocab> <merges-out> [max_steps] [fast] [verbose]
+// verbose=1 prints the reference's per-merge line (:309) to stderr as each merge is learned, so a long
+// run (tools/make_golden_big.py) leaves a usable prefix behind if it is stopped early.
 #include <fstream>
 #include <iterator>
 int main(int argc, char** argv) {
@@ -610,9 +612,10 @@ int main(int argc, char** argv) {
     std::vector<uint8_t> text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
     long max_steps = argc > 5 ? atol(argv[5]) : -1;
     bool fast = argc > 6 && atoi(argv[6]) != 0;
+    bool verbose = argc > 7 && atoi(argv[7]) != 0;
     BasicTokenizer tk;
     auto t0 = Clock::now();
-    int rc = tk.train(text.data(), text.size(), (unsigned)atoi(argv[3]), false, max_steps, fast);
+    int rc = tk.train(text.data(), text.size(), (unsigned)atoi(argv[3]), verbose, max_steps, fast);
     double ms = ms_since(t0);
     if (rc) { fprintf(stderr, "train failed: %d\n", rc); return 1; }
     tk.serialize(argv[4]);
