@@ -71,3 +71,27 @@ def test_sharded_encode_matches_single_process(ora, tmp_path, case, world):
     got = np.concatenate([res[r]["ids"] for r in range(world)])
     want = ora.encode(dist_worker.make_case(case), dist_worker.ENCODE_MERGES[case], linear=False)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("case,world", [("taylor", 2), ("taylor", 3), ("taylor_odd", 3), ("taylor_odd", 4), ("rand4", 3)])
+def test_sharded_segment_encode(ora, tmp_path, case, world):
+    """The segment-resident encoder across shards: every rank sees 512 bytes of its neighbours' text, windows lie on
+    a global grid, and the concatenation of the ranks' ids is the single-process encoding (tokens that straddle a
+    shard boundary included). All ranks must have taken the segment path."""
+    res = _run(case, 300, world, tmp_path, mode="encode")
+    got = np.concatenate([res[r]["ids"] for r in range(world)])
+    want = ora.encode(dist_worker.make_case(case), dist_worker.encode_merges(case), linear=True)
+    assert np.array_equal(got, want)
+    assert all(int(res[r]["path"]) == 1 for r in range(world))
+    # each rank holds exactly the tokens that start inside its shard
+    data = dist_worker.make_case(case)
+    bounds = dist_worker.shard_bounds(case, len(data), world)
+    lens = {b: 1 for b in range(256)}
+    for a, b, z in dist_worker.encode_merges(case):
+        lens[z] = lens[a] + lens[b]
+    pos = 0
+    for r in range(world):
+        for t in res[r]["ids"]:
+            assert bounds[r] <= pos < bounds[r + 1]
+            pos += lens[int(t)]
+    assert pos == len(data)

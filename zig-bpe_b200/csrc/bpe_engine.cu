@@ -15,6 +15,7 @@
 
 #include "../../include/bpe_b200.h"
 #include "bpe_kernels.cuh"
+#include "bpe_segenc.cuh"
 #include "tiebreak_host.hpp"
 #include "dist_comm.hpp"
 
@@ -56,7 +57,7 @@ struct bpe_ctx {
     std::string err;
     // options
     long verify_recount = 0, force_slow_tiebreak = 0, check_tiebreak = 0, compact_pct = 85, table_log2 = 0,
-         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 6, encode_filter = 0;
+         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 6, encode_filter = 0, encode_geom = 0;
     int num_sms = 148;
     DistComm dist;  // world == 1 when single GPU
     uint64_t launches = 0;
@@ -849,19 +850,19 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
 // (new id below 256, equal to a component, already mentioned earlier, or a repeated pair) act as barriers
 // and run alone, in list position.
 struct EncStep { int single; uint32_t off, cnt; };  // single >= 0: merges[single] as one merge pass; else a level pass over ents[off, off+cnt)
-static void build_encode_schedule(const bpe_merge_t* merges, size_t m, bool levels, std::vector<EncStep>& steps,
-                                  std::vector<LevelEntry>& ents) {
-    steps.clear();
-    ents.clear();
-    if (!levels) {
-        for (size_t i = 0; i < m; i++) steps.push_back(EncStep{(int)i, 0u, 0u});
-        return;
-    }
-    std::vector<uint32_t> lastZ(65536, 0), lastF(65536, 0), lastS(65536, 0), lvl(m, 0);
-    std::vector<uint8_t> used(65536, 0), alone(m, 0);
+
+// Level of every merge (1-based) and whether it has to run alone. Returns true when the whole list is
+// *regular* (what a trained tokenizer writes: every new id >= 256, different from its components, not
+// mentioned earlier, no repeated pair) — the precondition of the segment-resident encoder.
+static bool merge_levels(const bpe_merge_t* merges, size_t m, std::vector<uint32_t>& lvl, std::vector<uint8_t>& alone) {
+    std::vector<uint32_t> lastZ(65536, 0), lastF(65536, 0), lastS(65536, 0);
+    std::vector<uint8_t> used(65536, 0);
     std::unordered_set<uint32_t> seen;
     seen.reserve(m * 2 + 16);
+    lvl.assign(m, 0);
+    alone.assign(m, 0);
     uint32_t floor_lvl = 0, max_lvl = 0;
+    bool all_regular = true;
     for (size_t i = 0; i < m; i++) {
         const uint32_t a = merges[i].first, b = merges[i].second, z = merges[i].new_token, key = pair_key(a, b);
         const bool regular = z >= 256 && z != a && z != b && !used[z] && !seen.count(key);
@@ -873,6 +874,7 @@ static void build_encode_schedule(const bpe_merge_t* merges, size_t m, bool leve
             l = max_lvl + 1;
             floor_lvl = l;
             alone[i] = 1;
+            all_regular = false;
         }
         lvl[i] = l;
         lastF[a] = std::max(lastF[a], l); lastS[b] = std::max(lastS[b], l); lastZ[z] = std::max(lastZ[z], l);
@@ -880,6 +882,20 @@ static void build_encode_schedule(const bpe_merge_t* merges, size_t m, bool leve
         seen.insert(key);
         max_lvl = std::max(max_lvl, l);
     }
+    return all_regular;
+}
+
+static void build_encode_schedule(const bpe_merge_t* merges, size_t m, bool levels, std::vector<EncStep>& steps,
+                                  std::vector<LevelEntry>& ents) {
+    steps.clear();
+    ents.clear();
+    if (!levels) {
+        for (size_t i = 0; i < m; i++) steps.push_back(EncStep{(int)i, 0u, 0u});
+        return;
+    }
+    std::vector<uint32_t> lvl;
+    std::vector<uint8_t> alone;
+    merge_levels(merges, m, lvl, alone);
     std::vector<uint32_t> order(m);
     for (size_t i = 0; i < m; i++) order[i] = (uint32_t)i;
     std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return lvl[x] < lvl[y]; });
@@ -899,6 +915,193 @@ static void build_encode_schedule(const bpe_merge_t* merges, size_t m, bool leve
             if (alone[order[k]]) steps.push_back(EncStep{(int)order[k], 0u, 0u});
         i = j;
     }
+}
+
+// -----------------------------------------------------------------------------------------
+// segment-resident encode (bpe_segenc.cuh): one launch over the text + the final squeeze
+// -----------------------------------------------------------------------------------------
+template <int C, int M, int NT>
+static int launch_segenc(bpe_ctx* ctx, const uint8_t* d_text, long long n, const uint8_t* halo_l, int hl, const uint8_t* halo_r, int hr,
+                         long long g_lo, long long k_first, long long k_last, const SegTab& T, uint16_t* slots, uint32_t* d_fail) {
+    auto kern = segenc_kernel<C, M, NT>;
+    const size_t smem = segenc_smem_bytes<C, M, NT>();
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long cores = k_last - k_first + 1;
+    const long long tiles = (cores + (NT - 2) - 1) / (NT - 2);
+    if (tiles > 0x7FFFFFFFll) return fail(ctx, BPE_ERR_INVALID_ARG, "input too large for one launch");
+    BPE_LAUNCH_SMEM(kern, (unsigned)tiles, NT, smem, ctx->stream, d_text, n, halo_l, hl, halo_r, hr, g_lo, k_first, k_last, T, slots, d_fail);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return BPE_OK;
+}
+
+// *used = false when this path does not apply (irregular list, id 65535, seam without a common token):
+// nothing has been written to d_out then and the caller runs the level-scheduled passes.
+static int encode_segments(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bpe_merge_t* merges, size_t m, uint16_t* d_out,
+                           size_t* out_n, bpe_stats_t* st, bool* used) {
+    *used = false;
+    if (m == 0) return BPE_OK;
+    std::vector<uint32_t> lvl;
+    std::vector<uint8_t> alone;
+    if (!merge_levels(merges, m, lvl, alone)) return BPE_OK;
+    for (size_t i = 0; i < m; i++)
+        if (merges[i].first == 0xFFFF || merges[i].second == 0xFFFF || merges[i].new_token == 0xFFFF) return BPE_OK;
+    const int world = ctx->dist.world, rank = ctx->dist.rank;
+    const bool multi = world > 1;
+    // ---- tables: byte pairs dense, the rest hashed; byte length of every id ----
+    size_t nhash = 0;
+    for (size_t i = 0; i < m; i++) nhash += (merges[i].first | merges[i].second) >= 256;
+    uint32_t hlog = 6;
+    while (((size_t)1 << hlog) < 2 * nhash + 2) hlog++;
+    const size_t hcap = (size_t)1 << hlog;
+    std::vector<uint32_t> host((size_t)65536 + 2 * hcap + 65536 / 2);
+    uint32_t* bp = host.data();
+    uint32_t* hk = bp + 65536;
+    uint16_t* len = reinterpret_cast<uint16_t*>(hk + 2 * hcap);
+    for (size_t i = 0; i < 65536; i++) bp[i] = SEG_NONE;
+    for (size_t i = 0; i < hcap; i++) { hk[2 * i] = EMPTY_KEY; hk[2 * i + 1] = SEG_NONE; }
+    for (size_t i = 0; i < 65536; i++) len[i] = 1;
+    for (size_t i = 0; i < m; i++) {
+        const uint32_t a = merges[i].first, b = merges[i].second, z = merges[i].new_token;
+        const uint32_t val = lvl[i] | (z << 16);
+        if ((a | b) < 256) bp[a | (b << 8)] = val;
+        else {
+            const uint32_t key = pair_key(a, b);
+            uint32_t s = (key * 0x9E3779B1u) >> (32 - hlog);
+            while (hk[2 * s] != EMPTY_KEY) s = (s + 1) & (uint32_t)(hcap - 1);
+            hk[2 * s] = key; hk[2 * s + 1] = val;
+        }
+        len[z] = (uint16_t)std::min<uint32_t>(65535u, (uint32_t)len[a] + (uint32_t)len[b]);
+    }
+    DevBuf tab, slots, failbuf, halo, tile_live, tile_off, total;
+    CU(tab.alloc(host.size() * 4));
+    CU(cudaMemcpyAsync(tab.p, host.data(), host.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SegTab T;
+    T.bp = tab.as<uint32_t>();
+    T.hk = reinterpret_cast<const uint2*>(tab.as<uint32_t>() + 65536);
+    T.hmask = (uint32_t)(hcap - 1);
+    T.hshift = 32 - hlog;
+    T.len = reinterpret_cast<const uint16_t*>(tab.as<uint32_t>() + 65536 + 2 * hcap);
+    // ---- multi-GPU: shard offsets and SEG_HALO bytes of text on both sides of the shard ----
+    long long g_lo = 0, g_total = (long long)n;
+    int hl = 0, hr = 0;
+    CU(halo.alloc(2 * SEG_HALO));
+    if (multi) {
+        // every rank contributes [n (2 words) | first SEG_HALO bytes | last SEG_HALO bytes]; the sum over ranks of
+        // buffers that are zero outside the own slot is an all-gather
+        const size_t W = 2 + 2 * SEG_HALO / 4;
+        std::vector<uint32_t> all((size_t)world * W, 0u);
+        std::vector<uint8_t> ends(2 * SEG_HALO, 0);
+        const size_t nf = std::min<size_t>(n, SEG_HALO);
+        if (nf) {
+            CU(cudaMemcpyAsync(ends.data(), d_text, nf, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(ends.data() + SEG_HALO, d_text + (n - nf), nf, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+        uint32_t* mine = all.data() + (size_t)rank * W;
+        mine[0] = (uint32_t)(n & 0xFFFFFFFFu); mine[1] = (uint32_t)((uint64_t)n >> 32);
+        memcpy(mine + 2, ends.data(), 2 * SEG_HALO);
+        DevBuf xb;
+        CU(xb.alloc(all.size() * 4));
+        CU(cudaMemcpyAsync(xb.p, all.data(), all.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (!ctx->dist.allreduce(xb.p, all.size(), DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-gather of the shard ends failed");
+        CU(cudaMemcpyAsync(all.data(), xb.p, all.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        auto size_of = [&](int r) { return (long long)(((uint64_t)all[(size_t)r * W + 1] << 32) | all[(size_t)r * W]); };
+        g_total = 0;
+        for (int r = 0; r < world; r++) { if (r == rank) g_lo = g_total; g_total += size_of(r); }
+        std::vector<uint8_t> hb(2 * SEG_HALO, 0);
+        // left halo: the last bytes of the ranks before me, nearest first, written right-aligned into hb[0, SEG_HALO)
+        for (int r = rank - 1; r >= 0 && hl < SEG_HALO; r--) {
+            const long long sz = size_of(r);
+            const int have = (int)std::min<long long>(sz, SEG_HALO);        // bytes of rank r held in its "last" block
+            const uint8_t* last = reinterpret_cast<const uint8_t*>(all.data() + (size_t)r * W + 2) + SEG_HALO;
+            const int take = std::min(have, SEG_HALO - hl);
+            memcpy(hb.data() + SEG_HALO - hl - take, last + (have - take), (size_t)take);
+            hl += take;
+        }
+        if (hl < SEG_HALO) memmove(hb.data(), hb.data() + SEG_HALO - hl, (size_t)hl);  // left-align: kernel reads halo_l[hl + p], p in [-hl, 0)
+        for (int r = rank + 1; r < world && hr < SEG_HALO; r++) {
+            const long long sz = size_of(r);
+            const int have = (int)std::min<long long>(sz, SEG_HALO);
+            const uint8_t* first = reinterpret_cast<const uint8_t*>(all.data() + (size_t)r * W + 2);
+            const int take = std::min(have, SEG_HALO - hr);
+            memcpy(hb.data() + SEG_HALO + hr, first, (size_t)take);
+            hr += take;
+        }
+        CU(cudaMemcpyAsync(halo.p, hb.data(), 2 * SEG_HALO, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));  // hb lives on this frame
+    }
+    // ---- geometry ----
+    int C = 64;
+    if (ctx->encode_geom == 1) C = 128;
+    else if (ctx->encode_geom == 2) C = 96;
+    else if (ctx->encode_geom == 3) C = 32;
+    const long long g_hi = g_lo + (long long)n;
+    const long long k_text_last = g_total > 0 ? (g_total - 1) / C : 0;
+    long long k_first = g_lo / C - 2, k_last = g_hi / C + 2;
+    if (k_first < 0) k_first = 0;
+    if (k_last > k_text_last) k_last = k_text_last;
+    const size_t n_slots = round_up(n ? n : 1, TILE);
+    CU(slots.alloc(n_slots * 2));
+    CU(failbuf.alloc(4));
+    CU(cudaMemsetAsync(failbuf.p, 0, 4, ctx->stream));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, ctx->stream));
+    int rc = BPE_OK;
+    if (n > 0 && g_total > 0) {
+        const uint8_t* hlp = halo.as<uint8_t>();
+        const uint8_t* hrp = halo.as<uint8_t>() + SEG_HALO;
+        uint16_t* sl = slots.as<uint16_t>();
+        uint32_t* fl = failbuf.as<uint32_t>();
+        switch (ctx->encode_geom) {
+            case 1: rc = launch_segenc<128, 32, 128>(ctx, d_text, (long long)n, hlp, hl, hrp, hr, g_lo, k_first, k_last, T, sl, fl); break;
+            case 2: rc = launch_segenc<96, 32, 128>(ctx, d_text, (long long)n, hlp, hl, hrp, hr, g_lo, k_first, k_last, T, sl, fl); break;
+            case 3: rc = launch_segenc<32, 12, 32>(ctx, d_text, (long long)n, hlp, hl, hrp, hr, g_lo, k_first, k_last, T, sl, fl); break;
+            default: rc = launch_segenc<64, 32, 128>(ctx, d_text, (long long)n, hlp, hl, hrp, hr, g_lo, k_first, k_last, T, sl, fl); break;
+        }
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(e1, ctx->stream));
+    // a seam without a common token anywhere (on any rank) sends every rank to the level-scheduled passes
+    if (multi && !ctx->dist.allreduce(failbuf.p, 1, DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-reduce of the seam status failed");
+    uint32_t nfail = 0;
+    CU(cudaMemcpyAsync(&nfail, failbuf.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float kms = 0;
+    cudaEventElapsedTime(&kms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (st) { st->kernel_ms[11] = kms; st->kernel_calls[11] = nfail ? 2 : 1; }
+    if (nfail) {
+        if (ctx->debug) fprintf(stderr, "[bpe r%d] segment encode: %u seams without a common token, falling back to level passes\n", rank, nfail);
+        return BPE_OK;
+    }
+    *used = true;
+    if (n == 0) { *out_n = 0; return BPE_OK; }
+    // ---- squeeze the holes out, straight into the caller's buffer ----
+    if (n_slots > n) {
+        BPE_LAUNCH_NS(fill_holes_kernel<uint16_t>, grid_for(n_slots - n, 256), 256, ctx->stream, slots.as<uint16_t>(), n, n_slots);
+        ctx->launches++;
+    }
+    const size_t ntl = n_slots / TILE;
+    if (ntl > 0x7FFFFFFFull) return fail(ctx, BPE_ERR_INVALID_ARG, "input too large");
+    CU(tile_live.alloc(ntl * 4)); CU(tile_off.alloc(ntl * 8)); CU(total.alloc(8));
+    BPE_LAUNCH(tile_count_kernel<uint16_t>, (unsigned)ntl, THREADS, ctx->stream, slots.as<uint16_t>(), tile_live.as<uint32_t>());
+    BPE_LAUNCH(tile_scan_kernel, 1, THREADS, ctx->stream, tile_live.as<uint32_t>(), (uint32_t)ntl, tile_off.as<unsigned long long>(),
+               total.as<unsigned long long>());
+    BPE_LAUNCH((compact_scatter_kernel<uint16_t, uint16_t>), (unsigned)ntl, THREADS, ctx->stream, slots.as<uint16_t>(),
+               tile_off.as<unsigned long long>(), d_out);
+    ctx->launches += 3;
+    CU(cudaGetLastError());
+    unsigned long long tot = 0;
+    CU(cudaMemcpyAsync(&tot, total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *out_n = (size_t)tot;
+    if (st) st->scanned_slots += n;
+    return BPE_OK;
 }
 
 template <class TokT>
@@ -935,7 +1138,7 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
     };
     std::vector<EncStep> steps;
     std::vector<LevelEntry> ents;
-    build_encode_schedule(merges, m, ctx->encode_impl == 0, steps, ents);
+    build_encode_schedule(merges, m, ctx->encode_impl != 1, steps, ents);
     DevBuf ents_buf;
     if (!ents.empty()) {
         CU(ents_buf.alloc(ents.size() * sizeof(LevelEntry)));
@@ -1063,19 +1266,29 @@ static int encode_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
     const uint64_t l0 = ctx->launches;
     if (n == 0 && ctx->dist.world == 1) { if (stats_out) *stats_out = st; return BPE_OK; }
     if (n && !d_out) return fail(ctx, BPE_ERR_INVALID_ARG, "out is null");
-    if (n >= 0xFFFFFFF0ull) return fail(ctx, BPE_ERR_INVALID_ARG, "input of %zu bytes exceeds the 32-bit position range", n);
     CU(cudaSetDevice(ctx->device));
     cudaEvent_t ev0, ev1;
     CU(cudaEventCreate(&ev0));
     CU(cudaEventCreate(&ev1));
     CU(cudaEventRecord(ev0, ctx->stream));
-    // id 65535 is the u16 hole marker: lists that mention it run on u32 slots
-    bool wide = false;
-    for (size_t i = 0; i < m; i++)
-        if (merges[i].first == 0xFFFF || merges[i].second == 0xFFFF || merges[i].new_token == 0xFFFF) wide = true;
-    int rc = wide ? encode_passes<uint32_t>(ctx, d_text, n, merges, m, d_out, out_n, &st)
+    int rc = BPE_OK;
+    bool done = false;
+    // encode_impl 0 (default): segment-resident kernel when the list is regular, else the level passes
+    if (ctx->encode_impl == 0 || ctx->encode_impl == 3) {
+        rc = encode_segments(ctx, d_text, n, merges, m, d_out, out_n, &st, &done);
+        if (rc) return rc;
+        if (!done && ctx->encode_impl == 3) return fail(ctx, BPE_ERR_INTERNAL, "encode_impl = 3: the segment-resident encoder does not apply to this input");
+    }
+    if (!done) {
+        if (n >= 0xFFFFFFF0ull) return fail(ctx, BPE_ERR_INVALID_ARG, "input of %zu bytes exceeds the 32-bit position range of the pass-based encoder", n);
+        // id 65535 is the u16 hole marker: lists that mention it run on u32 slots
+        bool wide = false;
+        for (size_t i = 0; i < m; i++)
+            if (merges[i].first == 0xFFFF || merges[i].second == 0xFFFF || merges[i].new_token == 0xFFFF) wide = true;
+        rc = wide ? encode_passes<uint32_t>(ctx, d_text, n, merges, m, d_out, out_n, &st)
                   : encode_passes<uint16_t>(ctx, d_text, n, merges, m, d_out, out_n, &st);
-    if (rc) return rc;
+        if (rc) return rc;
+    }
     CU(cudaEventRecord(ev1, ctx->stream));
     CU(cudaEventSynchronize(ev1));
     float ms = 0;
@@ -1333,6 +1546,7 @@ int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value) {
     else if (s == "encode_impl") ctx->encode_impl = value;
     else if (s == "encode_grid") ctx->encode_grid = value;
     else if (s == "encode_filter") ctx->encode_filter = value;
+    else if (s == "encode_geom") ctx->encode_geom = value;
     else return fail(ctx, BPE_ERR_INVALID_ARG, "unknown option '%s'", name);
     return BPE_OK;
 }
