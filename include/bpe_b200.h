@@ -58,7 +58,8 @@ typedef struct bpe_stats_t {
      * [0] load+initial count  [1] argmax+ties  [2] tie occupancy kernels  [3] table replay
      * [4] halo  [5] merge  [6] apply deltas  [7] compaction  [8] table rebuild / zcnt rebuild
      * [9] host gap (status read-back until the next launch)  [10] profile 3: slots scanned by the sampled
-     * merge launches  [11] reserved */
+     * merge launches  [11] encode: time of the segment-resident kernel; kernel_calls[11] = 1 when it produced the
+     * result, 2 when its seams failed and the level passes ran instead, 0 when it was not tried */
     double kernel_ms[12];
     uint64_t kernel_calls[12];
 } bpe_stats_t;
@@ -94,13 +95,21 @@ const char* bpe_last_error(const bpe_ctx* ctx);
  *   "compact_pct"         live/slots percentage below which the sequence is compacted (default 85)
  *   "table_log2"          log2 of the initial pair-table capacity (default: sized from n)
  *   "max_steps"           stop training after this many merges (0 = no limit)
- *   "encode_impl"         0 (default): level-scheduled encode — merges that commute (no shared produced token, no
- *                         token that is second of one pair and first of another) are applied in one pass per
- *                         level; 1: one pass per merge, in list order. Both give the reference's result.
+ *   "encode_impl"         0 (default): picks by cost between the segment-resident kernel (3) and the level passes (2):
+ *                         lists whose level schedule has more than "encode_seg_min_steps" steps (default 450), and inputs
+ *                         of 4 GiB or more, go to the segment kernel. 1: one pass per merge, in list order. 2: level-
+ *                         scheduled passes — merges that commute (no shared produced token, no token that is second of
+ *                         one pair and first of another) share one pass. 3: segment-resident kernel (every thread encodes
+ *                         a window of the text in shared memory, neighbouring windows are stitched at a token they share;
+ *                         regular lists only; BPE_ERR_INTERNAL if it does not apply). All give the reference's result;
+ *                         0 falls back from 3 to 2 by itself (irregular list, id 65535, windows without a common token).
+ *   "encode_geom"         window geometry of the segment kernel: 4 (default) 64-byte cores + 2 x 32 bytes of margin, 64
+ *                         threads per CTA; 0: same, 128 threads; 1: 128 + 2 x 32; 2 / 5: 96 + 2 x 32 with 128 / 64 threads;
+ *                         3: 32 + 2 x 12 (tests)
  *   "encode_grid"         CTAs per SM of a level pass (default 6; they take the tiles round-robin); 0: one CTA per
  *                         tile; negative: absolute CTA count (tests).
- *   "encode_filter"       1: level pass with one role byte per id and an in-register successor filter (used when
- *                         every id of the list is below 16384); 0 (default): 1-bit role map over all ids.
+ *   "encode_filter"       1 (default): level pass with one role byte per id and an in-register successor filter (used when
+ *                         every id of the list is below 16384); 0: 1-bit role map over all ids.
  *   "merge_impl"          0 (default): register-streaming merge kernel, one CTA per tile;
  *                         1: merge pass fed by a TMA ring (cp.async.bulk + mbarrier, persistent CTAs) —
  *                            measured slower on B200 for this access pattern, kept for comparison

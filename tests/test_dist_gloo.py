@@ -78,7 +78,7 @@ def test_sharded_segment_encode(ora, tmp_path, case, world):
     """The segment-resident encoder across shards: every rank sees 512 bytes of its neighbours' text, windows lie on
     a global grid, and the concatenation of the ranks' ids is the single-process encoding (tokens that straddle a
     shard boundary included). All ranks must have taken the segment path."""
-    res = _run(case, 300, world, tmp_path, mode="encode")
+    res = _run(case, 300, world, tmp_path, "encode_seg_min_steps=0", mode="encode")
     got = np.concatenate([res[r]["ids"] for r in range(world)])
     want = ora.encode(dist_worker.make_case(case), dist_worker.encode_merges(case), linear=True)
     assert np.array_equal(got, want)

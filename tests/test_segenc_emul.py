@@ -17,13 +17,15 @@ def _enc(eng, data, merges, geom=0, impl=0):
     try:
         eng.set_option("encode_geom", geom)
         eng.set_option("encode_impl", impl)
+        eng.set_option("encode_seg_min_steps", 0)  # impl 0 picks by cost; 0 steps: always try the segment kernel first
         return eng.encode(data, merges), _path(eng)
     finally:
-        eng.set_option("encode_geom", 0)
+        eng.set_option("encode_geom", 4)
         eng.set_option("encode_impl", 0)
+        eng.set_option("encode_seg_min_steps", 450)
 
 
-@pytest.mark.parametrize("geom", [0, 1, 2, 3])
+@pytest.mark.parametrize("geom", [0, 1, 2, 3, 4, 5])
 def test_taylor_golden_list_every_geometry(emu, ora, taylor, golden_merges, geom):
     data = taylor[:60000]
     ids, path = _enc(emu, data, golden_merges, geom)
@@ -129,6 +131,19 @@ def test_fuzzed_regular_lists(emu, ora):
         fell += path == SEG_FELL_BACK
         assert np.array_equal(ids, ora.encode(data, merges, linear=False)), (it, merges, geom)
     assert used > 30 and used + fell == 120
+
+
+def test_default_dispatch_by_cost(emu, ora, taylor, golden_merges):
+    """encode_impl = 0: short lists (few levels) take the level passes, lists with more than encode_seg_min_steps
+    schedule steps the segment kernel"""
+    ids = emu.encode(taylor[:20000], golden_merges)
+    assert _path(emu) == 0 and np.array_equal(ids, ora.encode(taylor[:20000], golden_merges, linear=True))
+    try:
+        emu.set_option("encode_seg_min_steps", 5)
+        ids = emu.encode(taylor[:20000], golden_merges)  # 44 merges -> 6 levels + 1 run merge
+        assert _path(emu) == SEG_USED and np.array_equal(ids, ora.encode(taylor[:20000], golden_merges, linear=True))
+    finally:
+        emu.set_option("encode_seg_min_steps", 450)
 
 
 def test_matches_level_and_per_merge_paths(emu, ora, taylor):

@@ -57,7 +57,7 @@ struct bpe_ctx {
     std::string err;
     // options
     long verify_recount = 0, force_slow_tiebreak = 0, check_tiebreak = 0, compact_pct = 85, table_log2 = 0,
-         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 6, encode_filter = 0, encode_geom = 0;
+         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 6, encode_filter = 1, encode_geom = 4, encode_seg_min_steps = 450;
     int num_sms = 148;
     DistComm dist;  // world == 1 when single GPU
     uint64_t launches = 0;
@@ -1035,7 +1035,7 @@ static int encode_segments(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const 
     // ---- geometry ----
     int C = 64;
     if (ctx->encode_geom == 1) C = 128;
-    else if (ctx->encode_geom == 2) C = 96;
+    else if (ctx->encode_geom == 2 || ctx->encode_geom == 5) C = 96;
     else if (ctx->encode_geom == 3) C = 32;
     const long long g_hi = g_lo + (long long)n;
     const long long k_text_last = g_total > 0 ? (g_total - 1) / C : 0;
@@ -1057,6 +1057,8 @@ static int encode_segments(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const 
         uint16_t* sl = slots.as<uint16_t>();
         uint32_t* fl = failbuf.as<uint32_t>();
         switch (ctx->encode_geom) {
+            case 4: rc = launch_segenc<64, 32, 64>(ctx, d_text, (long long)n, hlp, hl, hrp, hr, g_lo, k_first, k_last, T, sl, fl); break;
+            case 5: rc = launch_segenc<96, 32, 64>(ctx, d_text, (long long)n, hlp, hl, hrp, hr, g_lo, k_first, k_last, T, sl, fl); break;
             case 1: rc = launch_segenc<128, 32, 128>(ctx, d_text, (long long)n, hlp, hl, hrp, hr, g_lo, k_first, k_last, T, sl, fl); break;
             case 2: rc = launch_segenc<96, 32, 128>(ctx, d_text, (long long)n, hlp, hl, hrp, hr, g_lo, k_first, k_last, T, sl, fl); break;
             case 3: rc = launch_segenc<32, 12, 32>(ctx, d_text, (long long)n, hlp, hl, hrp, hr, g_lo, k_first, k_last, T, sl, fl); break;
@@ -1273,8 +1275,18 @@ static int encode_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
     CU(cudaEventRecord(ev0, ctx->stream));
     int rc = BPE_OK;
     bool done = false;
-    // encode_impl 0 (default): segment-resident kernel when the list is regular, else the level passes
-    if (ctx->encode_impl == 0 || ctx->encode_impl == 3) {
+    // encode_impl 0 (default) picks by cost: the level passes sweep the sequence once per level (C3's 7,936 merges:
+    // ~190 sweeps, 0.12 s per GB), the segment-resident kernel costs ~0.3 s per GB whatever the list (measured on
+    // B200) and needs no exchange between GPUs inside it. 3 forces the segment kernel, 2 the
+    // level passes, 1 one pass per merge.
+    bool try_segments = ctx->encode_impl == 3;
+    if (ctx->encode_impl == 0 && m > 0) {
+        std::vector<EncStep> steps;
+        std::vector<LevelEntry> ents;
+        build_encode_schedule(merges, m, true, steps, ents);
+        try_segments = steps.size() > (size_t)ctx->encode_seg_min_steps || n >= 0xFFFFFFF0ull;
+    }
+    if (try_segments) {
         rc = encode_segments(ctx, d_text, n, merges, m, d_out, out_n, &st, &done);
         if (rc) return rc;
         if (!done && ctx->encode_impl == 3) return fail(ctx, BPE_ERR_INTERNAL, "encode_impl = 3: the segment-resident encoder does not apply to this input");
@@ -1547,6 +1559,7 @@ int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value) {
     else if (s == "encode_grid") ctx->encode_grid = value;
     else if (s == "encode_filter") ctx->encode_filter = value;
     else if (s == "encode_geom") ctx->encode_geom = value;
+    else if (s == "encode_seg_min_steps") ctx->encode_seg_min_steps = value;
     else return fail(ctx, BPE_ERR_INVALID_ARG, "unknown option '%s'", name);
     return BPE_OK;
 }

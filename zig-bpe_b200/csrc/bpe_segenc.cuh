@@ -54,8 +54,9 @@ __device__ __forceinline__ uint32_t seg_lookup(const SegTab& T, uint32_t a, uint
 }
 
 template <int C, int M, int NT> __host__ __device__ constexpr size_t segenc_smem_bytes() {
-    // columns [L][NT] u32 + hit/dirty list [L][NT] u8 + max(byte span, output tile) + per-thread seam scratch
-    return (size_t)(C + 2 * M) * NT * 5 + (size_t)(NT - 2) * C * 2 + (size_t)NT * 3 * 4 + 64;
+    // columns [L][NT] u32 + max(hit/dirty list [L][NT] u8, output tile built in its place) + per-thread seam scratch
+    const size_t lst = (size_t)(C + 2 * M) * NT, tile = (size_t)(NT - 2) * C * 2;
+    return (size_t)(C + 2 * M) * NT * 4 + ((lst > tile ? lst : tile) + 15) / 16 * 16 + (size_t)NT * 3 * 4 + 64;
 }
 
 // Geometry: thread t of a CTA owns core k = k_tile + t - 1 (threads 0 and NT-1 repeat the neighbouring
@@ -72,15 +73,12 @@ __global__ void __launch_bounds__(NT) segenc_kernel(const uint8_t* __restrict__ 
     static_assert(C >= 2 * M, "the seam zones of one window must not overlap");
     static_assert(3 * C + M <= SEG_HALO, "halo too small for this geometry");
     static_assert(NT % 32 == 0, "whole warps");
-    constexpr int SPAN = NT * C + 2 * M;                    // bytes the CTA's windows cover
-    constexpr int SPAN_PHYS = SPAN + 4 * (SPAN / C + 1);    // 4 bytes of skew per core: lanes hit distinct banks
     constexpr int TILE_SLOTS = (NT - 2) * C;
-    static_assert(SPAN_PHYS <= TILE_SLOTS * 2, "the byte span is staged where the output tile is built later");
+    constexpr int REGION = ((L * NT > TILE_SLOTS * 2 ? L * NT : TILE_SLOTS * 2) + 15) / 16 * 16;  // lists, then the output tile
     uint32_t* col = bpe_dyn_smem();                         // [L][NT] token | level << 16
     uint8_t* lst = reinterpret_cast<uint8_t*>(col + L * NT);  // [L][NT] hits from the front, dirty slots from the back
-    uint8_t* span = lst + L * NT;                           // staged bytes, later the output tile
-    uint16_t* tile = reinterpret_cast<uint16_t*>(span);
-    int* s_cnt = reinterpret_cast<int*>(span + TILE_SLOTS * 2);
+    uint16_t* tile = reinterpret_cast<uint16_t*>(lst);      // after the rounds: the CTA's output tile
+    int* s_cnt = reinterpret_cast<int*>(lst + REGION);
     int* s_ws = s_cnt + NT;
     int* s_c = s_ws + NT;
     const int t = (int)threadIdx.x;
@@ -97,27 +95,23 @@ __global__ void __launch_bounds__(NT) segenc_kernel(const uint8_t* __restrict__ 
     if (origin + we > vhi) we = (int)(vhi - origin);
     const bool active = active_core && we > ws;
 
-    // ---- stage the CTA's byte span (coalesced), skewed by 4 bytes per core ----
-    for (int i = t; i < SPAN; i += NT) {
-        const long long p = origin + i;
-        uint8_t b = 0;
-        if (p >= vlo && p < vhi) b = p < 0 ? halo_l[hl + p] : (p >= n ? halo_r[p - n] : text[p]);
-        span[i + 4 * (i / C)] = b;
-    }
-    __syncthreads();
-
     int cnt = 0;
     if (active) {
-        // ---- initial tokens + levels of the byte pairs ----
+        // ---- initial tokens + levels of the byte pairs (bytes straight from global memory: neighbouring lanes
+        // read neighbouring 64-byte pieces, every line is used in full through L1) ----
         cnt = we - ws;
         uint32_t m = LV_INF;
         int nh = 0;
-        uint32_t prev = span[ws + 4 * (ws / C)];
+        const long long p0 = origin + ws;
+        const bool inner = p0 >= 0 && p0 + cnt <= n;
+        auto fetch = [&](long long p) -> uint32_t {
+            return p < 0 ? halo_l[hl + p] : (p >= n ? halo_r[p - n] : text[p]);
+        };
+        uint32_t prev = inner ? (uint32_t)text[p0] : fetch(p0);
         for (int s = 0; s < cnt; s++) {
             uint32_t lv = LV_INF, nxt = 0;
             if (s + 1 < cnt) {
-                const int i = ws + s + 1;
-                nxt = span[i + 4 * (i / C)];
+                nxt = inner ? (uint32_t)text[p0 + s + 1] : fetch(p0 + s + 1);
                 lv = T.bp[prev | (nxt << 8)] & 0xFFFFu;
             }
             COL(s) = prev | (lv << 16);
@@ -147,16 +141,22 @@ __global__ void __launch_bounds__(NT) segenc_kernel(const uint8_t* __restrict__ 
             int w = 0, nd = 0;
             uint32_t m2 = LV_INF;
             nh = 0;
-            for (int s = 0; s < cnt; s++) {
-                const uint32_t v = COL(s), lv = v >> 16;
-                if (lv == LV_DEAD) continue;
-                if (w != s) COL(w) = v;
-                if (lv == LV_DIRTY) { LST(L - 1 - nd) = (uint8_t)w; nd++; }
-                else if (lv != LV_INF) {
-                    if (lv < m2) { m2 = lv; nh = 0; }
-                    if (lv == m2) LST(nh++) = (uint8_t)w;
+            {
+                const uint32_t* rp = col + t;
+                uint32_t* wp = col + t;
+                uint8_t* hp = lst + t;
+                uint8_t* dp = lst + (L - 1) * NT + t;
+                for (int s = 0; s < cnt; s++, rp += NT) {
+                    const uint32_t v = *rp, lv = v >> 16;
+                    if (lv == LV_DEAD) continue;
+                    *wp = v;
+                    wp += NT;
+                    if (lv < LV_DEAD) {
+                        if (lv < m2) { m2 = lv; nh = 0; hp = lst + t; }
+                        if (lv == m2) { *hp = (uint8_t)w; hp += NT; nh++; }
+                    } else if (lv == LV_DIRTY) { *dp = (uint8_t)w; dp -= NT; nd++; }
+                    w++;
                 }
-                w++;
             }
             cnt = w;
             // D: levels of the changed pairs
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(NT) segenc_kernel(const uint8_t* __restrict__ 
     }
     s_cnt[t] = active ? cnt : 0;
     s_ws[t] = ws;
-    __syncthreads();  // every window is final; the byte span is no longer needed
+    __syncthreads();  // every window is final
 
     // ---- seam with the window on my right: first common (position, token) in the overlap ----
     int cstar = we;
@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(NT) segenc_kernel(const uint8_t* __restrict__ 
         if (cstar < 0) { atomicAdd(fail, 1u); cstar = (t + 1) * C + M; }
     }
     s_c[t] = cstar;
+    __syncthreads();  // the lists are dead: their memory becomes the output tile
     // the output tile: cores of threads 1..NT-2, clipped to the shard
     long long tlo = origin + C + M, thi = tlo + TILE_SLOTS;
     if (tlo < 0) tlo = 0;
