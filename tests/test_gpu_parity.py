@@ -300,7 +300,7 @@ def test_c3_full_size_golden(gpu, ora, synth):
     n = 1_000_000_000
     gm, gc, rec = _golden_big("c3")
     k = len(gm)
-    assert k >= 1000
+    assert k >= 500
     data = synth.generate(n, synth.SEED_C3, synth.BYTE)
     assert hashlib.sha256(data.tobytes()).hexdigest() == rec["corpus_sha256"]
     m, c = gpu.train(data, 8192)

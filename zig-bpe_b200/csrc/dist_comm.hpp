@@ -4,6 +4,7 @@
 // e.g. the one bundled with PyTorch).
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -94,36 +95,69 @@ struct DistComm {
     void* peer_mapped[MAX_PEERS] = {nullptr};
     uint32_t epoch_base = 0;   // arrival flags only ever grow, across training calls
     static size_t mbox_slot_words() { return (size_t)2 * 65552 + 16 + 16 * MAX_PEERS; }
-    // allocate this rank's mailbox, exchange IPC handles through NCCL, map every peer's mailbox
+    // Allocate this rank's mailbox, exchange IPC handles through NCCL, map every peer's mailbox. Collective: every
+    // rank takes part in the all-gather and in the final agreement whatever happened locally (a rank whose
+    // allocation or mapping failed sends a zeroed handle and votes 0), so either all ranks use the mailboxes or
+    // all of them use the NCCL all-reduce — a split would leave the ranks waiting for each other in different
+    // protocols. BPE_TEST_PEER_FAIL_RANK=<r> makes rank r fail locally (tests).
     bool init_peers(std::string* err) {
         if (world < 2 || world > MAX_PEERS) { if (err) *err = "peer exchange supports 2..8 ranks"; return false; }
         const size_t slot = mbox_slot_words();
         const size_t words = (size_t)2 * world * slot + 64;
-        if (cudaMalloc(&mbox_local, words * 4) != cudaSuccess) { if (err) *err = "mailbox allocation failed"; cudaGetLastError(); return false; }
-        cudaMemset(mbox_local, 0, words * 4);
+        bool local_ok = true;
+        std::string why;
+        auto local_fail = [&](const char* msg) { if (local_ok) why = msg; local_ok = false; cudaGetLastError(); };
+        const char* tf = getenv("BPE_TEST_PEER_FAIL_RANK");
+        if (tf && atoi(tf) == rank) local_fail("forced failure (BPE_TEST_PEER_FAIL_RANK)");
         cudaIpcMemHandle_t mine;
-        if (cudaIpcGetMemHandle(&mine, mbox_local) != cudaSuccess) { if (err) *err = "cudaIpcGetMemHandle failed"; cudaGetLastError(); return false; }
+        memset(&mine, 0, sizeof mine);
+        if (local_ok && cudaMalloc(&mbox_local, words * 4) != cudaSuccess) { mbox_local = nullptr; local_fail("mailbox allocation failed"); }
+        if (local_ok) {
+            cudaMemset(mbox_local, 0, words * 4);
+            if (cudaIpcGetMemHandle(&mine, mbox_local) != cudaSuccess) { memset(&mine, 0, sizeof mine); local_fail("cudaIpcGetMemHandle failed"); }
+        }
+        // [world handles | my handle | vote]: one buffer for the all-gather and the agreement
         void* d_h = nullptr;
-        if (cudaMalloc(&d_h, sizeof(mine) * (size_t)(world + 1)) != cudaSuccess) { cudaGetLastError(); return false; }
-        cudaMemcpy((char*)d_h + sizeof(mine) * world, &mine, sizeof(mine), cudaMemcpyHostToDevice);
-        bool ok = allgather_bytes((char*)d_h + sizeof(mine) * world, d_h, sizeof(mine));
+        const size_t hb = sizeof(mine);
+        if (cudaMalloc(&d_h, hb * (size_t)(world + 1) + 8) != cudaSuccess) {
+            // cannot even take part in the collective: this is the one failure that cannot be agreed on
+            if (err) *err = "device allocation for the handle exchange failed";
+            cudaGetLastError();
+            destroy_peers();
+            return false;
+        }
+        cudaMemcpy((char*)d_h + hb * world, &mine, hb, cudaMemcpyHostToDevice);
+        bool coll_ok = allgather_bytes((char*)d_h + hb * world, d_h, hb);
         cudaStreamSynchronize(stream);
         std::vector<cudaIpcMemHandle_t> all((size_t)world);
-        cudaMemcpy(all.data(), d_h, sizeof(mine) * world, cudaMemcpyDeviceToHost);
-        cudaFree(d_h);
-        if (!ok) { if (err) *err = "all-gather of IPC handles failed"; return false; }
-        for (int p = 0; p < world; p++) {
+        cudaMemcpy(all.data(), d_h, hb * world, cudaMemcpyDeviceToHost);
+        if (!coll_ok) local_fail("all-gather of IPC handles failed");
+        static const cudaIpcMemHandle_t zero_handle = {};
+        for (int p = 0; p < world && local_ok; p++) {
             void* base = mbox_local;
             if (p != rank) {
+                if (memcmp(&all[(size_t)p], &zero_handle, hb) == 0) { local_fail("a peer has no mailbox"); break; }
                 if (cudaIpcOpenMemHandle(&base, all[(size_t)p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-                    if (err) *err = "cudaIpcOpenMemHandle failed (no peer access?)";
-                    cudaGetLastError();
-                    return false;
+                    local_fail("cudaIpcOpenMemHandle failed (no peer access?)");
+                    break;
                 }
                 peer_mapped[p] = base;
             }
             peers.mbox[p] = (uint32_t*)base;
             peers.flags[p] = (uint32_t*)base + (size_t)2 * world * slot;
+        }
+        // agreement: minimum of the local verdicts
+        unsigned long long vote = local_ok ? 1ull : 0ull;
+        void* d_vote = (char*)d_h + hb * (size_t)(world + 1);
+        cudaMemcpy(d_vote, &vote, 8, cudaMemcpyHostToDevice);
+        const bool red_ok = allreduce(d_vote, 1, DIST_U64_MIN);
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(&vote, d_vote, 8, cudaMemcpyDeviceToHost);
+        cudaFree(d_h);
+        if (!red_ok || vote == 0) {
+            if (err) *err = local_ok ? "a peer could not set up its mailbox" : why;
+            destroy_peers();
+            return false;
         }
         peers.slot_words = (uint32_t)slot;
         peer_ok = true;
