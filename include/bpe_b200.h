@@ -58,10 +58,12 @@ typedef struct bpe_stats_t {
      * [0] load+initial count  [1] argmax+ties  [2] tie occupancy kernels  [3] table replay
      * [4] halo  [5] merge  [6] apply deltas  [7] compaction  [8] table rebuild / zcnt rebuild
      * [9] host gap (status read-back until the next launch)  [10] profile 3: slots scanned by the sampled
-     * merge launches  [11] encode: time of the segment-resident kernel; kernel_calls[11] = 1 when it produced the
-     * result, 2 when its seams failed and the level passes ran instead, 0 when it was not tried */
+     * merge launches; encode: kernel_calls[10] = the encoder that produced the ids (0 passes, 1 segment kernel,
+     * 2 tile kernel)  [11] encode: time of the tile / segment kernel; kernel_calls[11] = 1 when it produced the
+     * result, 2 when it gave up (no common token at a seam, ...) and another encoder ran instead, 0 when not tried */
     double kernel_ms[12];
     uint64_t kernel_calls[12];
+    uint64_t aeqb_steps;      /* train: steps whose merge has first == second (they take the run-chaining halo pass) */
 } bpe_stats_t;
 
 enum {
@@ -95,9 +97,14 @@ const char* bpe_last_error(const bpe_ctx* ctx);
  *   "compact_pct"         live/slots percentage below which the sequence is compacted (default 85)
  *   "table_log2"          log2 of the initial pair-table capacity (default: sized from n)
  *   "max_steps"           stop training after this many merges (0 = no limit)
- *   "encode_impl"         0 (default): picks by cost between the segment-resident kernel (3) and the level passes (2):
- *                         lists whose level schedule has more than "encode_seg_min_steps" steps (default 450), and inputs
- *                         of 4 GiB or more, go to the segment kernel. 1: one pass per merge, in list order. 2: level-
+ *   "encode_impl"         0 (default): the tile-resident kernel (4) for every list a trained tokenizer can write; when it
+ *                         does not apply or gives up, the choice between the segment-resident kernel (3) and the level
+ *                         passes (2) is made by cost: lists whose level schedule has more than "encode_seg_min_steps" steps
+ *                         (default 450), and inputs of 4 GiB or more, go to the segment kernel. 4: tile-resident kernel — a
+ *                         CTA keeps a window of the text ("encode_tile" bytes, default and maximum 8192, + 2 x 64 bytes of
+ *                         margin) in shared memory through all merges, one launch, the text is read once; neighbouring
+ *                         windows are stitched at a token they share (BPE_ERR_INTERNAL if it does not apply).
+ *                         1: one pass per merge, in list order. 2: level-
  *                         scheduled passes — merges that commute (no shared produced token, no token that is second of
  *                         one pair and first of another) share one pass. 3: segment-resident kernel (every thread encodes
  *                         a window of the text in shared memory, neighbouring windows are stitched at a token they share;
@@ -116,6 +123,9 @@ const char* bpe_last_error(const bpe_ctx* ctx);
  *                         2: candidate-scan path (single GPU, experimental, currently slower): one barrier-free
  *                            streaming scan queues the A's that can start an occurrence, a resolve + a write kernel
  *                            finish the step (no tiles / halos)
+ *   "fuse_halo"           1 (default): the apply kernel of a step also gathers the tile halos of the next step (two launches
+ *                         per merge step: merge, apply); steps whose merge has first == second take the stand-alone
+ *                         run-chaining halo pass. 0: a halo launch before every merge pass.
  *   "xchg_impl"           multi-GPU per-step exchange. 0 (default): peer-memory mailboxes over NVLink (each rank
  *                         writes its deltas into every peer's mailbox and raises a flag; falls back to 1 when
  *                         peer access is unavailable); 1: NCCL all-reduce

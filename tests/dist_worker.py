@@ -32,6 +32,11 @@ def main():
                 t = torch.from_numpy(a.astype(np.int64))  # exact: sums stay far below 2^63
                 dist.all_reduce(t, op=dist.ReduceOp.SUM)
                 a[:] = (t.numpy() & 0xFFFFFFFF).astype(np.uint32)
+            elif kind == 3:  # u64 sum (the byte-pair histogram; test inputs stay far below 2^63)
+                a = np.ctypeslib.as_array(ctypes.cast(buf, ctypes.POINTER(ctypes.c_uint64)), shape=(count,))
+                t = torch.from_numpy(a.view(np.int64).copy())
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                a[:] = t.numpy().view(np.uint64)
             else:
                 a = np.ctypeslib.as_array(ctypes.cast(buf, ctypes.POINTER(ctypes.c_uint64)), shape=(count,))
                 # order-preserving map of u64 onto i64 so that gloo's signed min/max are exact
@@ -49,6 +54,22 @@ def main():
     assert lib.bpe_ctx_create_dist_cb(ctypes.byref(ctx), rank, world, cb) == 0
     eng = zb.Engine.__new__(zb.Engine)
     eng.lib, eng._ctx, eng.rank, eng.world, eng.last_stats = lib, ctx, rank, world, {}
+    shm = None
+    if os.environ.get("PEER_SHM"):
+        # the default data plane of the GPU build — peer mailboxes written by the last CTA of the merge pass, summed by
+        # the apply kernel — with the mailboxes in a shared-memory file instead of NVLink peer memory
+        lib.bpe_peer_shm_bytes.restype = ctypes.c_size_t
+        lib.bpe_peer_shm_bytes.argtypes = [ctypes.c_int]
+        lib.bpe_ctx_set_peer_shm.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+        nbytes = lib.bpe_peer_shm_bytes(world)
+        path = os.environ["PEER_SHM"]
+        if rank == 0:
+            with open(path, "wb") as f:
+                f.truncate(nbytes)
+        dist.barrier()
+        shm = np.memmap(path, dtype=np.uint8, mode="r+", shape=(nbytes,))
+        assert lib.bpe_ctx_set_peer_shm(ctx, shm.ctypes.data, nbytes) == 0
+        dist.barrier()
     eng.set_option("table_log2", 13)
     for opt in sys.argv[4:]:
         k, v = opt.split("=")
@@ -61,7 +82,7 @@ def main():
         # sharded encode with a fixed merge list: the concatenation of the ranks' ids must equal the
         # single-process encoding of the whole text
         ids = eng.encode(shard, encode_merges(case))
-        np.savez(f"{out_path}.{rank}.npz", ids=ids, path=eng.last_stats["kernel_calls"][11])
+        np.savez(f"{out_path}.{rank}.npz", ids=ids, path=eng.last_stats["kernel_calls"][11], who=eng.last_stats["kernel_calls"][10])
         dist.barrier()
         dist.destroy_process_group()
         return
@@ -86,14 +107,14 @@ ENCODE_MERGES = {
 
 
 def encode_merges(case):
-    if case in ("taylor", "taylor_odd"):  # the reference's committed merges.txt
+    if case in ("taylor", "taylor_odd", "taylor_even"):  # the reference's committed merges.txt
         return [tuple(int(x) for x in line.split(",")) for line in open(os.path.join(ROOT, "tests", "golden", "merges_300.txt"))]
     return ENCODE_MERGES[case]
 
 
 def make_case(case):
     rng = np.random.default_rng(1234)
-    if case in ("taylor", "taylor_odd"):
+    if case in ("taylor", "taylor_odd", "taylor_even"):
         return open(os.path.join(ROOT, "tests", "golden", "taylorswift.txt"), "rb").read()[:30000]
     if case == "aaaa":
         return b"a" * 3001
@@ -116,6 +137,8 @@ def shard_bounds(case, n, world):
     if case == "taylor_odd":  # shards of very different sizes, one shorter than the halo, cuts off the 64-byte core grid
         b = [0, 301, 301 + 77, 20011][: world] + [n]
         return b
+    if case == "taylor_even":  # uneven shards, all above the tile encoder's minimum, cut at odd offsets
+        return [0, 1031, 1031 + 7777, 20011][: world] + [n]
     if case == "tiny":  # some ranks get one byte or nothing
         b = [0, 1] + [n] * (world - 1)
         return b[: world + 1] if world >= 2 else [0, n]

@@ -23,6 +23,8 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
+#define __grid_constant__
 #define __shared__ static
 #define __restrict__
 #define __launch_bounds__(...)
@@ -63,8 +65,8 @@ static inline int __syncthreads_or(int pred) {
 }
 // a warp-wide rendezvous (only meaningful in fiber kernels; plain-loop kernels never call it)
 static inline void __syncwarp(unsigned = 0xffffffffu) { (void)emul::warp_exchange(0u, 5 /* EMUL_ANY */, 0); }
-static inline void __threadfence() {}
-static inline void __threadfence_system() {}
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 template <class T> static inline T __ldcg(const T* p) { return *p; }
 
 // ---- atomics (single OS thread: plain read-modify-write) --------------------------------

@@ -23,16 +23,19 @@ def _free_port():
     return p
 
 
-def _run(case, vocab, world, tmp_path, *opts, mode="train"):
+def _run(case, vocab, world, tmp_path, *opts, mode="train", peer_shm=False):
     out = str(tmp_path / f"{case}_{world}_{mode}")
     port = _free_port()
     procs = []
+    shm_path = f"/dev/shm/bpe_b200_test_{os.getpid()}_{port}" if peer_shm else ""
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
-                   OMP_NUM_THREADS="1", DIST_MODE=mode)
+                   OMP_NUM_THREADS="1", DIST_MODE=mode, PEER_SHM=shm_path)
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_worker.py"), case, str(vocab), out, *opts],
                                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     logs = [p.communicate(timeout=600)[0] for p in procs]
+    if shm_path and os.path.exists(shm_path):
+        os.unlink(shm_path)
     for r, p in enumerate(procs):
         assert p.returncode == 0, f"rank {r} failed:\n{logs[r][-3000:]}"
     return [np.load(f"{out}.{r}.npz") for r in range(world)]
@@ -78,7 +81,7 @@ def test_sharded_segment_encode(ora, tmp_path, case, world):
     """The segment-resident encoder across shards: every rank sees 512 bytes of its neighbours' text, windows lie on
     a global grid, and the concatenation of the ranks' ids is the single-process encoding (tokens that straddle a
     shard boundary included). All ranks must have taken the segment path."""
-    res = _run(case, 300, world, tmp_path, "encode_seg_min_steps=0", mode="encode")
+    res = _run(case, 300, world, tmp_path, "encode_seg_min_steps=0", "encode_try_tiles=0", mode="encode")
     got = np.concatenate([res[r]["ids"] for r in range(world)])
     want = ora.encode(dist_worker.make_case(case), dist_worker.encode_merges(case), linear=True)
     assert np.array_equal(got, want)
@@ -95,3 +98,40 @@ def test_sharded_segment_encode(ora, tmp_path, case, world):
             assert bounds[r] <= pos < bounds[r + 1]
             pos += lens[int(t)]
     assert pos == len(data)
+
+
+@pytest.mark.parametrize("case,world,tile", [("taylor", 2, 1024), ("taylor", 3, 2048), ("taylor_even", 4, 1024), ("rand4", 3, 1024), ("rand4", 2, 8192)])
+def test_sharded_tile_encode(ora, tmp_path, case, world, tile):
+    """The tile-resident encoder across shards: around every shard boundary both ranks encode the same bridge window and
+    stitch it between their edge tiles, so the concatenation of the ranks' ids is the single-process encoding and every
+    rank holds exactly the tokens that start inside its shard — with nothing exchanged but 512 bytes of text."""
+    res = _run(case, 300, world, tmp_path, f"encode_tile={tile}", mode="encode")
+    data = dist_worker.make_case(case)
+    got = np.concatenate([res[r]["ids"] for r in range(world)])
+    want = ora.encode(data, dist_worker.encode_merges(case), linear=True)
+    assert np.array_equal(got, want)
+    assert all(int(res[r]["who"]) == 2 and int(res[r]["path"]) == 1 for r in range(world))
+    bounds = dist_worker.shard_bounds(case, len(data), world)
+    lens = {b: 1 for b in range(256)}
+    for a, b, z in dist_worker.encode_merges(case):
+        lens[z] = lens[a] + lens[b]
+    pos = 0
+    for r in range(world):
+        for t in res[r]["ids"]:
+            assert bounds[r] <= pos < bounds[r + 1]
+            pos += lens[int(t)]
+    assert pos == len(data)
+
+
+@pytest.mark.parametrize("case,vocab,world", [("taylor", 290, 2), ("runs", 280, 3), ("rand4", 290, 2), ("rand256", 300, 3), ("abab", 268, 2),
+                                              ("tiny", 270, 2)])
+def test_sharded_train_through_peer_mailboxes(ora, tmp_path, case, vocab, world):
+    """The default multi-GPU data plane: the last CTA of every rank's merge pass writes its deltas and shard ends into
+    every peer's mailbox and raises a flag, the apply kernel waits for the flags and sums the slots (and its halo CTAs
+    read the neighbours' shard ends straight from the mailbox). Here the ranks are processes and the mailboxes a
+    shared-memory file; on GPUs it is NVLink peer memory. Same merges as the oracle on the unsharded corpus."""
+    res = _run(case, vocab, world, tmp_path, peer_shm=True)
+    om, oc = ora.train(dist_worker.make_case(case), vocab, fast=True)
+    for r in range(world):
+        assert np.array_equal(res[r]["merges"], om), f"rank {r}"
+        assert np.array_equal(res[r]["counts"], oc), f"rank {r}"

@@ -47,6 +47,43 @@ def test_train_golden_prefix(emu, ora, taylor):
     assert st["kernel_launches"] > 0
 
 
+def test_count_overflow_is_detected(emu, zb, ora, taylor):
+    """The pair table counts in 32 bits (the reference in usize, :47,265): a corpus whose most frequent byte pair does not
+    fit is refused with BPE_ERR_INTERNAL instead of wrapping silently. `count_limit_log2` scales the limit down so that
+    the check runs on a small input; at the real limit (2^32 - 1) the same input trains as usual."""
+    data = taylor[:30000]
+    try:
+        emu.set_option("count_limit_log2", 9)  # ('e',' ') occurs far more than 511 times in 30 KB of English
+        with pytest.raises(zb.BpeError) as e:
+            emu.train(data, 270)
+        assert e.value.code == zb.BPE_ERR_INTERNAL and "32-bit pair counts" in str(e.value)
+        emu.set_option("count_limit_log2", 12)  # 4,095: every pair fits
+        m, c = emu.train(data, 270)
+        assert int(c.max()) <= 4095
+    finally:
+        emu.set_option("count_limit_log2", 32)
+    m2, c2 = emu.train(data, 270)
+    assert np.array_equal(m, m2) and np.array_equal(c, c2)
+
+
+def test_fused_halo_equals_a_halo_pass_per_step(emu, ora, taylor):
+    """fuse_halo = 1 (default: the apply kernel gathers the next step's halos, first == second steps take the
+    run-chaining halo pass through a halt) learns what fuse_halo = 0 (one halo launch per step) learns"""
+    rng = np.random.default_rng(3)
+    for data, vocab in ((taylor[:20000], 330), (bytes(rng.integers(97, 100, size=5000, dtype=np.uint8)), 300),
+                        (b"xyz" + b"a" * 700 + b"b" + b"a" * 513 + b"cc" + b"a" * 1024 + b"q", 280)):
+        om, oc = ora.train(data, vocab, fast=True)
+        for fh in (1, 0):
+            try:
+                emu.set_option("fuse_halo", fh)
+                m, c = emu.train(data, vocab)
+                assert np.array_equal(merges_array(m), om) and np.array_equal(c, oc), fh
+                if fh:
+                    assert emu.last_stats["aeqb_steps"] == int((om[:, 0] == om[:, 1]).sum())
+            finally:
+                emu.set_option("fuse_halo", 1)
+
+
 def test_invalid_vocab(emu, zb):
     with pytest.raises(zb.InvalidVocabSize):
         emu.train(b"abc", 255)

@@ -226,6 +226,39 @@ def test_encode_arbitrary_lists(gpu, ora, seed):
     assert np.array_equal(gpu.encode(data, merges), ora.encode(data, merges, linear=False))
 
 
+def test_tile_encoder_on_gpu(gpu, ora, synth, taylor, golden_merges):
+    """the tile-resident kernel (encode_impl = 4) against the oracle: the golden list, a trained list on unseen text, every
+    tile size, runs of equal tokens, odd sizes; and the default dispatch must pick it for regular lists"""
+    def enc(data, merges, tile=8192, impl=4):
+        try:
+            gpu.set_option("encode_impl", impl)
+            gpu.set_option("encode_tile", tile)
+            return gpu.encode(data, merges)
+        finally:
+            gpu.set_option("encode_impl", 0)
+            gpu.set_option("encode_tile", 8192)
+    want = ora.encode(taylor, golden_merges, linear=True)
+    for tile in (512, 2048, 8192):
+        assert np.array_equal(enc(taylor, golden_merges, tile), want)
+    ids = gpu.encode(taylor, golden_merges)
+    assert np.array_equal(ids, want) and gpu.last_stats["kernel_calls"][10] == 2 and gpu.last_stats["kernel_calls"][11] == 1
+    train = bytes(synth.generate(2_000_000, synth.SEED_C3, synth.BYTE))
+    om, _ = ora.train(train, 256 + 2000, fast=True)
+    other = bytes(synth.generate(3_000_000, synth.SEED_C5, synth.BYTE))
+    want = ora.encode(other, om, linear=True)
+    for tile in (1024, 4096, 8192):
+        assert np.array_equal(enc(other, om, tile), want), tile
+    for n in (1, 2, 65, 8191, 8192, 8193, 12289, 100_001):
+        assert np.array_equal(enc(other[:n], om), ora.encode(other[:n], om, linear=True)), n
+    merges = [(97, 97, 256), (256, 256, 257), (98, 257, 258), (257, 257, 259)]
+    rng = np.random.default_rng(5)
+    data = b"".join(b"a" * int(rng.integers(1, 12)) + bytes(rng.integers(98, 102, size=int(rng.integers(1, 6)), dtype=np.uint8)) for _ in range(40000))
+    assert np.array_equal(enc(data, merges), ora.encode(data, merges, linear=False))
+    data = b"q" + b"a" * 50001 + b"b"  # a run no window can take: the default dispatch falls back
+    ids = gpu.encode(data, merges)
+    assert np.array_equal(ids, ora.encode(data, merges, linear=False)) and gpu.last_stats["kernel_calls"][11] == 2
+
+
 def test_decode_semantics(gpu, zb):
     with pytest.raises(zb.InvalidToken):
         gpu.decode([256], [(256, 97, 256)])  # cyclic definition (stack overflow in the reference)

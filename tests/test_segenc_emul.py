@@ -18,11 +18,13 @@ def _enc(eng, data, merges, geom=0, impl=0):
         eng.set_option("encode_geom", geom)
         eng.set_option("encode_impl", impl)
         eng.set_option("encode_seg_min_steps", 0)  # impl 0 picks by cost; 0 steps: always try the segment kernel first
+        eng.set_option("encode_try_tiles", 0)      # (the tile-resident kernel has its own tests: test_tilenc_emul.py)
         return eng.encode(data, merges), _path(eng)
     finally:
         eng.set_option("encode_geom", 4)
         eng.set_option("encode_impl", 0)
         eng.set_option("encode_seg_min_steps", 450)
+        eng.set_option("encode_try_tiles", 1)
 
 
 @pytest.mark.parametrize("geom", [0, 1, 2, 3, 4, 5])
@@ -136,6 +138,7 @@ def test_fuzzed_regular_lists(emu, ora):
 def test_default_dispatch_by_cost(emu, ora, taylor, golden_merges):
     """encode_impl = 0: short lists (few levels) take the level passes, lists with more than encode_seg_min_steps
     schedule steps the segment kernel"""
+    emu.set_option("encode_try_tiles", 0)
     ids = emu.encode(taylor[:20000], golden_merges)
     assert _path(emu) == 0 and np.array_equal(ids, ora.encode(taylor[:20000], golden_merges, linear=True))
     try:
@@ -144,6 +147,7 @@ def test_default_dispatch_by_cost(emu, ora, taylor, golden_merges):
         assert _path(emu) == SEG_USED and np.array_equal(ids, ora.encode(taylor[:20000], golden_merges, linear=True))
     finally:
         emu.set_option("encode_seg_min_steps", 450)
+        emu.set_option("encode_try_tiles", 1)
 
 
 def test_matches_level_and_per_merge_paths(emu, ora, taylor):

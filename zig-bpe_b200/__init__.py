@@ -80,6 +80,7 @@ class bpe_stats_t(ctypes.Structure):
         ("compactions", c_uint64),
         ("kernel_ms", c_double * 12),
         ("kernel_calls", c_uint64 * 12),
+        ("aeqb_steps", c_uint64),
     ]
 
     def as_dict(self):

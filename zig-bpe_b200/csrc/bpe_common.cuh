@@ -88,6 +88,7 @@ enum : uint32_t {
     ERR_VERIFY_MISMATCH = 1u << 3,
     ERR_ZCNT_OVERFLOW = 1u << 4,
     ERR_PEER_TIMEOUT = 1u << 5,   // a peer's deltas did not arrive (multi-GPU peer exchange)
+    ERR_COUNT_OVERFLOW = 1u << 6, // a pair occurs more often than the 32-bit counts of the pair table can hold
 };
 
 // tie-resolution verdicts (StepCtl::tie_status)
@@ -101,9 +102,10 @@ enum : uint32_t {
     H_ZCAP = 3,      // zcnt models another capacity of the reference's table: host rebuilds it
     H_REPLAY = 4,    // tie that needs the full table replay on the host
     H_CLASSIC = 5,   // candidate-scan merge path cannot take this step (A == B, or too many candidates): host runs the tiled pass
+    H_AEQB = 6,      // the chosen merge has first == second: the host runs this step with the run-chaining halo pass
 };
 // StepCtl::flags
-enum : uint32_t { F_FORCE_REPLAY = 1u << 0, F_CHECK_TIES = 1u << 1 };
+enum : uint32_t { F_FORCE_REPLAY = 1u << 0, F_CHECK_TIES = 1u << 1, F_HALT_AEQB = 1u << 2 };
 
 struct MergeRec { uint32_t key; uint32_t count; };  // one learned merge: pair key + its count
 
@@ -143,6 +145,8 @@ struct StepCtl {
     uint32_t last_merged;  // occurrences merged by the last applied step
     uint32_t cand_n;       // candidate-scan merge path: queued A positions ...
     uint32_t w_n;          // ... and token writes decided for them
+    uint32_t pass_step;    // 1 + index of the last step whose merge pass really ran (not halted), written by that pass
+    uint32_t pad0;
     unsigned long long live_tokens;
     unsigned long long fast_ties;   // tie steps settled on the device
     unsigned long long local_live;  // live tokens of this GPU's shard (multi-GPU; live_tokens is the global count)

@@ -16,6 +16,7 @@
 #include "../../include/bpe_b200.h"
 #include "bpe_kernels.cuh"
 #include "bpe_segenc.cuh"
+#include "bpe_tilenc.cuh"
 #include "tiebreak_host.hpp"
 #include "dist_comm.hpp"
 
@@ -57,12 +58,13 @@ struct bpe_ctx {
     std::string err;
     // options
     long verify_recount = 0, force_slow_tiebreak = 0, check_tiebreak = 0, compact_pct = 85, table_log2 = 0,
-         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 6, encode_filter = 1, encode_geom = 4, encode_seg_min_steps = 450;
+         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 6, encode_filter = 1, encode_geom = 4, encode_seg_min_steps = 450, encode_tile = 8192, encode_try_tiles = 1, fuse_halo = 1, count_limit_log2 = 32;
     int num_sms = 148;
     DistComm dist;  // world == 1 when single GPU
     uint64_t launches = 0;
     BufCache cache;
     std::vector<cudaEvent_t> ev_pool;  // profiling events, created on first use
+    struct DecodeCache* decode_cache = nullptr;  // decode tables of the last merge list seen (built once per list)
 };
 
 static std::string g_create_err;
@@ -291,7 +293,7 @@ struct EvProfile {
     }
 };
 
-__global__ void hist_nonzero_kernel(const uint32_t* __restrict__ hist, StepCtl* ctl) {
+__global__ void hist_nonzero_kernel(const unsigned long long* __restrict__ hist, StepCtl* ctl) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 65536u && hist[i]) atomicAdd(&ctl->hist_nonzero, 1u);
 }
@@ -312,7 +314,8 @@ struct TrainRun {
     bpe_ctx* ctx;
     Sequence<uint16_t> sq;
     TableMem tm;
-    DevBuf delta, hist, ctl, rec, firstpos, recount, live_chk, heavy, cand, wr;
+    DevBuf delta, hist, ctl, rec, firstpos, recount, live_chk, heavy, cand, wr, push_dev;
+    size_t push_slots = 0, push_tail = 0;  // sequence geometry the device copy of PushArgs was written for
     uint32_t cand_cap = 0;  // candidate-scan merge path: queue capacity
     uint32_t vcap = 0;   // stride of the cntL / cntR halves of `delta`
     uint32_t theta = 0;  // heavy-list threshold (0 = list invalid)
@@ -320,6 +323,7 @@ struct TrainRun {
     HostBuf h_ctl;
     bpe_stats_t st;
     EvProfile prof;
+    uint64_t aeqb_steps = 0;                // steps that took the run-chaining halo pass (first == second)
     std::vector<uint32_t> pending_samples;  // profile 3: sampled steps enqueued in the current batch
     uint64_t sampled_noop = 0;              // sampled launches that turned out to be no-ops (batch halted earlier)
     StepCtl* d_ctl() const { return ctl.as<StepCtl>(); }
@@ -488,7 +492,7 @@ static int sync_zcap(bpe_ctx* ctx, TrainRun& R, uint32_t d) {
 template <class TokT, bool DELTAS, bool FROMCTL>
 static int launch_merge(bpe_ctx* ctx, TokT* tok, const TileHalo<TokT>* halo, uint32_t nt, const StepCtl* d_ctl, uint32_t* cntL,
                         uint32_t* cntR, uint32_t* nxx, uint32_t* nab, uint32_t A, uint32_t B, uint32_t X, uint32_t bins_min,
-                        int backwards) {
+                        int backwards, const PushArgs* d_push = nullptr, uint32_t parity = 0, uint32_t epoch = 0, uint32_t* push_counter = nullptr) {
     if (ctx->merge_impl == 1) {
         auto kern = merge_tma_kernel<TokT, DELTAS, FROMCTL>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem_bytes<TokT>()));
@@ -497,7 +501,7 @@ static int launch_merge(bpe_ctx* ctx, TokT* tok, const TileHalo<TokT>* halo, uin
                         bins_min, nt);
     } else {
         BPE_LAUNCH((merge_kernel<TokT, DELTAS, FROMCTL>), nt, THREADS, ctx->stream, tok, halo, d_ctl, cntL, cntR, nxx, nab, A, B, X, bins_min,
-                   backwards);
+                   backwards, d_push, parity, epoch, push_counter);
     }
     ctx->launches++;
     return BPE_OK;
@@ -519,48 +523,71 @@ static int enqueue_step_tail_scan(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uin
     R.prof.mark(K_APPLY);
     PeerSet none;
     memset(&none, 0, sizeof none);
+    HaloArgs no_halo;
+    memset(&no_halo, 0, sizeof no_halo);
     BPE_LAUNCH(apply_kernel, (4 * n_ids + 3 + 255) / 256, 256, ctx->stream, R.tm.view(), R.delta.as<uint32_t>(), R.vcap, R.d_ctl(),
-               R.tm.zig(), n_ids, R.hl(), R.d_rec(), fuse_select ? 1 : 0, 0, none, 0, 1, 0u, 0u, (uint32_t)R.edge_off);
+               R.tm.zig(), n_ids, R.hl(), R.d_rec(), fuse_select ? 1 : 0, 0, none, 0, 1, 0u, 0u, (uint32_t)R.edge_off, no_halo);
     ctx->launches += 4;
     CU(cudaGetLastError());
     return BPE_OK;
 }
 
-// the part of a step after the merge has been chosen: halo, merge, apply (all read the merge from ctl)
-static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uint32_t step_index, bool fuse_select) {
+// The part of a step after the merge has been chosen: merge pass, exchange (multi-GPU), apply. All read the merge from
+// ctl. The halos of the pass were gathered by the previous step's apply kernel (fused halo CTAs) or by the host after
+// a compaction; classic_halo = true runs the stand-alone halo pass first — the only one that chains runs of equal
+// tokens across tiles, needed when the merge has first == second (the loop halts with H_AEQB for those steps).
+static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uint32_t step_index, bool fuse_select, bool classic_halo = false) {
     const uint32_t nt = R.sq.ntiles();
     R.prof.sample_now = (step_index % 8u) == 0;
     if (R.prof.level == 3 && R.prof.sample_now) R.pending_samples.push_back(step_index);  // credited once the step is known to have run
-    R.prof.mark(K_HALO);
-    BPE_LAUNCH((halo_kernel<uint16_t, true>), (nt + HALO_THREADS - 1) / HALO_THREADS, HALO_THREADS, ctx->stream, R.sq.tok(),
-               R.sq.n_slots, nt, R.sq.halo.as<TileHalo<uint16_t>>(), (const StepCtl*)R.d_ctl(), 0u, 0, R.sq.run_local.as<uint32_t>(),
-               R.sq.run_full.as<uint8_t>(), R.sq.done_counter.as<uint32_t>(), R.nxx(), R.edges(), ctx->dist.rank, ctx->dist.world);
+    if (classic_halo) {
+        R.prof.mark(K_HALO);
+        BPE_LAUNCH((halo_kernel<uint16_t, true>), (nt + HALO_THREADS - 1) / HALO_THREADS, HALO_THREADS, ctx->stream, R.sq.tok(),
+                   R.sq.n_slots, nt, R.sq.halo.as<TileHalo<uint16_t>>(), (const StepCtl*)R.d_ctl(), 0u, 0, R.sq.run_local.as<uint32_t>(),
+                   R.sq.run_full.as<uint8_t>(), R.sq.done_counter.as<uint32_t>(), (uint32_t*)nullptr, R.edges(), ctx->dist.rank, ctx->dist.world);
+        ctx->launches++;
+    }
+    const bool peer = ctx->dist.world > 1 && ctx->dist.peer_ok && ctx->xchg_impl == 0 && ctx->merge_impl != 1 &&
+                      R.exchange_words() <= ctx->dist.peers.slot_words;
+    const uint32_t parity = step_index & 1u, epoch = ctx->dist.epoch_base + step_index + 1u;
+    if (peer && (R.push_slots != R.sq.n_slots || R.push_tail != R.sq.dense_end || !R.push_dev.p)) {
+        // what the last CTA of the merge pass needs to push this rank's deltas + shard ends into every peer's mailbox
+        // (device copy, refreshed when the sequence geometry changes)
+        PushArgs pa;
+        memset(&pa, 0, sizeof pa);
+        pa.on = 1; pa.delta = R.delta.as<uint32_t>(); pa.edge_off = (uint32_t)R.edge_off; pa.zero_vecs = (uint32_t)(2 * R.vcap / 4);
+        pa.n_slots = R.sq.n_slots; pa.tail_hint = R.sq.dense_end; pa.ps = ctx->dist.peers; pa.rank = ctx->dist.rank; pa.world = ctx->dist.world;
+        pa.ctl = R.d_ctl(); pa.done_counter = R.sq.done_counter.as<uint32_t>();
+        if (!R.push_dev.p) CU(R.push_dev.alloc(sizeof(PushArgs)));
+        CU(cudaMemcpyAsync(R.push_dev.p, &pa, sizeof pa, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));  // `pa` lives on this frame (happens at the start and after compactions only)
+        R.push_slots = R.sq.n_slots; R.push_tail = R.sq.dense_end;
+    }
     R.prof.mark(K_MERGE);
     {
         int rcm = launch_merge<uint16_t, true, true>(ctx, R.sq.tok(), R.sq.halo.as<TileHalo<uint16_t>>(), nt, (const StepCtl*)R.d_ctl(),
-                                                     R.cntL(), R.cntR(), R.nxx(), R.nab(), 0u, 0u, 0u, 4u * nt, (int)(step_index & 1u));
+                                                     R.cntL(), R.cntR(), R.nxx(), R.nab(), 0u, 0u, 0u, 4u * nt, (int)(step_index & 1u),
+                                                     peer ? R.push_dev.as<PushArgs>() : nullptr, parity, epoch, R.sq.done_counter.as<uint32_t>());
         if (rcm) return rcm;
     }
     R.prof.mark(K_APPLY);
-    const bool peer = ctx->dist.world > 1 && ctx->dist.peer_ok && ctx->xchg_impl == 0 && R.exchange_words() <= ctx->dist.peers.slot_words;
-    const uint32_t parity = step_index & 1u, epoch = ctx->dist.epoch_base + step_index + 1u;
-    if (peer) {
-        // push this rank's deltas + shard ends into every peer's mailbox over NVLink and raise the arrival flag
-        BPE_LAUNCH(xchg_kernel<uint16_t>, 32, 256, ctx->stream, R.sq.tok(), R.sq.n_slots, R.sq.dense_end, R.delta.as<uint32_t>(),
-                   (uint32_t)R.edge_off, (uint32_t)(2 * R.vcap / 4), R.nab(), ctx->dist.peers, ctx->dist.rank, ctx->dist.world, parity, epoch,
-                   R.d_ctl(), R.sq.done_counter.as<uint32_t>());
-        ctx->launches++;
-    } else if (ctx->dist.world > 1) {
+    if (!peer && ctx->dist.world > 1) {
         // describe this shard's (post-merge) ends, then one all-reduce sums the deltas and gathers the edges
         BPE_LAUNCH(edge_kernel<uint16_t>, 1, 32, ctx->stream, R.sq.tok(), R.sq.n_slots, R.sq.dense_end, R.edges(), ctx->dist.rank, ctx->dist.world,
                       R.d_ctl(), R.nab(), 1);
         ctx->launches++;
         if (!ctx->dist.allreduce(R.delta.p, R.exchange_words(), DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-reduce of the merge deltas failed");
     }
-    BPE_LAUNCH(apply_kernel, (4 * n_ids + 3 + 255) / 256, 256, ctx->stream, R.tm.view(), R.delta.as<uint32_t>(), R.vcap, R.d_ctl(),
+    HaloArgs ha;
+    ha.tok = R.sq.tok(); ha.n_slots = R.sq.n_slots; ha.ntiles = nt; ha.halo = R.sq.halo.as<TileHalo<uint16_t>>();
+    ha.apply_blocks = (4 * n_ids + 3 + 255) / 256;
+    ha.step1 = step_index + 1u;
+    if (ctx->fuse_halo == 0 || ctx->merge_impl != 0) ha.tok = nullptr;
+    const uint32_t grid = ha.apply_blocks + (ha.tok ? (nt + 255) / 256 : 0u);
+    BPE_LAUNCH(apply_kernel, grid, 256, ctx->stream, R.tm.view(), R.delta.as<uint32_t>(), R.vcap, R.d_ctl(),
                   R.tm.zig(), n_ids, R.hl(), R.d_rec(), fuse_select ? 1 : 0, peer ? 1 : 0, ctx->dist.peers, ctx->dist.rank, ctx->dist.world,
-                  parity, epoch, (uint32_t)R.edge_off);
-    ctx->launches += 2;
+                  parity, epoch, (uint32_t)R.edge_off, ha);
+    ctx->launches += 1;
     CU(cudaGetLastError());
     return BPE_OK;
 }
@@ -598,7 +625,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     if (rc) return rc;
     R.vcap = ((uint32_t)vocab_size + 2u) & ~1u;  // even, so the cntL|cntR block is a whole number of 16-byte vectors
     R.edge_off = ((size_t)2 * R.vcap + 2 + 15) / 16 * 16;
-    CU(R.delta.alloc(R.exchange_words() * 4)); CU(R.hist.alloc(65536 * 4));
+    CU(R.delta.alloc(R.exchange_words() * 4)); CU(R.hist.alloc(65536 * 8));
     CU(R.ctl.alloc(sizeof(StepCtl))); CU(R.rec.alloc(want * sizeof(MergeRec)));
     const bool scan_path = ctx->merge_impl == 2 && !multi;
     if (scan_path) {
@@ -607,9 +634,13 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
         CU(R.wr.alloc((size_t)R.cand_cap * 2 * sizeof(TokWrite)));
     }
     uint32_t scan_not_before = 0;  // first step that may use the candidate-scan path again (set after a dense step)
+    // fused halo: the apply kernel of step t gathers the tile halos of step t + 1; the host gathers them at the start and
+    // after every compaction, and first == second steps halt the loop for the run-chaining halo pass (H_AEQB)
+    const bool fused_halo = ctx->fuse_halo != 0 && ctx->merge_impl == 0;
+    bool halo_stale = true;
     CU(R.h_ctl.alloc(sizeof(StepCtl)));
     CU(cudaMemsetAsync(R.delta.p, 0, R.exchange_words() * 4, ctx->stream));
-    CU(cudaMemsetAsync(R.hist.p, 0, 65536 * 4, ctx->stream));
+    CU(cudaMemsetAsync(R.hist.p, 0, 65536 * 8, ctx->stream));
     CU(cudaMemsetAsync(R.ctl.p, 0, sizeof(StepCtl), ctx->stream));
 
     // initial count (countCodePointPairs :257-278 on the byte sequence)
@@ -623,10 +654,10 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
         }
         const unsigned hgrid = (unsigned)std::max<size_t>(1, std::min<size_t>(148, (n + HIST_PASS - 1) / HIST_PASS));
         BPE_LAUNCH_SMEM(byte_pair_hist_kernel, hgrid, HIST_THREADS, HIST_SMEM, ctx->stream, d_text, n, (const EdgeInfo*)R.edges(),
-                        ctx->dist.rank, ctx->dist.world, R.hist.as<uint32_t>());
-        if (multi && !ctx->dist.allreduce(R.hist.p, 65536, DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-reduce of the byte-pair histogram failed");
+                        ctx->dist.rank, ctx->dist.world, R.hist.as<unsigned long long>());
+        if (multi && !ctx->dist.allreduce(R.hist.p, 65536, DIST_U64_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-reduce of the byte-pair histogram failed");
     }
-    BPE_LAUNCH_NS(hist_nonzero_kernel, 65536 / 256, 256, ctx->stream, R.hist.as<uint32_t>(), R.d_ctl());
+    BPE_LAUNCH_NS(hist_nonzero_kernel, 65536 / 256, 256, ctx->stream, R.hist.as<unsigned long long>(), R.d_ctl());
     ctx->launches += 2;
     CU(cudaGetLastError());
     rc = read_ctl(ctx, R, false);
@@ -640,7 +671,10 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     // the heavy list can hold every key of the table, so it cannot overflow even when the whole table ties
     // (e.g. the late phase of a long training on random bytes, where every pair occurs once)
     CU(R.heavy.alloc((size_t)cap * 4));
-    BPE_LAUNCH_NS(seed_table_kernel, 65536 / 256, 256, ctx->stream, R.hist.as<uint32_t>(), R.tm.view(), R.d_ctl());
+    // pair counts are 32 bits wide in the table: refuse a corpus whose most frequent pair does not fit ("count_limit_log2"
+    // lowers the limit for tests)
+    const unsigned long long count_limit = ctx->count_limit_log2 >= 32 ? 0xFFFFFFFFull : ((1ull << ctx->count_limit_log2) - 1ull);
+    BPE_LAUNCH_NS(seed_table_kernel, 65536 / 256, 256, ctx->stream, R.hist.as<unsigned long long>(), R.tm.view(), R.d_ctl(), count_limit);
     ctx->launches += 1;
     CU(cudaGetLastError());
     {   // device-side loop state
@@ -649,13 +683,16 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
         init.want_steps = (uint32_t)want;
         init.live_tokens = n;  // multi-GPU: only local_live is meaningful
         init.local_live = n;
-        init.flags = (ctx->force_slow_tiebreak ? F_FORCE_REPLAY : 0u) | (ctx->check_tiebreak ? F_CHECK_TIES : 0u);
+        init.flags = (ctx->force_slow_tiebreak ? F_FORCE_REPLAY : 0u) | (ctx->check_tiebreak ? F_CHECK_TIES : 0u) |
+                     (fused_halo ? F_HALT_AEQB : 0u);
         CU(cudaMemcpyAsync(&R.d_ctl()->step, &init.step, offsetof(StepCtl, tie_keys) - offsetof(StepCtl, step),
                            cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));  // `init` lives on this stack frame
     }
     rc = read_ctl(ctx, R, false);
     if (rc) return rc;
+    if (R.hc()->err & ERR_COUNT_OVERFLOW)
+        return fail(ctx, BPE_ERR_INTERNAL, "a byte pair occurs more than %llu times: beyond the 32-bit pair counts of this engine (the reference counts in usize)", count_limit);
     rc = sync_zcap(ctx, R, R.hc()->live_keys);
     if (rc) return rc;
 
@@ -669,8 +706,8 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
         uint32_t K = (uint32_t)std::min<size_t>(max_batch, want - steps_done);
         const uint64_t per_step_inserts = 2ull * (256 + steps_done + K + 1) + 1;
         prof.mark(K_TABLE);
-        if (((uint64_t)hc->n_inserted + (uint64_t)K * per_step_inserts) * 4 > (uint64_t)R.tm.cap * 3) {
-            rc = grow_table(ctx, R, (uint64_t)K * per_step_inserts);
+        if (((uint64_t)hc->n_inserted + (uint64_t)(K + 2) * per_step_inserts) * 4 > (uint64_t)R.tm.cap * 3) {
+            rc = grow_table(ctx, R, (uint64_t)(K + 2) * per_step_inserts);
             if (rc) return rc;
             rc = sync_zcap(ctx, R, hc->live_keys);
             if (rc) return rc;
@@ -682,6 +719,13 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
             rc = seq_compact(ctx, R.sq, nullptr);
             if (rc) return rc;
             R.st.compactions++;
+            halo_stale = true;
+        }
+        if (fused_halo && halo_stale) {
+            prof.mark(K_HALO);
+            rc = launch_halo(ctx, R.sq, 0, false, R.edges());
+            if (rc) return rc;
+            halo_stale = false;
         }
         // ---- one batch of device-driven steps ----
         for (uint32_t k = 0; k < K; k++) {
@@ -693,7 +737,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
             selection_pending = !debug_sync;
             const bool use_scan = scan_path && steps_done >= scan_not_before && (uint64_t)hc->max_count * 4 < R.cand_cap;
             rc = use_scan ? enqueue_step_tail_scan(ctx, R, 256 + steps_done + k + 1, steps_done + k, selection_pending)
-                          : enqueue_step_tail(ctx, R, 256 + steps_done + k + 1, steps_done + k, selection_pending);
+                          : enqueue_step_tail(ctx, R, 256 + steps_done + k + 1, steps_done + k, selection_pending, !fused_halo);
             if (rc) return rc;
         }
         prof.mark(K_HOSTGAP);
@@ -710,9 +754,9 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
         R.sq.live = multi ? hc->local_live : hc->live_tokens;
         if (debug_sync && hc->halt == H_NONE) { rc = verify_state(ctx, R, steps_done); if (rc) return rc; hc = R.hc(); }
         if (ctx->debug && (hc->halt != H_NONE || ctx->debug > 1))
-            fprintf(stderr, "[bpe r%d] step %u halt %u max %u ntied %u live_keys %u inserted %u cap %u n_heavy %u theta %u zcap %u slots %zu live %llu\n",
-                    ctx->dist.rank, hc->step, hc->halt, hc->max_count, hc->ntied, hc->live_keys, hc->n_inserted, R.tm.cap, hc->n_heavy,
-                    R.theta, R.tm.zcap, R.sq.n_slots, (unsigned long long)R.sq.live);
+            fprintf(stderr, "[bpe r%d] step %u halt %u (%u,%u)->%u max %u ntied %u live_keys %u inserted %u cap %u n_heavy %u theta %u zcap %u slots %zu live %llu err 0x%x\n",
+                    ctx->dist.rank, hc->step, hc->halt, hc->A, hc->B, hc->X, hc->max_count, hc->ntied, hc->live_keys, hc->n_inserted, R.tm.cap, hc->n_heavy,
+                    R.theta, R.tm.zcap, R.sq.n_slots, (unsigned long long)R.sq.live, hc->err);
         if (hc->halt != H_NONE) selection_pending = false;  // the host intervenes: start the next batch with a select_kernel
         switch (hc->halt) {
             case H_NONE: break;
@@ -750,7 +794,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
                 if (hc->A != hc->B) scan_not_before = steps_done + 64;
                 BPE_LAUNCH_NS(ctl_set_kernel, 1, 1, ctx->stream, R.d_ctl(), R.d_rec(), 0, 0u, 0, 0u, 1, 0, 0u, 0u);
                 ctx->launches++;
-                rc = enqueue_step_tail(ctx, R, 256 + steps_done + 1, steps_done, false);
+                rc = enqueue_step_tail(ctx, R, 256 + steps_done + 1, steps_done, false, true);
                 if (rc) return rc;
                 rc = read_ctl(ctx, R, false);
                 if (rc) return rc;
@@ -764,6 +808,31 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
                 steps_done = hc->step;
                 R.sq.live = hc->live_tokens;
                 if (debug_sync) { rc = verify_state(ctx, R, steps_done); if (rc) return rc; }
+                break;
+            }
+            case H_AEQB: {
+                // the merge is chosen and recorded; its pass needs the run-chaining halo. Nothing is read back: the
+                // step is known to run, and its apply kernel already selects the following merge.
+                BPE_LAUNCH_NS(ctl_set_kernel, 1, 1, ctx->stream, R.d_ctl(), R.d_rec(), 0, 0u, 0, 0u, 1, 0, 0u, 0u);
+                ctx->launches++;
+                rc = enqueue_step_tail(ctx, R, 256 + steps_done + 1, steps_done, !debug_sync, true);
+                if (rc) return rc;
+                R.aeqb_steps++;
+                if (debug_sync) {
+                    rc = read_ctl(ctx, R, false);
+                    if (rc) return rc;
+                    hc = R.hc();
+                    if (hc->err) return fail(ctx, BPE_ERR_INTERNAL, "device error flags 0x%x near step %u", hc->err, hc->step);
+                    R.st.scanned_slots += R.sq.n_slots;
+                    steps_done = hc->step;
+                    R.sq.live = multi ? hc->local_live : hc->live_tokens;
+                    rc = verify_state(ctx, R, steps_done);
+                    if (rc) return rc;
+                } else {
+                    R.st.scanned_slots += R.sq.n_slots;
+                    steps_done += 1;
+                    selection_pending = true;
+                }
                 break;
             }
             case H_REPLAY: {
@@ -781,7 +850,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
                 if (!had_fast) R.st.tie_slow_steps++;
                 BPE_LAUNCH_NS(ctl_set_kernel, 1, 1, ctx->stream, R.d_ctl(), R.d_rec(), 0, 0u, 0, 0u, 1, 1, w, maxc);
                 ctx->launches++;
-                rc = enqueue_step_tail(ctx, R, 256 + steps_done + 1, steps_done, false);
+                rc = enqueue_step_tail(ctx, R, 256 + steps_done + 1, steps_done, false, !fused_halo || (w & 0xFFFFu) == (w >> 16));
                 if (rc) return rc;
                 rc = read_ctl(ctx, R, false);
                 if (rc) return rc;
@@ -822,6 +891,7 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     }
     *out_n = steps_done;
     R.st.tie_steps += R.hc()->fast_ties;
+    R.st.aeqb_steps = R.aeqb_steps;
     R.st.device_ms = dev_ms;
     R.st.total_ms = now_ms() - t_host0;
     R.st.kernel_launches = ctx->launches - launches0;
@@ -935,20 +1005,14 @@ static int launch_segenc(bpe_ctx* ctx, const uint8_t* d_text, long long n, const
     return BPE_OK;
 }
 
-// *used = false when this path does not apply (irregular list, id 65535, seam without a common token):
-// nothing has been written to d_out then and the caller runs the level-scheduled passes.
-static int encode_segments(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bpe_merge_t* merges, size_t m, uint16_t* d_out,
-                           size_t* out_n, bpe_stats_t* st, bool* used) {
-    *used = false;
-    if (m == 0) return BPE_OK;
-    std::vector<uint32_t> lvl;
-    std::vector<uint8_t> alone;
-    if (!merge_levels(merges, m, lvl, alone)) return BPE_OK;
-    for (size_t i = 0; i < m; i++)
-        if (merges[i].first == 0xFFFF || merges[i].second == 0xFFFF || merges[i].new_token == 0xFFFF) return BPE_OK;
-    const int world = ctx->dist.world, rank = ctx->dist.rank;
-    const bool multi = world > 1;
-    // ---- tables: byte pairs dense, the rest hashed; byte length of every id ----
+// ---- pieces shared by the segment-resident and the tile-resident encoders ----
+// pair -> (level, new id) tables on the device: byte pairs dense, the rest hashed; byte length of every id
+struct SegTables {
+    DevBuf tab;
+    SegTab T;
+    uint32_t max_level = 0;
+};
+static int build_seg_tables(bpe_ctx* ctx, const bpe_merge_t* merges, size_t m, const std::vector<uint32_t>& lvl, SegTables& st) {
     size_t nhash = 0;
     for (size_t i = 0; i < m; i++) nhash += (merges[i].first | merges[i].second) >= 256;
     uint32_t hlog = 6;
@@ -961,9 +1025,11 @@ static int encode_segments(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const 
     for (size_t i = 0; i < 65536; i++) bp[i] = SEG_NONE;
     for (size_t i = 0; i < hcap; i++) { hk[2 * i] = EMPTY_KEY; hk[2 * i + 1] = SEG_NONE; }
     for (size_t i = 0; i < 65536; i++) len[i] = 1;
+    st.max_level = 0;
     for (size_t i = 0; i < m; i++) {
         const uint32_t a = merges[i].first, b = merges[i].second, z = merges[i].new_token;
         const uint32_t val = lvl[i] | (z << 16);
+        st.max_level = std::max(st.max_level, lvl[i]);
         if ((a | b) < 256) bp[a | (b << 8)] = val;
         else {
             const uint32_t key = pair_key(a, b);
@@ -973,65 +1039,203 @@ static int encode_segments(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const 
         }
         len[z] = (uint16_t)std::min<uint32_t>(65535u, (uint32_t)len[a] + (uint32_t)len[b]);
     }
-    DevBuf tab, slots, failbuf, halo, tile_live, tile_off, total;
-    CU(tab.alloc(host.size() * 4));
-    CU(cudaMemcpyAsync(tab.p, host.data(), host.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-    SegTab T;
-    T.bp = tab.as<uint32_t>();
-    T.hk = reinterpret_cast<const uint2*>(tab.as<uint32_t>() + 65536);
-    T.hmask = (uint32_t)(hcap - 1);
-    T.hshift = 32 - hlog;
-    T.len = reinterpret_cast<const uint16_t*>(tab.as<uint32_t>() + 65536 + 2 * hcap);
-    // ---- multi-GPU: shard offsets and SEG_HALO bytes of text on both sides of the shard ----
-    long long g_lo = 0, g_total = (long long)n;
+    CU(st.tab.alloc(host.size() * 4));
+    CU(cudaMemcpyAsync(st.tab.p, host.data(), host.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // `host` lives on this frame
+    st.T.bp = st.tab.as<uint32_t>();
+    st.T.hk = reinterpret_cast<const uint2*>(st.tab.as<uint32_t>() + 65536);
+    st.T.hmask = (uint32_t)(hcap - 1);
+    st.T.hshift = 32 - hlog;
+    st.T.len = reinterpret_cast<const uint16_t*>(st.tab.as<uint32_t>() + 65536 + 2 * hcap);
+    return BPE_OK;
+}
+
+// multi-GPU: where this shard lies in the whole text, and up to SEG_HALO bytes of text on both sides of it
+struct ShardHalo {
+    DevBuf halo;  // [SEG_HALO left, right-aligned data moved to the front | SEG_HALO right]
     int hl = 0, hr = 0;
-    CU(halo.alloc(2 * SEG_HALO));
-    if (multi) {
-        // every rank contributes [n (2 words) | first SEG_HALO bytes | last SEG_HALO bytes]; the sum over ranks of
-        // buffers that are zero outside the own slot is an all-gather
-        const size_t W = 2 + 2 * SEG_HALO / 4;
-        std::vector<uint32_t> all((size_t)world * W, 0u);
-        std::vector<uint8_t> ends(2 * SEG_HALO, 0);
-        const size_t nf = std::min<size_t>(n, SEG_HALO);
-        if (nf) {
-            CU(cudaMemcpyAsync(ends.data(), d_text, nf, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaMemcpyAsync(ends.data() + SEG_HALO, d_text + (n - nf), nf, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
-        }
-        uint32_t* mine = all.data() + (size_t)rank * W;
-        mine[0] = (uint32_t)(n & 0xFFFFFFFFu); mine[1] = (uint32_t)((uint64_t)n >> 32);
-        memcpy(mine + 2, ends.data(), 2 * SEG_HALO);
-        DevBuf xb;
-        CU(xb.alloc(all.size() * 4));
-        CU(cudaMemcpyAsync(xb.p, all.data(), all.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-        if (!ctx->dist.allreduce(xb.p, all.size(), DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-gather of the shard ends failed");
-        CU(cudaMemcpyAsync(all.data(), xb.p, all.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    long long g_lo = 0, g_total = 0, min_shard = 0;
+    const uint8_t* left() const { return halo.as<uint8_t>(); }
+    const uint8_t* right() const { return halo.as<uint8_t>() + SEG_HALO; }
+};
+static int exchange_shard_halo(bpe_ctx* ctx, const uint8_t* d_text, size_t n, ShardHalo& sh) {
+    const int world = ctx->dist.world, rank = ctx->dist.rank;
+    sh.g_lo = 0; sh.g_total = (long long)n; sh.hl = sh.hr = 0; sh.min_shard = (long long)n;
+    CU(sh.halo.alloc(2 * SEG_HALO));
+    if (world == 1) return BPE_OK;
+    // every rank contributes [n (2 words) | first SEG_HALO bytes | last SEG_HALO bytes]; the sum over ranks of
+    // buffers that are zero outside the own slot is an all-gather
+    const size_t W = 2 + 2 * SEG_HALO / 4;
+    std::vector<uint32_t> all((size_t)world * W, 0u);
+    std::vector<uint8_t> ends(2 * SEG_HALO, 0);
+    const size_t nf = std::min<size_t>(n, SEG_HALO);
+    if (nf) {
+        CU(cudaMemcpyAsync(ends.data(), d_text, nf, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(ends.data() + SEG_HALO, d_text + (n - nf), nf, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
-        auto size_of = [&](int r) { return (long long)(((uint64_t)all[(size_t)r * W + 1] << 32) | all[(size_t)r * W]); };
-        g_total = 0;
-        for (int r = 0; r < world; r++) { if (r == rank) g_lo = g_total; g_total += size_of(r); }
-        std::vector<uint8_t> hb(2 * SEG_HALO, 0);
-        // left halo: the last bytes of the ranks before me, nearest first, written right-aligned into hb[0, SEG_HALO)
-        for (int r = rank - 1; r >= 0 && hl < SEG_HALO; r--) {
-            const long long sz = size_of(r);
-            const int have = (int)std::min<long long>(sz, SEG_HALO);        // bytes of rank r held in its "last" block
-            const uint8_t* last = reinterpret_cast<const uint8_t*>(all.data() + (size_t)r * W + 2) + SEG_HALO;
-            const int take = std::min(have, SEG_HALO - hl);
-            memcpy(hb.data() + SEG_HALO - hl - take, last + (have - take), (size_t)take);
-            hl += take;
-        }
-        if (hl < SEG_HALO) memmove(hb.data(), hb.data() + SEG_HALO - hl, (size_t)hl);  // left-align: kernel reads halo_l[hl + p], p in [-hl, 0)
-        for (int r = rank + 1; r < world && hr < SEG_HALO; r++) {
-            const long long sz = size_of(r);
-            const int have = (int)std::min<long long>(sz, SEG_HALO);
-            const uint8_t* first = reinterpret_cast<const uint8_t*>(all.data() + (size_t)r * W + 2);
-            const int take = std::min(have, SEG_HALO - hr);
-            memcpy(hb.data() + SEG_HALO + hr, first, (size_t)take);
-            hr += take;
-        }
-        CU(cudaMemcpyAsync(halo.p, hb.data(), 2 * SEG_HALO, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));  // hb lives on this frame
     }
+    uint32_t* mine = all.data() + (size_t)rank * W;
+    mine[0] = (uint32_t)(n & 0xFFFFFFFFu); mine[1] = (uint32_t)((uint64_t)n >> 32);
+    memcpy(mine + 2, ends.data(), 2 * SEG_HALO);
+    DevBuf xb;
+    CU(xb.alloc(all.size() * 4));
+    CU(cudaMemcpyAsync(xb.p, all.data(), all.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->dist.allreduce(xb.p, all.size(), DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-gather of the shard ends failed");
+    CU(cudaMemcpyAsync(all.data(), xb.p, all.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    auto size_of = [&](int r) { return (long long)(((uint64_t)all[(size_t)r * W + 1] << 32) | all[(size_t)r * W]); };
+    sh.g_total = 0;
+    for (int r = 0; r < world; r++) { if (r == rank) sh.g_lo = sh.g_total; sh.g_total += size_of(r); sh.min_shard = std::min(sh.min_shard, size_of(r)); }
+    std::vector<uint8_t> hb(2 * SEG_HALO, 0);
+    int hl = 0, hr = 0;
+    // left halo: the last bytes of the ranks before me, nearest first, written right-aligned into hb[0, SEG_HALO)
+    for (int r = rank - 1; r >= 0 && hl < SEG_HALO; r--) {
+        const long long sz = size_of(r);
+        const int have = (int)std::min<long long>(sz, SEG_HALO);        // bytes of rank r held in its "last" block
+        const uint8_t* last = reinterpret_cast<const uint8_t*>(all.data() + (size_t)r * W + 2) + SEG_HALO;
+        const int take = std::min(have, SEG_HALO - hl);
+        memcpy(hb.data() + SEG_HALO - hl - take, last + (have - take), (size_t)take);
+        hl += take;
+    }
+    if (hl < SEG_HALO) memmove(hb.data(), hb.data() + SEG_HALO - hl, (size_t)hl);  // left-align: kernels read halo_l[hl + p], p in [-hl, 0)
+    for (int r = rank + 1; r < world && hr < SEG_HALO; r++) {
+        const long long sz = size_of(r);
+        const int have = (int)std::min<long long>(sz, SEG_HALO);
+        const uint8_t* first = reinterpret_cast<const uint8_t*>(all.data() + (size_t)r * W + 2);
+        const int take = std::min(have, SEG_HALO - hr);
+        memcpy(hb.data() + SEG_HALO + hr, first, (size_t)take);
+        hr += take;
+    }
+    sh.hl = hl; sh.hr = hr;
+    CU(cudaMemcpyAsync(sh.halo.p, hb.data(), 2 * SEG_HALO, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // hb lives on this frame
+    return BPE_OK;
+}
+
+// squeeze the holes out of a u16 slot array of n slots (allocated to a whole number of tiles), straight into d_out
+static int squeeze_slots(bpe_ctx* ctx, DevBuf& slots, size_t n, uint16_t* d_out, size_t* out_n) {
+    const size_t n_slots = round_up(n ? n : 1, TILE);
+    if (n_slots > n) {
+        BPE_LAUNCH_NS(fill_holes_kernel<uint16_t>, grid_for(n_slots - n, 256), 256, ctx->stream, slots.as<uint16_t>(), n, n_slots);
+        ctx->launches++;
+    }
+    const size_t ntl = n_slots / TILE;
+    if (ntl > 0x7FFFFFFFull) return fail(ctx, BPE_ERR_INVALID_ARG, "input too large");
+    DevBuf tile_live, tile_off, total;
+    CU(tile_live.alloc(ntl * 4)); CU(tile_off.alloc(ntl * 8)); CU(total.alloc(8));
+    BPE_LAUNCH(tile_count_kernel<uint16_t>, (unsigned)ntl, THREADS, ctx->stream, slots.as<uint16_t>(), tile_live.as<uint32_t>());
+    BPE_LAUNCH(tile_scan_kernel, 1, THREADS, ctx->stream, tile_live.as<uint32_t>(), (uint32_t)ntl, tile_off.as<unsigned long long>(),
+               total.as<unsigned long long>());
+    BPE_LAUNCH((compact_scatter_kernel<uint16_t, uint16_t>), (unsigned)ntl, THREADS, ctx->stream, slots.as<uint16_t>(),
+               tile_off.as<unsigned long long>(), d_out);
+    ctx->launches += 3;
+    CU(cudaGetLastError());
+    unsigned long long tot = 0;
+    CU(cudaMemcpyAsync(&tot, total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *out_n = (size_t)tot;
+    return BPE_OK;
+}
+
+static bool mentions_id_65535(const bpe_merge_t* merges, size_t m) {
+    for (size_t i = 0; i < m; i++)
+        if (merges[i].first == 0xFFFF || merges[i].second == 0xFFFF || merges[i].new_token == 0xFFFF) return true;
+    return false;
+}
+
+// -----------------------------------------------------------------------------------------
+// tile-resident encode (bpe_tilenc.cuh): one launch over the text + the final squeeze
+// -----------------------------------------------------------------------------------------
+// *used = false when this path does not apply (irregular list, id 65535, more than TL_MAXLVL levels, a shard
+// shorter than TN_MIN_SHARD on several GPUs) or gave up (seam without a common token, a token longer than 255
+// bytes, a run of more than 255 equal tokens): nothing has been written to d_out then and the caller goes on
+// to the next encoder.
+static int encode_tiles(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bpe_merge_t* merges, size_t m, uint16_t* d_out,
+                        size_t* out_n, bpe_stats_t* st, bool* used) {
+    *used = false;
+    if (m == 0) return BPE_OK;
+    std::vector<uint32_t> lvl;
+    std::vector<uint8_t> alone;
+    if (!merge_levels(merges, m, lvl, alone) || mentions_id_65535(merges, m)) return BPE_OK;
+    SegTables tb;
+    int rc = build_seg_tables(ctx, merges, m, lvl, tb);
+    if (rc) return rc;
+    if (tb.max_level > TL_MAXLVL) return BPE_OK;
+    const int world = ctx->dist.world, rank = ctx->dist.rank;
+    const bool multi = world > 1;
+    ShardHalo sh;
+    rc = exchange_shard_halo(ctx, d_text, n, sh);
+    if (rc) return rc;
+    if (multi && sh.min_shard < (long long)TN_MIN_SHARD) return BPE_OK;  // (the same decision on every rank)
+    int tile_max = (int)ctx->encode_tile;
+    tile_max = std::max(multi ? 1024 : 512, std::min(tile_max, (int)TN_TMAX)) / 16 * 16;
+    const bool left_text = multi && sh.g_lo > 0, right_text = multi && sh.g_lo + (long long)n < sh.g_total;
+    const TileGeom g = tn_geometry((long long)n, sh.hl, sh.hr, left_text, right_text, tile_max);
+    const long long nwin = g.bwl + g.ntile + g.bwr;
+    if (nwin > 0x7FFFFFFFll) return fail(ctx, BPE_ERR_INVALID_ARG, "input too large for one launch");
+    const size_t n_slots = round_up(n ? n : 1, TILE);
+    DevBuf slots, zone, flags;
+    CU(slots.alloc(n_slots * 2));
+    CU(zone.alloc((size_t)nwin * TN_ZONE * 2));
+    CU(flags.alloc(((size_t)nwin + 2) * 4));  // [flags | ticket | fail]
+    CU(cudaMemsetAsync(flags.p, 0, ((size_t)nwin + 2) * 4, ctx->stream));
+    uint32_t* d_ticket = flags.as<uint32_t>() + nwin;
+    uint32_t* d_fail = d_ticket + 1;
+    const size_t smem = tilenc_smem_bytes(tile_max, tb.max_level);
+    CU(cudaFuncSetAttribute(tilenc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, ctx->stream));
+    if (n > 0) {
+        BPE_LAUNCH_SMEM(tilenc_kernel, (unsigned)nwin, TN_THREADS, smem, ctx->stream, d_text, sh.left(), sh.right(), g, tile_max, tb.T,
+                        tb.max_level, slots.as<uint16_t>(), zone.as<uint16_t>(), flags.as<uint32_t>(), d_ticket, d_fail);
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(e1, ctx->stream));
+    // a window that gave up anywhere (on any rank) sends every rank to the next encoder
+    if (multi && !ctx->dist.allreduce(d_fail, 1, DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-reduce of the seam status failed");
+    uint32_t nfail = 0;
+    CU(cudaMemcpyAsync(&nfail, d_fail, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float kms = 0;
+    cudaEventElapsedTime(&kms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (st) { st->kernel_ms[11] = kms; st->kernel_calls[11] = nfail ? 2 : 1; }
+    if (nfail) {
+        if (ctx->debug) fprintf(stderr, "[bpe r%d] tile encode: %u windows gave up, falling back\n", rank, nfail);
+        return BPE_OK;
+    }
+    *used = true;
+    if (n == 0) { *out_n = 0; return BPE_OK; }
+    rc = squeeze_slots(ctx, slots, n, d_out, out_n);
+    if (rc) return rc;
+    if (st) st->scanned_slots += n;
+    return BPE_OK;
+}
+
+// *used = false when this path does not apply (irregular list, id 65535, seam without a common token):
+// nothing has been written to d_out then and the caller runs the level-scheduled passes.
+static int encode_segments(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bpe_merge_t* merges, size_t m, uint16_t* d_out,
+                           size_t* out_n, bpe_stats_t* st, bool* used) {
+    *used = false;
+    if (m == 0) return BPE_OK;
+    std::vector<uint32_t> lvl;
+    std::vector<uint8_t> alone;
+    if (!merge_levels(merges, m, lvl, alone) || mentions_id_65535(merges, m)) return BPE_OK;
+    const int world = ctx->dist.world, rank = ctx->dist.rank;
+    const bool multi = world > 1;
+    SegTables tb;
+    int rc = build_seg_tables(ctx, merges, m, lvl, tb);
+    if (rc) return rc;
+    const SegTab& T = tb.T;
+    ShardHalo sh;
+    rc = exchange_shard_halo(ctx, d_text, n, sh);
+    if (rc) return rc;
+    const long long g_lo = sh.g_lo, g_total = sh.g_total;
+    const int hl = sh.hl, hr = sh.hr;
     // ---- geometry ----
     int C = 64;
     if (ctx->encode_geom == 1) C = 128;
@@ -1043,6 +1247,7 @@ static int encode_segments(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const 
     if (k_first < 0) k_first = 0;
     if (k_last > k_text_last) k_last = k_text_last;
     const size_t n_slots = round_up(n ? n : 1, TILE);
+    DevBuf slots, failbuf;
     CU(slots.alloc(n_slots * 2));
     CU(failbuf.alloc(4));
     CU(cudaMemsetAsync(failbuf.p, 0, 4, ctx->stream));
@@ -1050,10 +1255,9 @@ static int encode_segments(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const 
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, ctx->stream));
-    int rc = BPE_OK;
     if (n > 0 && g_total > 0) {
-        const uint8_t* hlp = halo.as<uint8_t>();
-        const uint8_t* hrp = halo.as<uint8_t>() + SEG_HALO;
+        const uint8_t* hlp = sh.left();
+        const uint8_t* hrp = sh.right();
         uint16_t* sl = slots.as<uint16_t>();
         uint32_t* fl = failbuf.as<uint32_t>();
         switch (ctx->encode_geom) {
@@ -1083,25 +1287,8 @@ static int encode_segments(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const 
     }
     *used = true;
     if (n == 0) { *out_n = 0; return BPE_OK; }
-    // ---- squeeze the holes out, straight into the caller's buffer ----
-    if (n_slots > n) {
-        BPE_LAUNCH_NS(fill_holes_kernel<uint16_t>, grid_for(n_slots - n, 256), 256, ctx->stream, slots.as<uint16_t>(), n, n_slots);
-        ctx->launches++;
-    }
-    const size_t ntl = n_slots / TILE;
-    if (ntl > 0x7FFFFFFFull) return fail(ctx, BPE_ERR_INVALID_ARG, "input too large");
-    CU(tile_live.alloc(ntl * 4)); CU(tile_off.alloc(ntl * 8)); CU(total.alloc(8));
-    BPE_LAUNCH(tile_count_kernel<uint16_t>, (unsigned)ntl, THREADS, ctx->stream, slots.as<uint16_t>(), tile_live.as<uint32_t>());
-    BPE_LAUNCH(tile_scan_kernel, 1, THREADS, ctx->stream, tile_live.as<uint32_t>(), (uint32_t)ntl, tile_off.as<unsigned long long>(),
-               total.as<unsigned long long>());
-    BPE_LAUNCH((compact_scatter_kernel<uint16_t, uint16_t>), (unsigned)ntl, THREADS, ctx->stream, slots.as<uint16_t>(),
-               tile_off.as<unsigned long long>(), d_out);
-    ctx->launches += 3;
-    CU(cudaGetLastError());
-    unsigned long long tot = 0;
-    CU(cudaMemcpyAsync(&tot, total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    *out_n = (size_t)tot;
+    rc = squeeze_slots(ctx, slots, n, d_out, out_n);
+    if (rc) return rc;
     if (st) st->scanned_slots += n;
     return BPE_OK;
 }
@@ -1275,21 +1462,31 @@ static int encode_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
     CU(cudaEventRecord(ev0, ctx->stream));
     int rc = BPE_OK;
     bool done = false;
-    // encode_impl 0 (default) picks by cost: the level passes sweep the sequence once per level (C3's 7,936 merges:
-    // ~190 sweeps, 0.12 s per GB), the segment-resident kernel costs ~0.3 s per GB whatever the list (measured on
-    // B200) and needs no exchange between GPUs inside it. 3 forces the segment kernel, 2 the
-    // level passes, 1 one pass per merge.
+    // encode_impl 0 (default): the tile-resident kernel (one launch, the text is read once) for every list a trained
+    // tokenizer can produce; if it does not apply or gives up, the choice between the segment-resident kernel and
+    // the level passes is made by cost (the passes sweep the sequence once per level, the segment kernel costs
+    // ~0.3 s per GB whatever the list). 4 / 3 force the tile / segment kernel, 2 the level passes, 1 one pass per merge.
+    // kernel_calls[10] records the encoder that produced the ids (1 segment, 2 tile; 0 passes).
+    if ((ctx->encode_impl == 0 && ctx->encode_try_tiles) || ctx->encode_impl == 4) {
+        rc = encode_tiles(ctx, d_text, n, merges, m, d_out, out_n, &st, &done);
+        if (rc) return rc;
+        if (done) st.kernel_calls[10] = 2;
+        else if (ctx->encode_impl == 4) return fail(ctx, BPE_ERR_INTERNAL, "encode_impl = 4: the tile-resident encoder does not apply to this input");
+    }
     bool try_segments = ctx->encode_impl == 3;
-    if (ctx->encode_impl == 0 && m > 0) {
+    if (!done && ctx->encode_impl == 0 && m > 0) {
         std::vector<EncStep> steps;
         std::vector<LevelEntry> ents;
         build_encode_schedule(merges, m, true, steps, ents);
         try_segments = steps.size() > (size_t)ctx->encode_seg_min_steps || n >= 0xFFFFFFF0ull;
     }
-    if (try_segments) {
+    if (!done && try_segments) {
+        const uint64_t tile_verdict = st.kernel_calls[11];
         rc = encode_segments(ctx, d_text, n, merges, m, d_out, out_n, &st, &done);
         if (rc) return rc;
-        if (!done && ctx->encode_impl == 3) return fail(ctx, BPE_ERR_INTERNAL, "encode_impl = 3: the segment-resident encoder does not apply to this input");
+        if (done) st.kernel_calls[10] = 1;
+        else if (ctx->encode_impl == 3) return fail(ctx, BPE_ERR_INTERNAL, "encode_impl = 3: the segment-resident encoder does not apply to this input");
+        if (!done && tile_verdict == 2) st.kernel_calls[11] = 2;
     }
     if (!done) {
         if (n >= 0xFFFFFFF0ull) return fail(ctx, BPE_ERR_INVALID_ARG, "input of %zu bytes exceeds the 32-bit position range of the pass-based encoder", n);
@@ -1319,28 +1516,31 @@ static int encode_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
 // -----------------------------------------------------------------------------------------
 // decode (src/basic_tokenizer.zig:90-138)
 // -----------------------------------------------------------------------------------------
-struct Vocab {
-    std::vector<uint32_t> off, len;  // per id; len 0 = unknown id, 0xFFFFFFFF = expansion too large
+// findMerge (:109-116) returns the FIRST merge whose new_token matches; decodeMerge (:118-138) expands first then
+// second, recursively. Ids whose expansion is undefined (unknown component or a cycle, which would overflow the
+// reference's stack) get length 0 and fail only if they are used. Lengths are computed over the merge DAG (no
+// expansion is materialised for that), expansions of up to VOC_FLAT_MAX bytes are flattened for the scatter kernel,
+// longer ones (e.g. a doubling chain over a run of one byte) are decoded by descending through the DAG, so there
+// is no limit on the length of a token's expansion short of the 32-bit length itself.
+struct DecodeVocabHost {
+    std::vector<uint32_t> len, off, pair;  // per id
     std::vector<uint8_t> bytes;
 };
-static const uint32_t VOC_TOO_BIG = 0xFFFFFFFFu;
-static const uint32_t VOC_MAX_LEN = 1u << 19;
-static const size_t VOC_MAX_TOTAL = (size_t)1 << 28;  // all expansions together (host memory guard against doubling chains)
+static const uint32_t VOC_FLAT_MAX = 4096;
+static const size_t VOC_FLAT_TOTAL = (size_t)64 << 20;
+static const uint32_t VOC_LEN_SAT = 0xFFFFFFFEu;  // expansions of 4 GiB or more: the decode of such a token cannot be addressed
 
-// findMerge (:109-116) returns the FIRST merge whose new_token matches; decodeMerge (:118-138)
-// expands first then second, recursively. Ids whose expansion is undefined (unknown component or
-// a cycle, which would overflow the reference's stack) get len 0 and fail only if they are used.
-static void build_vocab(const bpe_merge_t* merges, size_t m, Vocab& v) {
+static void build_vocab(const bpe_merge_t* merges, size_t m, DecodeVocabHost& v) {
     const uint32_t NID = 65536;
     std::vector<int32_t> def(NID, -1);
     for (size_t i = 0; i < m; i++)
         if (def[merges[i].new_token] < 0) def[merges[i].new_token] = (int32_t)i;
     std::vector<uint8_t> state(NID, 0);  // 0 new, 1 open, 2 done
-    std::vector<std::vector<uint8_t>> exp(NID);
     v.len.assign(NID, 0);
-    for (uint32_t b = 0; b < 256; b++) { exp[b].assign(1, (uint8_t)b); state[b] = 2; v.len[b] = 1; }
-    std::vector<uint32_t> stack;
-    size_t total_exp = 256;
+    v.pair.assign(NID, 0);
+    v.off.assign(NID, VOC_NOT_FLAT);
+    for (uint32_t b = 0; b < 256; b++) { state[b] = 2; v.len[b] = 1; }
+    std::vector<uint32_t> stack, order;  // order: ids in an order where components come first
     for (uint32_t id = 256; id < NID; id++) {
         if (state[id] || def[id] < 0) continue;
         stack.push_back(id);
@@ -1350,38 +1550,56 @@ static void build_vocab(const bpe_merge_t* merges, size_t m, Vocab& v) {
             state[t] = 1;
             const bpe_merge_t& mg = merges[def[t]];
             uint32_t parts[2] = {mg.first, mg.second};
-            bool wait = false, bad = false, big = false;
+            bool wait = false, bad = false;
             for (uint32_t p : parts) {
                 if (p < 256) continue;
                 if (def[p] < 0) { bad = true; break; }
                 if (state[p] == 0) { stack.push_back(p); wait = true; break; }
                 if (state[p] == 1) { bad = true; break; }  // cycle
                 if (v.len[p] == 0) { bad = true; break; }
-                if (v.len[p] == VOC_TOO_BIG) big = true;
             }
             if (wait) continue;
             if (bad) v.len[t] = 0;
-            else if (big || (uint64_t)v.len[parts[0]] + v.len[parts[1]] > VOC_MAX_LEN ||
-                     total_exp + v.len[parts[0]] + v.len[parts[1]] > VOC_MAX_TOTAL) v.len[t] = VOC_TOO_BIG;
             else {
-                total_exp += (size_t)v.len[parts[0]] + v.len[parts[1]];
-                exp[t] = exp[parts[0]];
-                exp[t].insert(exp[t].end(), exp[parts[1]].begin(), exp[parts[1]].end());
-                v.len[t] = (uint32_t)exp[t].size();
+                const uint64_t l = (uint64_t)v.len[parts[0]] + v.len[parts[1]];
+                v.len[t] = l >= VOC_LEN_SAT ? VOC_LEN_SAT : (uint32_t)l;
+                v.pair[t] = parts[0] | (parts[1] << 16);
+                order.push_back(t);
             }
             state[t] = 2;
             stack.pop_back();
         }
     }
-    v.off.assign(NID, 0);
-    size_t total = 0;
-    for (uint32_t id = 0; id < NID; id++) {
-        if (v.len[id] && v.len[id] != VOC_TOO_BIG) { v.off[id] = (uint32_t)total; total += exp[id].size(); }
+    // flatten the short expansions (components first, so a token's bytes are the concatenation of two flattened ones)
+    v.bytes.resize(256);
+    for (uint32_t b = 0; b < 256; b++) { v.bytes[b] = (uint8_t)b; v.off[b] = b; }
+    for (uint32_t t : order) {
+        const uint32_t f = v.pair[t] & 0xFFFFu, s2 = v.pair[t] >> 16;
+        if (v.len[t] > VOC_FLAT_MAX || v.off[f] == VOC_NOT_FLAT || v.off[s2] == VOC_NOT_FLAT || v.bytes.size() + v.len[t] > VOC_FLAT_TOTAL) continue;
+        v.off[t] = (uint32_t)v.bytes.size();
+        const size_t at = v.bytes.size();
+        v.bytes.resize(at + v.len[t]);
+        memcpy(&v.bytes[at], &v.bytes[v.off[f]], v.len[f]);
+        memcpy(&v.bytes[at + v.len[f]], &v.bytes[v.off[s2]], v.len[s2]);
     }
-    v.bytes.resize(total ? total : 1);
-    for (uint32_t id = 0; id < NID; id++)
-        if (v.len[id] && v.len[id] != VOC_TOO_BIG) memcpy(&v.bytes[v.off[id]], exp[id].data(), exp[id].size());
 }
+
+// device copy of the decode tables, kept in the context for the merge list they were built from
+struct DecodeCache {
+    uint64_t fingerprint = 0;
+    size_t m = 0;
+    bool valid = false;
+    DevBuf len, off, pair, bytes;
+    bool has_saturated = false;
+    DecVocab view() const { DecVocab d; d.len = len.as<uint32_t>(); d.off = off.as<uint32_t>(); d.pair = pair.as<uint32_t>(); d.bytes = bytes.as<uint8_t>(); return d; }
+};
+static uint64_t merges_fingerprint(const bpe_merge_t* merges, size_t m) {
+    uint64_t h = 0xcbf29ce484222325ull ^ (uint64_t)m;
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(merges);
+    for (size_t i = 0; i < m * sizeof(bpe_merge_t); i++) { h ^= p[i]; h *= 0x100000001b3ull; }
+    return h;
+}
+static int ensure_decode_vocab(bpe_ctx* ctx, const bpe_merge_t* merges, size_t m);
 
 __global__ void decode_flag_big_kernel(const uint16_t* __restrict__ toks, size_t n, const uint32_t* __restrict__ voc_len, StepCtl* ctl) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1389,7 +1607,7 @@ __global__ void decode_flag_big_kernel(const uint16_t* __restrict__ toks, size_t
     for (; i < n; i += stride) {
         uint32_t l = voc_len[toks[i]];
         if (l == 0) atomicOr(&ctl->err, (uint32_t)ERR_KEY_MISSING);
-        else if (l == 0xFFFFFFFFu) atomicOr(&ctl->err, (uint32_t)ERR_TABLE_FULL);
+        else if (l >= 0xFFFFFFFEu) atomicOr(&ctl->err, (uint32_t)ERR_TABLE_FULL);
     }
 }
 
@@ -1405,40 +1623,40 @@ static int decode_device(bpe_ctx* ctx, const uint16_t* d_toks, size_t n, const b
     const uint64_t l0 = ctx->launches;
     if (n == 0) { if (stats_out) *stats_out = st; return BPE_OK; }
     CU(cudaSetDevice(ctx->device));
-    Vocab v;
-    build_vocab(merges, m, v);
-    DevBuf voff, vlen, vbytes, ctl, tile_bytes, tile_off, total;
+    int rc = ensure_decode_vocab(ctx, merges, m);
+    if (rc) return rc;
+    DecodeCache& dc = *ctx->decode_cache;
+    DevBuf ctl, tile_bytes, tile_off, total;
     const size_t nt = (n + TILE - 1) / TILE;
-    CU(voff.alloc(65536 * 4)); CU(vlen.alloc(65536 * 4)); CU(vbytes.alloc(v.bytes.size()));
-    CU(ctl.alloc(sizeof(StepCtl))); CU(tile_bytes.alloc(nt * 4)); CU(tile_off.alloc(nt * 8)); CU(total.alloc(8));
+    if (nt > 0x7FFFFFFFull) return fail(ctx, BPE_ERR_INVALID_ARG, "input too large");
+    CU(ctl.alloc(sizeof(StepCtl))); CU(tile_bytes.alloc(nt * 8)); CU(tile_off.alloc(nt * 8)); CU(total.alloc(8));
     cudaEvent_t ev0, ev1;
     CU(cudaEventCreate(&ev0));
     CU(cudaEventCreate(&ev1));
     CU(cudaEventRecord(ev0, ctx->stream));
-    CU(cudaMemcpyAsync(voff.p, v.off.data(), 65536 * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(vlen.p, v.len.data(), 65536 * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(vbytes.p, v.bytes.data(), v.bytes.size(), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(ctl.p, 0, sizeof(StepCtl), ctx->stream));
-    BPE_LAUNCH_NS(decode_flag_big_kernel, grid_for(n, 256), 256, ctx->stream, d_toks, n, vlen.as<uint32_t>(), ctl.as<StepCtl>());
+    BPE_LAUNCH(decode_len_kernel, (unsigned)nt, THREADS, ctx->stream, d_toks, n, dc.len.as<uint32_t>(), tile_bytes.as<unsigned long long>(), ctl.as<StepCtl>());
     ctx->launches++;
-    uint32_t err = 0;
-    CU(cudaMemcpyAsync(&err, &ctl.as<StepCtl>()->err, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    if (err & ERR_KEY_MISSING) return fail(ctx, BPE_ERR_INVALID_TOKEN, "token id without a merge (error.InvalidToken)");
-    if (err & ERR_TABLE_FULL) return fail(ctx, BPE_ERR_OOM, "a token expands to more than %u bytes", VOC_MAX_LEN);
-    BPE_LAUNCH(decode_len_kernel, (unsigned)nt, THREADS, ctx->stream, d_toks, n, vlen.as<uint32_t>(), tile_bytes.as<uint32_t>(), ctl.as<StepCtl>());
-    BPE_LAUNCH(tile_scan_kernel, 1, THREADS, ctx->stream, tile_bytes.as<uint32_t>(), (uint32_t)nt,
+    if (dc.has_saturated) {
+        BPE_LAUNCH_NS(decode_flag_big_kernel, grid_for(n, 256), 256, ctx->stream, d_toks, n, dc.len.as<uint32_t>(), ctl.as<StepCtl>());
+        ctx->launches++;
+    }
+    BPE_LAUNCH(tile_scan64_kernel, 1, THREADS, ctx->stream, tile_bytes.as<unsigned long long>(), (uint32_t)nt,
                tile_off.as<unsigned long long>(), total.as<unsigned long long>());
-    ctx->launches += 2;
+    ctx->launches++;
     CU(cudaGetLastError());
+    uint32_t err = 0;
     unsigned long long tot = 0;
+    CU(cudaMemcpyAsync(&err, &ctl.as<StepCtl>()->err, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(&tot, total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (err & ERR_KEY_MISSING) return fail(ctx, BPE_ERR_INVALID_TOKEN, "token id without a merge (error.InvalidToken)");
+    if (err & ERR_TABLE_FULL) return fail(ctx, BPE_ERR_OOM, "a token expands to 4 GiB or more");
     *out_n = (size_t)tot;
     if (d_out) {
         if ((size_t)tot > cap) return fail(ctx, BPE_ERR_OOM, "decode needs %llu bytes, buffer has %zu", tot, cap);
-        BPE_LAUNCH(decode_scatter_kernel, (unsigned)nt, THREADS, ctx->stream, d_toks, n, voff.as<uint32_t>(), vlen.as<uint32_t>(),
-                   vbytes.as<uint8_t>(), tile_off.as<unsigned long long>(), d_out, cap);
+        BPE_LAUNCH(decode_scatter_kernel, (unsigned)nt, THREADS, ctx->stream, d_toks, n, dc.view(), tile_off.as<unsigned long long>(),
+                   tile_bytes.as<unsigned long long>(), d_out, cap);
         ctx->launches++;
         CU(cudaGetLastError());
     }
@@ -1458,6 +1676,35 @@ static int decode_device(bpe_ctx* ctx, const uint16_t* d_toks, size_t n, const b
 // -----------------------------------------------------------------------------------------
 // C ABI
 // -----------------------------------------------------------------------------------------
+static int ensure_decode_vocab(bpe_ctx* ctx, const bpe_merge_t* merges, size_t m) {
+    if (!ctx->decode_cache) ctx->decode_cache = new DecodeCache();
+    DecodeCache& dc = *ctx->decode_cache;
+    const uint64_t fp = merges_fingerprint(merges, m);
+    if (dc.valid && dc.m == m && dc.fingerprint == fp) return BPE_OK;
+    dc.valid = false;
+    DecodeVocabHost v;
+    build_vocab(merges, m, v);
+    dc.has_saturated = false;
+    for (uint32_t l : v.len) if (l >= VOC_LEN_SAT) dc.has_saturated = true;
+    BufCache* saved = tl_cache;
+    tl_cache = nullptr;  // these buffers outlive the call: plain cudaMalloc, freed with the context
+    cudaError_t e = dc.len.alloc(65536 * 4);
+    if (e == cudaSuccess) e = dc.off.alloc(65536 * 4);
+    if (e == cudaSuccess) e = dc.pair.alloc(65536 * 4);
+    if (e == cudaSuccess) e = dc.bytes.alloc(v.bytes.size());
+    tl_cache = saved;
+    if (e != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of the decode tables failed");
+    CU(cudaMemcpyAsync(dc.len.p, v.len.data(), 65536 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dc.off.p, v.off.data(), 65536 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dc.pair.p, v.pair.data(), 65536 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dc.bytes.p, v.bytes.data(), v.bytes.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // `v` lives on this frame
+    dc.fingerprint = fp;
+    dc.m = m;
+    dc.valid = true;
+    return BPE_OK;
+}
+
 struct CacheScope {
     BufCache* prev;
     explicit CacheScope(bpe_ctx* ctx) : prev(tl_cache) { tl_cache = ctx ? &ctx->cache : nullptr; }
@@ -1528,6 +1775,13 @@ int bpe_ctx_create_dist_cb(bpe_ctx** out, int rank, int world, dist_allreduce_cb
     (*out)->dist.cb = cb;
     return BPE_OK;
 }
+// emulation build only (tests): the per-step exchange through peer mailboxes in a shared-memory segment, exactly the
+// kernels the GPU build runs over NVLink peer memory (the last CTA of merge_kernel pushes, apply_kernel waits and sums)
+int bpe_ctx_set_peer_shm(bpe_ctx* ctx, void* base, size_t bytes) {
+    if (!ctx || !base) return BPE_ERR_INVALID_ARG;
+    return ctx->dist.init_peers_shm(base, bytes) ? BPE_OK : BPE_ERR_INVALID_ARG;
+}
+size_t bpe_peer_shm_bytes(int world) { return (size_t)world * DistComm::mbox_words(world) * 4; }
 #endif
 
 void bpe_ctx_destroy(bpe_ctx* ctx) {
@@ -1536,6 +1790,7 @@ void bpe_ctx_destroy(bpe_ctx* ctx) {
     ctx->dist.destroy_peers();
     ctx->dist.destroy();
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    delete ctx->decode_cache;
     ctx->cache.clear();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1560,6 +1815,10 @@ int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value) {
     else if (s == "encode_filter") ctx->encode_filter = value;
     else if (s == "encode_geom") ctx->encode_geom = value;
     else if (s == "encode_seg_min_steps") ctx->encode_seg_min_steps = value;
+    else if (s == "encode_tile") ctx->encode_tile = value;
+    else if (s == "encode_try_tiles") ctx->encode_try_tiles = value;
+    else if (s == "fuse_halo") ctx->fuse_halo = value;
+    else if (s == "count_limit_log2") ctx->count_limit_log2 = value;
     else return fail(ctx, BPE_ERR_INVALID_ARG, "unknown option '%s'", name);
     return BPE_OK;
 }

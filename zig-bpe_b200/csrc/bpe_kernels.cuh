@@ -55,7 +55,11 @@ __global__ void fill_holes_kernel(TokT* tok, size_t from, size_t to) {
 // next_byte: first byte of the following shard (multi-GPU), -1 if none
 // =========================================================================================
 // Block-private bins in shared memory: 65,536 u16 counters (128 KB, two per word), flushed to the
-// global u32 histogram after every pass of HIST_PASS bytes so that no counter can overflow.
+// global histogram after every pass of HIST_PASS bytes so that no counter can overflow. The global histogram is
+// 64 bits wide (the reference counts in usize, :47,265; a 10 GB corpus can hold a pair more than 2^32 times, and the
+// sum over the shards is taken in 64 bits too); the pair table keeps 32-bit counts, so seed_table_kernel refuses a
+// histogram that does not fit — no later count can exceed the largest initial one (a new pair occurs at most as
+// often as the pair it came from), so this one check covers the whole training.
 constexpr int HIST_THREADS = 1024;
 constexpr int HIST_BPT = 32;                       // bytes per thread per pass
 constexpr int HIST_PASS = HIST_THREADS * HIST_BPT;  // 32,768 pairs per pass < 65,536
@@ -63,7 +67,7 @@ constexpr size_t HIST_SMEM = 65536 * 2;
 
 __global__ void __launch_bounds__(HIST_THREADS, 1) byte_pair_hist_kernel(const uint8_t* __restrict__ text, size_t n,
                                                                          const EdgeInfo* __restrict__ edges, int rank, int world,
-                                                                         uint32_t* __restrict__ hist) {
+                                                                         unsigned long long* __restrict__ hist) {
     uint32_t* bins = bpe_dyn_smem();  // [32768] words
     int next_byte = -1;  // first byte of the following shards (multi-GPU), none otherwise
     if (edges) for (int q = rank + 1; q < world; q++) if (edges[q].nfirst) { next_byte = (int)edges[q].first[0]; break; }
@@ -104,8 +108,8 @@ __global__ void __launch_bounds__(HIST_THREADS, 1) byte_pair_hist_kernel(const u
             uint32_t wv = bins[i];
             if (wv) {
                 bins[i] = 0;
-                if (wv & 0xFFFFu) atomicAdd(&hist[2 * i], wv & 0xFFFFu);
-                if (wv >> 16) atomicAdd(&hist[2 * i + 1], wv >> 16);
+                if (wv & 0xFFFFu) atomicAdd(&hist[2 * i], (unsigned long long)(wv & 0xFFFFu));
+                if (wv >> 16) atomicAdd(&hist[2 * i + 1], (unsigned long long)(wv >> 16));
             }
         }
         __syncthreads();
@@ -113,11 +117,13 @@ __global__ void __launch_bounds__(HIST_THREADS, 1) byte_pair_hist_kernel(const u
 }
 
 // hist (already summed over GPUs) -> pair table + reference-home population
-__global__ void seed_table_kernel(const uint32_t* __restrict__ hist, PairTable tbl, StepCtl* ctl) {
+__global__ void seed_table_kernel(const unsigned long long* __restrict__ hist, PairTable tbl, StepCtl* ctl, unsigned long long count_limit) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 65536u) return;
-    uint32_t c = hist[i];
-    if (!c) return;
+    const unsigned long long c64 = hist[i];
+    if (!c64) return;
+    if (c64 > count_limit) { atomicOr(&ctl->err, (uint32_t)ERR_COUNT_OVERFLOW); return; }
+    const uint32_t c = (uint32_t)c64;
     uint32_t key = pair_key(i & 255u, i >> 8);
     uint32_t s = tbl_find_or_insert(tbl, key, &ctl->n_inserted);
     if (s == EMPTY_KEY) { atomicOr(&ctl->err, (uint32_t)ERR_TABLE_FULL); return; }
@@ -231,6 +237,8 @@ __device__ __forceinline__ void commit_merge(StepCtl* ctl, MergeRec* rec, uint32
     ctl->X = 256u + ctl->step;
     rec[ctl->step].key = key;
     rec[ctl->step].count = count;
+    // first == second: the merge pass needs run lengths across tiles, which the fused halo does not produce
+    if ((ctl->flags & F_HALT_AEQB) && (key & 0xFFFFu) == (key >> 16)) ctl->halt = H_AEQB;
 }
 
 // ---- tie fast path (device) -------------------------------------------------------------
@@ -460,6 +468,70 @@ __global__ void heavy_ties_kernel(PairTable tbl, HeavyList hl, StepCtl* ctl) {
 // every thread replays its range from its carry-in — linear work even on "aaaa..." inputs).
 // zero2 (nullable): the two scalar merge deltas (cntXX, cntAB) to clear before the merge pass.
 constexpr int HALO_THREADS = 128;
+
+// Where a shard's neighbours' end tokens come from: the local copy of the exchanged EdgeInfo slots (single GPU:
+// none; NCCL path and host-driven passes: the exchange buffer) or, inside the fused apply + halo kernel of the
+// peer-memory path, the mailbox slots themselves (valid once the sender's arrival flag shows this step's epoch).
+struct EdgeSrc {
+    const EdgeInfo* local;      // nullptr: single GPU
+    const uint32_t* mbox;       // != nullptr: read rank r's EdgeInfo from mbox + r * slot_words + edge_off + r * 16
+    const uint32_t* flags;      // arrival flags of this rank's mailbox
+    uint32_t slot_words, edge_off, epoch;
+    uint32_t* err;
+};
+__device__ __forceinline__ EdgeInfo edge_get(const EdgeSrc& es, int r) {
+    if (!es.mbox) return es.local[r];
+    uint32_t spins = 0;
+    while ((int32_t)(((volatile const uint32_t*)es.flags)[r] - es.epoch) < 0) {
+        if (++spins > (1u << 28)) { atomicOr(es.err, (uint32_t)ERR_PEER_TIMEOUT); break; }
+    }
+    __threadfence();
+    EdgeInfo e;
+    const uint32_t* src = es.mbox + (size_t)r * es.slot_words + es.edge_off + (uint32_t)r * 16u;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&e);
+    for (int w = 0; w < 16; w++) dst[w] = __ldcg(src + w);
+    return e;
+}
+
+// the live tokens around tile t (holes are skipped, the search continues in the neighbouring shards)
+template <class TokT>
+__device__ __forceinline__ void halo_gather(const TokT* __restrict__ tok, size_t n_slots, uint32_t t, TileHalo<TokT>* halo,
+                                            const EdgeSrc& es, int rank, int world) {
+    const TokT H = (TokT)TokTraits<TokT>::hole;
+    const bool have_edges = es.local != nullptr || es.mbox != nullptr;
+    TileHalo<TokT> h;
+    TokT l[2] = {H, H};
+    int nl = 0;
+    for (size_t i = (size_t)t * TILE; i > 0 && nl < 2;) {
+        --i;
+        TokT v = tok[i];
+        if (v != H) l[nl++] = v;
+    }
+    if (nl < 2 && have_edges) {  // fell off the shard: continue in the shards before this one
+        for (int r = rank - 1; r >= 0 && nl < 2; r--) {
+            const EdgeInfo e = edge_get(es, r);
+            for (uint32_t k = 0; k < e.nlast && nl < 2; k++) l[nl++] = (TokT)e.last[k];
+        }
+    }
+    h.l1 = l[0];
+    h.l2 = (l[0] == H) ? H : l[1];
+    TokT r3[3] = {H, H, H};
+    int nr = 0;
+    for (size_t i = (size_t)(t + 1) * TILE; i < n_slots && nr < 3; i++) {
+        TokT v = tok[i];
+        if (v != H) r3[nr++] = v;
+    }
+    if (nr < 3 && have_edges) {  // continue in the shards after this one
+        for (int q = rank + 1; q < world && nr < 3; q++) {
+            const EdgeInfo e = edge_get(es, q);
+            for (uint32_t k = 0; k < e.nfirst && nr < 3; k++) r3[nr++] = (TokT)e.first[k];
+        }
+    }
+    h.r0 = r3[0]; h.r1 = r3[1]; h.r2 = r3[2];
+    h.runA = 0;
+    halo[t] = h;
+}
+
 template <class TokT, bool FROMCTL>
 __global__ void __launch_bounds__(HALO_THREADS) halo_kernel(const TokT* __restrict__ tok, size_t n_slots, uint32_t ntiles,
                             TileHalo<TokT>* halo, const StepCtl* __restrict__ ctl, uint32_t Au, int aeqb,
@@ -477,35 +549,9 @@ __global__ void __launch_bounds__(HALO_THREADS) halo_kernel(const TokT* __restri
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t == 0 && zero2) { zero2[0] = 0; zero2[1] = 0; }
     if (t < ntiles) {
-        TileHalo<TokT> h;
-        // left: last two live tokens before slot t*TILE
-        TokT l[2] = {H, H};
-        int nl = 0;
-        for (size_t i = (size_t)t * TILE; i > 0 && nl < 2;) {
-            --i;
-            TokT v = tok[i];
-            if (v != H) l[nl++] = v;
-        }
-        if (nl < 2 && edges) {  // fell off the shard: continue in the shards before this one
-            for (int r = rank - 1; r >= 0 && nl < 2; r--)
-                for (uint32_t k = 0; k < edges[r].nlast && nl < 2; k++) l[nl++] = (TokT)edges[r].last[k];
-        }
-        h.l1 = l[0];
-        h.l2 = (l[0] == H) ? H : l[1];
-        // right: first three live tokens at/after slot (t+1)*TILE
-        TokT r[3] = {H, H, H};
-        int nr = 0;
-        for (size_t i = (size_t)(t + 1) * TILE; i < n_slots && nr < 3; i++) {
-            TokT v = tok[i];
-            if (v != H) r[nr++] = v;
-        }
-        if (nr < 3 && edges) {  // continue in the shards after this one
-            for (int q = rank + 1; q < world && nr < 3; q++)
-                for (uint32_t k = 0; k < edges[q].nfirst && nr < 3; k++) r[nr++] = (TokT)edges[q].first[k];
-        }
-        h.r0 = r[0]; h.r1 = r[1]; h.r2 = r[2];
-        h.runA = 0;
-        halo[t] = h;
+        EdgeSrc es;
+        es.local = edges; es.mbox = nullptr; es.flags = nullptr; es.slot_words = es.edge_off = es.epoch = 0; es.err = nullptr;
+        halo_gather<TokT>(tok, n_slots, t, halo, es, rank, world);
         if (aeqb) {
             // live A's walking back from the tile's left edge, inside the previous tile only
             const TokT A = (TokT)Au;
@@ -652,47 +698,46 @@ __global__ void edge_kernel(const TokT* __restrict__ tok, size_t n_slots, size_t
     edge_body<TokT>(tok, n_slots, tail_hint, all, rank, world, ctl, nab_local, account, true);
 }
 
-// xchg_kernel (multi-GPU, peer-memory path): block 0 describes the shard's ends, then all blocks push
-// this rank's deltas (+ its EdgeInfo) into slot `rank` of every peer's mailbox over NVLink, clear the
-// local deltas, and the last block to finish raises this rank's arrival flag on every peer.
+// Peer-memory exchange (multi-GPU): the CTA that finishes the merge pass last describes the shard's ends, pushes this
+// rank's deltas (+ its EdgeInfo) into slot `rank` of every peer's mailbox over NVLink with 16-byte stores, clears the
+// local deltas for the next pass and raises this rank's arrival flag on every peer. It runs inside merge_kernel (no
+// launch of its own); the consumer is the apply kernel of the same step on every rank.
+struct PushArgs {
+    int on;                 // 0: single GPU or NCCL path
+    uint32_t* delta;        // [cntL | cntR | cntXX cntAB | pad | EdgeInfo x world]
+    uint32_t edge_off;      // word offset of the EdgeInfo slots
+    uint32_t zero_vecs;     // 16-byte vectors of the cntL | cntR block (cleared after the push)
+    size_t n_slots, tail_hint;
+    PeerSet ps;
+    int rank, world;
+    StepCtl* ctl;
+    uint32_t* done_counter;
+};
+// `ap` lives in device memory (written by the host at the start of a run and after every compaction), so the merge
+// kernel carries one pointer instead of a 200-byte parameter block
 template <class TokT>
-__global__ void __launch_bounds__(256) xchg_kernel(const TokT* __restrict__ tok, size_t n_slots, size_t tail_hint,
-                                                   uint32_t* __restrict__ delta, uint32_t edge_off, uint32_t zero_vecs,
-                                                   const uint32_t* nab_local, PeerSet ps, int rank, int world,
-                                                   uint32_t parity, uint32_t epoch, StepCtl* ctl, uint32_t* done_counter) {
-    __shared__ uint32_t s_last;
-    if (ctl->halt) return;
-    EdgeInfo* edges = reinterpret_cast<EdgeInfo*>(delta + edge_off);
-    const size_t slot = ((size_t)parity * (size_t)world + (size_t)rank) * ps.slot_words;
-    if (blockIdx.x == 0) {
-        if (threadIdx.x < 32) edge_body<TokT>(tok, n_slots, tail_hint, edges, rank, world, ctl, nab_local, 1, false);
-        __syncthreads();
-        // my EdgeInfo slot (16 words) to every peer
-        for (uint32_t i = threadIdx.x; i < 16u * (uint32_t)world; i += blockDim.x) {
-            const uint32_t p = i / 16u, w = i % 16u;
-            ps.mbox[p][slot + edge_off + (uint32_t)rank * 16u + w] = delta[edge_off + (uint32_t)rank * 16u + w];
-        }
+__device__ __noinline__ void push_deltas(const TokT* __restrict__ tok, const PushArgs* __restrict__ ap, uint32_t parity, uint32_t epoch,
+                                         const uint32_t* nab_local) {
+    const PushArgs a = *ap;
+    EdgeInfo* edges = reinterpret_cast<EdgeInfo*>(a.delta + a.edge_off);
+    const size_t slot = ((size_t)parity * (size_t)a.world + (size_t)a.rank) * a.ps.slot_words;
+    if (threadIdx.x < 32) edge_body<TokT>(tok, a.n_slots, a.tail_hint, edges, a.rank, a.world, a.ctl, nab_local, 1, false);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 16u * (uint32_t)a.world; i += blockDim.x) {  // my EdgeInfo slot to every peer
+        const uint32_t p = i / 16u, w = i % 16u;
+        a.ps.mbox[p][slot + a.edge_off + (uint32_t)a.rank * 16u + w] = a.delta[a.edge_off + (uint32_t)a.rank * 16u + w];
     }
-    // deltas: 16-byte stores to every peer, then clear the local copy for the next merge pass
-    const uint32_t nvec = edge_off / 4u;
-    uint4* dl = reinterpret_cast<uint4*>(delta);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
+    const uint32_t nvec = a.edge_off / 4u;
+    uint4* dl = reinterpret_cast<uint4*>(a.delta);
+    for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) {
         const uint4 v = dl[i];
-        for (int p = 0; p < world; p++) reinterpret_cast<uint4*>(ps.mbox[p] + slot)[i] = v;
-        // (the vector holding cntXX / cntAB is left alone: block 0 still reads it, the next halo pass clears it)
-        if (i < zero_vecs && (v.x | v.y | v.z | v.w)) dl[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int p = 0; p < a.world; p++) reinterpret_cast<uint4*>(a.ps.mbox[p] + slot)[i] = v;
+        // (the vector holding cntXX / cntAB is left to the apply kernel, which also reads the local copy)
+        if (i < a.zero_vecs && (v.x | v.y | v.z | v.w)) dl[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t prev = atomicAdd(done_counter, 1u);
-        s_last = (prev == gridDim.x - 1u) ? 1u : 0u;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence_system();
-    if ((int)threadIdx.x < world) *((volatile uint32_t*)&ps.flags[threadIdx.x][rank]) = epoch;
-    if (threadIdx.x == 0) *done_counter = 0;
+    if ((int)threadIdx.x < a.world) *((volatile uint32_t*)&a.ps.flags[threadIdx.x][a.rank]) = epoch;
     __threadfence_system();
 }
 
@@ -981,7 +1026,8 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(Tok
                                                         const StepCtl* __restrict__ ctl, uint32_t* __restrict__ cntL,
                                                         uint32_t* __restrict__ cntR, uint32_t* nxx_out, uint32_t* nab_out,
                                                         uint32_t Au, uint32_t Bu, uint32_t Xu, uint32_t bins_min_count,
-                                                        int backwards) {
+                                                        int backwards, const PushArgs* __restrict__ push, uint32_t push_parity,
+                                                        uint32_t push_epoch, uint32_t* push_counter) {
     __shared__ __align__(16) TokT ext[EXT];
     // block-private bins for the neighbour deltas: key = token id (+ 0x10000 for the right side)
     __shared__ uint32_t bin_key[DELTAS ? MERGE_NBIN : 1];
@@ -1012,6 +1058,9 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(Tok
         if (ctl->halt) return;
         Au = ctl->A; Bu = ctl->B; Xu = ctl->X;
         use_bins = DELTAS && ctl->max_count >= bins_min_count;
+        // tell the apply kernel of this step that the pass ran (its halo CTAs cannot look at `halt`: the selection
+        // at the end of that very kernel may set it while they are still starting)
+        if (blockIdx.x == 0 && threadIdx.x == 0) const_cast<StepCtl*>(ctl)->pass_step = ctl->step + 1u;
     }
     const TokT A = (TokT)Au;
     uint32_t hitbits = 0;  // which of my vectors hold an A
@@ -1019,12 +1068,26 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(Tok
     for (int k = 0; k < NV; k++) hitbits |= vec_has<TokT>(v[k], Au) ? (1u << k) : 0u;
     any = hitbits != 0;
     if (threadIdx.x == 0 && h.l1 == A) any = true;  // possible head duty
-    if (!__syncthreads_or(any ? 1 : 0)) return;
-    uint32_t nAB = 0, nXX = 0;
-    tile_staged_path<TokT, DELTAS, true, NV>(ext, v, tok, base, h, hitbits, Au, Bu, Xu, use_bins, bin_key, bin_val, q_pos, &q_n, &sh_runA,
-                                             cntL, cntR, nAB, nXX);
-    if (nAB) atomicAdd(nab_out, nAB);
-    if (DELTAS && nXX) atomicAdd(nxx_out, nXX);
+    if (__syncthreads_or(any ? 1 : 0)) {
+        uint32_t nAB = 0, nXX = 0;
+        tile_staged_path<TokT, DELTAS, true, NV>(ext, v, tok, base, h, hitbits, Au, Bu, Xu, use_bins, bin_key, bin_val, q_pos, &q_n, &sh_runA,
+                                                 cntL, cntR, nAB, nXX);
+        if (nAB) atomicAdd(nab_out, nAB);
+        if (DELTAS && nXX) atomicAdd(nxx_out, nXX);
+    }
+    if (!push) return;
+    // multi-GPU peer path: the last CTA to finish the pass sends this rank's deltas to every peer
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(push_counter, 1u);
+        q_n = (prev == gridDim.x - 1u) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!q_n) return;
+    if (threadIdx.x == 0) *push_counter = 0;
+    __threadfence();
+    push_deltas<TokT>(tok, push, push_parity, push_epoch, nab_out);
 }
 
 // =========================================================================================
@@ -1265,10 +1328,39 @@ __global__ void write_kernel(TokT* __restrict__ tok, StepCtl* ctl, const TokWrit
 // =========================================================================================
 // Peer mode (ps_on): the deltas are the sum over the mailbox slots the peers filled; wait for their
 // arrival flags first, and copy the gathered EdgeInfo slots to where the next halo pass reads them.
+// Fused halo: the CTAs after the first `apply_blocks` gather the tile halos for the NEXT merge pass (they only need
+// the sequence as the pass of this step left it, not the merge that is being chosen), so the per-step halo launch
+// and its latency disappear behind the table updates. Steps with first == second additionally need run lengths
+// that depend on the chosen token: select_body halts the loop for them (H_AEQB) and the host runs the classic
+// halo_kernel for that step.
+struct HaloArgs {
+    const uint16_t* tok;     // nullptr: no fused halo
+    size_t n_slots;
+    uint32_t ntiles;
+    TileHalo<uint16_t>* halo;
+    uint32_t apply_blocks;
+    uint32_t step1;          // 1 + index of the step this launch belongs to (compared with StepCtl::pass_step)
+};
 __global__ void __launch_bounds__(256) apply_kernel(PairTable tbl, uint32_t* __restrict__ delta, uint32_t vcap, StepCtl* ctl,
                              ZigPop z, uint32_t n_ids, HeavyList hl, MergeRec* rec, int fuse_select,
-                             int ps_on, PeerSet ps, int rank, int world, uint32_t parity, uint32_t epoch, uint32_t edge_off) {
-    if (ctl->halt) return;
+                             int ps_on, PeerSet ps, int rank, int world, uint32_t parity, uint32_t epoch, uint32_t edge_off,
+                             HaloArgs ha) {
+    if (ha.tok ? (ctl->pass_step != ha.step1) : (ctl->halt != 0u)) return;  // this step did not run (the loop was halted before it)
+    if (ha.tok && blockIdx.x >= ha.apply_blocks) {
+        const uint32_t t = (blockIdx.x - ha.apply_blocks) * blockDim.x + threadIdx.x;
+        if (t >= ha.ntiles) return;
+        EdgeSrc es;
+        es.local = world > 1 ? reinterpret_cast<const EdgeInfo*>(delta + edge_off) : nullptr;
+        es.mbox = nullptr; es.flags = nullptr; es.slot_words = 0; es.edge_off = edge_off; es.epoch = epoch; es.err = &ctl->err;
+        if (ps_on) {  // peer path: the neighbours' shard ends of this step sit in the mailbox (apply block 0 copies them later)
+            es.mbox = ps.mbox[rank] + (size_t)parity * (size_t)world * ps.slot_words;
+            es.flags = ps.flags[rank];
+            es.slot_words = ps.slot_words;
+        }
+        halo_gather<uint16_t>(ha.tok, ha.n_slots, t, ha.halo, es, rank, world);
+        return;
+    }
+    const uint32_t n_apply = ha.tok ? ha.apply_blocks : gridDim.x;
     const uint32_t* mb = nullptr;
     if (ps_on) {
         if (threadIdx.x == 0) {
@@ -1339,7 +1431,7 @@ __global__ void __launch_bounds__(256) apply_kernel(PairTable tbl, uint32_t* __r
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t prev = atomicAdd(&ctl->apply_done, 1u);
-        s_is_last = (prev == gridDim.x - 1u) ? 1u : 0u;
+        s_is_last = (prev == n_apply - 1u) ? 1u : 0u;
     }
     __syncthreads();
     if (!s_is_last) return;
@@ -1566,22 +1658,49 @@ __global__ void __launch_bounds__(THREADS, sizeof(TokT) == 2 ? 6 : 4) level_kern
 }
 
 // =========================================================================================
-// compaction: squeeze the holes out (ballot-free v1: per-tile counts, scan, scatter)
+// compaction: squeeze the holes out. Two streaming passes over the sequence: per-tile live counts (tile_count),
+// a scan of the counts (tile_scan, one CTA), and the scatter, which compacts a tile in shared memory and writes
+// it out as one contiguous, 16-byte-vectorised range (compact_scatter). Both passes read the tile with the same
+// interleaved 128-bit loads as merge_kernel.
 // =========================================================================================
+template <class TokT> __device__ __forceinline__ uint32_t vec_live_count(const uint4& v);
+template <> __device__ __forceinline__ uint32_t vec_live_count<uint16_t>(const uint4& v) {
+    // halfwords equal to 0xFFFF: exact zero-halfword test of ~w (see vec_mask)
+    auto holes = [](uint32_t w) { const uint32_t x = ~w; return (uint32_t)__popc(~(((x & 0x7FFF7FFFu) + 0x7FFF7FFFu) | x) & 0x80008000u); };
+    return 8u - holes(v.x) - holes(v.y) - holes(v.z) - holes(v.w);
+}
+template <> __device__ __forceinline__ uint32_t vec_live_count<uint32_t>(const uint4& v) {
+    return (v.x != 0xFFFFFFFFu) + (v.y != 0xFFFFFFFFu) + (v.z != 0xFFFFFFFFu) + (v.w != 0xFFFFFFFFu);
+}
+__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v) {
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t d = 1; d < 32u; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
+    }
+    return v;
+}
+
 template <class TokT>
 __global__ void __launch_bounds__(THREADS) tile_count_kernel(const TokT* __restrict__ tok, uint32_t* __restrict__ tile_live) {
-    __shared__ uint32_t sh[THREADS];
-    const TokT H = (TokT)TokTraits<TokT>::hole;
-    const size_t base = (size_t)blockIdx.x * TILE + (size_t)threadIdx.x * SPT;
+    __shared__ uint32_t sh[THREADS / 32];
+    constexpr int VEC = 16 / (int)sizeof(TokT);
+    constexpr int NV = TILE / VEC / THREADS;
+    const uint4* src = reinterpret_cast<const uint4*>(tok + (size_t)blockIdx.x * TILE);
+    uint4 v[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) v[k] = src[k * THREADS + (int)threadIdx.x];
     uint32_t c = 0;
-    for (int k = 0; k < SPT; k++) c += (tok[base + k] != H);
-    sh[threadIdx.x] = c;
+#pragma unroll
+    for (int k = 0; k < NV; k++) c += vec_live_count<TokT>(v[k]);
+    c = warp_inclusive_scan(c);
+    if ((threadIdx.x & 31u) == 31u) sh[threadIdx.x >> 5] = c;
     __syncthreads();
-    for (int off = THREADS / 2; off > 0; off >>= 1) {
-        if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
-        __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < THREADS / 32; w++) t += sh[w];
+        tile_live[blockIdx.x] = t;
     }
-    if (threadIdx.x == 0) tile_live[blockIdx.x] = sh[0];
 }
 
 // single CTA: exclusive scan of tile_live[0..ntiles) into tile_off (u64), total -> *total
@@ -1608,15 +1727,64 @@ template <class TokT, class OutT>
 __global__ void __launch_bounds__(THREADS) compact_scatter_kernel(const TokT* __restrict__ tok,
                                                                   const unsigned long long* __restrict__ tile_off,
                                                                   OutT* __restrict__ dst) {
-    __shared__ uint32_t sh[THREADS];
-    const TokT H = (TokT)TokTraits<TokT>::hole;
-    const size_t base = (size_t)blockIdx.x * TILE + (size_t)threadIdx.x * SPT;
-    TokT v[SPT];
-    uint32_t c = 0;
-    for (int k = 0; k < SPT; k++) { v[k] = tok[base + k]; c += (v[k] != H); }
-    uint32_t off = block_exclusive_scan<THREADS>(c, sh, nullptr);
-    size_t o = (size_t)tile_off[blockIdx.x] + off;
-    for (int k = 0; k < SPT; k++) if (v[k] != H) dst[o++] = (OutT)v[k];
+    constexpr int VEC = 16 / (int)sizeof(TokT);
+    constexpr int NV = TILE / VEC / THREADS;
+    constexpr int VO = 16 / (int)sizeof(OutT);  // output slots per 16-byte vector
+    constexpr int NW = THREADS / 32;
+    __shared__ __align__(16) OutT stage[TILE + VO];
+    __shared__ uint32_t wsum[NV * NW];
+    const uint32_t H = TokTraits<TokT>::hole;
+    const uint4* src = reinterpret_cast<const uint4*>(tok + (size_t)blockIdx.x * TILE);
+    uint4 v[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) v[k] = src[k * THREADS + (int)threadIdx.x];
+    // slot order = (k, thread, slot in vector): scan the per-vector live counts in that order
+    uint32_t incl[NV], cnt[NV];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        cnt[k] = vec_live_count<TokT>(v[k]);
+        incl[k] = warp_inclusive_scan(cnt[k]);
+        if (lane == 31u) wsum[k * NW + (int)warp] = incl[k];
+    }
+    __syncthreads();
+    // the tile's output starts at dst + tile_off; stage it with the same offset inside a 16-byte vector
+    OutT* out0 = dst + tile_off[blockIdx.x];
+    const uint32_t a = (uint32_t)(((size_t)out0 & 15u) / sizeof(OutT));
+    uint32_t run = 0, total = 0;
+    uint32_t base[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        base[k] = 0;
+        for (int w = 0; w < NW; w++) {
+            const uint32_t sv = wsum[k * NW + w];
+            if ((uint32_t)w == warp) base[k] = run;
+            run += sv;
+        }
+    }
+    total = run;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        uint32_t o = a + base[k] + incl[k] - cnt[k];
+        uint32_t tv[VEC];
+        unpack_vec<TokT>(v[k], tv);
+#pragma unroll
+        for (int i = 0; i < VEC; i++)
+            if (tv[i] != H) stage[o++] = (OutT)tv[i];
+    }
+    __syncthreads();
+    // stage[a, a + total) -> out0[0, total): scalar head up to the first 16-byte boundary, vectors, scalar tail
+    const uint32_t end = a + total;
+    const uint32_t body_lo = a ? (uint32_t)VO : 0u, body_hi = end / VO * VO;
+    if (body_hi > body_lo) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(stage);
+        uint4* d4 = reinterpret_cast<uint4*>(out0 - a);
+        for (uint32_t i = body_lo / VO + threadIdx.x; i < body_hi / VO; i += THREADS) d4[i] = s4[i];
+    }
+    const uint32_t head_hi = body_hi > body_lo ? body_lo : end;  // no whole vector: everything is "head"
+    for (uint32_t i = a + threadIdx.x; i < head_hi; i += THREADS) out0[i - a] = stage[i];
+    if (body_hi > body_lo)
+        for (uint32_t i = body_hi + threadIdx.x; i < end; i += THREADS) out0[i - a] = stage[i];
 }
 
 // =========================================================================================
@@ -1636,19 +1804,42 @@ __global__ void table_rehash_kernel(PairTable src, PairTable dst, StepCtl* ctl, 
 }
 
 // =========================================================================================
-// decode (src/basic_tokenizer.zig:90-138): ids -> byte lengths -> offsets -> bytes
-// vocab expansions are flattened on the host: voc_off[id], voc_len[id], voc_bytes[]
+// decode (src/basic_tokenizer.zig:90-138): ids -> byte lengths -> offsets -> bytes.
+// The host builds, once per merge list, for every id: its byte length (0: the id has no valid expansion), the
+// offset of its flattened expansion in voc_bytes (VOC_NOT_FLAT for the rare ids whose expansion is too long to
+// flatten) and its two components (for those: byte k of an id is found by descending through the merge DAG with
+// the lengths, which needs no per-token limit at all).
+// decode_len: per-tile byte totals (+ unknown-id detection). decode_scatter: a CTA decodes a tile of ids into shared
+// memory and writes it out as one contiguous, 16-byte-vectorised range; tiles that do not fit the stage write
+// straight to global memory.
 // =========================================================================================
+constexpr uint32_t VOC_NOT_FLAT = 0xFFFFFFFFu;
+constexpr int DEC_STAGE = 40 * 1024;  // bytes of a tile's output staged in shared memory (+ 16 for alignment)
+struct DecVocab {
+    const uint32_t* len;    // [65536] bytes of the id's expansion, 0 = invalid id
+    const uint32_t* off;    // [65536] offset in `bytes`, VOC_NOT_FLAT if not flattened
+    const uint32_t* pair;   // [65536] first | second << 16
+    const uint8_t* bytes;
+};
+__device__ __forceinline__ uint8_t dec_byte_by_descent(const DecVocab& v, uint32_t id, uint32_t k) {
+    while (id >= 256u) {
+        const uint32_t pr = v.pair[id], f = pr & 0xFFFFu;
+        const uint32_t lf = v.len[f];
+        if (k < lf) id = f; else { k -= lf; id = pr >> 16; }
+    }
+    return (uint8_t)id;
+}
+
 __global__ void __launch_bounds__(THREADS) decode_len_kernel(const uint16_t* __restrict__ toks, size_t n,
                                                              const uint32_t* __restrict__ voc_len,
-                                                             uint32_t* __restrict__ tile_bytes, StepCtl* ctl) {
-    __shared__ uint32_t sh[THREADS];
-    const size_t base = (size_t)blockIdx.x * TILE + (size_t)threadIdx.x * SPT;
-    uint32_t c = 0;
+                                                             unsigned long long* __restrict__ tile_bytes, StepCtl* ctl) {
+    __shared__ unsigned long long sh[THREADS];
+    const size_t base = (size_t)blockIdx.x * TILE;
+    unsigned long long c = 0;
     for (int k = 0; k < SPT; k++) {
-        size_t i = base + k;
+        const size_t i = base + (size_t)k * THREADS + threadIdx.x;  // interleaved: coalesced loads
         if (i < n) {
-            uint32_t l = voc_len[toks[i]];
+            const uint32_t l = voc_len[toks[i]];
             if (l == 0) atomicOr(&ctl->err, (uint32_t)ERR_KEY_MISSING);  // unknown id
             c += l;
         }
@@ -1662,26 +1853,81 @@ __global__ void __launch_bounds__(THREADS) decode_len_kernel(const uint16_t* __r
     if (threadIdx.x == 0) tile_bytes[blockIdx.x] = sh[0];
 }
 
-__global__ void __launch_bounds__(THREADS) decode_scatter_kernel(const uint16_t* __restrict__ toks, size_t n,
-                                                                 const uint32_t* __restrict__ voc_off,
-                                                                 const uint32_t* __restrict__ voc_len,
-                                                                 const uint8_t* __restrict__ voc_bytes,
+// single CTA: exclusive scan of 64-bit per-tile totals
+__global__ void tile_scan64_kernel(const unsigned long long* __restrict__ tile_bytes, uint32_t ntiles,
+                                   unsigned long long* __restrict__ tile_off, unsigned long long* total) {
+    __shared__ unsigned long long part[THREADS];
+    const uint32_t per = (ntiles + THREADS - 1) / THREADS;
+    const uint32_t lo = threadIdx.x * per;
+    unsigned long long s = 0;
+    for (uint32_t k = 0; k < per; k++) if (lo + k < ntiles) s += tile_bytes[lo + k];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long acc = 0;
+        for (int i = 0; i < THREADS; i++) { unsigned long long v = part[i]; part[i] = acc; acc += v; }
+        *total = acc;
+    }
+    __syncthreads();
+    unsigned long long acc = part[threadIdx.x];
+    for (uint32_t k = 0; k < per; k++) if (lo + k < ntiles) { tile_off[lo + k] = acc; acc += tile_bytes[lo + k]; }
+}
+
+__global__ void __launch_bounds__(THREADS) decode_scatter_kernel(const uint16_t* __restrict__ toks, size_t n, DecVocab v,
                                                                  const unsigned long long* __restrict__ tile_off,
+                                                                 const unsigned long long* __restrict__ tile_bytes,
                                                                  uint8_t* __restrict__ out, size_t cap) {
-    __shared__ uint32_t sh[THREADS];
+    __shared__ __align__(16) uint8_t stage[DEC_STAGE + 16];
+    __shared__ unsigned long long sh[THREADS];
+    // thread t owns the SPT consecutive ids [base + t * SPT, ...): their bytes are consecutive in the output
     const size_t base = (size_t)blockIdx.x * TILE + (size_t)threadIdx.x * SPT;
-    uint32_t c = 0;
-    for (int k = 0; k < SPT; k++) { size_t i = base + k; if (i < n) c += voc_len[toks[i]]; }
-    uint32_t off = block_exclusive_scan<THREADS>(c, sh, nullptr);
-    size_t o = (size_t)tile_off[blockIdx.x] + off;
+    unsigned long long c = 0;
+    for (int k = 0; k < SPT; k++) { const size_t i = base + k; if (i < n) c += v.len[toks[i]]; }
+    // exclusive scan over the threads (64-bit: a tile of long tokens can exceed 4 GB)
+    sh[threadIdx.x] = c;
+    __syncthreads();
+    for (int off = 1; off < THREADS; off <<= 1) {
+        const unsigned long long add = ((int)threadIdx.x >= off) ? sh[threadIdx.x - off] : 0ull;
+        __syncthreads();
+        sh[threadIdx.x] += add;
+        __syncthreads();
+    }
+    const unsigned long long my_off = sh[threadIdx.x] - c;
+    const unsigned long long total = tile_bytes[blockIdx.x];
+    const unsigned long long o0 = tile_off[blockIdx.x];
+    uint8_t* dst = out + o0;
+    const bool staged = total <= (unsigned long long)DEC_STAGE;
+    const uint32_t a = (uint32_t)((size_t)dst & 15u);  // stage with the destination's offset inside a 16-byte vector
+    uint8_t* w = staged ? stage + a + my_off : dst + my_off;
+    unsigned long long room = o0 + my_off < cap ? cap - (o0 + my_off) : 0ull;  // (the caller checked total <= cap; belt and braces)
     for (int k = 0; k < SPT; k++) {
-        size_t i = base + k;
+        const size_t i = base + k;
         if (i >= n) break;
-        uint32_t id = toks[i];
-        uint32_t l = voc_len[id];
-        const uint8_t* src = voc_bytes + voc_off[id];
-        for (uint32_t b = 0; b < l; b++) if (o + b < cap) out[o + b] = src[b];
-        o += l;
+        const uint32_t id = toks[i];
+        const uint32_t l = v.len[id];
+        if ((unsigned long long)l > room) break;
+        const uint32_t fo = v.off[id];
+        if (fo != VOC_NOT_FLAT) {
+            const uint8_t* src = v.bytes + fo;
+            for (uint32_t b = 0; b < l; b++) w[b] = src[b];
+        } else {
+            for (uint32_t b = 0; b < l; b++) w[b] = dec_byte_by_descent(v, id, b);
+        }
+        w += l;
+        room -= l;
+    }
+    if (!staged) return;
+    __syncthreads();
+    const uint32_t end = a + (uint32_t)total;
+    const uint32_t body_lo = a ? 16u : 0u, body_hi = end / 16u * 16u;
+    if (body_hi > body_lo) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(stage);
+        uint4* d4 = reinterpret_cast<uint4*>(dst - a);
+        for (uint32_t i = body_lo / 16u + threadIdx.x; i < body_hi / 16u; i += THREADS) d4[i] = s4[i];
+        for (uint32_t i = a + threadIdx.x; i < body_lo; i += THREADS) dst[i - a] = stage[i];
+        for (uint32_t i = body_hi + threadIdx.x; i < end; i += THREADS) dst[i - a] = stage[i];
+    } else {
+        for (uint32_t i = a + threadIdx.x; i < end; i += THREADS) dst[i - a] = stage[i];
     }
 }
 

@@ -61,7 +61,7 @@ inline bool dist_unique_id(void* out128, std::string* err) {
     return true;
 }
 
-enum { DIST_U32_SUM = 0, DIST_U64_MIN = 1, DIST_U64_MAX = 2 };
+enum { DIST_U32_SUM = 0, DIST_U64_MIN = 1, DIST_U64_MAX = 2, DIST_U64_SUM = 3 };
 struct DistComm {
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
@@ -81,7 +81,7 @@ struct DistComm {
     bool allreduce(void* buf, size_t count, int kind) {
         if (world == 1) return true;
         int dt = kind == DIST_U32_SUM ? ncclUint32 : ncclUint64;
-        int op = kind == DIST_U32_SUM ? ncclSum : (kind == DIST_U64_MIN ? ncclMin : ncclMax);
+        int op = (kind == DIST_U32_SUM || kind == DIST_U64_SUM) ? ncclSum : (kind == DIST_U64_MIN ? ncclMin : ncclMax);
         return nccl_api().AllReduce(buf, buf, count, dt, op, comm, stream) == ncclSuccess;
     }
     bool allgather_bytes(const void* src, void* dst, size_t bytes_per_rank) {
@@ -172,7 +172,7 @@ struct DistComm {
 #else
 // emulation build (tests only): the exchange is delegated to a callback so that a world_size-2
 // gloo test on the CPU can drive the same host logic
-enum { DIST_U32_SUM = 0, DIST_U64_MIN = 1, DIST_U64_MAX = 2 };
+enum { DIST_U32_SUM = 0, DIST_U64_MIN = 1, DIST_U64_MAX = 2, DIST_U64_SUM = 3 };
 typedef int (*dist_allreduce_cb)(void* buf, size_t count, int kind);
 inline bool dist_unique_id(void* out128, std::string*) { memset(out128, 0, 128); return true; }
 struct DistComm {
@@ -182,6 +182,21 @@ struct DistComm {
     bool peer_ok = false;
     uint32_t epoch_base = 0;
     void destroy_peers() {}
+    static size_t mbox_slot_words() { return (size_t)2 * 65552 + 16 + 16 * MAX_PEERS; }
+    static size_t mbox_words(int world) { return (size_t)2 * world * mbox_slot_words() + 64; }
+    // tests: the ranks are processes on one host and `base` is a zero-filled shared-memory segment that holds the
+    // mailboxes of all ranks back to back (the GPU build maps the peers' device memory with cudaIpc instead)
+    bool init_peers_shm(void* base, size_t bytes) {
+        if (world < 2 || world > MAX_PEERS || bytes < (size_t)world * mbox_words(world) * 4) return false;
+        for (int p = 0; p < world; p++) {
+            uint32_t* mb = (uint32_t*)base + (size_t)p * mbox_words(world);
+            peers.mbox[p] = mb;
+            peers.flags[p] = mb + (size_t)2 * world * mbox_slot_words();
+        }
+        peers.slot_words = (uint32_t)mbox_slot_words();
+        peer_ok = true;
+        return true;
+    }
     bool init(int, int, const void*, int, std::string* err) { if (err) *err = "no NCCL in the emulation build"; return false; }
     void destroy() {}
     bool allreduce(void* buf, size_t count, int kind) {

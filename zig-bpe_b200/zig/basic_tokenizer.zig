@@ -38,6 +38,7 @@ const bpe_stats_t = extern struct {
     compactions: u64,
     kernel_ms: [12]f64,
     kernel_calls: [12]u64,
+    aeqb_steps: u64,
 };
 extern fn bpe_ctx_create(out: *?*bpe_ctx, device: c_int) c_int;
 extern fn bpe_ctx_destroy(ctx: ?*bpe_ctx) void;
