@@ -272,7 +272,7 @@ def main():
     for kv in filter(None, os.environ.get("BPE_OPTS", "").split(",")):  # measurement aid: BPE_OPTS=merge_impl=1,...
         k, v = kv.split("=")
         eng.set_option(k, int(v))
-    eng.set_option("profile", 3)  # CUDA-event marks around the merge kernel of every 8th step (sampled: ~1 us/step of overhead)
+    eng.set_option("profile", 3)  # CUDA-event marks around the merge kernel of every 32nd step (sampled: ~1 us/step of overhead)
     for _ in range(args.warmup):
         merges, counts, st = step_device()
     clocks = ClockSampler(local_rank)
@@ -398,7 +398,7 @@ def main():
             for r in range(1, world):
                 cnt = torch.zeros(1, dtype=torch.int64, device=dev)
                 dist.recv(cnt, src=r)
-                buf = torch.empty(int(cnt[0]), dtype=torch.int16, device=dev)
+                buf = torch.empty(2 * int(cnt[0]), dtype=torch.uint8, device=dev)  # (NCCL has no 16-bit integer type)
                 dist.recv(buf, src=r)
                 h.update(buf.cpu().numpy().tobytes())
                 del buf
@@ -406,7 +406,7 @@ def main():
             parity["encode_ids"] = ids_total
         else:
             dist.send(torch.tensor([n_ids], dtype=torch.int64, device=dev), dst=0)
-            dist.send(ids_dev.contiguous(), dst=0)
+            dist.send(ids_dev.contiguous().view(torch.uint8), dst=0)
         # decode of this rank's ids back to its shard (round trip) + throughput
         # (a token that straddles two shards belongs to the left one, so a rank's ids decode to its shard shifted by a few bytes at N > 1)
         cap = n + (1 << 16)
@@ -458,7 +458,7 @@ def main():
         return
     peak, peak_src = peaks()
     alg_bytes = scanned * 2  # u16 slots, all launches
-    samp_bytes = sampled_slots * 2  # the launches whose duration was measured (every 8th merge step)
+    samp_bytes = sampled_slots * 2  # the launches whose duration was measured (every 32nd merge step)
     traffic = None  # DRAM bytes per launch from the committed ncu --set full capture (ratio to algorithmic bytes)
     for tp in (os.path.join(ROOT, "profiles", "r02_merge_traffic.json"), os.path.join(ROOT, "profiles", "r01_merge_traffic.json")):
         if os.path.exists(tp) and merge_calls:
@@ -482,7 +482,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic, "kernel": "merge_kernel<u16>", "peak_source": peak_src,
                      "bytes_per_launch": samp_bytes / max(merge_calls, 1), "avg_launch_ms": merge_ms / max(merge_calls, 1),
-                     "launches_timed": int(merge_calls), "sampling": "every 8th merge step, CUDA events on the library's stream",
+                     "launches_timed": int(merge_calls), "sampling": "every 32nd merge step, CUDA events on the library's stream",
                      "kernel_share_of_step": est_merge_ms_all / dev_ms if dev_ms and est_merge_ms_all else None,
                      "whole_step_scan_GBps": alg_bytes / 1e9 / (dev_ms / 1000.0) if dev_ms else None,
                      "frac_of_nominal_8TBps": (achieved / 8000.0) if achieved else None},

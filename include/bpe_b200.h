@@ -132,7 +132,7 @@ const char* bpe_last_error(const bpe_ctx* ctx);
  *   "time_phases"         1: fill the reference's TimeStats buckets (synchronises per phase)
  *   "profile"             1: fill bpe_stats_t.kernel_ms / kernel_calls for every kernel class;
  *                         2: only the merge kernel (two event records per merge step)
- *                         3: the merge kernel of every 8th step only; kernel_ms[10] then holds the token slots
+ *                         3: the merge kernel of every 32nd step only; kernel_ms[10] then holds the token slots
  *                            those sampled launches scanned (lowest overhead; what bench.py uses)
  */
 int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value);

@@ -135,3 +135,13 @@ def test_sharded_train_through_peer_mailboxes(ora, tmp_path, case, vocab, world)
     for r in range(world):
         assert np.array_equal(res[r]["merges"], om), f"rank {r}"
         assert np.array_equal(res[r]["counts"], oc), f"rank {r}"
+
+
+def test_sharded_streaming_encode(ora, tmp_path):
+    """several ranks, each streaming its shard through the device in chunks: shard boundaries and chunk boundaries are
+    handled by the same bridge windows"""
+    res = _run("taylor", 300, 2, tmp_path, "encode_tile=1024", "stream_chunk_bytes=4096", mode="encode")
+    data = dist_worker.make_case("taylor")
+    got = np.concatenate([res[r]["ids"] for r in range(2)])
+    assert np.array_equal(got, ora.encode(data, dist_worker.encode_merges("taylor"), linear=True))
+    assert all(int(res[r]["who"]) == 2 and int(res[r]["path"]) == 1 for r in range(2))

@@ -137,3 +137,34 @@ def test_matches_the_other_encoders(emu, ora, taylor):
     a, who, _ = _enc(emu, taylor[:60000], om, 1024, impl=0)
     b, _, _ = _enc(emu, taylor[:60000], om, impl=2)
     assert who == TILE_PATH and np.array_equal(a, b)
+
+
+def test_streaming_from_host_buffers(emu, ora, synth, taylor, golden_merges):
+    """bpe_encode on an input of several chunks: the chunks stream through the device (text in, ids out) and are encoded like
+    the shards of a multi-GPU run — halos from the neighbouring chunks, bridge windows at both ends — so their ids
+    concatenate to the encoding of the whole text; sizes that leave a short last chunk, runs across chunk boundaries"""
+    train = bytes(synth.generate(200_000, synth.SEED_C3, synth.BYTE))
+    om, _ = ora.train(train, 256 + 500, fast=True)
+    try:
+        emu.set_option("stream_chunk_bytes", 8192)
+        emu.set_option("encode_tile", 1024)
+        for data, merges in ((train[:70_001], om), (taylor[:33_333], golden_merges), (taylor[:16_384], golden_merges)):
+            ids = emu.encode(data, merges)
+            st = emu.last_stats
+            assert st["kernel_calls"][10] == 2 and st["kernel_calls"][11] == 1 and st["kernel_calls"][9] == -(-len(data) // 8192)
+            assert np.array_equal(ids, ora.encode(data, merges, linear=True))
+        merges = [(97, 97, 256), (256, 256, 257), (98, 257, 258), (257, 257, 259)]
+        rng = np.random.default_rng(15)
+        data = b"".join(b"a" * int(rng.integers(1, 12)) + bytes(rng.integers(98, 102, size=int(rng.integers(1, 6)), dtype=np.uint8)) for _ in range(6000))
+        ids = emu.encode(data, merges)
+        assert emu.last_stats["kernel_calls"][10] == 2 and np.array_equal(ids, ora.encode(data, merges, linear=False))
+        # a window that gives up in some chunk: the whole call falls back to the resident encoders
+        data = data[:20000] + b"q" + b"a" * 5001 + b"b" + data[20000:40000]
+        ids = emu.encode(data, merges)
+        assert emu.last_stats["kernel_calls"][10] != 2 and np.array_equal(ids, ora.encode(data, merges, linear=False))
+        # small inputs (fewer than two chunks) do not stream
+        ids = emu.encode(taylor[:9000], golden_merges)
+        assert emu.last_stats["kernel_calls"][9] == 0 and np.array_equal(ids, ora.encode(taylor[:9000], golden_merges, linear=True))
+    finally:
+        emu.set_option("stream_chunk_bytes", 0)
+        emu.set_option("encode_tile", 8192)

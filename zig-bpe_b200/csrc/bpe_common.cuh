@@ -171,9 +171,10 @@ static_assert(sizeof(EdgeInfo) == 64, "EdgeInfo is 16 words");
 // [2 parities][world slots][xw words] + one arrival flag per sender; peers write their deltas straight
 // into it and raise their flag, the consumer sums the slots while it applies them.
 constexpr int MAX_PEERS = 8;
+constexpr uint32_t PEER_FLAG_STRIDE = 1056;  // flags per sender: one per apply CTA (at most (4 * 65536 + 3 + 255) / 256 = 1025)
 struct PeerSet {
     uint32_t* mbox[MAX_PEERS];   // mailbox base of every rank (own entry = local pointer)
-    uint32_t* flags[MAX_PEERS];  // flags[p][sender] on rank p
+    uint32_t* flags[MAX_PEERS];  // flags[p][sender * PEER_FLAG_STRIDE + cta] on rank p
     uint32_t slot_words;         // capacity of one mailbox slot in words
 };
 

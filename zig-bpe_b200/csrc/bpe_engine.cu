@@ -58,13 +58,14 @@ struct bpe_ctx {
     std::string err;
     // options
     long verify_recount = 0, force_slow_tiebreak = 0, check_tiebreak = 0, compact_pct = 85, table_log2 = 0,
-         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 6, encode_filter = 1, encode_geom = 4, encode_seg_min_steps = 450, encode_tile = 8192, encode_try_tiles = 1, fuse_halo = 1, count_limit_log2 = 32;
+         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 6, encode_filter = 1, encode_geom = 4, encode_seg_min_steps = 450, encode_tile = 8192, encode_try_tiles = 1, fuse_halo = 1, count_limit_log2 = 32, stream_chunk_mb = 128, stream_chunk_bytes = 0;
     int num_sms = 148;
     DistComm dist;  // world == 1 when single GPU
     uint64_t launches = 0;
     BufCache cache;
     std::vector<cudaEvent_t> ev_pool;  // profiling events, created on first use
     struct DecodeCache* decode_cache = nullptr;  // decode tables of the last merge list seen (built once per list)
+    cudaStream_t copy_in = 0, copy_out = 0;      // streaming encode: host -> device text chunks, device -> host ids (created on first use)
 };
 
 static std::string g_create_err;
@@ -249,7 +250,7 @@ static int table_ensure_zcnt(bpe_ctx* ctx, TableMem& tm, StepCtl* d_ctl, uint32_
 // of the earlier one. Nothing synchronises until the pool is exhausted or finish().
 enum { K_INIT = 0, K_ARGMAX, K_TIE, K_REPLAY, K_HALO, K_MERGE, K_APPLY, K_COMPACT, K_TABLE, K_HOSTGAP, K_NB = 12 };
 struct EvProfile {
-    int level = 0;  // 0 off, 1 all buckets, 2 merge kernel only (2 records per step), 3 merge kernel of every 8th step
+    int level = 0;  // 0 off, 1 all buckets, 2 merge kernel only (2 records per step), 3 merge kernel of every 32nd step
     cudaStream_t st = 0;
     std::vector<cudaEvent_t>* ev = nullptr;  // pool owned by the context (reused across calls)
     std::vector<int> bucket;
@@ -314,8 +315,7 @@ struct TrainRun {
     bpe_ctx* ctx;
     Sequence<uint16_t> sq;
     TableMem tm;
-    DevBuf delta, hist, ctl, rec, firstpos, recount, live_chk, heavy, cand, wr, push_dev;
-    size_t push_slots = 0, push_tail = 0;  // sequence geometry the device copy of PushArgs was written for
+    DevBuf delta, hist, ctl, rec, firstpos, recount, live_chk, heavy, cand, wr;
     uint32_t cand_cap = 0;  // candidate-scan merge path: queue capacity
     uint32_t vcap = 0;   // stride of the cntL / cntR halves of `delta`
     uint32_t theta = 0;  // heavy-list threshold (0 = list invalid)
@@ -492,7 +492,7 @@ static int sync_zcap(bpe_ctx* ctx, TrainRun& R, uint32_t d) {
 template <class TokT, bool DELTAS, bool FROMCTL>
 static int launch_merge(bpe_ctx* ctx, TokT* tok, const TileHalo<TokT>* halo, uint32_t nt, const StepCtl* d_ctl, uint32_t* cntL,
                         uint32_t* cntR, uint32_t* nxx, uint32_t* nab, uint32_t A, uint32_t B, uint32_t X, uint32_t bins_min,
-                        int backwards, const PushArgs* d_push = nullptr, uint32_t parity = 0, uint32_t epoch = 0, uint32_t* push_counter = nullptr) {
+                        int backwards) {
     if (ctx->merge_impl == 1) {
         auto kern = merge_tma_kernel<TokT, DELTAS, FROMCTL>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem_bytes<TokT>()));
@@ -501,7 +501,7 @@ static int launch_merge(bpe_ctx* ctx, TokT* tok, const TileHalo<TokT>* halo, uin
                         bins_min, nt);
     } else {
         BPE_LAUNCH((merge_kernel<TokT, DELTAS, FROMCTL>), nt, THREADS, ctx->stream, tok, halo, d_ctl, cntL, cntR, nxx, nab, A, B, X, bins_min,
-                   backwards, d_push, parity, epoch, push_counter);
+                   backwards);
     }
     ctx->launches++;
     return BPE_OK;
@@ -510,7 +510,7 @@ static int launch_merge(bpe_ctx* ctx, TokT* tok, const TileHalo<TokT>* halo, uin
 // candidate-scan variant of the step tail (single GPU, A != B): scan, resolve, write, apply
 static int enqueue_step_tail_scan(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uint32_t step_index, bool fuse_select) {
     const uint32_t nt = R.sq.ntiles();
-    R.prof.sample_now = (step_index % 8u) == 0;
+    R.prof.sample_now = (step_index % 32u) == 0;
     if (R.prof.level == 3 && R.prof.sample_now) R.pending_samples.push_back(step_index);
     R.prof.mark(K_MERGE);
     BPE_LAUNCH_NS(scan_kernel<uint16_t>, nt, THREADS, ctx->stream, R.sq.tok(), R.d_ctl(), R.cand.as<uint32_t>(), R.cand_cap,
@@ -526,7 +526,7 @@ static int enqueue_step_tail_scan(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uin
     HaloArgs no_halo;
     memset(&no_halo, 0, sizeof no_halo);
     BPE_LAUNCH(apply_kernel, (4 * n_ids + 3 + 255) / 256, 256, ctx->stream, R.tm.view(), R.delta.as<uint32_t>(), R.vcap, R.d_ctl(),
-               R.tm.zig(), n_ids, R.hl(), R.d_rec(), fuse_select ? 1 : 0, 0, none, 0, 1, 0u, 0u, (uint32_t)R.edge_off, no_halo);
+               R.tm.zig(), n_ids, R.hl(), R.d_rec(), fuse_select ? 1 : 0, 0, none, 0, 1, 0u, 0u, (uint32_t)R.edge_off, no_halo, PushArgs{0, 0, nullptr});
     ctx->launches += 4;
     CU(cudaGetLastError());
     return BPE_OK;
@@ -538,7 +538,7 @@ static int enqueue_step_tail_scan(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uin
 // tokens across tiles, needed when the merge has first == second (the loop halts with H_AEQB for those steps).
 static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uint32_t step_index, bool fuse_select, bool classic_halo = false) {
     const uint32_t nt = R.sq.ntiles();
-    R.prof.sample_now = (step_index % 8u) == 0;
+    R.prof.sample_now = (step_index % 32u) == 0;
     if (R.prof.level == 3 && R.prof.sample_now) R.pending_samples.push_back(step_index);  // credited once the step is known to have run
     if (classic_halo) {
         R.prof.mark(K_HALO);
@@ -550,24 +550,10 @@ static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uint32_t
     const bool peer = ctx->dist.world > 1 && ctx->dist.peer_ok && ctx->xchg_impl == 0 && ctx->merge_impl != 1 &&
                       R.exchange_words() <= ctx->dist.peers.slot_words;
     const uint32_t parity = step_index & 1u, epoch = ctx->dist.epoch_base + step_index + 1u;
-    if (peer && (R.push_slots != R.sq.n_slots || R.push_tail != R.sq.dense_end || !R.push_dev.p)) {
-        // what the last CTA of the merge pass needs to push this rank's deltas + shard ends into every peer's mailbox
-        // (device copy, refreshed when the sequence geometry changes)
-        PushArgs pa;
-        memset(&pa, 0, sizeof pa);
-        pa.on = 1; pa.delta = R.delta.as<uint32_t>(); pa.edge_off = (uint32_t)R.edge_off; pa.zero_vecs = (uint32_t)(2 * R.vcap / 4);
-        pa.n_slots = R.sq.n_slots; pa.tail_hint = R.sq.dense_end; pa.ps = ctx->dist.peers; pa.rank = ctx->dist.rank; pa.world = ctx->dist.world;
-        pa.ctl = R.d_ctl(); pa.done_counter = R.sq.done_counter.as<uint32_t>();
-        if (!R.push_dev.p) CU(R.push_dev.alloc(sizeof(PushArgs)));
-        CU(cudaMemcpyAsync(R.push_dev.p, &pa, sizeof pa, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));  // `pa` lives on this frame (happens at the start and after compactions only)
-        R.push_slots = R.sq.n_slots; R.push_tail = R.sq.dense_end;
-    }
     R.prof.mark(K_MERGE);
     {
         int rcm = launch_merge<uint16_t, true, true>(ctx, R.sq.tok(), R.sq.halo.as<TileHalo<uint16_t>>(), nt, (const StepCtl*)R.d_ctl(),
-                                                     R.cntL(), R.cntR(), R.nxx(), R.nab(), 0u, 0u, 0u, 4u * nt, (int)(step_index & 1u),
-                                                     peer ? R.push_dev.as<PushArgs>() : nullptr, parity, epoch, R.sq.done_counter.as<uint32_t>());
+                                                     R.cntL(), R.cntR(), R.nxx(), R.nab(), 0u, 0u, 0u, 4u * nt, (int)(step_index & 1u));
         if (rcm) return rcm;
     }
     R.prof.mark(K_APPLY);
@@ -578,6 +564,10 @@ static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uint32_t
         ctx->launches++;
         if (!ctx->dist.allreduce(R.delta.p, R.exchange_words(), DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-reduce of the merge deltas failed");
     }
+    // peer path: every apply CTA first stores its cells of this rank's deltas into every peer's mailbox over NVLink
+    PushArgs pa;
+    memset(&pa, 0, sizeof pa);
+    pa.n_slots = R.sq.n_slots; pa.tail_hint = R.sq.dense_end; pa.tok = R.sq.tok();
     HaloArgs ha;
     ha.tok = R.sq.tok(); ha.n_slots = R.sq.n_slots; ha.ntiles = nt; ha.halo = R.sq.halo.as<TileHalo<uint16_t>>();
     ha.apply_blocks = (4 * n_ids + 3 + 255) / 256;
@@ -586,7 +576,7 @@ static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uint32_t
     const uint32_t grid = ha.apply_blocks + (ha.tok ? (nt + 255) / 256 : 0u);
     BPE_LAUNCH(apply_kernel, grid, 256, ctx->stream, R.tm.view(), R.delta.as<uint32_t>(), R.vcap, R.d_ctl(),
                   R.tm.zig(), n_ids, R.hl(), R.d_rec(), fuse_select ? 1 : 0, peer ? 1 : 0, ctx->dist.peers, ctx->dist.rank, ctx->dist.world,
-                  parity, epoch, (uint32_t)R.edge_off, ha);
+                  parity, epoch, (uint32_t)R.edge_off, ha, pa);
     ctx->launches += 1;
     CU(cudaGetLastError());
     return BPE_OK;
@@ -1053,14 +1043,16 @@ static int build_seg_tables(bpe_ctx* ctx, const bpe_merge_t* merges, size_t m, c
 // multi-GPU: where this shard lies in the whole text, and up to SEG_HALO bytes of text on both sides of it
 struct ShardHalo {
     DevBuf halo;  // [SEG_HALO left, right-aligned data moved to the front | SEG_HALO right]
+    std::vector<uint8_t> host;  // the same bytes on the host (the streaming encoder builds per-chunk halos from them)
     int hl = 0, hr = 0;
     long long g_lo = 0, g_total = 0, min_shard = 0;
     const uint8_t* left() const { return halo.as<uint8_t>(); }
     const uint8_t* right() const { return halo.as<uint8_t>() + SEG_HALO; }
 };
-static int exchange_shard_halo(bpe_ctx* ctx, const uint8_t* d_text, size_t n, ShardHalo& sh) {
+static int exchange_shard_halo(bpe_ctx* ctx, const uint8_t* d_text, size_t n, ShardHalo& sh, bool text_on_host = false) {
     const int world = ctx->dist.world, rank = ctx->dist.rank;
     sh.g_lo = 0; sh.g_total = (long long)n; sh.hl = sh.hr = 0; sh.min_shard = (long long)n;
+    sh.host.assign(2 * SEG_HALO, 0);
     CU(sh.halo.alloc(2 * SEG_HALO));
     if (world == 1) return BPE_OK;
     // every rank contributes [n (2 words) | first SEG_HALO bytes | last SEG_HALO bytes]; the sum over ranks of
@@ -1069,7 +1061,10 @@ static int exchange_shard_halo(bpe_ctx* ctx, const uint8_t* d_text, size_t n, Sh
     std::vector<uint32_t> all((size_t)world * W, 0u);
     std::vector<uint8_t> ends(2 * SEG_HALO, 0);
     const size_t nf = std::min<size_t>(n, SEG_HALO);
-    if (nf) {
+    if (nf && text_on_host) {
+        memcpy(ends.data(), d_text, nf);
+        memcpy(ends.data() + SEG_HALO, d_text + (n - nf), nf);
+    } else if (nf) {
         CU(cudaMemcpyAsync(ends.data(), d_text, nf, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(ends.data() + SEG_HALO, d_text + (n - nf), nf, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
@@ -1107,6 +1102,7 @@ static int exchange_shard_halo(bpe_ctx* ctx, const uint8_t* d_text, size_t n, Sh
         hr += take;
     }
     sh.hl = hl; sh.hr = hr;
+    sh.host = hb;
     CU(cudaMemcpyAsync(sh.halo.p, hb.data(), 2 * SEG_HALO, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));  // hb lives on this frame
     return BPE_OK;
@@ -1146,6 +1142,34 @@ static bool mentions_id_65535(const bpe_merge_t* merges, size_t m) {
 // -----------------------------------------------------------------------------------------
 // tile-resident encode (bpe_tilenc.cuh): one launch over the text + the final squeeze
 // -----------------------------------------------------------------------------------------
+static int tile_size_for(const bpe_ctx* ctx, bool has_bridges) {
+    int tile_max = (int)ctx->encode_tile;
+    return std::max(has_bridges ? 1024 : 512, std::min(tile_max, (int)TN_TMAX)) / 16 * 16;
+}
+// one launch of tilenc_kernel over n bytes at d_text (plus hl / hr bytes of text before / after it); zone / flags are
+// (re)allocated as needed; *d_fail points at the counter of windows that gave up (read it after the stream has drained)
+static int launch_tilenc(bpe_ctx* ctx, cudaStream_t stream, const uint8_t* d_text, size_t n, const uint8_t* d_halo_l, int hl, const uint8_t* d_halo_r,
+                         int hr, bool left_text, bool right_text, const SegTables& tb, int tile_max, uint16_t* d_slots, DevBuf& zone, DevBuf& flags,
+                         uint32_t** d_fail) {
+    const TileGeom g = tn_geometry((long long)n, hl, hr, left_text, right_text, tile_max);
+    const long long nwin = g.bwl + g.ntile + g.bwr;
+    if (nwin > 0x7FFFFFFFll) return fail(ctx, BPE_ERR_INVALID_ARG, "input too large for one launch");
+    if (zone.bytes < (size_t)nwin * TN_ZONE * 2) CU(zone.alloc((size_t)nwin * TN_ZONE * 2));
+    if (flags.bytes < ((size_t)nwin + 2) * 4) CU(flags.alloc(((size_t)nwin + 2) * 4));  // [flags | ticket | fail]
+    CU(cudaMemsetAsync(flags.p, 0, ((size_t)nwin + 2) * 4, stream));
+    uint32_t* d_ticket = flags.as<uint32_t>() + nwin;
+    *d_fail = d_ticket + 1;
+    const size_t smem = tilenc_smem_bytes(tile_max, tb.max_level);
+    CU(cudaFuncSetAttribute(tilenc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (n > 0) {
+        BPE_LAUNCH_SMEM(tilenc_kernel, (unsigned)nwin, TN_THREADS, smem, stream, d_text, d_halo_l, d_halo_r, g, tile_max, tb.T,
+                        tb.max_level, d_slots, zone.as<uint16_t>(), flags.as<uint32_t>(), d_ticket, *d_fail);
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
+    return BPE_OK;
+}
+
 // *used = false when this path does not apply (irregular list, id 65535, more than TL_MAXLVL levels, a shard
 // shorter than TN_MIN_SHARD on several GPUs) or gave up (seam without a common token, a token longer than 255
 // bytes, a run of more than 255 equal tokens): nothing has been written to d_out then and the caller goes on
@@ -1167,32 +1191,19 @@ static int encode_tiles(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bpe
     rc = exchange_shard_halo(ctx, d_text, n, sh);
     if (rc) return rc;
     if (multi && sh.min_shard < (long long)TN_MIN_SHARD) return BPE_OK;  // (the same decision on every rank)
-    int tile_max = (int)ctx->encode_tile;
-    tile_max = std::max(multi ? 1024 : 512, std::min(tile_max, (int)TN_TMAX)) / 16 * 16;
     const bool left_text = multi && sh.g_lo > 0, right_text = multi && sh.g_lo + (long long)n < sh.g_total;
-    const TileGeom g = tn_geometry((long long)n, sh.hl, sh.hr, left_text, right_text, tile_max);
-    const long long nwin = g.bwl + g.ntile + g.bwr;
-    if (nwin > 0x7FFFFFFFll) return fail(ctx, BPE_ERR_INVALID_ARG, "input too large for one launch");
+    const int tile_max = tile_size_for(ctx, left_text || right_text);
     const size_t n_slots = round_up(n ? n : 1, TILE);
     DevBuf slots, zone, flags;
     CU(slots.alloc(n_slots * 2));
-    CU(zone.alloc((size_t)nwin * TN_ZONE * 2));
-    CU(flags.alloc(((size_t)nwin + 2) * 4));  // [flags | ticket | fail]
-    CU(cudaMemsetAsync(flags.p, 0, ((size_t)nwin + 2) * 4, ctx->stream));
-    uint32_t* d_ticket = flags.as<uint32_t>() + nwin;
-    uint32_t* d_fail = d_ticket + 1;
-    const size_t smem = tilenc_smem_bytes(tile_max, tb.max_level);
-    CU(cudaFuncSetAttribute(tilenc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint32_t* d_fail = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, ctx->stream));
-    if (n > 0) {
-        BPE_LAUNCH_SMEM(tilenc_kernel, (unsigned)nwin, TN_THREADS, smem, ctx->stream, d_text, sh.left(), sh.right(), g, tile_max, tb.T,
-                        tb.max_level, slots.as<uint16_t>(), zone.as<uint16_t>(), flags.as<uint32_t>(), d_ticket, d_fail);
-        ctx->launches++;
-        CU(cudaGetLastError());
-    }
+    rc = launch_tilenc(ctx, ctx->stream, d_text, n, sh.left(), sh.hl, sh.right(), sh.hr, left_text, right_text, tb, tile_max, slots.as<uint16_t>(),
+                       zone, flags, &d_fail);
+    if (rc) return rc;
     CU(cudaEventRecord(e1, ctx->stream));
     // a window that gave up anywhere (on any rank) sends every rank to the next encoder
     if (multi && !ctx->dist.allreduce(d_fail, 1, DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-reduce of the seam status failed");
@@ -1213,6 +1224,120 @@ static int encode_tiles(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bpe
     rc = squeeze_slots(ctx, slots, n, d_out, out_n);
     if (rc) return rc;
     if (st) st->scanned_slots += n;
+    return BPE_OK;
+}
+
+// -----------------------------------------------------------------------------------------
+// streaming encode from host buffers (the reference reads the whole file into memory, src/utils/read_file.zig:3-13, and
+// encodes it in place; here the text never has to fit the GPU): the text is cut into chunks, chunk c + 1 travels
+// host -> device and the ids of chunk c - 1 device -> host while the tile-resident kernel encodes chunk c. A chunk is
+// encoded exactly like a shard of a multi-GPU run — 512 bytes of the neighbouring chunks as halos, bridge windows
+// at both ends — so the concatenation of the chunks' ids is the encoding of the whole text. Device memory: two text
+// chunks, one slot array, two id buffers (8 bytes per chunk byte) whatever the size of the input.
+// *used = false when the path does not apply or a window gave up: the caller then encodes the resident way.
+// -----------------------------------------------------------------------------------------
+static int encode_stream(bpe_ctx* ctx, const uint8_t* text, size_t n, const bpe_merge_t* merges, size_t m, uint16_t* out, size_t* out_n,
+                         bpe_stats_t* st, bool* used) {
+    *used = false;
+    const size_t chunk_target = ctx->stream_chunk_bytes > 0 ? (size_t)ctx->stream_chunk_bytes : (size_t)ctx->stream_chunk_mb << 20;
+    if (m == 0 || chunk_target < 4096 || n < 2 * chunk_target) return BPE_OK;
+    std::vector<uint32_t> lvl;
+    std::vector<uint8_t> alone;
+    if (!merge_levels(merges, m, lvl, alone) || mentions_id_65535(merges, m)) return BPE_OK;
+    SegTables tb;
+    int rc = build_seg_tables(ctx, merges, m, lvl, tb);
+    if (rc) return rc;
+    if (tb.max_level > TL_MAXLVL) return BPE_OK;
+    const bool multi = ctx->dist.world > 1;
+    ShardHalo sh;
+    rc = exchange_shard_halo(ctx, text, n, sh, true);
+    if (rc) return rc;
+    if (multi && sh.min_shard < (long long)(2 * chunk_target)) return BPE_OK;  // every rank streams, or none (the same decision everywhere)
+    const size_t nchunk = (n + chunk_target - 1) / chunk_target;
+    const size_t ch = round_up((n + nchunk - 1) / nchunk, 16);  // even chunks: none is shorter than half the target
+    const int tile_max = tile_size_for(ctx, true);
+    if (!ctx->copy_in) CU(cudaStreamCreate(&ctx->copy_in));
+    if (!ctx->copy_out) CU(cudaStreamCreate(&ctx->copy_out));
+    DevBuf d_text[2], d_halo[2], d_ids[2], slots, zone, flags;
+    for (int b = 0; b < 2; b++) {
+        CU(d_text[b].alloc(ch));
+        CU(d_halo[b].alloc(2 * SEG_HALO));
+        CU(d_ids[b].alloc(ch * 2));
+    }
+    CU(slots.alloc(round_up(ch, TILE) * 2));
+    cudaEvent_t h2d_ev[2], d2h_ev[2];
+    for (int b = 0; b < 2; b++) { CU(cudaEventCreate(&h2d_ev[b])); CU(cudaEventCreate(&d2h_ev[b])); }
+    std::vector<uint8_t> hb[2];
+    auto chunk_lo = [&](size_t c) { return std::min(n, c * ch); };
+    auto send = [&](size_t c) -> int {  // text and halos of chunk c, host -> device, on the copy-in stream
+        const int b = (int)(c & 1);
+        const size_t lo = chunk_lo(c), hi = chunk_lo(c + 1);
+        hb[b].assign(2 * SEG_HALO, 0);
+        int hl, hr;
+        if (c == 0) { hl = sh.hl; memcpy(hb[b].data(), sh.host.data(), (size_t)hl); }
+        else { hl = (int)std::min<size_t>(SEG_HALO, lo); memcpy(hb[b].data(), text + lo - hl, (size_t)hl); }
+        if (c + 1 == nchunk) { hr = sh.hr; memcpy(hb[b].data() + SEG_HALO, sh.host.data() + SEG_HALO, (size_t)hr); }
+        else { hr = (int)std::min<size_t>(SEG_HALO, n - hi); memcpy(hb[b].data() + SEG_HALO, text + hi, (size_t)hr); }
+        CU(cudaMemcpyAsync(d_halo[b].p, hb[b].data(), 2 * SEG_HALO, cudaMemcpyHostToDevice, ctx->copy_in));
+        CU(cudaMemcpyAsync(d_text[b].p, text + lo, hi - lo, cudaMemcpyHostToDevice, ctx->copy_in));
+        CU(cudaEventRecord(h2d_ev[b], ctx->copy_in));
+        return BPE_OK;
+    };
+    const double t0 = now_ms();
+    rc = send(0);
+    if (rc) return rc;
+    size_t out_off = 0, prev_cnt = 0;
+    bool gave_up = false;
+    for (size_t c = 0; c < nchunk && !gave_up; c++) {
+        const int b = (int)(c & 1);
+        const size_t lo = chunk_lo(c), hi = chunk_lo(c + 1), len = hi - lo;
+        const bool left_text = c > 0 || (multi && sh.g_lo > 0), right_text = c + 1 < nchunk || (multi && sh.g_lo + (long long)n < sh.g_total);
+        const int hl = c == 0 ? sh.hl : (int)std::min<size_t>(SEG_HALO, lo), hr = c + 1 == nchunk ? sh.hr : (int)std::min<size_t>(SEG_HALO, n - hi);
+        CU(cudaStreamWaitEvent(ctx->stream, h2d_ev[b], 0));
+        uint32_t* d_fail = nullptr;
+        rc = launch_tilenc(ctx, ctx->stream, d_text[b].as<uint8_t>(), len, d_halo[b].as<uint8_t>(), hl, d_halo[b].as<uint8_t>() + SEG_HALO, hr,
+                           left_text, right_text, tb, tile_max, slots.as<uint16_t>(), zone, flags, &d_fail);
+        if (rc) return rc;
+        if (c + 1 < nchunk) { rc = send(c + 1); if (rc) return rc; }  // travels while chunk c is being encoded
+        if (c > 0) {  // the ids of chunk c - 1 leave while chunk c is being encoded
+            CU(cudaMemcpyAsync(out + out_off, d_ids[b ^ 1].p, prev_cnt * 2, cudaMemcpyDeviceToHost, ctx->copy_out));
+            CU(cudaEventRecord(d2h_ev[b ^ 1], ctx->copy_out));
+            out_off += prev_cnt;
+        }
+        if (c >= 2) CU(cudaStreamWaitEvent(ctx->stream, d2h_ev[b], 0));  // d_ids[b] still held the ids of chunk c - 2
+        size_t cnt = 0;
+        rc = squeeze_slots(ctx, slots, len, d_ids[b].as<uint16_t>(), &cnt);  // (synchronises the compute stream)
+        if (rc) return rc;
+        uint32_t nfail = 0;
+        CU(cudaMemcpyAsync(&nfail, d_fail, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (nfail) gave_up = true;
+        prev_cnt = cnt;
+    }
+    // a window that gave up anywhere (on any rank) sends every rank to the resident encoders
+    if (multi) {
+        DevBuf fl;
+        CU(fl.alloc(4));
+        uint32_t v = gave_up ? 1u : 0u;
+        CU(cudaMemcpyAsync(fl.p, &v, 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (!ctx->dist.allreduce(fl.p, 1, DIST_U32_SUM)) return fail(ctx, BPE_ERR_CUDA, "all-reduce of the seam status failed");
+        CU(cudaMemcpyAsync(&v, fl.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        gave_up = v != 0;
+    }
+    if (!gave_up) {
+        const int b = (int)((nchunk - 1) & 1);
+        CU(cudaMemcpyAsync(out + out_off, d_ids[b].p, prev_cnt * 2, cudaMemcpyDeviceToHost, ctx->copy_out));
+        out_off += prev_cnt;
+    }
+    CU(cudaStreamSynchronize(ctx->copy_in));
+    CU(cudaStreamSynchronize(ctx->copy_out));
+    for (int b = 0; b < 2; b++) { cudaEventDestroy(h2d_ev[b]); cudaEventDestroy(d2h_ev[b]); }
+    if (st) { st->kernel_ms[11] = now_ms() - t0; st->kernel_calls[11] = gave_up ? 2 : 1; st->kernel_calls[9] = nchunk; }
+    if (gave_up) return BPE_OK;
+    *used = true;
+    *out_n = out_off;
+    if (st) { st->kernel_calls[10] = 2; st->scanned_slots += n; }
     return BPE_OK;
 }
 
@@ -1389,10 +1514,11 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
         const EncStep& es = steps[si];
         const bool last_step = si + 1 == steps.size();
         if (es.single < 0) {
-            // a level pass can remove a large share of the tokens: look at the live count after each one
+            // a level pass can remove a large share of the tokens: the first ones do most of the merging, so the live count
+            // is read back (one host round trip) after each of the first 8 level passes and after every 4th later on
             rc = one_pass(0, 0, 0, es.off, es.cnt);
             if (rc) return rc;
-            since_check += 32;
+            since_check += (pass_index <= 8u) ? 32 : 8;
         } else {
             const uint32_t A = merges[es.single].first, B = merges[es.single].second, X = merges[es.single].new_token;
             rc = one_pass(A, B, X);
@@ -1791,6 +1917,8 @@ void bpe_ctx_destroy(bpe_ctx* ctx) {
     ctx->dist.destroy();
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     delete ctx->decode_cache;
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     ctx->cache.clear();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1819,6 +1947,8 @@ int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value) {
     else if (s == "encode_try_tiles") ctx->encode_try_tiles = value;
     else if (s == "fuse_halo") ctx->fuse_halo = value;
     else if (s == "count_limit_log2") ctx->count_limit_log2 = value;
+    else if (s == "stream_chunk_mb") ctx->stream_chunk_mb = value;
+    else if (s == "stream_chunk_bytes") ctx->stream_chunk_bytes = value;
     else return fail(ctx, BPE_ERR_INVALID_ARG, "unknown option '%s'", name);
     return BPE_OK;
 }
@@ -1862,6 +1992,25 @@ int bpe_encode(bpe_ctx* ctx, const uint8_t* text, size_t n, const bpe_merge_t* m
     if (n && (!text || !out)) return fail(ctx, BPE_ERR_INVALID_ARG, "text/out is null");
     const double t0 = now_ms();
     CU(cudaSetDevice(ctx->device));
+    if (m && !merges) return fail(ctx, BPE_ERR_INVALID_ARG, "merges is null");
+    if (ctx->encode_impl == 0 || ctx->encode_impl == 4) {
+        // large inputs: chunks stream through the GPU (copies overlap the encoder, device memory stays bounded)
+        bpe_stats_t sst;
+        memset(&sst, 0, sizeof sst);
+        const uint64_t l0 = ctx->launches;
+        bool streamed = false;
+        int rcs = encode_stream(ctx, text, n, merges, m, out, out_n, &sst, &streamed);
+        if (rcs) return rcs;
+        if (streamed) {
+            sst.total_ms = now_ms() - t0;
+            sst.device_ms = sst.kernel_ms[11];
+            sst.kernel_launches = ctx->launches - l0;
+            sst.replace_pair_calls = m;
+            if (stats) *stats = sst;
+            return BPE_OK;
+        }
+        *out_n = 0;
+    }
     DevBuf d_in, d_out;
     if (cudaMalloc(&d_in.p, n ? n : 1) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", n);
     if (cudaMalloc(&d_out.p, n ? n * 2 : 2) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", n * 2);

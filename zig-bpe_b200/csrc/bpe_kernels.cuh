@@ -472,6 +472,12 @@ constexpr int HALO_THREADS = 128;
 // Where a shard's neighbours' end tokens come from: the local copy of the exchanged EdgeInfo slots (single GPU:
 // none; NCCL path and host-driven passes: the exchange buffer) or, inside the fused apply + halo kernel of the
 // peer-memory path, the mailbox slots themselves (valid once the sender's arrival flag shows this step's epoch).
+__device__ __forceinline__ void peer_wait(const uint32_t* flags, uint32_t idx, uint32_t epoch, uint32_t* err) {
+    uint32_t spins = 0;
+    while ((int32_t)(((volatile const uint32_t*)flags)[idx] - epoch) < 0) {
+        if (++spins > (1u << 28)) { atomicOr(err, (uint32_t)ERR_PEER_TIMEOUT); break; }
+    }
+}
 struct EdgeSrc {
     const EdgeInfo* local;      // nullptr: single GPU
     const uint32_t* mbox;       // != nullptr: read rank r's EdgeInfo from mbox + r * slot_words + edge_off + r * 16
@@ -481,10 +487,7 @@ struct EdgeSrc {
 };
 __device__ __forceinline__ EdgeInfo edge_get(const EdgeSrc& es, int r) {
     if (!es.mbox) return es.local[r];
-    uint32_t spins = 0;
-    while ((int32_t)(((volatile const uint32_t*)es.flags)[r] - es.epoch) < 0) {
-        if (++spins > (1u << 28)) { atomicOr(es.err, (uint32_t)ERR_PEER_TIMEOUT); break; }
-    }
+    peer_wait(es.flags, (uint32_t)r * PEER_FLAG_STRIDE, es.epoch, es.err);  // the sender's CTA 0 sends its EdgeInfo
     __threadfence();
     EdgeInfo e;
     const uint32_t* src = es.mbox + (size_t)r * es.slot_words + es.edge_off + (uint32_t)r * 16u;
@@ -698,48 +701,16 @@ __global__ void edge_kernel(const TokT* __restrict__ tok, size_t n_slots, size_t
     edge_body<TokT>(tok, n_slots, tail_hint, all, rank, world, ctl, nab_local, account, true);
 }
 
-// Peer-memory exchange (multi-GPU): the CTA that finishes the merge pass last describes the shard's ends, pushes this
-// rank's deltas (+ its EdgeInfo) into slot `rank` of every peer's mailbox over NVLink with 16-byte stores, clears the
-// local deltas for the next pass and raises this rank's arrival flag on every peer. It runs inside merge_kernel (no
-// launch of its own); the consumer is the apply kernel of the same step on every rank.
+// Peer-memory exchange (multi-GPU), inside the apply kernel. Every apply CTA owns the delta cells of 64 token ids
+// (the cells its threads fold into the table). Phase 1: the CTA stores its cells of THIS rank into slot `rank` of every
+// peer's mailbox over NVLink (CTA 0 also describes the shard's ends and sends its EdgeInfo), then raises the flag
+// (this rank, this CTA) on every peer. Phase 2: it waits for the same CTA's flag of every peer and reads a cell as
+// local value + the peers' slots. A CTA therefore depends only on the same-numbered CTA of the other ranks — never on
+// another CTA of its own grid — so transfer, reduction and table update are one kernel without a grid-wide wait.
 struct PushArgs {
-    int on;                 // 0: single GPU or NCCL path
-    uint32_t* delta;        // [cntL | cntR | cntXX cntAB | pad | EdgeInfo x world]
-    uint32_t edge_off;      // word offset of the EdgeInfo slots
-    uint32_t zero_vecs;     // 16-byte vectors of the cntL | cntR block (cleared after the push)
-    size_t n_slots, tail_hint;
-    PeerSet ps;
-    int rank, world;
-    StepCtl* ctl;
-    uint32_t* done_counter;
+    size_t n_slots, tail_hint;  // sequence geometry for the shard-end scan
+    const uint16_t* tok;
 };
-// `ap` lives in device memory (written by the host at the start of a run and after every compaction), so the merge
-// kernel carries one pointer instead of a 200-byte parameter block
-template <class TokT>
-__device__ __noinline__ void push_deltas(const TokT* __restrict__ tok, const PushArgs* __restrict__ ap, uint32_t parity, uint32_t epoch,
-                                         const uint32_t* nab_local) {
-    const PushArgs a = *ap;
-    EdgeInfo* edges = reinterpret_cast<EdgeInfo*>(a.delta + a.edge_off);
-    const size_t slot = ((size_t)parity * (size_t)a.world + (size_t)a.rank) * a.ps.slot_words;
-    if (threadIdx.x < 32) edge_body<TokT>(tok, a.n_slots, a.tail_hint, edges, a.rank, a.world, a.ctl, nab_local, 1, false);
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < 16u * (uint32_t)a.world; i += blockDim.x) {  // my EdgeInfo slot to every peer
-        const uint32_t p = i / 16u, w = i % 16u;
-        a.ps.mbox[p][slot + a.edge_off + (uint32_t)a.rank * 16u + w] = a.delta[a.edge_off + (uint32_t)a.rank * 16u + w];
-    }
-    const uint32_t nvec = a.edge_off / 4u;
-    uint4* dl = reinterpret_cast<uint4*>(a.delta);
-    for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const uint4 v = dl[i];
-        for (int p = 0; p < a.world; p++) reinterpret_cast<uint4*>(a.ps.mbox[p] + slot)[i] = v;
-        // (the vector holding cntXX / cntAB is left to the apply kernel, which also reads the local copy)
-        if (i < a.zero_vecs && (v.x | v.y | v.z | v.w)) dl[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < a.world) *((volatile uint32_t*)&a.ps.flags[threadIdx.x][a.rank]) = epoch;
-    __threadfence_system();
-}
 
 // =========================================================================================
 // tile staging: ext[] = [holes | l2 l1 | TILE slots | r0 r1 r2 | holes], tile data at OFF
@@ -1026,8 +997,7 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(Tok
                                                         const StepCtl* __restrict__ ctl, uint32_t* __restrict__ cntL,
                                                         uint32_t* __restrict__ cntR, uint32_t* nxx_out, uint32_t* nab_out,
                                                         uint32_t Au, uint32_t Bu, uint32_t Xu, uint32_t bins_min_count,
-                                                        int backwards, const PushArgs* __restrict__ push, uint32_t push_parity,
-                                                        uint32_t push_epoch, uint32_t* push_counter) {
+                                                        int backwards) {
     __shared__ __align__(16) TokT ext[EXT];
     // block-private bins for the neighbour deltas: key = token id (+ 0x10000 for the right side)
     __shared__ uint32_t bin_key[DELTAS ? MERGE_NBIN : 1];
@@ -1068,26 +1038,12 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(Tok
     for (int k = 0; k < NV; k++) hitbits |= vec_has<TokT>(v[k], Au) ? (1u << k) : 0u;
     any = hitbits != 0;
     if (threadIdx.x == 0 && h.l1 == A) any = true;  // possible head duty
-    if (__syncthreads_or(any ? 1 : 0)) {
-        uint32_t nAB = 0, nXX = 0;
-        tile_staged_path<TokT, DELTAS, true, NV>(ext, v, tok, base, h, hitbits, Au, Bu, Xu, use_bins, bin_key, bin_val, q_pos, &q_n, &sh_runA,
-                                                 cntL, cntR, nAB, nXX);
-        if (nAB) atomicAdd(nab_out, nAB);
-        if (DELTAS && nXX) atomicAdd(nxx_out, nXX);
-    }
-    if (!push) return;
-    // multi-GPU peer path: the last CTA to finish the pass sends this rank's deltas to every peer
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t prev = atomicAdd(push_counter, 1u);
-        q_n = (prev == gridDim.x - 1u) ? 1u : 0u;
-    }
-    __syncthreads();
-    if (!q_n) return;
-    if (threadIdx.x == 0) *push_counter = 0;
-    __threadfence();
-    push_deltas<TokT>(tok, push, push_parity, push_epoch, nab_out);
+    if (!__syncthreads_or(any ? 1 : 0)) return;
+    uint32_t nAB = 0, nXX = 0;
+    tile_staged_path<TokT, DELTAS, true, NV>(ext, v, tok, base, h, hitbits, Au, Bu, Xu, use_bins, bin_key, bin_val, q_pos, &q_n, &sh_runA,
+                                             cntL, cntR, nAB, nXX);
+    if (nAB) atomicAdd(nab_out, nAB);
+    if (DELTAS && nXX) atomicAdd(nxx_out, nXX);
 }
 
 // =========================================================================================
@@ -1344,7 +1300,7 @@ struct HaloArgs {
 __global__ void __launch_bounds__(256) apply_kernel(PairTable tbl, uint32_t* __restrict__ delta, uint32_t vcap, StepCtl* ctl,
                              ZigPop z, uint32_t n_ids, HeavyList hl, MergeRec* rec, int fuse_select,
                              int ps_on, PeerSet ps, int rank, int world, uint32_t parity, uint32_t epoch, uint32_t edge_off,
-                             HaloArgs ha) {
+                             HaloArgs ha, PushArgs pa) {
     if (ha.tok ? (ctl->pass_step != ha.step1) : (ctl->halt != 0u)) return;  // this step did not run (the loop was halted before it)
     if (ha.tok && blockIdx.x >= ha.apply_blocks) {
         const uint32_t t = (blockIdx.x - ha.apply_blocks) * blockDim.x + threadIdx.x;
@@ -1362,37 +1318,53 @@ __global__ void __launch_bounds__(256) apply_kernel(PairTable tbl, uint32_t* __r
     }
     const uint32_t n_apply = ha.tok ? ha.apply_blocks : gridDim.x;
     const uint32_t* mb = nullptr;
+    // thread t: token id p = t / 4, side = left/right neighbour, op = retire the old pair / credit the new one.
+    // The two ops of a (p, side) sit in adjacent lanes so the four table round trips overlap.
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t p = t >> 2, side = (t >> 1) & 1u, op = t & 1u;
+    const uint32_t t0 = 4u * n_ids;  // three more threads: adjacent occurrences, the merged pair itself, bookkeeping
+    const uint32_t my_cell = (p < n_ids) ? (side ? vcap + p : p) : (t == t0 ? 2u * vcap : (t == t0 + 2u ? 2u * vcap + 1u : 0xFFFFFFFFu));
     if (ps_on) {
-        if (threadIdx.x == 0) {
-            const volatile uint32_t* fl = ps.flags[rank];
-            for (int r = 0; r < world; r++) {
-                uint32_t spins = 0;
-                while ((int32_t)(fl[r] - epoch) < 0) {
-                    if (++spins > (1u << 28)) { atomicOr(&ctl->err, (uint32_t)ERR_PEER_TIMEOUT); break; }
-                }
+        // ---- phase 1: my cells of this rank's deltas into slot `rank` of every peer's mailbox ----
+        const size_t slot = ((size_t)parity * (size_t)world + (size_t)rank) * ps.slot_words;
+        if (blockIdx.x == 0) {
+            EdgeInfo* edges = reinterpret_cast<EdgeInfo*>(delta + edge_off);
+            if (threadIdx.x < 32) edge_body<uint16_t>(pa.tok, pa.n_slots, pa.tail_hint, edges, rank, world, ctl, nullptr, 0, false);
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < 16u * (uint32_t)world; i += blockDim.x) {
+                const uint32_t q = i / 16u, w = i % 16u;
+                if ((int)q != rank) ps.mbox[q][slot + edge_off + (uint32_t)rank * 16u + w] = delta[edge_off + (uint32_t)rank * 16u + w];
             }
+        }
+        if (my_cell != 0xFFFFFFFFu && (op == 0u || p >= n_ids)) {
+            const uint32_t c_local = delta[my_cell];
+            for (int q = 0; q < world; q++) if (q != rank) ps.mbox[q][slot + my_cell] = c_local;
+        }
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < world && (int)threadIdx.x != rank)
+            *((volatile uint32_t*)&ps.flags[threadIdx.x][(uint32_t)rank * PEER_FLAG_STRIDE + blockIdx.x]) = epoch;
+        // ---- phase 2: the same CTA's cells from every peer ----
+        if ((int)threadIdx.x < world && (int)threadIdx.x != rank) {
+            peer_wait(ps.flags[rank], threadIdx.x * PEER_FLAG_STRIDE + blockIdx.x, epoch, &ctl->err);  // (CTA 0's flag also covers the EdgeInfo)
         }
         __syncthreads();
         __threadfence();
         mb = ps.mbox[rank] + (size_t)parity * (size_t)world * ps.slot_words;
-        if (blockIdx.x == 0 && threadIdx.x < 16u * (uint32_t)world) {  // gathered shard ends for the next halo pass
+        if (blockIdx.x == 0 && threadIdx.x < 16u * (uint32_t)world) {  // gathered shard ends for host-driven halo passes
             const uint32_t r = threadIdx.x / 16u, w = threadIdx.x % 16u;
-            delta[edge_off + r * 16u + w] = __ldcg(mb + (size_t)r * ps.slot_words + edge_off + r * 16u + w);
+            if ((int)r != rank) delta[edge_off + r * 16u + w] = __ldcg(mb + (size_t)r * ps.slot_words + edge_off + r * 16u + w);
         }
     }
     auto cell_value = [&](uint32_t idx) -> uint32_t {
-        if (!ps_on) return delta[idx];
-        uint32_t sum = 0;
-        for (int r = 0; r < world; r++) sum += __ldcg(mb + (size_t)r * ps.slot_words + idx);
+        uint32_t sum = delta[idx];
+        if (ps_on)
+            for (int r = 0; r < world; r++) if (r != rank) sum += __ldcg(mb + (size_t)r * ps.slot_words + idx);
         return sum;
     };
-    // thread t: token id p = t / 4, side = left/right neighbour, op = retire the old pair / credit the new one.
-    // The two ops of a (p, side) sit in adjacent lanes so the four table round trips overlap.
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t A = ctl->A, B = ctl->B, X = ctl->X;
     z.zmask = ctl->zcap - 1;
     hl.theta = ctl->theta;
-    const uint32_t p = t >> 2, side = (t >> 1) & 1u, op = t & 1u;
     uint32_t c = 0;
     uint32_t cell = 0;
     if (p < n_ids && p <= X) {
@@ -1402,10 +1374,9 @@ __global__ void __launch_bounds__(256) apply_kernel(PairTable tbl, uint32_t* __r
     __syncwarp();
     if (c) {
         if (op == 0) tbl_sub(tbl, side ? pair_key(B, p) : pair_key(p, A), c, ctl, z);
-        else { if (!ps_on) delta[cell] = 0; tbl_add(tbl, side ? pair_key(X, p) : pair_key(p, X), c, ctl, z, hl); }
+        else { delta[cell] = 0; tbl_add(tbl, side ? pair_key(X, p) : pair_key(p, X), c, ctl, z, hl); }
     }
-    const uint32_t t0 = 4u * n_ids;  // three more threads: adjacent occurrences, the merged pair itself, bookkeeping
-    // (t0 is a multiple of 4, so these three threads share a warp: all read the scalars, then one clears them)
+    // (t0 is a multiple of 4, so the three scalar threads share a warp: all read the scalars, then one clears them)
     uint32_t scalar = 0;
     if (t == t0 || t == t0 + 1) scalar = cell_value(2 * vcap);
     else if (t == t0 + 2) scalar = cell_value(2 * vcap + 1);
@@ -1415,6 +1386,7 @@ __global__ void __launch_bounds__(256) apply_kernel(PairTable tbl, uint32_t* __r
     } else if (t == t0 + 1) {
         if (scalar) tbl_add(tbl, pair_key(X, X), scalar, ctl, z, hl);
     } else if (t == t0 + 2) {
+        if (ps_on) ctl->local_live -= delta[2 * vcap + 1];  // this shard's own merged occurrences (the sum is global)
         delta[2 * vcap] = 0;      // local scalars ready for the next merge pass
         delta[2 * vcap + 1] = 0;
         ctl->cand_n = 0;          // candidate-scan path: queues ready for the next step

@@ -24,7 +24,8 @@
 //   back[e] = distance from the last byte e of a token to its first (previous token = (s-1) - back[s-1])
 // Rounds go through the levels in ascending order, a RANGE of up to 64 levels at a time: two passes over the window
 // count the slots of every level of the range and lay their positions out level by level (`sorted`); pairs that
-// come into being inside the range are chained into per-level lists (`late`) by the round that creates them. Most
+// come into being inside the range go into small per-level buckets (`late`) by the round that creates them (a bucket
+// that overflows ends the range before its level; the next scan finds everything). Most
 // levels hold a handful of occurrences per window, so ONE warp works through such sparse levels with nothing but
 // __syncwarp between its steps while the other warps of the CTA wait at a barrier; levels with more than TN_SPARSE
 // entries (the first few levels, where most of the merging happens) are taken by the whole CTA. Per round and entry:
@@ -47,8 +48,9 @@ constexpr int TN_BR = 192;        // half width of a bridge window
 constexpr int TN_ZONE = 256;      // slots a window publishes for its successor (>= TN_BR + TN_M, >= 2 * TN_M)
 constexpr int TN_TMAX = 8192;     // largest tile
 constexpr int TN_QCAP = 2048;     // positions laid out per range (`sorted`)
-constexpr int TN_LCAP = 1024;     // pairs created inside a range that can be chained (`late`)
+constexpr int TN_BUCKET = 16;     // pairs created inside a range that a level of the range can take (`late`), else the range ends there
 constexpr int TN_RANGE = 64;      // levels per range
+constexpr int TN_LCAP = TN_BUCKET * TN_RANGE;
 constexpr int TN_SPARSE = 64;     // a level with at most this many entries is worked through by one warp
 constexpr int TN_THREADS = 256;
 constexpr uint32_t TL_INF = 0x7FFFu, TL_DEAD = 0x7FFEu, TL_MAXLVL = 0x7FF0u, TL_CLAIM = 0x80000000u;
@@ -96,7 +98,7 @@ __host__ __device__ __forceinline__ void tn_window(const TileGeom& g, long long 
 
 __host__ __device__ constexpr size_t tilenc_smem_bytes(int tile_max, uint32_t max_level) {
     const size_t W = (size_t)tile_max + 2 * TN_M;
-    return W * 4 + W * 2 + W + W + (size_t)TN_QCAP * 2 + (size_t)TN_LCAP * 4 + (size_t)TN_RANGE * 5 * 4 + 8 +
+    return W * 4 + W * 2 + W + W + (size_t)TN_QCAP * 2 + (size_t)TN_LCAP * 2 + (size_t)TN_RANGE * 4 * 4 + 8 +
            ((size_t)max_level / 32 + 2) * 4 + (size_t)TN_ZONE * 2 + 64;
 }
 
@@ -111,18 +113,16 @@ __global__ void __launch_bounds__(TN_THREADS, 3) tilenc_kernel(const uint8_t* __
     uint8_t* len = reinterpret_cast<uint8_t*>(nx + WCAP);
     uint8_t* back = len + WCAP;
     uint16_t* sorted = reinterpret_cast<uint16_t*>(back + WCAP);  // WCAP is a multiple of 16: still aligned
-    uint16_t* late_pos = sorted + TN_QCAP;
-    uint16_t* late_next = late_pos + TN_LCAP;
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(late_next + TN_LCAP);  // [TN_RANGE] slots per level of the range
+    uint16_t* late_pos = sorted + TN_QCAP;                              // [TN_RANGE][TN_BUCKET]
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(late_pos + TN_LCAP);    // [TN_RANGE] slots per level of the range
     uint32_t* start = cnt + TN_RANGE;                                    // [TN_RANGE + 1] segment of the level in `sorted`
     uint32_t* fill = start + TN_RANGE + 1;                               // [TN_RANGE] placement cursors
-    uint32_t* late_head = fill + TN_RANGE;                               // [TN_RANGE] first chained entry (TN_LCAP: none)
-    uint32_t* late_cnt = late_head + TN_RANGE;                           // [TN_RANGE]
+    uint32_t* late_cnt = fill + TN_RANGE;                                // [TN_RANGE] entries in the level's bucket (may exceed TN_BUCKET)
     uint32_t* present = late_cnt + TN_RANGE + 1;
     const uint32_t LW = max_level / 32 + 2;
     uint16_t* zoneP = reinterpret_cast<uint16_t*>(present + LW);
     uint32_t* sc = reinterpret_cast<uint32_t*>(zoneP + TN_ZONE);  // scalars
-    uint32_t& s_win = sc[0]; uint32_t& late_n = sc[1]; uint32_t& late_drop = sc[2]; uint32_t& s_rr = sc[3]; uint32_t& s_fail = sc[4];
+    uint32_t& s_win = sc[0]; uint32_t& late_drop = sc[2]; uint32_t& s_rr = sc[3]; uint32_t& s_fail = sc[4];
     int& s_c = reinterpret_cast<int*>(sc)[5];
     uint32_t& s_hi = sc[6]; uint32_t& s_partial = sc[7]; uint32_t& s_progress = sc[8];
     const int t = (int)threadIdx.x;
@@ -215,12 +215,9 @@ __global__ void __launch_bounds__(TN_THREADS, 3) tilenc_kernel(const uint8_t* __
                 if (lv <= rr) { s_fail = 1; return; }  // cannot happen for a regular list (fact 1)
                 atomicOr(&present[lv >> 5], 1u << (lv & 31u));
                 if (lv < hi && lv != old) {
-                    const uint32_t at = atomicAdd(&late_n, 1u);
-                    if (at < (uint32_t)TN_LCAP) {
-                        late_pos[at] = (uint16_t)s;
-                        late_next[at] = (uint16_t)atomicExch(&late_head[lv - base], at);
-                        atomicAdd(&late_cnt[lv - base], 1u);
-                    } else atomicMin(&late_drop, lv);
+                    const uint32_t at = atomicAdd(&late_cnt[lv - base], 1u);
+                    if (at < (uint32_t)TN_BUCKET) late_pos[(lv - base) * TN_BUCKET + at] = (uint16_t)s;
+                    else atomicMin(&late_drop, lv);
                 }
             };
             const uint32_t X = cell[p] & 0xFFFFu;
@@ -245,19 +242,12 @@ __global__ void __launch_bounds__(TN_THREADS, 3) tilenc_kernel(const uint8_t* __
         const int G = whole_cta ? NT : 32, g = whole_cta ? t : (t & 31);
         const uint32_t li = rr - base;
         const uint32_t n_seg = cnt[li] < (uint32_t)TN_QCAP - start[li] ? cnt[li] : (uint32_t)TN_QCAP - start[li], s0 = start[li];
-        for (uint32_t k = 0; k < n_seg; k += (uint32_t)G) {
+        const uint32_t n_late = late_cnt[li] < (uint32_t)TN_BUCKET ? late_cnt[li] : (uint32_t)TN_BUCKET;
+        const uint32_t n_all = n_seg + n_late;
+        for (uint32_t k = 0; k < n_all; k += (uint32_t)G) {
             const uint32_t e = k + (uint32_t)g;
-            const bool valid = e < n_seg;
-            chunk(rr, base, hi, valid ? (int)sorted[s0 + e] : 0, valid, whole_cta);
-        }
-        uint32_t idx = late_head[li];
-        while (idx < (uint32_t)TN_LCAP) {  // (every thread of the group walks the same chain)
-            int p = 0;
-            bool valid = false;
-            for (int j = 0; j < G && idx < (uint32_t)TN_LCAP; j++) {
-                if (j == g) { p = late_pos[idx]; valid = true; }
-                idx = late_next[idx];
-            }
+            const bool valid = e < n_all;
+            const int p = !valid ? 0 : (e < n_seg ? (int)sorted[s0 + e] : (int)late_pos[li * TN_BUCKET + (e - n_seg)]);
             chunk(rr, base, hi, p, valid, whole_cta);
         }
     };
@@ -271,12 +261,22 @@ __global__ void __launch_bounds__(TN_THREADS, 3) tilenc_kernel(const uint8_t* __
         if (hi > max_level + 1u) hi = max_level + 1u;
         const uint32_t nl = hi - base;
         __syncthreads();  // everybody has read the state of the previous range
-        for (uint32_t i = (uint32_t)t; i < (uint32_t)TN_RANGE; i += NT) { cnt[i] = 0; fill[i] = 0; late_head[i] = TN_LCAP; late_cnt[i] = 0; }
-        if (t == 0) { late_n = 0; late_drop = 0xFFFFu; s_progress = 0; }
+        for (uint32_t i = (uint32_t)t; i < (uint32_t)TN_RANGE; i += NT) { cnt[i] = 0; fill[i] = 0; late_cnt[i] = 0; }
+        if (t == 0) { late_drop = 0xFFFFu; s_progress = 0; }
         __syncthreads();
-        for (int s = t; s < W; s += NT) {  // pass 1: slots per level
-            const uint32_t lv = (cell[s] >> 16) & 0x7FFFu;
-            if (lv - base < nl) atomicAdd(&cnt[lv - base], 1u);
+        const int W4 = W / 4;
+        for (int s4 = t; s4 < W4; s4 += NT) {  // pass 1: slots per level (four slots per load)
+            const uint4 c4 = reinterpret_cast<const uint4*>(cell)[s4];
+            const uint32_t l0 = ((c4.x >> 16) & 0x7FFFu) - base, l1 = ((c4.y >> 16) & 0x7FFFu) - base, l2 = ((c4.z >> 16) & 0x7FFFu) - base,
+                           l3 = ((c4.w >> 16) & 0x7FFFu) - base;
+            if (l0 < nl) atomicAdd(&cnt[l0], 1u);
+            if (l1 < nl) atomicAdd(&cnt[l1], 1u);
+            if (l2 < nl) atomicAdd(&cnt[l2], 1u);
+            if (l3 < nl) atomicAdd(&cnt[l3], 1u);
+        }
+        for (int s = W4 * 4 + t; s < W; s += NT) {
+            const uint32_t lv = ((cell[s] >> 16) & 0x7FFFu) - base;
+            if (lv < nl) atomicAdd(&cnt[lv], 1u);
         }
         __syncthreads();
         if (t == 0) {
@@ -297,12 +297,23 @@ __global__ void __launch_bounds__(TN_THREADS, 3) tilenc_kernel(const uint8_t* __
         __syncthreads();
         hi = s_hi;
         const bool partial = s_partial != 0u;
-        for (int s = t; s < W; s += NT) {  // pass 2: positions, level by level
-            const uint32_t lv = (cell[s] >> 16) & 0x7FFFu;
-            if (lv - base < hi - base) {
-                const uint32_t at = start[lv - base] + atomicAdd(&fill[lv - base], 1u);
-                if (at < (uint32_t)TN_QCAP) sorted[at] = (uint16_t)s;
-            }
+        const uint32_t nh = hi - base;
+        auto place = [&](uint32_t li, int s) {
+            const uint32_t at = start[li] + atomicAdd(&fill[li], 1u);
+            if (at < (uint32_t)TN_QCAP) sorted[at] = (uint16_t)s;
+        };
+        for (int s4 = t; s4 < W4; s4 += NT) {  // pass 2: positions, level by level
+            const uint4 c4 = reinterpret_cast<const uint4*>(cell)[s4];
+            const uint32_t l0 = ((c4.x >> 16) & 0x7FFFu) - base, l1 = ((c4.y >> 16) & 0x7FFFu) - base, l2 = ((c4.z >> 16) & 0x7FFFu) - base,
+                           l3 = ((c4.w >> 16) & 0x7FFFu) - base;
+            if (l0 < nh) place(l0, s4 * 4);
+            if (l1 < nh) place(l1, s4 * 4 + 1);
+            if (l2 < nh) place(l2, s4 * 4 + 2);
+            if (l3 < nh) place(l3, s4 * 4 + 3);
+        }
+        for (int s = W4 * 4 + t; s < W; s += NT) {
+            const uint32_t lv = ((cell[s] >> 16) & 0x7FFFu) - base;
+            if (lv < nh) place(lv, s);
         }
         __syncthreads();
         uint32_t rr = base;

@@ -103,7 +103,7 @@ struct DistComm {
     bool init_peers(std::string* err) {
         if (world < 2 || world > MAX_PEERS) { if (err) *err = "peer exchange supports 2..8 ranks"; return false; }
         const size_t slot = mbox_slot_words();
-        const size_t words = (size_t)2 * world * slot + 64;
+        const size_t words = (size_t)2 * world * slot + (size_t)MAX_PEERS * PEER_FLAG_STRIDE + 64;
         bool local_ok = true;
         std::string why;
         auto local_fail = [&](const char* msg) { if (local_ok) why = msg; local_ok = false; cudaGetLastError(); };
@@ -183,7 +183,7 @@ struct DistComm {
     uint32_t epoch_base = 0;
     void destroy_peers() {}
     static size_t mbox_slot_words() { return (size_t)2 * 65552 + 16 + 16 * MAX_PEERS; }
-    static size_t mbox_words(int world) { return (size_t)2 * world * mbox_slot_words() + 64; }
+    static size_t mbox_words(int world) { return (size_t)2 * world * mbox_slot_words() + (size_t)MAX_PEERS * PEER_FLAG_STRIDE + 64; }
     // tests: the ranks are processes on one host and `base` is a zero-filled shared-memory segment that holds the
     // mailboxes of all ranks back to back (the GPU build maps the peers' device memory with cudaIpc instead)
     bool init_peers_shm(void* base, size_t bytes) {
