@@ -280,9 +280,10 @@ def main():
     if rank == 0:
         clocks.start()
     t0 = time.perf_counter()
-    launches = 0; merge_ms = 0.0; merge_calls = 0; scanned = 0; sampled_slots = 0.0; dev_ms = 0.0; got = 0
+    launches = 0; merge_ms = 0.0; merge_calls = 0; scanned = 0; sampled_slots = 0.0; dev_ms = 0.0; got = 0; lib_ms = 0.0
     for _ in range(args.steps):
         merges, counts, st = step_device()
+        lib_ms += st["total_ms"]
         launches += st["kernel_launches"]; merge_ms += st["kernel_ms"][5]; merge_calls += st["kernel_calls"][5]
         scanned += st["scanned_slots"]; sampled_slots += st["kernel_ms"][10]; dev_ms += st["device_ms"]; got += len(merges)
     barrier()
@@ -476,6 +477,8 @@ def main():
                          "passes alternate direction so the tail of one pass is reused from L2 by the next; no explicit flush",
                    "timing": "host clock between barrier+synchronize pairs, max over ranks; the library's CUDA-event device_ms is reported beside it"},
         "device_ms_per_step": dev_ms_max / args.steps,
+        "library_call_ms_per_step": lib_ms / args.steps,  # host clock inside bpe_train_device (rank 0); the rest of ms_per_step is the Python binding + barriers
+        "aeqb_steps": int(st.get("aeqb_steps", 0)),
         "gpu_launches": int(launches),
         "clocks": clk,
         "e2e": e2e,

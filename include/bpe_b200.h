@@ -101,7 +101,7 @@ const char* bpe_last_error(const bpe_ctx* ctx);
  *                         does not apply or gives up, the choice between the segment-resident kernel (3) and the level
  *                         passes (2) is made by cost: lists whose level schedule has more than "encode_seg_min_steps" steps
  *                         (default 450), and inputs of 4 GiB or more, go to the segment kernel. 4: tile-resident kernel — a
- *                         CTA keeps a window of the text ("encode_tile" bytes, default and maximum 8192, + 2 x 64 bytes of
+ *                         CTA keeps a window of the text ("encode_tile" bytes, default 7936, maximum 8192, + 2 x 64 bytes of
  *                         margin) in shared memory through all merges, one launch, the text is read once; neighbouring
  *                         windows are stitched at a token they share (BPE_ERR_INTERNAL if it does not apply).
  *                         1: one pass per merge, in list order. 2: level-
@@ -123,6 +123,15 @@ const char* bpe_last_error(const bpe_ctx* ctx);
  *                         2: candidate-scan path (single GPU, experimental, currently slower): one barrier-free
  *                            streaming scan queues the A's that can start an occurrence, a resolve + a write kernel
  *                            finish the step (no tiles / halos)
+ *   "merge_filter"        1: the merge pass rules out, in registers, every A whose next slot holds a live token other than B;
+ *                         a tile goes through the staged path only if a candidate is left. 0 (default): every tile that
+ *                         holds an A is staged (measured 14 % faster on C3: early steps stage nearly every tile anyway and
+ *                         the filter's instructions sit on the streaming path).
+ *   "batch_steps"         merge steps enqueued between two read-backs of the control block (default 16)
+ *   "stream_chunk_mb"     bpe_encode / host buffers: inputs of two chunks or more (default chunk 128 MiB) stream through the
+ *                         GPU in chunks — copies overlap the tile-resident encoder, device memory stays at 8 bytes per chunk
+ *                         byte ("stream_chunk_bytes" sets the chunk size in bytes, for tests)
+ *   "count_limit_log2"    tests: lowers the limit (2^32 - 1) above which a pair count is refused
  *   "fuse_halo"           1 (default): the apply kernel of a step also gathers the tile halos of the next step (two launches
  *                         per merge step: merge, apply); steps whose merge has first == second take the stand-alone
  *                         run-chaining halo pass. 0: a halo launch before every merge pass.

@@ -71,6 +71,7 @@ def test_verbose_output_format(zb, gpu, capsys):
     assert "merge 1/44: (101,108) -> 256 had 2 occurrences" in err  # printMergeInfo :308-317
     assert "No more pairs to merge. Stopping early." in err  # :189
     assert "Time statistics:" in err and "sortCodePointPairs:" in err
+    assert "generateInitialTokens runtime: " in err and " seconds" in err  # :156-160
 
 
 # ---- golden vectors ---------------------------------------------------------------------------
@@ -240,8 +241,12 @@ def test_tile_encoder_on_gpu(gpu, ora, synth, taylor, golden_merges):
     want = ora.encode(taylor, golden_merges, linear=True)
     for tile in (512, 2048, 8192):
         assert np.array_equal(enc(taylor, golden_merges, tile), want)
-    ids = gpu.encode(taylor, golden_merges)
-    assert np.array_equal(ids, want) and gpu.last_stats["kernel_calls"][10] == 2 and gpu.last_stats["kernel_calls"][11] == 1
+    try:
+        gpu.set_option("encode_try_tiles", 2)  # encode_impl 0 picks by cost; 2: the tile kernel first whatever the list
+        ids = gpu.encode(taylor, golden_merges)
+        assert np.array_equal(ids, want) and gpu.last_stats["kernel_calls"][10] == 2 and gpu.last_stats["kernel_calls"][11] == 1
+    finally:
+        gpu.set_option("encode_try_tiles", 1)
     train = bytes(synth.generate(2_000_000, synth.SEED_C3, synth.BYTE))
     om, _ = ora.train(train, 256 + 2000, fast=True)
     other = bytes(synth.generate(3_000_000, synth.SEED_C5, synth.BYTE))
@@ -254,9 +259,13 @@ def test_tile_encoder_on_gpu(gpu, ora, synth, taylor, golden_merges):
     rng = np.random.default_rng(5)
     data = b"".join(b"a" * int(rng.integers(1, 12)) + bytes(rng.integers(98, 102, size=int(rng.integers(1, 6)), dtype=np.uint8)) for _ in range(40000))
     assert np.array_equal(enc(data, merges), ora.encode(data, merges, linear=False))
-    data = b"q" + b"a" * 50001 + b"b"  # a run no window can take: the default dispatch falls back
-    ids = gpu.encode(data, merges)
-    assert np.array_equal(ids, ora.encode(data, merges, linear=False)) and gpu.last_stats["kernel_calls"][11] == 2
+    data = b"q" + b"a" * 50001 + b"b"  # a run no window can take: the dispatch falls back to the other encoders
+    try:
+        gpu.set_option("encode_try_tiles", 2)
+        ids = gpu.encode(data, merges)
+        assert np.array_equal(ids, ora.encode(data, merges, linear=False)) and gpu.last_stats["kernel_calls"][11] == 2
+    finally:
+        gpu.set_option("encode_try_tiles", 1)
 
 
 def test_decode_semantics(gpu, zb):

@@ -96,3 +96,40 @@ def test_synthcorpus_deterministic(synth):
     text[: 1 << 19].decode("utf-8", errors="strict") if False else text.decode("utf-8", errors="ignore")
     import hashlib
     assert hashlib.sha256(bytes(a[:1000])).hexdigest() == hashlib.sha256(bytes(synth.generate(1000, synth.SEED_C3, synth.BYTE))).hexdigest()
+
+
+def test_cpp_mirror_deserialize_edge_cases(ora, tmp_path):
+    """The C++ host mirror's merges.txt reader (zig-bpe_b200/host/basic_tokenizer.hpp, no GPU involved) against the
+    oracle's restatement of deserializeMerges (:332-348) on the malformed files of test_oracle.py"""
+    import subprocess
+    src = tmp_path / "rd.cpp"
+    src.write_text('''#include "basic_tokenizer.hpp"
+#include <cstdio>
+int main(int argc, char** argv) {
+    std::vector<zigbpe::Merge> ms;
+    const char* err = "OK";
+    std::string what;
+    try { zigbpe::BasicTokenizer::readMergesFile(argv[1], ms); } catch (const std::exception& e) { err = "ERR"; what = e.what(); }
+    std::printf("%s %s %zu", err, what.c_str(), ms.size());
+    for (auto& m : ms) std::printf(" %u,%u,%u", (unsigned)m.pair.first, (unsigned)m.pair.second, (unsigned)m.new_token);
+    std::printf("\\n");
+    return 0;
+}
+''')
+    exe = tmp_path / "rd"
+    subprocess.run(["g++", "-O1", "-std=c++17", f"-I{ROOT}/include", f"-I{ROOT}/zig-bpe_b200/host", str(src), "-o", str(exe)], check=True)
+    cases = [(b"1,2,3\n4,5,6", 2), (b"1,2,3,99\n", 1), (b"1,2\n", -106), (b"1,2,\n", -20), (b"\n", -20), (b"1,2,3\r\n", -20),
+             (b"1,2,65536\n", -21), (b"1, 2,3\n", -20), (b"+1,2,3\n", 1), (b"1_0,2,3\n", 1), (b"1,2,3\n" + b"9" * 100 + b"\n", -22),
+             (b"1,2,3\n" + b"7," * 49 + b"7\n", 2), (b"", 0), (b"1,2,3", 1)]
+    name = {-20: "InvalidCharacter", -21: "Overflow", -22: "StreamTooLong", -106: "InvalidFormat"}
+    for content, err in cases:
+        p = tmp_path / "m.txt"
+        p.write_bytes(content)
+        r, parsed = ora.deserialize(p)
+        assert r == err
+        out = subprocess.run([str(exe), str(p)], capture_output=True, text=True, check=True).stdout.split()
+        got = [tuple(int(x) for x in t.split(",")) for t in out[3:]] if err < 0 else [tuple(int(x) for x in t.split(",")) for t in out[2:]]
+        if err >= 0:
+            assert out[0] == "OK" and got == parsed, (content, out)
+        else:
+            assert out[0] == "ERR" and name[err] in out[1] and got == parsed, (content, out)

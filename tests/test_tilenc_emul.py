@@ -12,11 +12,13 @@ def _enc(eng, data, merges, tile=512, impl=0):
     try:
         eng.set_option("encode_tile", tile)
         eng.set_option("encode_impl", impl)
+        eng.set_option("encode_try_tiles", 2)  # impl 0 picks by cost (short lists on one GPU go to the level passes); 2: tiles first
         ids = eng.encode(data, merges)
         return ids, eng.last_stats["kernel_calls"][10], eng.last_stats["kernel_calls"][11]
     finally:
         eng.set_option("encode_tile", 8192)
         eng.set_option("encode_impl", 0)
+        eng.set_option("encode_try_tiles", 1)
 
 
 @pytest.mark.parametrize("tile", [512, 1024, 2048, 8192])
@@ -168,3 +170,16 @@ def test_streaming_from_host_buffers(emu, ora, synth, taylor, golden_merges):
     finally:
         emu.set_option("stream_chunk_bytes", 0)
         emu.set_option("encode_tile", 8192)
+
+
+def test_default_dispatch_by_cost(emu, ora, taylor, golden_merges):
+    """encode_impl = 0 on one GPU: a short list (few levels) takes the level passes, a list whose schedule is longer than
+    encode_seg_min_steps the tile-resident kernel"""
+    ids = emu.encode(taylor[:20000], golden_merges)
+    assert emu.last_stats["kernel_calls"][10] == 0 and np.array_equal(ids, ora.encode(taylor[:20000], golden_merges, linear=True))
+    try:
+        emu.set_option("encode_seg_min_steps", 5)
+        ids = emu.encode(taylor[:20000], golden_merges)  # 44 merges -> 6 levels + 1 run merge
+        assert emu.last_stats["kernel_calls"][10] == TILE_PATH and np.array_equal(ids, ora.encode(taylor[:20000], golden_merges, linear=True))
+    finally:
+        emu.set_option("encode_seg_min_steps", 450)

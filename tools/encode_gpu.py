@@ -15,8 +15,10 @@ eng = zb.Engine(device=0)
 d_text = torch.from_numpy(sc.generate(n, sc.SEED_C3, sc.BYTE)).cuda()
 m, _ = eng.train(None, vocab, device_ptr=d_text.data_ptr(), n=min(n, train_bytes))
 out = {"bytes": n, "merges": int(len(m)), "train_ms": round(eng.last_stats["device_ms"], 1)}
+if os.environ.get("ENC_DEBUG"):
+    eng.set_option("debug", 1)  # the tile encoder reports ranges / rounds per window on stderr
 ref = None
-DEFAULTS = {"encode_grid": 6, "encode_filter": 1, "encode_geom": 4, "encode_tile": 8192}
+DEFAULTS = {"encode_grid": 6, "encode_filter": 1, "encode_geom": 4, "encode_tile": 7936}
 for var in variants:
     parts = var.split(":")
     eng.set_option("encode_impl", int(parts[0]))

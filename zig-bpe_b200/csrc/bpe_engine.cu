@@ -58,7 +58,7 @@ struct bpe_ctx {
     std::string err;
     // options
     long verify_recount = 0, force_slow_tiebreak = 0, check_tiebreak = 0, compact_pct = 85, table_log2 = 0,
-         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 6, encode_filter = 1, encode_geom = 4, encode_seg_min_steps = 450, encode_tile = 8192, encode_try_tiles = 1, fuse_halo = 1, count_limit_log2 = 32, stream_chunk_mb = 128, stream_chunk_bytes = 0;
+         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 6, encode_filter = 1, encode_geom = 4, encode_seg_min_steps = 450, encode_tile = 7936, encode_try_tiles = 1, fuse_halo = 1, count_limit_log2 = 32, stream_chunk_mb = 128, stream_chunk_bytes = 0, merge_filter = 0, batch_steps = 16;
     int num_sms = 148;
     DistComm dist;  // world == 1 when single GPU
     uint64_t launches = 0;
@@ -66,6 +66,7 @@ struct bpe_ctx {
     std::vector<cudaEvent_t> ev_pool;  // profiling events, created on first use
     struct DecodeCache* decode_cache = nullptr;  // decode tables of the last merge list seen (built once per list)
     cudaStream_t copy_in = 0, copy_out = 0;      // streaming encode: host -> device text chunks, device -> host ids (created on first use)
+    void* h_ctl = nullptr;                       // pinned StepCtl read-back buffer of the train loop
 };
 
 static std::string g_create_err;
@@ -320,14 +321,14 @@ struct TrainRun {
     uint32_t vcap = 0;   // stride of the cntL / cntR halves of `delta`
     uint32_t theta = 0;  // heavy-list threshold (0 = list invalid)
     HeavyList hl() const { HeavyList h; h.slots = heavy.as<uint32_t>(); h.cap = (uint32_t)(heavy.bytes / 4); h.theta = theta; return h; }
-    HostBuf h_ctl;
+    void* h_ctl_p = nullptr;  // pinned read-back buffer, owned by the context (page-locking per call costs tens of ms)
     bpe_stats_t st;
     EvProfile prof;
     uint64_t aeqb_steps = 0;                // steps that took the run-chaining halo pass (first == second)
     std::vector<uint32_t> pending_samples;  // profile 3: sampled steps enqueued in the current batch
     uint64_t sampled_noop = 0;              // sampled launches that turned out to be no-ops (batch halted earlier)
     StepCtl* d_ctl() const { return ctl.as<StepCtl>(); }
-    StepCtl* hc() const { return h_ctl.as<StepCtl>(); }
+    StepCtl* hc() const { return (StepCtl*)h_ctl_p; }
     MergeRec* d_rec() const { return rec.as<MergeRec>(); }
     uint32_t* cntL() const { return delta.as<uint32_t>(); }
     uint32_t* cntR() const { return delta.as<uint32_t>() + vcap; }
@@ -341,7 +342,7 @@ struct TrainRun {
 
 static int read_ctl(bpe_ctx* ctx, TrainRun& R, bool with_ties) {
     size_t bytes = with_ties ? sizeof(StepCtl) : offsetof(StepCtl, tie_keys);
-    CU(cudaMemcpyAsync(R.h_ctl.p, R.ctl.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(R.h_ctl_p, R.ctl.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return BPE_OK;
 }
@@ -500,8 +501,12 @@ static int launch_merge(bpe_ctx* ctx, TokT* tok, const TileHalo<TokT>* halo, uin
         BPE_LAUNCH_SMEM(kern, grid, THREADS, ring_smem_bytes<TokT>(), ctx->stream, tok, halo, d_ctl, cntL, cntR, nxx, nab, A, B, X,
                         bins_min, nt);
     } else {
-        BPE_LAUNCH((merge_kernel<TokT, DELTAS, FROMCTL>), nt, THREADS, ctx->stream, tok, halo, d_ctl, cntL, cntR, nxx, nab, A, B, X, bins_min,
-                   backwards);
+        if (ctx->merge_filter)
+            BPE_LAUNCH((merge_kernel<TokT, DELTAS, FROMCTL, true>), nt, THREADS, ctx->stream, tok, halo, d_ctl, cntL, cntR, nxx, nab, A, B, X, bins_min,
+                       backwards);
+        else
+            BPE_LAUNCH((merge_kernel<TokT, DELTAS, FROMCTL, false>), nt, THREADS, ctx->stream, tok, halo, d_ctl, cntL, cntR, nxx, nab, A, B, X, bins_min,
+                       backwards);
     }
     ctx->launches++;
     return BPE_OK;
@@ -628,7 +633,8 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     // after every compaction, and first == second steps halt the loop for the run-chaining halo pass (H_AEQB)
     const bool fused_halo = ctx->fuse_halo != 0 && ctx->merge_impl == 0;
     bool halo_stale = true;
-    CU(R.h_ctl.alloc(sizeof(StepCtl)));
+    if (!ctx->h_ctl) CU(cudaMallocHost(&ctx->h_ctl, sizeof(StepCtl)));
+    R.h_ctl_p = ctx->h_ctl;
     CU(cudaMemsetAsync(R.delta.p, 0, R.exchange_words() * 4, ctx->stream));
     CU(cudaMemsetAsync(R.hist.p, 0, 65536 * 8, ctx->stream));
     CU(cudaMemsetAsync(R.ctl.p, 0, sizeof(StepCtl), ctx->stream));
@@ -692,7 +698,9 @@ static int train_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, uint16_t 
     while (!finished) {
         StepCtl* hc = R.hc();
         // ---- housekeeping between batches (the table and the sequence are quiescent here) ----
-        const uint32_t max_batch = debug_sync ? 1u : 32u;
+        // steps enqueued between two read-backs of the control block: after a halt the rest of a batch are no-op launches
+        // (~50 us each at 1 GB), so shorter batches waste less; every batch costs one host round trip
+        const uint32_t max_batch = debug_sync ? 1u : (uint32_t)std::max<long>(1, std::min<long>(ctx->batch_steps, 256));
         uint32_t K = (uint32_t)std::min<size_t>(max_batch, want - steps_done);
         const uint64_t per_step_inserts = 2ull * (256 + steps_done + K + 1) + 1;
         prof.mark(K_TABLE);
@@ -1155,15 +1163,16 @@ static int launch_tilenc(bpe_ctx* ctx, cudaStream_t stream, const uint8_t* d_tex
     const long long nwin = g.bwl + g.ntile + g.bwr;
     if (nwin > 0x7FFFFFFFll) return fail(ctx, BPE_ERR_INVALID_ARG, "input too large for one launch");
     if (zone.bytes < (size_t)nwin * TN_ZONE * 2) CU(zone.alloc((size_t)nwin * TN_ZONE * 2));
-    if (flags.bytes < ((size_t)nwin + 2) * 4) CU(flags.alloc(((size_t)nwin + 2) * 4));  // [flags | ticket | fail]
-    CU(cudaMemsetAsync(flags.p, 0, ((size_t)nwin + 2) * 4, stream));
+    if (flags.bytes < ((size_t)nwin + 6) * 4) CU(flags.alloc(((size_t)nwin + 6) * 4));  // [flags | ticket | fail | 4 debug counters]
+    CU(cudaMemsetAsync(flags.p, 0, ((size_t)nwin + 6) * 4, stream));
     uint32_t* d_ticket = flags.as<uint32_t>() + nwin;
     *d_fail = d_ticket + 1;
     const size_t smem = tilenc_smem_bytes(tile_max, tb.max_level);
     CU(cudaFuncSetAttribute(tilenc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (n > 0) {
         BPE_LAUNCH_SMEM(tilenc_kernel, (unsigned)nwin, TN_THREADS, smem, stream, d_text, d_halo_l, d_halo_r, g, tile_max, tb.T,
-                        tb.max_level, d_slots, zone.as<uint16_t>(), flags.as<uint32_t>(), d_ticket, *d_fail);
+                        tb.max_level, d_slots, zone.as<uint16_t>(), flags.as<uint32_t>(), d_ticket, *d_fail,
+                        ctx->debug ? *d_fail + 1 : (uint32_t*)nullptr);
         ctx->launches++;
         CU(cudaGetLastError());
     }
@@ -1215,10 +1224,14 @@ static int encode_tiles(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bpe
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (st) { st->kernel_ms[11] = kms; st->kernel_calls[11] = nfail ? 2 : 1; }
-    if (nfail) {
-        if (ctx->debug) fprintf(stderr, "[bpe r%d] tile encode: %u windows gave up, falling back\n", rank, nfail);
-        return BPE_OK;
+    if (ctx->debug) {
+        uint32_t dbg[4] = {0, 0, 0, 0};
+        cudaMemcpy(dbg, d_fail + 1, sizeof dbg, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[bpe r%d] tile encode: %zu bytes, tile %d, levels %u, %.3f ms; per window: %.1f ranges, %.1f one-warp rounds, %.1f CTA rounds, %.1f partial rounds; %u windows gave up\n",
+                rank, n, tile_max, tb.max_level, kms, dbg[0] / (double)std::max<size_t>(1, n / tile_max), dbg[1] / (double)std::max<size_t>(1, n / tile_max),
+                dbg[2] / (double)std::max<size_t>(1, n / tile_max), dbg[3] / (double)std::max<size_t>(1, n / tile_max), nfail);
     }
+    if (nfail) return BPE_OK;
     *used = true;
     if (n == 0) { *out_n = 0; return BPE_OK; }
     rc = squeeze_slots(ctx, slots, n, d_out, out_n);
@@ -1588,24 +1601,28 @@ static int encode_device(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
     CU(cudaEventRecord(ev0, ctx->stream));
     int rc = BPE_OK;
     bool done = false;
-    // encode_impl 0 (default): the tile-resident kernel (one launch, the text is read once) for every list a trained
-    // tokenizer can produce; if it does not apply or gives up, the choice between the segment-resident kernel and
-    // the level passes is made by cost (the passes sweep the sequence once per level, the segment kernel costs
-    // ~0.3 s per GB whatever the list). 4 / 3 force the tile / segment kernel, 2 the level passes, 1 one pass per merge.
-    // kernel_calls[10] records the encoder that produced the ids (1 segment, 2 tile; 0 passes).
-    if ((ctx->encode_impl == 0 && ctx->encode_try_tiles) || ctx->encode_impl == 4) {
+    // encode_impl 0 (default) picks by measured cost (B200). The level passes sweep the resident
+    // sequence once per level of the list (C3's 7,936 merges: ~190 sweeps, 0.09 s per GB on one GPU) but need one exchange
+    // and one host round trip per sweep across GPUs and 32-bit positions; the tile-resident kernel (one launch, ~0.15 s
+    // per GB for such a list, nothing exchanged between GPUs) takes the multi-GPU runs, inputs of 4 GiB or more and the
+    // lists whose schedule is longer than "encode_seg_min_steps". 4 / 3 force the tile / segment kernel, 2 the level
+    // passes, 1 one pass per merge. kernel_calls[10] records the encoder that produced the ids (1 segment, 2 tile; 0 passes).
+    size_t sched_steps = 0;
+    if (ctx->encode_impl == 0 && m > 0) {
+        std::vector<EncStep> steps;
+        std::vector<LevelEntry> ents;
+        build_encode_schedule(merges, m, true, steps, ents);
+        sched_steps = steps.size();
+    }
+    const bool prefer_tiles = ctx->dist.world > 1 || n >= 0xFFFFFFF0ull || sched_steps > (size_t)ctx->encode_seg_min_steps || ctx->encode_try_tiles > 1;
+    if ((ctx->encode_impl == 0 && ctx->encode_try_tiles && prefer_tiles) || ctx->encode_impl == 4) {
         rc = encode_tiles(ctx, d_text, n, merges, m, d_out, out_n, &st, &done);
         if (rc) return rc;
         if (done) st.kernel_calls[10] = 2;
         else if (ctx->encode_impl == 4) return fail(ctx, BPE_ERR_INTERNAL, "encode_impl = 4: the tile-resident encoder does not apply to this input");
     }
     bool try_segments = ctx->encode_impl == 3;
-    if (!done && ctx->encode_impl == 0 && m > 0) {
-        std::vector<EncStep> steps;
-        std::vector<LevelEntry> ents;
-        build_encode_schedule(merges, m, true, steps, ents);
-        try_segments = steps.size() > (size_t)ctx->encode_seg_min_steps || n >= 0xFFFFFFF0ull;
-    }
+    if (!done && ctx->encode_impl == 0 && m > 0) try_segments = sched_steps > (size_t)ctx->encode_seg_min_steps || n >= 0xFFFFFFF0ull;
     if (!done && try_segments) {
         const uint64_t tile_verdict = st.kernel_calls[11];
         rc = encode_segments(ctx, d_text, n, merges, m, d_out, out_n, &st, &done);
@@ -1917,6 +1934,7 @@ void bpe_ctx_destroy(bpe_ctx* ctx) {
     ctx->dist.destroy();
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     delete ctx->decode_cache;
+    if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     ctx->cache.clear();
@@ -1947,6 +1965,8 @@ int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value) {
     else if (s == "encode_try_tiles") ctx->encode_try_tiles = value;
     else if (s == "fuse_halo") ctx->fuse_halo = value;
     else if (s == "count_limit_log2") ctx->count_limit_log2 = value;
+    else if (s == "merge_filter") ctx->merge_filter = value;
+    else if (s == "batch_steps") ctx->batch_steps = value;
     else if (s == "stream_chunk_mb") ctx->stream_chunk_mb = value;
     else if (s == "stream_chunk_bytes") ctx->stream_chunk_bytes = value;
     else return fail(ctx, BPE_ERR_INVALID_ARG, "unknown option '%s'", name);
@@ -1967,8 +1987,8 @@ int bpe_train(bpe_ctx* ctx, const uint8_t* text, size_t n, uint16_t vocab_size, 
     if (n && !text) return fail(ctx, BPE_ERR_INVALID_ARG, "text is null");
     const double t0 = now_ms();
     CU(cudaSetDevice(ctx->device));
-    DevBuf d;
-    if (cudaMalloc(&d.p, n ? n : 1) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", n);
+    DevBuf d;  // (through the context's cache: cudaMalloc + cudaFree of a GB cost ~0.2 s per call)
+    if (d.alloc(n ? n : 1) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", n);
     CU(cudaMemcpyAsync(d.p, text, n, cudaMemcpyHostToDevice, ctx->stream));
     int rc = train_device(ctx, d.as<uint8_t>(), n, vocab_size, out_merges, out_counts, out_n, stats);
     if (stats) stats->total_ms = now_ms() - t0;
@@ -2012,8 +2032,8 @@ int bpe_encode(bpe_ctx* ctx, const uint8_t* text, size_t n, const bpe_merge_t* m
         *out_n = 0;
     }
     DevBuf d_in, d_out;
-    if (cudaMalloc(&d_in.p, n ? n : 1) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", n);
-    if (cudaMalloc(&d_out.p, n ? n * 2 : 2) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", n * 2);
+    if (d_in.alloc(n ? n : 1) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", n);
+    if (d_out.alloc(n ? n * 2 : 2) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", n * 2);
     CU(cudaMemcpyAsync(d_in.p, text, n, cudaMemcpyHostToDevice, ctx->stream));
     int rc = encode_device(ctx, d_in.as<uint8_t>(), n, merges, m, d_out.as<uint16_t>(), out_n, stats);
     if (rc) return rc;
@@ -2040,7 +2060,7 @@ int bpe_decode_size(bpe_ctx* ctx, const uint16_t* toks, size_t n, const bpe_merg
     if (!toks) return fail(ctx, BPE_ERR_INVALID_ARG, "toks is null");
     CU(cudaSetDevice(ctx->device));
     DevBuf d_in;
-    if (cudaMalloc(&d_in.p, n * 2) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", n * 2);
+    if (d_in.alloc(n * 2) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", n * 2);
     CU(cudaMemcpyAsync(d_in.p, toks, n * 2, cudaMemcpyHostToDevice, ctx->stream));
     return decode_device(ctx, d_in.as<uint16_t>(), n, merges, m, nullptr, 0, out_n, nullptr);
 }
@@ -2056,8 +2076,8 @@ int bpe_decode(bpe_ctx* ctx, const uint16_t* toks, size_t n, const bpe_merge_t* 
     const double t0 = now_ms();
     CU(cudaSetDevice(ctx->device));
     DevBuf d_in, d_out;
-    if (cudaMalloc(&d_in.p, n * 2) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", n * 2);
-    if (cudaMalloc(&d_out.p, cap ? cap : 1) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", cap);
+    if (d_in.alloc(n * 2) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", n * 2);
+    if (d_out.alloc(cap ? cap : 1) != cudaSuccess) return fail(ctx, BPE_ERR_OOM, "device allocation of %zu bytes failed", cap);
     CU(cudaMemcpyAsync(d_in.p, toks, n * 2, cudaMemcpyHostToDevice, ctx->stream));
     int rc = decode_device(ctx, d_in.as<uint16_t>(), n, merges, m, d_out.as<uint8_t>(), cap, out_n, stats);
     if (rc) return rc;

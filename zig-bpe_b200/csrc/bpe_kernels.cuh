@@ -794,6 +794,32 @@ template <> __device__ __forceinline__ bool vec_has<uint32_t>(const uint4& v, ui
     return v.x == a || v.y == a || v.z == a || v.w == a;
 }
 
+// Candidate filter. An A can only start an occurrence if its next live token is B; looking no further than the next
+// SLOT (inside the 16-byte vector, or the first slot of the following vector, which a shuffle brings in), an A whose
+// next slot holds a live token other than B is ruled out on the spot, in registers. What remains — next slot is B,
+// a hole (the next live token lies further on) or unknown (last lane of a warp) — is a candidate for the staged path.
+// Returns the candidates in vec_mask's bit layout. next_first: first slot of the following vector; next_known: it is valid.
+template <class TokT> __device__ __forceinline__ uint32_t vec_candidates(const uint4& v, uint32_t a, uint32_t b, uint32_t next_first, bool next_known);
+template <> __device__ __forceinline__ uint32_t vec_candidates<uint16_t>(const uint4& v, uint32_t a, uint32_t b, uint32_t next_first, bool next_known) {
+    const uint32_t ma = vec_mask<uint16_t>(v, a);
+    if (!ma) return 0u;
+    const uint32_t ms = vec_mask<uint16_t>(v, b) | vec_mask<uint16_t>(v, 0xFFFFu);  // slots holding B or a hole
+    const bool last_ok = !next_known || next_first == b || next_first == 0xFFFFu;
+    // bit i = slot 2i, bit 16 + i = slot 2i + 1: the successor of slot 2i is bit 16 + i, of slot 2i + 1 bit i + 1
+    const uint32_t succ = ((ms >> 16) & 0xFu) | (((ms & 0xEu) >> 1) << 16) | (last_ok ? (1u << 19) : 0u);
+    return ma & succ;
+}
+template <> __device__ __forceinline__ uint32_t vec_candidates<uint32_t>(const uint4& v, uint32_t a, uint32_t b, uint32_t next_first, bool next_known) {
+    const uint32_t ma = vec_mask<uint32_t>(v, a);
+    if (!ma) return 0u;
+    const uint32_t ms = vec_mask<uint32_t>(v, b) | vec_mask<uint32_t>(v, 0xFFFFFFFFu);
+    const bool last_ok = !next_known || next_first == b || next_first == 0xFFFFFFFFu;
+    return ma & (((ms >> 1) & 0x7u) | (last_ok ? 8u : 0u));
+}
+template <class TokT> __device__ __forceinline__ uint32_t vec_first_slot(const uint4& v);
+template <> __device__ __forceinline__ uint32_t vec_first_slot<uint16_t>(const uint4& v) { return v.x & 0xFFFFu; }
+template <> __device__ __forceinline__ uint32_t vec_first_slot<uint32_t>(const uint4& v) { return v.x; }
+
 // +1 for `key` in the block-private bins (open addressing, 8 probes), falling back to the global
 // arrays when the neighbourhood is too crowded
 template <int NBIN>
@@ -897,8 +923,10 @@ __device__ __forceinline__ void tile_staged_path(TokT* ext, const uint4 (&v)[NV]
         // positions of its A's; the CTA then works through the queue with all lanes busy.
 #pragma unroll
         for (int k = 0; k < NV; k++) {
+            // (the shuffle is executed by every lane; vectors k of neighbouring lanes are neighbours in the tile)
+            const uint32_t nf = __shfl_down_sync(0xffffffffu, vec_first_slot<TokT>(v[k]), 1);
             if (!((hitbits >> k) & 1u)) continue;
-            uint32_t mask = vec_mask<TokT>(v[k], Au);
+            uint32_t mask = vec_candidates<TokT>(v[k], Au, Bu, nf, (threadIdx.x & 31u) != 31u);
             const int s0 = OFF + (k * THREADS + (int)threadIdx.x) * VEC;
             uint32_t at = atomicAdd(q_n, (uint32_t)__popc(mask));
             while (mask) {
@@ -992,7 +1020,7 @@ __device__ __forceinline__ void tile_staged_path(TokT* ext, const uint4 (&v)[NV]
 #ifndef BPE_MERGE_MINBLOCKS
 #define BPE_MERGE_MINBLOCKS 6
 #endif
-template <class TokT, bool DELTAS, bool FROMCTL>
+template <class TokT, bool DELTAS, bool FROMCTL, bool FILTER>
 __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(TokT* __restrict__ tok, const TileHalo<TokT>* __restrict__ halo,
                                                         const StepCtl* __restrict__ ctl, uint32_t* __restrict__ cntL,
                                                         uint32_t* __restrict__ cntR, uint32_t* nxx_out, uint32_t* nab_out,
@@ -1036,7 +1064,17 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(Tok
     uint32_t hitbits = 0;  // which of my vectors hold an A
 #pragma unroll
     for (int k = 0; k < NV; k++) hitbits |= vec_has<TokT>(v[k], Au) ? (1u << k) : 0u;
-    any = hitbits != 0;
+    // The tile needs the staged path only if some A can start an occurrence (candidate filter above; a step whose A is
+    // a frequent token but whose pair is rare leaves most tiles on the streaming path) or, for first == second, if it
+    // holds an A at all (the run bookkeeping looks at every A).
+    if (!FILTER || Au == Bu) any = hitbits != 0;
+    else {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            const uint32_t nf = __shfl_down_sync(0xffffffffu, vec_first_slot<TokT>(v[k]), 1);
+            if (((hitbits >> k) & 1u) && vec_candidates<TokT>(v[k], Au, Bu, nf, (threadIdx.x & 31u) != 31u)) any = true;
+        }
+    }
     if (threadIdx.x == 0 && h.l1 == A) any = true;  // possible head duty
     if (!__syncthreads_or(any ? 1 : 0)) return;
     uint32_t nAB = 0, nXX = 0;

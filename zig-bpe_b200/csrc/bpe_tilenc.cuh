@@ -48,8 +48,8 @@ constexpr int TN_BR = 192;        // half width of a bridge window
 constexpr int TN_ZONE = 256;      // slots a window publishes for its successor (>= TN_BR + TN_M, >= 2 * TN_M)
 constexpr int TN_TMAX = 8192;     // largest tile
 constexpr int TN_QCAP = 2048;     // positions laid out per range (`sorted`)
-constexpr int TN_BUCKET = 16;     // pairs created inside a range that a level of the range can take (`late`), else the range ends there
-constexpr int TN_RANGE = 64;      // levels per range
+constexpr int TN_BUCKET = 64;     // pairs created inside a range that a level of the range can take (`late`), else the range ends there
+constexpr int TN_RANGE = 32;      // levels per range
 constexpr int TN_LCAP = TN_BUCKET * TN_RANGE;
 constexpr int TN_SPARSE = 64;     // a level with at most this many entries is worked through by one warp
 constexpr int TN_THREADS = 256;
@@ -105,7 +105,7 @@ __host__ __device__ constexpr size_t tilenc_smem_bytes(int tile_max, uint32_t ma
 __global__ void __launch_bounds__(TN_THREADS, 3) tilenc_kernel(const uint8_t* __restrict__ text, const uint8_t* __restrict__ halo_l,
                                                             const uint8_t* __restrict__ halo_r, TileGeom g, int tile_max, SegTab T,
                                                             uint32_t max_level, uint16_t* __restrict__ out_slots,
-                                                            uint16_t* zone_buf, uint32_t* flags, uint32_t* ticket, uint32_t* fail) {
+                                                            uint16_t* zone_buf, uint32_t* flags, uint32_t* ticket, uint32_t* fail, uint32_t* dbg) {
     constexpr int NT = TN_THREADS;
     const int WCAP = tile_max + 2 * TN_M;
     uint32_t* cell = bpe_dyn_smem();
@@ -166,88 +166,118 @@ __global__ void __launch_bounds__(TN_THREADS, 3) tilenc_kernel(const uint8_t* __
         while (!bits) { if (++w >= LW) return max_level + 1; bits = present[w]; }
         return w * 32u + (uint32_t)(__ffs((int)bits) - 1);
     };
-    auto lookup = [&](uint32_t a, uint32_t b, uint32_t* x) -> uint32_t {  // level of (a, b) or TL_INF
-        const uint32_t v = seg_lookup(T, a, b);
-        if (v == SEG_NONE) return TL_INF;
-        *x = v >> 16;
-        return v & 0xFFFFu;
+    // Hashed look-up in two halves, so that a thread can have the first probes of several pairs in flight at once
+    // (a round is a chain of dependent latencies; the table lives in L2)
+    struct Probe { uint32_t key, s; uint2 e; };
+    auto probe_start = [&](Probe& q, uint32_t a, uint32_t b) {
+        q.key = pair_key(a, b);
+        if ((a | b) < 256u) { q.e.x = q.key; q.e.y = T.bp[a | (b << 8)]; q.s = 0; return; }
+        q.s = (q.key * 0x9E3779B1u) >> T.hshift;
+        q.e = T.hk[q.s];
     };
-    // One entry (slot p, or none) per thread of the group: the three steps of a round, `sync` between them.
-    // base / hi: the range whose pairs may be chained into the late lists.
-    auto chunk = [&](uint32_t rr, uint32_t base, uint32_t hi, int p, bool valid, bool whole_cta) {
+    auto probe_finish = [&](Probe& q, uint32_t* x) -> uint32_t {  // level of the pair or TL_INF
+        while (q.e.x != q.key) {
+            if (q.e.x == EMPTY_KEY) return TL_INF;
+            q.s = (q.s + 1u) & T.hmask;
+            q.e = T.hk[q.s];
+        }
+        if (q.e.y == SEG_NONE) return TL_INF;
+        *x = q.e.y >> 16;
+        return q.e.y & 0xFFFFu;
+    };
+    // Up to two entries (slots p[0], p[1]) per thread of the group: the three steps of a round, a barrier of the group
+    // between them. base / hi: the range whose pairs may join the late buckets.
+    auto chunk = [&](uint32_t rr, uint32_t base, uint32_t hi, const int (&p)[2], const bool (&valid)[2], bool whole_cta) {
         // (a) decide + claim
-        bool mine = false;
-        if (valid) {
-            const uint32_t c = cell[p];
-            if ((c >> 16) == rr) {  // else: stale entry, or already claimed through a duplicate
-                uint32_t run = 0;
-                int q = p;
-                while (q > 0) {  // offset inside a run of equal pairs (only first == second pairs have equal-level neighbours)
-                    const int e1 = q - 1, pl = e1 - (int)back[e1];
-                    if (((cell[pl] >> 16) & 0x7FFFu) != rr) break;
-                    q = pl;
-                    if (++run > 255u) { s_fail = 1; break; }
-                }
-                if (!(run & 1u)) mine = atomicCAS(&cell[p], c, c | TL_CLAIM) == c;  // odd offset: consumed by the occurrence on its left
+        bool mine[2] = {false, false};
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            if (!valid[e]) continue;
+            const uint32_t c = cell[p[e]];
+            if ((c >> 16) != rr) continue;  // stale entry, or already claimed through a duplicate
+            uint32_t run = 0;
+            int q = p[e];
+            while (q > 0) {  // offset inside a run of equal pairs (only first == second pairs have equal-level neighbours)
+                const int e1 = q - 1, pl = e1 - (int)back[e1];
+                if (((cell[pl] >> 16) & 0x7FFFu) != rr) break;
+                q = pl;
+                if (++run > 255u) { s_fail = 1; break; }
             }
+            if (!(run & 1u)) mine[e] = atomicCAS(&cell[p[e]], c, c | TL_CLAIM) == c;  // odd offset: consumed by the occurrence on its left
         }
         if (whole_cta) __syncthreads(); else __syncwarp();
-        // (b) rewrite the claimed slot
-        if (mine) {
-            const int lp = len[p], q = p + lp, lq = len[q], nl = lp + lq;
-            if (nl > 255) { s_fail = 1; mine = false; }
-            else {
-                cell[p] = (uint32_t)nx[p] | (TL_INF << 16);
-                len[p] = (uint8_t)nl;
-                cell[q] = TL_DEAD << 16;
-                back[q + lq - 1] = (uint8_t)(nl - 1);
-                s_progress = 1;
-            }
+        // (b) rewrite the claimed slots
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            if (!mine[e]) continue;
+            const int lp = len[p[e]], q = p[e] + lp, lq = len[q], nl = lp + lq;
+            if (nl > 255) { s_fail = 1; mine[e] = false; continue; }
+            cell[p[e]] = (uint32_t)nx[p[e]] | (TL_INF << 16);
+            len[p[e]] = (uint8_t)nl;
+            cell[q] = TL_DEAD << 16;
+            back[q + lq - 1] = (uint8_t)(nl - 1);
+            s_progress = 1;
         }
         if (whole_cta) __syncthreads(); else __syncwarp();
-        // (c) levels of the pairs next to the new token
-        if (mine) {
-            auto set_level = [&](int s, uint32_t tok, uint32_t lv, uint32_t x) {
-                const uint32_t old = (cell[s] >> 16) & 0x7FFFu;
-                cell[s] = tok | (lv << 16);
-                nx[s] = (uint16_t)x;
-                if (lv == TL_INF) return;
-                if (lv <= rr) { s_fail = 1; return; }  // cannot happen for a regular list (fact 1)
-                atomicOr(&present[lv >> 5], 1u << (lv & 31u));
-                if (lv < hi && lv != old) {
-                    const uint32_t at = atomicAdd(&late_cnt[lv - base], 1u);
-                    if (at < (uint32_t)TN_BUCKET) late_pos[(lv - base) * TN_BUCKET + at] = (uint16_t)s;
-                    else atomicMin(&late_drop, lv);
-                }
-            };
-            const uint32_t X = cell[p] & 0xFFFFu;
-            const int n = p + (int)len[p];
-            uint32_t lv = TL_INF, x = 0;
-            if (n < W) lv = lookup(X, cell[n] & 0xFFFFu, &x);
-            uint32_t lv2 = TL_INF, x2 = 0, tp = 0;
-            int pl = -1;
-            if (p > 0) {
-                const int e1 = p - 1;
-                pl = e1 - (int)back[e1];
-                tp = cell[pl] & 0xFFFFu;
-                lv2 = lookup(tp, X, &x2);
+        // (c) levels of the pairs next to the new tokens: all first probes go out before any of them is waited for
+        auto set_level = [&](int s, uint32_t tok, uint32_t lv, uint32_t x) {
+            const uint32_t old = (cell[s] >> 16) & 0x7FFFu;
+            cell[s] = tok | (lv << 16);
+            nx[s] = (uint16_t)x;
+            if (lv == TL_INF) return;
+            if (lv <= rr) { s_fail = 1; return; }  // cannot happen for a regular list (fact 1)
+            atomicOr(&present[lv >> 5], 1u << (lv & 31u));
+            if (lv < hi && lv != old) {
+                const uint32_t at = atomicAdd(&late_cnt[lv - base], 1u);
+                if (at < (uint32_t)TN_BUCKET) late_pos[(lv - base) * TN_BUCKET + at] = (uint16_t)s;
+                else atomicMin(&late_drop, lv);
             }
-            set_level(p, X, lv, x);
-            if (pl >= 0) set_level(pl, tp, lv2, x2);
+        };
+        Probe pr[4];
+        int slot[4];
+        uint32_t tokv[4];
+        bool on[4] = {false, false, false, false};
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            if (!mine[e]) continue;
+            const uint32_t X = cell[p[e]] & 0xFFFFu;
+            const int n = p[e] + (int)len[p[e]];
+            slot[2 * e] = p[e]; tokv[2 * e] = X;
+            if (n < W) { on[2 * e] = true; probe_start(pr[2 * e], X, cell[n] & 0xFFFFu); }
+            else set_level(p[e], X, TL_INF, 0u);
+            if (p[e] > 0) {
+                const int e1 = p[e] - 1, pl = e1 - (int)back[e1];
+                const uint32_t tp = cell[pl] & 0xFFFFu;
+                slot[2 * e + 1] = pl; tokv[2 * e + 1] = tp;
+                on[2 * e + 1] = true;
+                probe_start(pr[2 * e + 1], tp, X);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (!on[i]) continue;
+            uint32_t x = 0;
+            const uint32_t lv = probe_finish(pr[i], &x);
+            set_level(slot[i], tokv[i], lv, x);
         }
         if (whole_cta) __syncthreads(); else __syncwarp();
     };
-    // all entries of level rr: its segment of `sorted`, then the entries chained to it; G threads, one entry each per chunk
+    // all entries of level rr: its segment of `sorted`, then its late bucket; G threads, two entries each per chunk
     auto round = [&](uint32_t rr, uint32_t base, uint32_t hi, bool whole_cta) {
         const int G = whole_cta ? NT : 32, g = whole_cta ? t : (t & 31);
         const uint32_t li = rr - base;
         const uint32_t n_seg = cnt[li] < (uint32_t)TN_QCAP - start[li] ? cnt[li] : (uint32_t)TN_QCAP - start[li], s0 = start[li];
         const uint32_t n_late = late_cnt[li] < (uint32_t)TN_BUCKET ? late_cnt[li] : (uint32_t)TN_BUCKET;
         const uint32_t n_all = n_seg + n_late;
-        for (uint32_t k = 0; k < n_all; k += (uint32_t)G) {
-            const uint32_t e = k + (uint32_t)g;
-            const bool valid = e < n_all;
-            const int p = !valid ? 0 : (e < n_seg ? (int)sorted[s0 + e] : (int)late_pos[li * TN_BUCKET + (e - n_seg)]);
+        for (uint32_t k = 0; k < n_all; k += 2u * (uint32_t)G) {
+            int p[2];
+            bool valid[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const uint32_t idx = k + (uint32_t)e * (uint32_t)G + (uint32_t)g;
+                valid[e] = idx < n_all;
+                p[e] = !valid[e] ? 0 : (idx < n_seg ? (int)sorted[s0 + idx] : (int)late_pos[li * TN_BUCKET + (idx - n_seg)]);
+            }
             chunk(rr, base, hi, p, valid, whole_cta);
         }
     };
@@ -260,6 +290,7 @@ __global__ void __launch_bounds__(TN_THREADS, 3) tilenc_kernel(const uint8_t* __
         uint32_t hi = base + (uint32_t)TN_RANGE;
         if (hi > max_level + 1u) hi = max_level + 1u;
         const uint32_t nl = hi - base;
+        if (dbg && t == 0) atomicAdd(&dbg[0], 1u);
         __syncthreads();  // everybody has read the state of the previous range
         for (uint32_t i = (uint32_t)t; i < (uint32_t)TN_RANGE; i += NT) { cnt[i] = 0; fill[i] = 0; late_cnt[i] = 0; }
         if (t == 0) { late_drop = 0xFFFFu; s_progress = 0; }
@@ -321,7 +352,7 @@ __global__ void __launch_bounds__(TN_THREADS, 3) tilenc_kernel(const uint8_t* __
             if (t < 32) {
                 // sparse levels: one warp, no CTA barrier
                 while (rr < hi && rr < late_drop && !s_fail && cnt[rr - base] + late_cnt[rr - base] <= (uint32_t)TN_SPARSE) {
-                    if (cnt[rr - base] + late_cnt[rr - base]) round(rr, base, hi, false);
+                    if (cnt[rr - base] + late_cnt[rr - base]) { round(rr, base, hi, false); if (dbg && t == 0) atomicAdd(&dbg[1], 1u); }
                     rr++;
                 }
                 if (t == 0) s_rr = rr;
@@ -330,6 +361,7 @@ __global__ void __launch_bounds__(TN_THREADS, 3) tilenc_kernel(const uint8_t* __
             rr = s_rr;
             if (rr >= hi || rr >= late_drop || s_fail) break;
             round(rr, base, hi, true);  // a dense level: the whole CTA (ends with a barrier)
+            if (dbg && t == 0) atomicAdd(&dbg[partial ? 3 : 2], 1u);
             rr++;
         }
         if (partial) {

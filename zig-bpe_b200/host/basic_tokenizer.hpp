@@ -71,6 +71,8 @@ public:
         timeStats.sort_pairs_time += (int64_t)st.sort_pairs_ms; timeStats.sort_pairs_calls += st.sort_pairs_calls;
         timeStats.replace_pair_time += (int64_t)st.replace_pair_ms; timeStats.replace_pair_calls += st.replace_pair_calls;
         timeStats.just_count_pairs_time += (int64_t)st.just_count_pairs_ms; timeStats.just_count_pairs_calls += st.just_count_pairs_calls;
+        // generateInitialTokens' own line (:156-160); the widening is the load kernel here
+        std::fprintf(stderr, "generateInitialTokens runtime: %.3f seconds\n", st.kernel_ms[0] / 1000.0);
         if (rc == BPE_ERR_INVALID_VOCAB) { printTimeStats(timeStats, (int64_t)st.total_ms); throw InvalidVocabSize(); }
         if (rc != BPE_OK) { printTimeStats(timeStats, (int64_t)st.total_ms); throw OutOfMemory(bpe_last_error(ctx_)); }
         for (size_t i = 0; i < n; i++) {
@@ -89,6 +91,7 @@ public:
         size_t n = 0;
         int rc = bpe_encode(ctx_, reinterpret_cast<const uint8_t*>(text.data()), text.size(), ms.data(), ms.size(), out.data(), &n, nullptr);
         if (rc != BPE_OK) throw OutOfMemory(bpe_last_error(ctx_));
+        std::fprintf(stderr, "generateInitialTokens runtime: 0.000 seconds\n");  // encode calls it too (:72); fused away here
         out.resize(n);
         return out;
     }
@@ -103,6 +106,7 @@ public:
         rc = bpe_decode(ctx_, tokens.data(), tokens.size(), ms.data(), ms.size(), reinterpret_cast<uint8_t*>(&out[0]), need, &n, nullptr);
         if (rc == BPE_ERR_INVALID_TOKEN) throw InvalidToken();
         if (rc != BPE_OK) throw OutOfMemory(bpe_last_error(ctx_));
+        std::fprintf(stderr, "generateInitialTokens runtime: 0.000 seconds\n");  // encode calls it too (:72); fused away here
         out.resize(n);
         return out;
     }
@@ -114,7 +118,11 @@ public:
         std::fclose(f);
     }
 
-    void deserializeMerges(const std::string& path) {  // :332-348: 100-byte line buffer, parseInt(u16), appends
+    void deserializeMerges(const std::string& path) { readMergesFile(path, merges); }  // :332-348
+
+    // the reader itself (no GPU involved): 100-byte line buffer, parseInt(u16), appends; merges parsed before a bad
+    // line stay appended, as in the reference
+    static void readMergesFile(const std::string& path, std::vector<Merge>& into) {
         FILE* f = std::fopen(path.c_str(), "rb");
         if (!f) throw std::runtime_error("FileNotFound: " + path);
         while (true) {
@@ -138,7 +146,7 @@ public:
                 try { v[k] = parse_u16(line + start, pos - start); } catch (...) { std::fclose(f); throw; }
                 pos++;  // skip ',' (or step past the end: no further field)
             }
-            put({v[0], v[1]}, v[2]);
+            into.push_back({{v[0], v[1]}, v[2]});
             if (eof) break;
         }
         std::fclose(f);
