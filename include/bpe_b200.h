@@ -115,8 +115,10 @@ const char* bpe_last_error(const bpe_ctx* ctx);
  *                         3: 32 + 2 x 12 (tests)
  *   "encode_grid"         CTAs per SM of a level pass (default 6; they take the tiles round-robin); 0: one CTA per
  *                         tile; negative: absolute CTA count (tests).
- *   "encode_filter"       1 (default): level pass with one role byte per id and an in-register successor filter (used when
- *                         every id of the list is below 16384); 0: 1-bit role map over all ids.
+ *   "encode_filter"       candidate filter of a level pass. 2 (default): a 65,536-bit Bloom filter over the level's PAIRS, probed
+ *                         with the pair a slot forms with its successor slot, so that practically only real occurrences reach
+ *                         the hash look-up; 1: one role byte per id and an in-register successor filter (used when every id of
+ *                         the list is below 16384); 0: 1-bit first-component map over all ids.
  *   "merge_impl"          0 (default): register-streaming merge kernel, one CTA per tile;
  *                         1: merge pass fed by a TMA ring (cp.async.bulk + mbarrier, persistent CTAs) —
  *                            measured slower on B200 for this access pattern, kept for comparison

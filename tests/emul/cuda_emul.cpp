@@ -54,6 +54,12 @@ void sync_threads() {
     swapcontext(&g_ctx[g_cur], &g_sched);
 }
 
+// a spinning thread lets the other threads of its block run (the fibers are cooperative; on a GPU they run anyway)
+void yield_thread() {
+    if (!g_in_fiber) return;
+    swapcontext(&g_ctx[g_cur], &g_sched);  // state stays "ready": it is resumed in the next sweep
+}
+
 uint32_t warp_exchange(uint32_t v, int op, uint32_t arg) {
     if (!g_in_fiber) { fprintf(stderr, "emul: warp intrinsic in a BPE_LAUNCH_NS kernel\n"); abort(); }
     int me = g_cur;

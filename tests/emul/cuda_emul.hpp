@@ -42,6 +42,7 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 namespace emul {
 extern dim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
 void sync_threads();
+void yield_thread();
 void launch(dim3 grid, dim3 block, const std::function<void()>& body, bool uses_sync);
 uint32_t warp_exchange(uint32_t v, int op, uint32_t arg);  // see cuda_emul.cpp
 extern uint64_t g_launches;
@@ -52,6 +53,9 @@ extern uint64_t g_launches;
 #define blockDim (emul::g_blockDim)
 #define gridDim (emul::g_gridDim)
 static inline void __syncthreads() { emul::sync_threads(); }
+#define BPE_SPIN_YIELD() emul::yield_thread()
+#define BPE_GRID_DEP_WAIT() ((void)0)
+#define BPE_GRID_DEP_LAUNCH() ((void)0)
 namespace emul { extern int g_sync_or_acc[2]; extern int g_sync_or_phase; }
 static inline int __syncthreads_or(int pred) {
     // two alternating accumulators so that back-to-back calls do not interfere
@@ -68,6 +72,10 @@ static inline void __syncwarp(unsigned = 0xffffffffu) { (void)emul::warp_exchang
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 template <class T> static inline T __ldcg(const T* p) { return *p; }
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+// 8-byte cells shared between processes (peer mailboxes in the tests): single 64-bit accesses, as on the GPU
+static inline void __stcg(uint2* p, uint2 v) { __atomic_store_n(reinterpret_cast<uint64_t*>(p), (uint64_t)v.x | ((uint64_t)v.y << 32), __ATOMIC_RELEASE); }
+static inline uint2 __ldcv(const uint2* p) { const uint64_t w = __atomic_load_n(reinterpret_cast<const uint64_t*>(p), __ATOMIC_ACQUIRE); return uint2{(uint32_t)w, (uint32_t)(w >> 32)}; }
 
 // ---- atomics (single OS thread: plain read-modify-write) --------------------------------
 template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = (T)(o + v); return o; }
@@ -141,6 +149,8 @@ static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEve
 #define BPE_LAUNCH(kern, grid, block, stream, ...) \
     emul::launch(dim3(grid), dim3(block), [&]() { kern(__VA_ARGS__); }, true)
 #define BPE_LAUNCH_SMEM(kern, grid, block, smem, stream, ...) \
+    emul::launch(dim3(grid), dim3(block), [&]() { kern(__VA_ARGS__); }, true)
+#define BPE_LAUNCH_PDL(kern, grid, block, stream, pdl, ...) \
     emul::launch(dim3(grid), dim3(block), [&]() { kern(__VA_ARGS__); }, true)
 namespace emul { extern uint32_t g_dyn_smem[64 * 1024]; }
 static inline uint32_t* bpe_dyn_smem() { return emul::g_dyn_smem; }  // up to 256 KB of "dynamic shared memory"

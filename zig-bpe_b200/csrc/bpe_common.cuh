@@ -23,6 +23,23 @@
 #define BPE_LAUNCH(kern, grid, block, stream, ...) kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 #define BPE_LAUNCH_NS(kern, grid, block, stream, ...) kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 #define BPE_LAUNCH_SMEM(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define BPE_SPIN_YIELD() ((void)0)
+// Programmatic dependent launch (sm_90+): a kernel launched with the attribute may start while its predecessor in the
+// stream is still draining; it must not touch anything the predecessor writes before BPE_GRID_DEP_WAIT() returns
+// (the predecessor has completed and its writes are visible then). BPE_GRID_DEP_LAUNCH() lets the successor start.
+#define BPE_GRID_DEP_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define BPE_GRID_DEP_LAUNCH() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+template <class... KArgs, class... Args>
+static inline cudaError_t bpe_launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, int pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#define BPE_LAUNCH_PDL(kern, grid, block, stream, pdl, ...) bpe_launch_pdl(kern, (grid), (block), 0, (stream), (pdl), __VA_ARGS__)
 extern __shared__ __align__(128) uint32_t bpe_dyn_smem_[];
 __device__ __forceinline__ uint32_t* bpe_dyn_smem() { return bpe_dyn_smem_; }
 
@@ -171,11 +188,10 @@ static_assert(sizeof(EdgeInfo) == 64, "EdgeInfo is 16 words");
 // [2 parities][world slots][xw words] + one arrival flag per sender; peers write their deltas straight
 // into it and raise their flag, the consumer sums the slots while it applies them.
 constexpr int MAX_PEERS = 8;
-constexpr uint32_t PEER_FLAG_STRIDE = 1056;  // flags per sender: one per apply CTA (at most (4 * 65536 + 3 + 255) / 256 = 1025)
 struct PeerSet {
-    uint32_t* mbox[MAX_PEERS];   // mailbox base of every rank (own entry = local pointer)
-    uint32_t* flags[MAX_PEERS];  // flags[p][sender * PEER_FLAG_STRIDE + cta] on rank p
-    uint32_t slot_words;         // capacity of one mailbox slot in words
+    uint32_t* mbox[MAX_PEERS];   // mailbox base of every rank (own entry = local pointer): [2 parities][world senders][slot_words] cells
+    uint32_t* flags[MAX_PEERS];  // (spare words behind the mailbox; the cells carry their own tags)
+    uint32_t slot_words;         // cells per mailbox slot; a cell is 8 bytes {value, epoch}
 };
 
 // Per-tile neighbourhood, produced by halo_kernel before each merge pass: what a tile needs to

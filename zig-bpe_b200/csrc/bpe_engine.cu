@@ -58,7 +58,7 @@ struct bpe_ctx {
     std::string err;
     // options
     long verify_recount = 0, force_slow_tiebreak = 0, check_tiebreak = 0, compact_pct = 85, table_log2 = 0,
-         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 6, encode_filter = 1, encode_geom = 4, encode_seg_min_steps = 450, encode_tile = 7936, encode_try_tiles = 1, fuse_halo = 1, count_limit_log2 = 32, stream_chunk_mb = 128, stream_chunk_bytes = 0, merge_filter = 0, batch_steps = 16;
+         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 6, encode_filter = 1, encode_geom = 4, encode_seg_min_steps = 450, encode_tile = 7936, encode_try_tiles = 1, fuse_halo = 1, count_limit_log2 = 32, stream_chunk_mb = 128, stream_chunk_bytes = 0, merge_filter = 0, batch_steps = 16, pdl = 1;
     int num_sms = 148;
     DistComm dist;  // world == 1 when single GPU
     uint64_t launches = 0;
@@ -501,12 +501,13 @@ static int launch_merge(bpe_ctx* ctx, TokT* tok, const TileHalo<TokT>* halo, uin
         BPE_LAUNCH_SMEM(kern, grid, THREADS, ring_smem_bytes<TokT>(), ctx->stream, tok, halo, d_ctl, cntL, cntR, nxx, nab, A, B, X,
                         bins_min, nt);
     } else {
+        const int pdl = (FROMCTL && ctx->pdl) ? 1 : 0;  // train loop: programmatic dependent of the previous apply kernel
         if (ctx->merge_filter)
-            BPE_LAUNCH((merge_kernel<TokT, DELTAS, FROMCTL, true>), nt, THREADS, ctx->stream, tok, halo, d_ctl, cntL, cntR, nxx, nab, A, B, X, bins_min,
-                       backwards);
+            BPE_LAUNCH_PDL((merge_kernel<TokT, DELTAS, FROMCTL, true>), nt, THREADS, ctx->stream, pdl, tok, halo, d_ctl, cntL, cntR, nxx, nab, A, B, X, bins_min,
+                           backwards);
         else
-            BPE_LAUNCH((merge_kernel<TokT, DELTAS, FROMCTL, false>), nt, THREADS, ctx->stream, tok, halo, d_ctl, cntL, cntR, nxx, nab, A, B, X, bins_min,
-                       backwards);
+            BPE_LAUNCH_PDL((merge_kernel<TokT, DELTAS, FROMCTL, false>), nt, THREADS, ctx->stream, pdl, tok, halo, d_ctl, cntL, cntR, nxx, nab, A, B, X, bins_min,
+                           backwards);
     }
     ctx->launches++;
     return BPE_OK;
@@ -579,9 +580,10 @@ static int enqueue_step_tail(bpe_ctx* ctx, TrainRun& R, uint32_t n_ids, uint32_t
     ha.step1 = step_index + 1u;
     if (ctx->fuse_halo == 0 || ctx->merge_impl != 0) ha.tok = nullptr;
     const uint32_t grid = ha.apply_blocks + (ha.tok ? (nt + 255) / 256 : 0u);
-    BPE_LAUNCH(apply_kernel, grid, 256, ctx->stream, R.tm.view(), R.delta.as<uint32_t>(), R.vcap, R.d_ctl(),
-                  R.tm.zig(), n_ids, R.hl(), R.d_rec(), fuse_select ? 1 : 0, peer ? 1 : 0, ctx->dist.peers, ctx->dist.rank, ctx->dist.world,
-                  parity, epoch, (uint32_t)R.edge_off, ha, pa);
+    // (a programmatic dependent of the merge pass when nothing else was enqueued in between)
+    BPE_LAUNCH_PDL(apply_kernel, grid, 256, ctx->stream, (ctx->pdl && (peer || ctx->dist.world == 1)) ? 1 : 0, R.tm.view(), R.delta.as<uint32_t>(), R.vcap, R.d_ctl(),
+                   R.tm.zig(), n_ids, R.hl(), R.d_rec(), fuse_select ? 1 : 0, peer ? 1 : 0, ctx->dist.peers, ctx->dist.rank, ctx->dist.world,
+                   parity, epoch, (uint32_t)R.edge_off, ha, pa);
     ctx->launches += 1;
     CU(cudaGetLastError());
     return BPE_OK;
@@ -1473,12 +1475,15 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
         CU(cudaFuncSetAttribute(level_kernel<TokT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)level_smem_bytes<TokT>(LVL_HASH_MAX)));
         CU(cudaFuncSetAttribute(level_kernel<TokT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)level_smem_bytes<TokT>(LVL_HASH_MAX, LVL_BYTE_IDS_MAX / 4)));
+        CU(cudaFuncSetAttribute(level_kernel<TokT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)level_smem_bytes<TokT>(LVL_HASH_MAX, 2 * LVL_ROLE_WORDS)));
     }
     // encode_filter = 1: byte role map + successor filter (level_kernel MODE 1) when every id fits the byte map
     uint32_t max_id = 255;
     for (size_t i = 0; i < m; i++) max_id = std::max(max_id, (uint32_t)std::max(merges[i].first, std::max(merges[i].second, merges[i].new_token)));
+    const bool pair_bloom = ctx->encode_filter == 2;
     const bool byte_roles = ctx->encode_filter == 1 && max_id < (uint32_t)LVL_BYTE_IDS_MAX;
-    const uint32_t role_words = byte_roles ? ((max_id + 1u + 15u) / 16u) * 4u : (uint32_t)LVL_ROLE_WORDS;
+    const uint32_t role_words = pair_bloom ? 2u * (uint32_t)LVL_ROLE_WORDS : byte_roles ? ((max_id + 1u + 15u) / 16u) * 4u : (uint32_t)LVL_ROLE_WORDS;
     // ent_cnt == 0: one merge pass for (A,B) -> X; else one level pass over ents[ent_off, ent_off + ent_cnt)
     auto one_pass = [&](uint32_t A, uint32_t B, uint32_t X, uint32_t ent_off = 0, uint32_t ent_cnt = 0) -> int {
         const uint32_t nt = sq.ntiles();
@@ -1505,7 +1510,10 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
             const size_t smem = level_smem_bytes<TokT>((int)(1u << hash_log2), (int)role_words);
             const TileHalo<TokT>* halo_p = sq.halo.template as<TileHalo<TokT>>();
             const LevelEntry* ents_p = (const LevelEntry*)ents_buf.template as<LevelEntry>() + ent_off;
-            if (byte_roles)
+            if (pair_bloom)
+                BPE_LAUNCH_SMEM((level_kernel<TokT, 2>), grid, THREADS, smem, ctx->stream, sq.tok(), halo_p, ents_p, ent_cnt, &d_ctl->cntAB, backwards,
+                                nt, hash_log2, role_words);
+            else if (byte_roles)
                 BPE_LAUNCH_SMEM((level_kernel<TokT, 1>), grid, THREADS, smem, ctx->stream, sq.tok(), halo_p, ents_p, ent_cnt, &d_ctl->cntAB, backwards,
                                 nt, hash_log2, role_words);
             else
@@ -1967,6 +1975,7 @@ int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value) {
     else if (s == "count_limit_log2") ctx->count_limit_log2 = value;
     else if (s == "merge_filter") ctx->merge_filter = value;
     else if (s == "batch_steps") ctx->batch_steps = value;
+    else if (s == "pdl") ctx->pdl = value;
     else if (s == "stream_chunk_mb") ctx->stream_chunk_mb = value;
     else if (s == "stream_chunk_bytes") ctx->stream_chunk_bytes = value;
     else return fail(ctx, BPE_ERR_INVALID_ARG, "unknown option '%s'", name);

@@ -472,27 +472,53 @@ constexpr int HALO_THREADS = 128;
 // Where a shard's neighbours' end tokens come from: the local copy of the exchanged EdgeInfo slots (single GPU:
 // none; NCCL path and host-driven passes: the exchange buffer) or, inside the fused apply + halo kernel of the
 // peer-memory path, the mailbox slots themselves (valid once the sender's arrival flag shows this step's epoch).
-__device__ __forceinline__ void peer_wait(const uint32_t* flags, uint32_t idx, uint32_t epoch, uint32_t* err) {
+// Mailbox cells are 8 bytes: {value, epoch}. One 8-byte store carries the value together with the tag that says which
+// step it belongs to, so a reader needs neither a separate arrival flag nor a fence between data and flag (the
+// "flag in data" scheme of low-latency collectives): it polls the cell until the tag is the step's epoch. Epochs grow
+// monotonically over steps and trainings, so a stale cell can never be mistaken for a fresh one.
+#ifdef BPE_EMUL
+constexpr uint32_t PEER_SPIN_LIMIT = 0xFFFFFFF0u;  // (the emulated peers are processes that take seconds per step)
+#else
+constexpr uint32_t PEER_SPIN_LIMIT = 1u << 24;
+#endif
+__device__ __forceinline__ void peer_put(uint32_t* mbox, size_t cell, uint32_t value, uint32_t epoch) {
+    __stcg(reinterpret_cast<uint2*>(mbox) + cell, make_uint2(value, epoch));
+}
+__device__ __forceinline__ uint32_t peer_get(const uint32_t* mbox, size_t cell, uint32_t epoch, uint32_t* err) {
     uint32_t spins = 0;
-    while ((int32_t)(((volatile const uint32_t*)flags)[idx] - epoch) < 0) {
-        if (++spins > (1u << 28)) { atomicOr(err, (uint32_t)ERR_PEER_TIMEOUT); break; }
+    while (true) {
+        const uint2 v = __ldcv(reinterpret_cast<const uint2*>(mbox) + cell);
+        if (v.y == epoch) return v.x;
+        BPE_SPIN_YIELD();
+        if (++spins > PEER_SPIN_LIMIT) { atomicOr(err, (uint32_t)ERR_PEER_TIMEOUT); return 0u; }  // (seconds: a peer is gone)
     }
 }
 struct EdgeSrc {
     const EdgeInfo* local;      // nullptr: single GPU
-    const uint32_t* mbox;       // != nullptr: read rank r's EdgeInfo from mbox + r * slot_words + edge_off + r * 16
-    const uint32_t* flags;      // arrival flags of this rank's mailbox
+    const uint32_t* mbox;       // != nullptr: read rank r's EdgeInfo from the tagged cells r * slot_words + edge_off + r * 16 ...
+    const uint32_t* flags;      // (unused)
     uint32_t slot_words, edge_off, epoch;
     uint32_t* err;
 };
 __device__ __forceinline__ EdgeInfo edge_get(const EdgeSrc& es, int r) {
     if (!es.mbox) return es.local[r];
-    peer_wait(es.flags, (uint32_t)r * PEER_FLAG_STRIDE, es.epoch, es.err);  // the sender's CTA 0 sends its EdgeInfo
-    __threadfence();
     EdgeInfo e;
-    const uint32_t* src = es.mbox + (size_t)r * es.slot_words + es.edge_off + (uint32_t)r * 16u;
+    const size_t c0 = (size_t)r * es.slot_words + es.edge_off + (uint32_t)r * 16u;
     uint32_t* dst = reinterpret_cast<uint32_t*>(&e);
-    for (int w = 0; w < 16; w++) dst[w] = __ldcg(src + w);
+    // all 16 cells are requested before any tag is looked at (one memory latency instead of sixteen)
+    const uint2* cells = reinterpret_cast<const uint2*>(es.mbox) + c0;
+    uint32_t spins = 0;
+    while (true) {
+        uint2 v[16];
+#pragma unroll
+        for (int w = 0; w < 16; w++) v[w] = __ldcv(cells + w);
+        bool ok = true;
+#pragma unroll
+        for (int w = 0; w < 16; w++) { ok = ok && v[w].y == es.epoch; dst[w] = v[w].x; }
+        if (ok) break;
+        BPE_SPIN_YIELD();
+        if (++spins > PEER_SPIN_LIMIT) { atomicOr(es.err, (uint32_t)ERR_PEER_TIMEOUT); break; }
+    }
     return e;
 }
 
@@ -701,12 +727,12 @@ __global__ void edge_kernel(const TokT* __restrict__ tok, size_t n_slots, size_t
     edge_body<TokT>(tok, n_slots, tail_hint, all, rank, world, ctl, nab_local, account, true);
 }
 
-// Peer-memory exchange (multi-GPU), inside the apply kernel. Every apply CTA owns the delta cells of 64 token ids
-// (the cells its threads fold into the table). Phase 1: the CTA stores its cells of THIS rank into slot `rank` of every
-// peer's mailbox over NVLink (CTA 0 also describes the shard's ends and sends its EdgeInfo), then raises the flag
-// (this rank, this CTA) on every peer. Phase 2: it waits for the same CTA's flag of every peer and reads a cell as
-// local value + the peers' slots. A CTA therefore depends only on the same-numbered CTA of the other ranks — never on
-// another CTA of its own grid — so transfer, reduction and table update are one kernel without a grid-wide wait.
+// Peer-memory exchange (multi-GPU), inside the apply kernel. Every apply thread owns one delta cell (the one it folds
+// into the table). It stores this rank's value of the cell, tagged with the step's epoch, into slot `rank` of every
+// peer's mailbox over NVLink (CTA 0 also describes the shard's ends and sends its EdgeInfo the same way), then reads
+// the cell as local value + the peers' values, polling each peer cell until it carries the epoch. A thread depends
+// only on the same thread of the other ranks — never on another CTA of its own grid, no flags, no fences — so
+// transfer, reduction and table update are one kernel and the exchange costs one NVLink store latency.
 struct PushArgs {
     size_t n_slots, tail_hint;  // sequence geometry for the shard-end scan
     const uint16_t* tok;
@@ -1048,9 +1074,16 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(Tok
     uint4 v[NV];
     bool any = false;
     TileHalo<TokT> h;
-    if (threadIdx.x == 0) h = halo[tile];
 #pragma unroll
     for (int k = 0; k < NV; k++) v[k] = src[k * THREADS + (int)threadIdx.x];
+    if (FROMCTL) {
+        // train loop: launched as a programmatic dependent of the apply kernel. The tile itself is only ever written
+        // by merge passes (all complete), so its loads are already in flight while that kernel finishes; the halos
+        // and the control block are its output.
+        BPE_GRID_DEP_WAIT();
+        BPE_GRID_DEP_LAUNCH();
+    }
+    if (threadIdx.x == 0) h = halo[tile];
     bool use_bins = false;  // dense steps privatise the deltas per CTA; sparse steps go straight to global
     if (FROMCTL) {
         if (ctl->halt) return;
@@ -1339,6 +1372,8 @@ __global__ void __launch_bounds__(256) apply_kernel(PairTable tbl, uint32_t* __r
                              ZigPop z, uint32_t n_ids, HeavyList hl, MergeRec* rec, int fuse_select,
                              int ps_on, PeerSet ps, int rank, int world, uint32_t parity, uint32_t epoch, uint32_t edge_off,
                              HaloArgs ha, PushArgs pa) {
+    BPE_GRID_DEP_WAIT();    // (launched as a programmatic dependent of the merge pass: everything below reads its output)
+    BPE_GRID_DEP_LAUNCH();  // the next merge pass may start and load its tiles; it waits for this kernel before anything else
     if (ha.tok ? (ctl->pass_step != ha.step1) : (ctl->halt != 0u)) return;  // this step did not run (the loop was halted before it)
     if (ha.tok && blockIdx.x >= ha.apply_blocks) {
         const uint32_t t = (blockIdx.x - ha.apply_blocks) * blockDim.x + threadIdx.x;
@@ -1347,8 +1382,8 @@ __global__ void __launch_bounds__(256) apply_kernel(PairTable tbl, uint32_t* __r
         es.local = world > 1 ? reinterpret_cast<const EdgeInfo*>(delta + edge_off) : nullptr;
         es.mbox = nullptr; es.flags = nullptr; es.slot_words = 0; es.edge_off = edge_off; es.epoch = epoch; es.err = &ctl->err;
         if (ps_on) {  // peer path: the neighbours' shard ends of this step sit in the mailbox (apply block 0 copies them later)
-            es.mbox = ps.mbox[rank] + (size_t)parity * (size_t)world * ps.slot_words;
-            es.flags = ps.flags[rank];
+            es.mbox = ps.mbox[rank] + 2 * ((size_t)parity * (size_t)world * ps.slot_words);
+            es.flags = nullptr;
             es.slot_words = ps.slot_words;
         }
         halo_gather<uint16_t>(ha.tok, ha.n_slots, t, ha.halo, es, rank, world);
@@ -1363,7 +1398,7 @@ __global__ void __launch_bounds__(256) apply_kernel(PairTable tbl, uint32_t* __r
     const uint32_t t0 = 4u * n_ids;  // three more threads: adjacent occurrences, the merged pair itself, bookkeeping
     const uint32_t my_cell = (p < n_ids) ? (side ? vcap + p : p) : (t == t0 ? 2u * vcap : (t == t0 + 2u ? 2u * vcap + 1u : 0xFFFFFFFFu));
     if (ps_on) {
-        // ---- phase 1: my cells of this rank's deltas into slot `rank` of every peer's mailbox ----
+        // ---- my cells of this rank's deltas into slot `rank` of every peer's mailbox (tagged 8-byte stores, no fence) ----
         const size_t slot = ((size_t)parity * (size_t)world + (size_t)rank) * ps.slot_words;
         if (blockIdx.x == 0) {
             EdgeInfo* edges = reinterpret_cast<EdgeInfo*>(delta + edge_off);
@@ -1371,33 +1406,31 @@ __global__ void __launch_bounds__(256) apply_kernel(PairTable tbl, uint32_t* __r
             __syncthreads();
             for (uint32_t i = threadIdx.x; i < 16u * (uint32_t)world; i += blockDim.x) {
                 const uint32_t q = i / 16u, w = i % 16u;
-                if ((int)q != rank) ps.mbox[q][slot + edge_off + (uint32_t)rank * 16u + w] = delta[edge_off + (uint32_t)rank * 16u + w];
+                if ((int)q != rank) peer_put(ps.mbox[q], slot + edge_off + (uint32_t)rank * 16u + w, delta[edge_off + (uint32_t)rank * 16u + w], epoch);
             }
         }
         if (my_cell != 0xFFFFFFFFu && (op == 0u || p >= n_ids)) {
             const uint32_t c_local = delta[my_cell];
-            for (int q = 0; q < world; q++) if (q != rank) ps.mbox[q][slot + my_cell] = c_local;
+            for (int q = 0; q < world; q++) if (q != rank) peer_put(ps.mbox[q], slot + my_cell, c_local, epoch);
         }
-        __threadfence_system();
-        __syncthreads();
-        if ((int)threadIdx.x < world && (int)threadIdx.x != rank)
-            *((volatile uint32_t*)&ps.flags[threadIdx.x][(uint32_t)rank * PEER_FLAG_STRIDE + blockIdx.x]) = epoch;
-        // ---- phase 2: the same CTA's cells from every peer ----
-        if ((int)threadIdx.x < world && (int)threadIdx.x != rank) {
-            peer_wait(ps.flags[rank], threadIdx.x * PEER_FLAG_STRIDE + blockIdx.x, epoch, &ctl->err);  // (CTA 0's flag also covers the EdgeInfo)
-        }
-        __syncthreads();
-        __threadfence();
-        mb = ps.mbox[rank] + (size_t)parity * (size_t)world * ps.slot_words;
+        mb = ps.mbox[rank] + 2 * ((size_t)parity * (size_t)world * ps.slot_words);
         if (blockIdx.x == 0 && threadIdx.x < 16u * (uint32_t)world) {  // gathered shard ends for host-driven halo passes
             const uint32_t r = threadIdx.x / 16u, w = threadIdx.x % 16u;
-            if ((int)r != rank) delta[edge_off + r * 16u + w] = __ldcg(mb + (size_t)r * ps.slot_words + edge_off + r * 16u + w);
+            if ((int)r != rank) delta[edge_off + r * 16u + w] = peer_get(mb, (size_t)r * ps.slot_words + edge_off + r * 16u + w, epoch, &ctl->err);
         }
     }
     auto cell_value = [&](uint32_t idx) -> uint32_t {
         uint32_t sum = delta[idx];
-        if (ps_on)
-            for (int r = 0; r < world; r++) if (r != rank) sum += __ldcg(mb + (size_t)r * ps.slot_words + idx);
+        if (ps_on) {
+            // the peers' cells, all requested at once; the ones that do not carry this step's tag yet are polled
+            uint2 v[MAX_PEERS];
+#pragma unroll
+            for (int r = 0; r < MAX_PEERS; r++)
+                if (r < world && r != rank) v[r] = __ldcv(reinterpret_cast<const uint2*>(mb) + ((size_t)r * ps.slot_words + idx));
+#pragma unroll
+            for (int r = 0; r < MAX_PEERS; r++)
+                if (r < world && r != rank) sum += v[r].y == epoch ? v[r].x : peer_get(mb, (size_t)r * ps.slot_words + idx, epoch, &ctl->err);
+        }
         return sum;
     };
     const uint32_t A = ctl->A, B = ctl->B, X = ctl->X;
@@ -1522,8 +1555,11 @@ struct LevelEntry { uint32_t key; uint32_t z; };
 constexpr int LVL_MAX = 1024;        // pairs per pass (larger levels are split; any subset of a level is a level)
 constexpr int LVL_HASH_MAX = 2048;   // hash slots for LVL_MAX pairs; smaller levels use fewer (power of two >= 2 * pairs)
 constexpr int LVL_ROLE_WORDS = 65536 / 32;  // 1 bit per id: "first component of a pair of this level"
+constexpr int LVL_QCAP = 2048;              // candidates of a tile worked off through the CTA-wide queue
 constexpr int LVL_BYTE_IDS_MAX = 16384;     // MODE 1 keeps one role byte per id (ids below this bound)
-// MODE 0: role_words = LVL_ROLE_WORDS (bitmap over all ids); MODE 1: role_words = ids / 4 (one byte per id)
+// MODE 0: role_words = LVL_ROLE_WORDS (bitmap over all ids); MODE 1: role_words = ids / 4 (one byte per id);
+// MODE 2: role_words = 2 * LVL_ROLE_WORDS (first-component bitmap + a 65,536-bit Bloom filter over the level's PAIRS)
+__host__ __device__ __forceinline__ uint32_t lvl_pair_hash(uint32_t a, uint32_t b) { return ((a * 40503u) ^ (b * 30011u) ^ (b >> 5)) & 0xFFFFu; }
 template <class TokT> __host__ __device__ constexpr size_t level_smem_bytes(int hash_slots, int role_words = LVL_ROLE_WORDS) {
     return (size_t)EXT * sizeof(TokT) + (size_t)role_words * 4 + (size_t)hash_slots * 4 + (size_t)hash_slots * 2;
 }
@@ -1553,6 +1589,10 @@ __device__ __forceinline__ uint32_t lvl_find(const uint32_t* hkey, const uint16_
 // ids < role_words * 4 <= LVL_BYTE_IDS_MAX) and a register-level filter — a slot stays a candidate only if its
 // in-vector successor is a second component of the level, a hole, or out of the vector — so that far fewer slots reach
 // the hash look-up.
+// MODE 2 (encode_filter = 2): the filter looks at the PAIR a slot forms with its successor slot (the next vector's first slot
+// comes in by shuffle): one bit of a 65,536-bit Bloom filter over the level's pairs decides (false positives ~ pairs / 65,536),
+// so that practically only real occurrences reach the hash look-up; a slot whose successor slot is a hole (or unknown) falls
+// back to the first-component bitmap.
 template <class TokT, int MODE>
 __global__ void __launch_bounds__(THREADS, sizeof(TokT) == 2 ? 6 : 4) level_kernel(TokT* __restrict__ tok, const TileHalo<TokT>* __restrict__ halo,
                                                         const LevelEntry* __restrict__ ents, uint32_t n_ent, uint32_t* nab_out,
@@ -1561,23 +1601,30 @@ __global__ void __launch_bounds__(THREADS, sizeof(TokT) == 2 ? 6 : 4) level_kern
     TokT* ext = reinterpret_cast<TokT*>(raw);
     uint32_t* role = reinterpret_cast<uint32_t*>(raw + (size_t)EXT * sizeof(TokT));
     if (MODE == 0) role_words = LVL_ROLE_WORDS;
+    if (MODE == 2) role_words = 2 * LVL_ROLE_WORDS;
     const unsigned char* role8 = reinterpret_cast<const unsigned char*>(role);
     uint32_t* hkey = role + role_words;
     const uint32_t hash_slots = 1u << hash_log2, hash_mask = hash_slots - 1u, hash_shift = 32u - hash_log2;
     uint16_t* hval = reinterpret_cast<uint16_t*>(hkey + hash_slots);
     __shared__ uint32_t sh_n;
+    __shared__ uint32_t lq_n;
+    __shared__ uint16_t lq_pos[LVL_QCAP];
     constexpr int VEC = 16 / (int)sizeof(TokT);
     constexpr int NV = TILE / VEC / THREADS;
     static_assert(NV * VEC <= 32, "candidate mask is 32 bits");
     const uint32_t H = TokTraits<TokT>::hole;
     for (uint32_t i = threadIdx.x; i < role_words; i += THREADS) role[i] = 0u;
     for (uint32_t i = threadIdx.x; i < hash_slots; i += THREADS) hkey[i] = EMPTY_KEY;
-    if (threadIdx.x == 0) sh_n = 0u;
+    if (threadIdx.x == 0) { sh_n = 0u; lq_n = 0u; }
     __syncthreads();
     for (uint32_t e = threadIdx.x; e < n_ent; e += THREADS) {
         const uint32_t key = ents[e].key, a = key & 0xFFFFu;
         if (MODE == 0) {
             atomicOr(&role[a >> 5], 1u << (a & 31u));
+        } else if (MODE == 2) {
+            const uint32_t h = lvl_pair_hash(a, key >> 16);
+            atomicOr(&role[a >> 5], 1u << (a & 31u));
+            atomicOr(&role[LVL_ROLE_WORDS + (h >> 5)], 1u << (h & 31u));
         } else {
             const uint32_t b = key >> 16;
             atomicOr(&role[a >> 2], 1u << ((a & 3u) * 8u));
@@ -1621,6 +1668,20 @@ __global__ void __launch_bounds__(THREADS, sizeof(TokT) == 2 ? 6 : 4) level_kern
                     const uint32_t bit = (role[t >> 5] >> (t & 31u)) & 1u;
                     cand |= ((sizeof(TokT) == 4 && tv[i] == H) ? 0u : bit) << (k * VEC + i);
                 }
+            } else if (MODE == 2) {
+                uint32_t nf = __shfl_down_sync(0xffffffffu, tv[0], 1);  // first slot of the next vector (every lane takes part)
+                if ((threadIdx.x & 31u) == 31u) nf = H;                    // unknown: treated like a hole
+                uint32_t cm = 0;
+#pragma unroll
+                for (int i = 0; i < VEC; i++) {
+                    const uint32_t a = tv[i], b = (i + 1 < VEC) ? tv[i + 1] : nf;
+                    const uint32_t ai = a & 0xFFFFu, h = lvl_pair_hash(ai, b & 0xFFFFu);
+                    const bool pair_known = b != H;
+                    const uint32_t w = pair_known ? (uint32_t)LVL_ROLE_WORDS + (h >> 5) : (ai >> 5), sh = pair_known ? (h & 31u) : (ai & 31u);
+                    const uint32_t bit = (role[w] >> sh) & 1u;
+                    cm |= (a != H ? bit : 0u) << i;
+                }
+                cand |= cm << (k * VEC);
             } else {
                 uint32_t fm = 0, sm = 0;  // first-component slots; slots that are a second component or a hole
 #pragma unroll
@@ -1634,6 +1695,27 @@ __global__ void __launch_bounds__(THREADS, sizeof(TokT) == 2 ? 6 : 4) level_kern
             }
         }
         // (u16 slots never hold id 65535 as a token, so its role bit is never set and holes drop out by themselves)
+        // The candidates are unevenly spread over the lanes (a walk with 5 of 32 lanes busy was half of the kernel's
+        // instructions, profiles/r02_level_kernel_and_tilenc_v5.csv): they go through a CTA-wide queue and are worked
+        // off with all lanes busy; what does not fit the queue is handled in place by its own thread.
+        auto process = [&](int s) {
+            const int j = next_live(ext, s);
+            if (j < 0) return;
+            const uint32_t z = lvl_find(hkey, hval, pair_key((uint32_t)ext[s], (uint32_t)ext[j]), hash_shift, hash_mask);
+            if (z == EMPTY_KEY) return;
+            ext[s] = (TokT)z;
+            if (j < OFF + TILE) ext[j] = (TokT)H;
+            merged++;
+        };
+        uint32_t at = cand ? atomicAdd(&lq_n, (uint32_t)__popc(cand)) : 0u;
+        uint32_t late = 0;  // my candidates that did not fit the queue
+        while (cand) {
+            const int c = __ffs((int)cand) - 1;
+            cand &= cand - 1u;
+            if (at < (uint32_t)LVL_QCAP) lq_pos[at] = (uint16_t)(OFF + ((c / VEC) * THREADS + (int)threadIdx.x) * VEC + (c % VEC));
+            else late |= 1u << c;
+            at++;
+        }
         __syncthreads();
         // (2) the tile's first live token may be the second component of a pair that starts in the previous tile
         if (threadIdx.x == 0) {
@@ -1642,19 +1724,17 @@ __global__ void __launch_bounds__(THREADS, sizeof(TokT) == 2 ? 6 : 4) level_kern
             if (p != H && f >= 0 && f < OFF + TILE && lvl_find(hkey, hval, pair_key(p, (uint32_t)ext[f]), hash_shift, hash_mask) != EMPTY_KEY)
                 ext[f] = (TokT)H;
         }
-        while (cand) {
-            const int c = __ffs((int)cand) - 1;
-            cand &= cand - 1u;
-            const int s = OFF + ((c / VEC) * THREADS + (int)threadIdx.x) * VEC + (c % VEC);
-            const int j = next_live(ext, s);
-            if (j < 0) continue;
-            const uint32_t z = lvl_find(hkey, hval, pair_key((uint32_t)ext[s], (uint32_t)ext[j]), hash_shift, hash_mask);
-            if (z == EMPTY_KEY) continue;
-            ext[s] = (TokT)z;
-            if (j < OFF + TILE) ext[j] = (TokT)H;
-            merged++;
+        {
+            const uint32_t nq = lq_n < (uint32_t)LVL_QCAP ? lq_n : (uint32_t)LVL_QCAP;
+            for (uint32_t i = threadIdx.x; i < nq; i += THREADS) process((int)lq_pos[i]);
+        }
+        while (late) {
+            const int c = __ffs((int)late) - 1;
+            late &= late - 1u;
+            process(OFF + ((c / VEC) * THREADS + (int)threadIdx.x) * VEC + (c % VEC));
         }
         __syncthreads();
+        if (threadIdx.x == 0) lq_n = 0u;  // (the next tile's pushes come after the barrier at the top of the loop)
         // (3) write back what changed
 #pragma unroll
         for (int k = 0; k < NV; k++) {

@@ -103,7 +103,7 @@ struct DistComm {
     bool init_peers(std::string* err) {
         if (world < 2 || world > MAX_PEERS) { if (err) *err = "peer exchange supports 2..8 ranks"; return false; }
         const size_t slot = mbox_slot_words();
-        const size_t words = (size_t)2 * world * slot + (size_t)MAX_PEERS * PEER_FLAG_STRIDE + 64;
+        const size_t words = (size_t)2 * ((size_t)2 * world * slot) + 64;  // 8-byte cells
         bool local_ok = true;
         std::string why;
         auto local_fail = [&](const char* msg) { if (local_ok) why = msg; local_ok = false; cudaGetLastError(); };
@@ -144,7 +144,7 @@ struct DistComm {
                 peer_mapped[p] = base;
             }
             peers.mbox[p] = (uint32_t*)base;
-            peers.flags[p] = (uint32_t*)base + (size_t)2 * world * slot;
+            peers.flags[p] = (uint32_t*)base + (size_t)2 * ((size_t)2 * world * slot);
         }
         // agreement: minimum of the local verdicts
         unsigned long long vote = local_ok ? 1ull : 0ull;
@@ -183,7 +183,7 @@ struct DistComm {
     uint32_t epoch_base = 0;
     void destroy_peers() {}
     static size_t mbox_slot_words() { return (size_t)2 * 65552 + 16 + 16 * MAX_PEERS; }
-    static size_t mbox_words(int world) { return (size_t)2 * world * mbox_slot_words() + (size_t)MAX_PEERS * PEER_FLAG_STRIDE + 64; }
+    static size_t mbox_words(int world) { return (size_t)2 * ((size_t)2 * world * mbox_slot_words()) + 64; }  // 8-byte cells
     // tests: the ranks are processes on one host and `base` is a zero-filled shared-memory segment that holds the
     // mailboxes of all ranks back to back (the GPU build maps the peers' device memory with cudaIpc instead)
     bool init_peers_shm(void* base, size_t bytes) {
@@ -191,7 +191,7 @@ struct DistComm {
         for (int p = 0; p < world; p++) {
             uint32_t* mb = (uint32_t*)base + (size_t)p * mbox_words(world);
             peers.mbox[p] = mb;
-            peers.flags[p] = mb + (size_t)2 * world * mbox_slot_words();
+            peers.flags[p] = mb + (size_t)2 * ((size_t)2 * world * mbox_slot_words());
         }
         peers.slot_words = (uint32_t)mbox_slot_words();
         peer_ok = true;
