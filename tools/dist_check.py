@@ -16,6 +16,8 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 box = [zb.Engine.nccl_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(box, src=0)
 eng = zb.Engine(device=lr, rank=rank, world=world, nccl_unique_id=box[0])
+for kv in filter(None, os.environ.get("BPE_OPTS", "").split(",")):  # e.g. BPE_OPTS=pdl=0,xchg_impl=1
+    eng.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 lo, hi = n_total * rank // world, n_total * (rank + 1) // world
 shard = sc.generate(hi - lo, sc.SEED_C3, sc.BYTE, offset=lo)
 for rep in range(2):

@@ -505,20 +505,14 @@ __device__ __forceinline__ EdgeInfo edge_get(const EdgeSrc& es, int r) {
     EdgeInfo e;
     const size_t c0 = (size_t)r * es.slot_words + es.edge_off + (uint32_t)r * 16u;
     uint32_t* dst = reinterpret_cast<uint32_t*>(&e);
-    // all 16 cells are requested before any tag is looked at (one memory latency instead of sixteen)
+    // all 16 cells are requested before any tag is looked at (one memory latency instead of sixteen); a cell that does
+    // not carry the epoch yet is polled on its own
     const uint2* cells = reinterpret_cast<const uint2*>(es.mbox) + c0;
-    uint32_t spins = 0;
-    while (true) {
-        uint2 v[16];
+    uint2 v[16];
 #pragma unroll
-        for (int w = 0; w < 16; w++) v[w] = __ldcv(cells + w);
-        bool ok = true;
+    for (int w = 0; w < 16; w++) v[w] = __ldcv(cells + w);
 #pragma unroll
-        for (int w = 0; w < 16; w++) { ok = ok && v[w].y == es.epoch; dst[w] = v[w].x; }
-        if (ok) break;
-        BPE_SPIN_YIELD();
-        if (++spins > PEER_SPIN_LIMIT) { atomicOr(es.err, (uint32_t)ERR_PEER_TIMEOUT); break; }
-    }
+    for (int w = 0; w < 16; w++) dst[w] = v[w].y == es.epoch ? v[w].x : peer_get(es.mbox, c0 + (size_t)w, es.epoch, es.err);
     return e;
 }
 
