@@ -140,7 +140,12 @@ const char* bpe_last_error(const bpe_ctx* ctx);
  *   "xchg_impl"           multi-GPU per-step exchange. 0 (default): peer-memory mailboxes over NVLink (each rank
  *                         writes its deltas into every peer's mailbox and raises a flag; falls back to 1 when
  *                         peer access is unavailable); 1: NCCL all-reduce
- *   "time_phases"         1: fill the reference's TimeStats buckets (synchronises per phase)
+ *   "time_phases"         1: fill the reference's TimeStats buckets (CUDA events recorded between the launches of the
+ *                         loop, resolved after the run: two event records per launch, no extra synchronisation)
+ *   "pdl"                 1 (default): the merge pass and the apply kernel of the train loop are launched as programmatic
+ *                         dependents of each other (the next kernel's CTAs start and prefetch while the previous one drains)
+ *   "cache_max_mb"        device memory the context keeps cached between calls (default 8192; the rest is freed when an
+ *                         API call returns; 0 = keep nothing)
  *   "profile"             1: fill bpe_stats_t.kernel_ms / kernel_calls for every kernel class;
  *                         2: only the merge kernel (two event records per merge step)
  *                         3: the merge kernel of every 32nd step only; kernel_ms[10] then holds the token slots

@@ -224,13 +224,15 @@ class Engine:
     def encode(self, text, merges) -> np.ndarray:
         a = _as_u8(text)
         m = _as_merges(merges)
-        out = np.zeros(max(a.size, 1), dtype=np.uint16)
+        out = np.empty(max(a.size, 1), dtype=np.uint16)  # the caller-allocated upper bound of the C ABI (n ids)
         out_n = c_size_t(0)
         st = bpe_stats_t()
         rc = self.lib.bpe_encode(self._ctx, a.ctypes.data, a.size, m.ctypes.data, len(m), out.ctypes.data, byref(out_n), byref(st))
         self.last_stats = st.as_dict()
         self._check(rc)
-        return out[: out_n.value].copy()
+        if out_n.value * 4 < out.size:  # small result in a big buffer: shrink (the Zig shim does the same with its allocator)
+            return out[: out_n.value].copy()
+        return out[: out_n.value]
 
     def encode_device(self, d_text: int, n: int, merges, d_out: int) -> int:
         m = _as_merges(merges)
@@ -248,7 +250,7 @@ class Engine:
         need = c_size_t(0)
         rc = self.lib.bpe_decode_size(self._ctx, t.ctypes.data, t.size, m.ctypes.data, len(m), byref(need))
         self._check(rc)
-        out = np.zeros(max(need.value, 1), dtype=np.uint8)
+        out = np.empty(max(need.value, 1), dtype=np.uint8)
         out_n = c_size_t(0)
         st = bpe_stats_t()
         rc = self.lib.bpe_decode(self._ctx, t.ctypes.data, t.size, m.ctypes.data, len(m), out.ctypes.data, need.value, byref(out_n), byref(st))

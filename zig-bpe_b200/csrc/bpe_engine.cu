@@ -47,6 +47,16 @@ struct BufCache {
         cached_bytes += bytes;
     }
     void clear() { for (Blk& b : free_list) cudaFree(b.p); free_list.clear(); cached_bytes = 0; }
+    // give memory back to the device until at most `keep` bytes stay cached (largest blocks first)
+    void trim(size_t keep) {
+        while (cached_bytes > keep && !free_list.empty()) {
+            size_t big = 0;
+            for (size_t i = 1; i < free_list.size(); i++) if (free_list[i].bytes > free_list[big].bytes) big = i;
+            cudaFree(free_list[big].p);
+            cached_bytes -= free_list[big].bytes;
+            free_list.erase(free_list.begin() + (long)big);
+        }
+    }
 };
 
 // -----------------------------------------------------------------------------------------
@@ -58,7 +68,7 @@ struct bpe_ctx {
     std::string err;
     // options
     long verify_recount = 0, force_slow_tiebreak = 0, check_tiebreak = 0, compact_pct = 85, table_log2 = 0,
-         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 6, encode_filter = 1, encode_geom = 4, encode_seg_min_steps = 450, encode_tile = 7936, encode_try_tiles = 1, fuse_halo = 1, count_limit_log2 = 32, stream_chunk_mb = 128, stream_chunk_bytes = 0, merge_filter = 0, batch_steps = 16, pdl = 1;
+         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 6, encode_filter = 1, encode_geom = 4, encode_seg_min_steps = 450, encode_tile = 7936, encode_try_tiles = 1, fuse_halo = 1, count_limit_log2 = 32, stream_chunk_mb = 128, stream_chunk_bytes = 0, merge_filter = 0, batch_steps = 16, pdl = 1, cache_max_mb = 8192;
     int num_sms = 148;
     DistComm dist;  // world == 1 when single GPU
     uint64_t launches = 0;
@@ -1858,8 +1868,11 @@ static int ensure_decode_vocab(bpe_ctx* ctx, const bpe_merge_t* merges, size_t m
 
 struct CacheScope {
     BufCache* prev;
-    explicit CacheScope(bpe_ctx* ctx) : prev(tl_cache) { tl_cache = ctx ? &ctx->cache : nullptr; }
-    ~CacheScope() { tl_cache = prev; }
+    bpe_ctx* ctx;
+    explicit CacheScope(bpe_ctx* c) : prev(tl_cache), ctx(c) { tl_cache = c ? &c->cache : nullptr; }
+    // at the end of every API call the cache is cut back to "cache_max_mb" so that other allocators of the process
+    // (torch, a second context, the caller) are not starved by memory that sits idle here
+    ~CacheScope() { if (ctx) ctx->cache.trim((size_t)std::max<long>(0, ctx->cache_max_mb) << 20); tl_cache = prev; }
 };
 
 extern "C" {
@@ -1976,6 +1989,7 @@ int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value) {
     else if (s == "merge_filter") ctx->merge_filter = value;
     else if (s == "batch_steps") ctx->batch_steps = value;
     else if (s == "pdl") ctx->pdl = value;
+    else if (s == "cache_max_mb") ctx->cache_max_mb = value;
     else if (s == "stream_chunk_mb") ctx->stream_chunk_mb = value;
     else if (s == "stream_chunk_bytes") ctx->stream_chunk_bytes = value;
     else return fail(ctx, BPE_ERR_INVALID_ARG, "unknown option '%s'", name);
