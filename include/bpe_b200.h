@@ -129,6 +129,10 @@ const char* bpe_last_error(const bpe_ctx* ctx);
  *                         a tile goes through the staged path only if a candidate is left. 0 (default): every tile that
  *                         holds an A is staged (measured 14 % faster on C3: early steps stage nearly every tile anyway and
  *                         the filter's instructions sit on the streaming path).
+ *   "merge_direct"        K (default 8): a train step whose pair occurs fewer than K times per tile on average takes the
+ *                         queue-less staged path (every thread looks its own A's up; no candidate masks, no
+ *                         shared-memory queue); 0: always the queued path (round 2's first profile: 45 % of the merge
+ *                         pass's instructions were candidate masks and queue traffic on steps with ~3 occurrences per tile)
  *   "batch_steps"         merge steps enqueued between two read-backs of the control block (default 16)
  *   "stream_chunk_mb"     bpe_encode / host buffers: inputs of two chunks or more (default chunk 128 MiB) stream through the
  *                         GPU in chunks — copies overlap the tile-resident encoder, device memory stays at 8 bytes per chunk

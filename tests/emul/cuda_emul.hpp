@@ -98,6 +98,12 @@ static inline unsigned __vcmpeq2(unsigned a, unsigned b) {
     if ((a >> 16) == (b >> 16)) r |= 0xffff0000u;
     return r;
 }
+// packed 16-bit unsigned minimum (VIMNMX.U16x2 / VIMNMX3.U16x2 on the GPU)
+static inline unsigned __vminu2(unsigned a, unsigned b) {
+    const unsigned lo = std::min(a & 0xffffu, b & 0xffffu), hi = std::min(a >> 16, b >> 16);
+    return lo | (hi << 16);
+}
+static inline unsigned __vimin3_u16x2(unsigned a, unsigned b, unsigned c) { return __vminu2(__vminu2(a, b), c); }
 // warp intrinsics (blockDim.x must be a multiple of 32 where these are used)
 enum { EMUL_BALLOT = 0, EMUL_SHFL = 1, EMUL_SHFL_UP = 2, EMUL_SHFL_DOWN = 3, EMUL_SHFL_XOR = 4, EMUL_ANY = 5 };
 static inline unsigned __ballot_sync(unsigned, int pred) { return emul::warp_exchange(pred ? 1u : 0u, EMUL_BALLOT, 0); }

@@ -42,6 +42,19 @@ def test_train_forced_replay_and_no_compaction(emu, ora):
     assert st["compactions"] > 0
 
 
+@pytest.mark.parametrize("direct", [0, 8, 1 << 20])
+def test_train_queued_and_queueless_step_paths(emu, ora, taylor, direct):
+    """merge_direct: 0 = every staged tile fills the candidate queue, 2^20 = no step does, 8 = the default mix (by the
+    pair's count per tile); with a recount of all pairs after every step"""
+    rng = np.random.default_rng(11)
+    try:
+        for data, vocab in ((taylor[:12000], 300), (bytes(rng.integers(97, 100, size=4000, dtype=np.uint8)), 290),
+                            (b"abab" * 300 + b"ba" * 200 + b"aab" * 100, 275)):
+            _train_check(emu, ora, data, vocab, verify_recount=1, merge_direct=direct)
+    finally:
+        emu.set_option("merge_direct", 8)
+
+
 def test_train_golden_prefix(emu, ora, taylor):
     st = _train_check(emu, ora, taylor[:40000], 300)
     assert st["kernel_launches"] > 0

@@ -804,11 +804,15 @@ template <> __device__ __forceinline__ void unpack_vec<uint32_t>(const uint4& v,
 }
 template <class TokT> __device__ __forceinline__ bool vec_has(const uint4& v, uint32_t a);
 template <> __device__ __forceinline__ bool vec_has<uint16_t>(const uint4& v, uint32_t a) {
-    // "has a zero halfword" of w ^ aa: (x - 0x00010001) & ~x & 0x80008000. A borrow can only flag a
-    // neighbouring lane falsely when a lower lane really is zero, so the any-test is exact.
+    // a slot equals `a` iff the 16-bit-lane minimum of the four words ^ aa has a zero lane: two packed-minimum
+    // instructions (VIMNMX3.U16x2 / VIMNMX.U16x2, the DPX unit of sm_90+) instead of three bit operations per word
+    // (round 2's first profile had 23 % of the merge pass's instructions in this test).
+    // "has a zero halfword": (m - 0x00010001) & ~m & 0x80008000. A borrow can only flag a neighbouring lane falsely
+    // when the lower lane really is zero, so the any-test is exact.
     const uint32_t aa = a | (a << 16);
-    auto t = [&](uint32_t w) { const uint32_t x = w ^ aa; return (x - 0x00010001u) & ~x; };
-    return ((t(v.x) | t(v.y) | t(v.z) | t(v.w)) & 0x80008000u) != 0u;
+    uint32_t m = __vimin3_u16x2(v.x ^ aa, v.y ^ aa, v.z ^ aa);
+    m = __vminu2(m, v.w ^ aa);
+    return ((m - 0x00010001u) & ~m & 0x80008000u) != 0u;
 }
 template <> __device__ __forceinline__ bool vec_has<uint32_t>(const uint4& v, uint32_t a) {
     return v.x == a || v.y == a || v.z == a || v.w == a;
@@ -870,7 +874,7 @@ constexpr int MERGE_QCAP = 2048;  // queued A positions per tile (denser tiles o
 template <class TokT, bool DELTAS, bool STAGE_FROM_REGS, int NV>
 __device__ __forceinline__ void tile_staged_path(TokT* ext, const uint4 (&v)[NV], TokT* __restrict__ tok, size_t base,
                                                  const TileHalo<TokT>& h, uint32_t hitbits, uint32_t Au, uint32_t Bu, uint32_t Xu,
-                                                 bool use_bins,
+                                                 bool use_bins, bool direct,
                                                  uint32_t* bin_key, uint32_t* bin_val, uint16_t* q_pos, uint32_t* q_n,
                                                  uint32_t* sh_runA, uint32_t* __restrict__ cntL, uint32_t* __restrict__ cntR,
                                                  uint32_t& nAB, uint32_t& nXX) {
@@ -939,6 +943,23 @@ __device__ __forceinline__ void tile_staged_path(TokT* ext, const uint4 (&v)[NV]
             int f = next_live(ext, OFF - 1);
             if (f >= 0 && f < OFF + TILE && ext[f] == B) tok[base + (size_t)(f - OFF)] = H;
         }
+        if (direct) {
+            // Sparse step (few occurrences per tile, the common case after the first few hundred merges: the pair is
+            // rare although its first token is not). Every thread looks its own A's up in the staged tile — no
+            // candidate masks, no queue, no shared-memory atomics, one barrier less. With a handful of occurrences per
+            // tile the idle lanes cost less than filling and draining a queue does.
+#pragma unroll
+            for (int k = 0; k < NV; k++) {
+                if (!((hitbits >> k) & 1u)) continue;
+                uint32_t mask = vec_mask<TokT>(v[k], Au);
+                const int s0 = OFF + (k * THREADS + (int)threadIdx.x) * VEC;
+                while (mask) {
+                    const int bit = __ffs((int)mask) - 1;
+                    mask &= mask - 1;
+                    process_ab(s0 + mask_bit_to_slot<TokT>(bit));
+                }
+            }
+        } else {
         // The A's are sparse and unevenly spread over the lanes, so each thread only queues the
         // positions of its A's; the CTA then works through the queue with all lanes busy.
 #pragma unroll
@@ -961,6 +982,7 @@ __device__ __forceinline__ void tile_staged_path(TokT* ext, const uint4 (&v)[NV]
         __syncthreads();
         const uint32_t nq = *q_n < (uint32_t)QCAP ? *q_n : (uint32_t)QCAP;
         for (uint32_t i = threadIdx.x; i < nq; i += THREADS) process_ab((int)q_pos[i]);
+        }
     } else {
 #pragma unroll
         for (int k = 0; k < NV; k++) {
@@ -1045,7 +1067,7 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(Tok
                                                         const StepCtl* __restrict__ ctl, uint32_t* __restrict__ cntL,
                                                         uint32_t* __restrict__ cntR, uint32_t* nxx_out, uint32_t* nab_out,
                                                         uint32_t Au, uint32_t Bu, uint32_t Xu, uint32_t bins_min_count,
-                                                        int backwards) {
+                                                        int backwards, uint32_t direct_max_count) {
     __shared__ __align__(16) TokT ext[EXT];
     // block-private bins for the neighbour deltas: key = token id (+ 0x10000 for the right side)
     __shared__ uint32_t bin_key[DELTAS ? MERGE_NBIN : 1];
@@ -1079,10 +1101,13 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(Tok
     }
     if (threadIdx.x == 0) h = halo[tile];
     bool use_bins = false;  // dense steps privatise the deltas per CTA; sparse steps go straight to global
+    bool direct = !FROMCTL && direct_max_count != 0u;  // sparse steps: no candidate queue (tile_staged_path)
     if (FROMCTL) {
         if (ctl->halt) return;
         Au = ctl->A; Bu = ctl->B; Xu = ctl->X;
-        use_bins = DELTAS && ctl->max_count >= bins_min_count;
+        const uint32_t mc = ctl->max_count;  // occurrences of (A,B) in the whole corpus
+        use_bins = DELTAS && mc >= bins_min_count;
+        direct = mc < direct_max_count;
         // tell the apply kernel of this step that the pass ran (its halo CTAs cannot look at `halt`: the selection
         // at the end of that very kernel may set it while they are still starting)
         if (blockIdx.x == 0 && threadIdx.x == 0) const_cast<StepCtl*>(ctl)->pass_step = ctl->step + 1u;
@@ -1105,7 +1130,7 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(Tok
     if (threadIdx.x == 0 && h.l1 == A) any = true;  // possible head duty
     if (!__syncthreads_or(any ? 1 : 0)) return;
     uint32_t nAB = 0, nXX = 0;
-    tile_staged_path<TokT, DELTAS, true, NV>(ext, v, tok, base, h, hitbits, Au, Bu, Xu, use_bins, bin_key, bin_val, q_pos, &q_n, &sh_runA,
+    tile_staged_path<TokT, DELTAS, true, NV>(ext, v, tok, base, h, hitbits, Au, Bu, Xu, use_bins, direct, bin_key, bin_val, q_pos, &q_n, &sh_runA,
                                              cntL, cntR, nAB, nXX);
     if (nAB) atomicAdd(nab_out, nAB);
     if (DELTAS && nXX) atomicAdd(nxx_out, nXX);
@@ -1227,7 +1252,7 @@ __global__ void __launch_bounds__(THREADS, RING_CTAS_PER_SM) merge_tma_kernel(To
         any = hitbits != 0;
         if (threadIdx.x == 0 && h.l1 == A) any = true;  // possible head duty
         if (__syncthreads_or(any ? 1 : 0)) {
-            tile_staged_path<TokT, DELTAS, false, NV>(ext, v, tok, (size_t)tile * TILE, h, hitbits, Au, Bu, Xu, use_bins, bin_key, bin_val,
+            tile_staged_path<TokT, DELTAS, false, NV>(ext, v, tok, (size_t)tile * TILE, h, hitbits, Au, Bu, Xu, use_bins, false, bin_key, bin_val,
                                                       q_pos, &q_n, &sh_runA, cntL, cntR, nAB, nXX);
             __syncthreads();  // every thread is done with this stage
         }
