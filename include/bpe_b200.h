@@ -133,6 +133,9 @@ const char* bpe_last_error(const bpe_ctx* ctx);
  *                         queue-less staged path (every thread looks its own A's up; no candidate masks, no
  *                         shared-memory queue); 0: always the queued path (round 2's first profile: 45 % of the merge
  *                         pass's instructions were candidate masks and queue traffic on steps with ~3 occurrences per tile)
+ *   "merge_prestage"      1 (default): the train loop's merge pass copies every tile into shared memory before the barrier
+ *                         that tells whether the tile holds an A at all, so a staged tile waits at one barrier, not two;
+ *                         0: stage only tiles that hold an A
  *   "batch_steps"         merge steps enqueued between two read-backs of the control block (default 16)
  *   "stream_chunk_mb"     bpe_encode / host buffers: inputs of two chunks or more (default chunk 128 MiB) stream through the
  *                         GPU in chunks — copies overlap the tile-resident encoder, device memory stays at 8 bytes per chunk

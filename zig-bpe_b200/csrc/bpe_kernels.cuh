@@ -871,21 +871,13 @@ constexpr int MERGE_QCAP = 2048;  // queued A positions per tile (denser tiles o
 // The staged path of one tile, shared by the register-streaming and the TMA-ring kernels: write the
 // halo margins, queue the A positions, resolve occurrences, write X / holes, emit the deltas.
 // h is valid in thread 0 only. Ends with all threads past their last read of ext.
-template <class TokT, bool DELTAS, bool STAGE_FROM_REGS, int NV>
-__device__ __forceinline__ void tile_staged_path(TokT* ext, const uint4 (&v)[NV], TokT* __restrict__ tok, size_t base,
-                                                 const TileHalo<TokT>& h, uint32_t hitbits, uint32_t Au, uint32_t Bu, uint32_t Xu,
-                                                 bool use_bins, bool direct,
-                                                 uint32_t* bin_key, uint32_t* bin_val, uint16_t* q_pos, uint32_t* q_n,
-                                                 uint32_t* sh_runA, uint32_t* __restrict__ cntL, uint32_t* __restrict__ cntR,
-                                                 uint32_t& nAB, uint32_t& nXX) {
-    constexpr int VEC = 16 / (int)sizeof(TokT);
-    constexpr int NBIN = MERGE_NBIN;
-    constexpr int QCAP = MERGE_QCAP;
+// stage the tile (+ halo margins, run length, empty queue, empty bins): everything tile_staged_path reads from shared
+// memory. h is valid in thread 0 only. The caller puts a barrier between this and tile_staged_path.
+template <class TokT, bool STAGE_FROM_REGS, int NV>
+__device__ __forceinline__ void tile_stage(TokT* ext, const uint4 (&v)[NV], const TileHalo<TokT>& h, bool use_bins,
+                                           uint32_t* bin_key, uint32_t* bin_val, uint32_t* q_n, uint32_t* sh_runA) {
     const TokT H = (TokT)TokTraits<TokT>::hole;
-    const TokT A = (TokT)Au, B = (TokT)Bu, X = (TokT)Xu;
-    const bool AEQB = (Au == Bu);
-    if (use_bins) for (int i = (int)threadIdx.x; i < NBIN; i += THREADS) { bin_key[i] = EMPTY_KEY; bin_val[i] = 0; }
-    // stage the tile (+ halo) so that neighbours can be looked up across thread boundaries
+    if (use_bins) for (int i = (int)threadIdx.x; i < MERGE_NBIN; i += THREADS) { bin_key[i] = EMPTY_KEY; bin_val[i] = 0; }
     if (STAGE_FROM_REGS) {
         uint4* dst = reinterpret_cast<uint4*>(ext + OFF);
 #pragma unroll
@@ -904,8 +896,31 @@ __device__ __forceinline__ void tile_staged_path(TokT* ext, const uint4 (&v)[NV]
         if (i < OFF - 2) ext[i] = H;
         else if (OFF + TILE + 3 + (i - (OFF - 2)) < EXT) ext[OFF + TILE + 3 + (i - (OFF - 2))] = H;
     }
-    __syncthreads();
+}
 
+template <class TokT, bool DELTAS, bool STAGE_FROM_REGS, int NV, bool PRESTAGED = false>
+__device__ __forceinline__ void tile_staged_path(TokT* ext, const uint4 (&v)[NV], TokT* __restrict__ tok, size_t base,
+                                                 const TileHalo<TokT>& h, uint32_t hitbits, uint32_t Au, uint32_t Bu, uint32_t Xu,
+                                                 bool use_bins, bool direct,
+                                                 uint32_t* bin_key, uint32_t* bin_val, uint16_t* q_pos, uint32_t* q_n,
+                                                 uint32_t* sh_runA, uint32_t* __restrict__ cntL, uint32_t* __restrict__ cntR,
+                                                 uint32_t& nAB, uint32_t& nXX) {
+    constexpr int VEC = 16 / (int)sizeof(TokT);
+    constexpr int NBIN = MERGE_NBIN;
+    constexpr int QCAP = MERGE_QCAP;
+    const TokT H = (TokT)TokTraits<TokT>::hole;
+    const TokT A = (TokT)Au, B = (TokT)Bu, X = (TokT)Xu;
+    const bool AEQB = (Au == Bu);
+    // stage the tile (+ halo) so that neighbours can be looked up across thread boundaries
+    if (!PRESTAGED) {
+        tile_stage<TokT, STAGE_FROM_REGS, NV>(ext, v, h, use_bins, bin_key, bin_val, q_n, sh_runA);
+        __syncthreads();
+    }
+
+    // a pre-staged tile is read back from shared memory, so that the 16 registers of v[] are free after the prologue
+    auto getv = [&](int k) -> uint4 {
+        return PRESTAGED ? reinterpret_cast<const uint4*>(ext + OFF)[k * THREADS + (int)threadIdx.x] : v[k];
+    };
     // one occurrence candidate: the A at ext index s (A != B). Writes X / hole, emits the deltas.
     auto process_ab = [&](int s) {
         const int j = next_live(ext, s);
@@ -951,7 +966,7 @@ __device__ __forceinline__ void tile_staged_path(TokT* ext, const uint4 (&v)[NV]
 #pragma unroll
             for (int k = 0; k < NV; k++) {
                 if (!((hitbits >> k) & 1u)) continue;
-                uint32_t mask = vec_mask<TokT>(v[k], Au);
+                uint32_t mask = vec_mask<TokT>(getv(k), Au);
                 const int s0 = OFF + (k * THREADS + (int)threadIdx.x) * VEC;
                 while (mask) {
                     const int bit = __ffs((int)mask) - 1;
@@ -965,9 +980,10 @@ __device__ __forceinline__ void tile_staged_path(TokT* ext, const uint4 (&v)[NV]
 #pragma unroll
         for (int k = 0; k < NV; k++) {
             // (the shuffle is executed by every lane; vectors k of neighbouring lanes are neighbours in the tile)
-            const uint32_t nf = __shfl_down_sync(0xffffffffu, vec_first_slot<TokT>(v[k]), 1);
+            const uint4 vk = getv(k);
+            const uint32_t nf = __shfl_down_sync(0xffffffffu, vec_first_slot<TokT>(vk), 1);
             if (!((hitbits >> k) & 1u)) continue;
-            uint32_t mask = vec_candidates<TokT>(v[k], Au, Bu, nf, (threadIdx.x & 31u) != 31u);
+            uint32_t mask = vec_candidates<TokT>(vk, Au, Bu, nf, (threadIdx.x & 31u) != 31u);
             const int s0 = OFF + (k * THREADS + (int)threadIdx.x) * VEC;
             uint32_t at = atomicAdd(q_n, (uint32_t)__popc(mask));
             while (mask) {
@@ -989,7 +1005,7 @@ __device__ __forceinline__ void tile_staged_path(TokT* ext, const uint4 (&v)[NV]
             if (!((hitbits >> k) & 1u)) continue;
             uint32_t mask = 0;  // A==B needs the slots in ascending order: bit = slot
             {
-                uint32_t m = vec_mask<TokT>(v[k], Au);
+                uint32_t m = vec_mask<TokT>(getv(k), Au);
                 while (m) { const int bit = __ffs((int)m) - 1; m &= m - 1; mask |= 1u << mask_bit_to_slot<TokT>(bit); }
             }
             const int s0 = OFF + (k * THREADS + (int)threadIdx.x) * VEC;
@@ -1062,7 +1078,7 @@ __device__ __forceinline__ void tile_staged_path(TokT* ext, const uint4 (&v)[NV]
 #ifndef BPE_MERGE_MINBLOCKS
 #define BPE_MERGE_MINBLOCKS 6
 #endif
-template <class TokT, bool DELTAS, bool FROMCTL, bool FILTER>
+template <class TokT, bool DELTAS, bool FROMCTL, bool FILTER, bool PRESTAGE = false>
 __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(TokT* __restrict__ tok, const TileHalo<TokT>* __restrict__ halo,
                                                         const StepCtl* __restrict__ ctl, uint32_t* __restrict__ cntL,
                                                         uint32_t* __restrict__ cntR, uint32_t* nxx_out, uint32_t* nab_out,
@@ -1128,9 +1144,13 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(Tok
         }
     }
     if (threadIdx.x == 0 && h.l1 == A) any = true;  // possible head duty
+    // The tile goes to shared memory before it is known whether anybody needs it there: four 16-byte stores per thread
+    // cost less than the second barrier a staged tile would otherwise wait at (the barrier below then also publishes the
+    // staged tile).
+    if (PRESTAGE) tile_stage<TokT, true, NV>(ext, v, h, use_bins, bin_key, bin_val, &q_n, &sh_runA);
     if (!__syncthreads_or(any ? 1 : 0)) return;
     uint32_t nAB = 0, nXX = 0;
-    tile_staged_path<TokT, DELTAS, true, NV>(ext, v, tok, base, h, hitbits, Au, Bu, Xu, use_bins, direct, bin_key, bin_val, q_pos, &q_n, &sh_runA,
+    tile_staged_path<TokT, DELTAS, true, NV, PRESTAGE>(ext, v, tok, base, h, hitbits, Au, Bu, Xu, use_bins, direct, bin_key, bin_val, q_pos, &q_n, &sh_runA,
                                              cntL, cntR, nAB, nXX);
     if (nAB) atomicAdd(nab_out, nAB);
     if (DELTAS && nXX) atomicAdd(nxx_out, nXX);
