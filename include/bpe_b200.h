@@ -133,6 +133,8 @@ const char* bpe_last_error(const bpe_ctx* ctx);
  *                         queue-less staged path (every thread looks its own A's up; no candidate masks, no
  *                         shared-memory queue); 0: always the queued path (round 2's first profile: 45 % of the merge
  *                         pass's instructions were candidate masks and queue traffic on steps with ~3 occurrences per tile)
+ *   "merge_pairfilter"    1 (default): on the queue-less path a vector's A's are reduced, in registers, to those whose next slot
+ *                         holds B or a hole (packed 16-bit minimum) before anything is looked up; 0: every A is looked up
  *   "merge_prestage"      1 (default): the train loop's merge pass copies every tile into shared memory before the barrier
  *                         that tells whether the tile holds an A at all, so a staged tile waits at one barrier, not two;
  *                         0: stage only tiles that hold an A

@@ -103,6 +103,10 @@ static inline unsigned __vminu2(unsigned a, unsigned b) {
     const unsigned lo = std::min(a & 0xffffu, b & 0xffffu), hi = std::min(a >> 16, b >> 16);
     return lo | (hi << 16);
 }
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
+    const uint64_t w = ((uint64_t)hi << 32) | lo;
+    return (unsigned)(w >> (shift & 31u));
+}
 static inline unsigned __vimin3_u16x2(unsigned a, unsigned b, unsigned c) { return __vminu2(__vminu2(a, b), c); }
 // warp intrinsics (blockDim.x must be a multiple of 32 where these are used)
 enum { EMUL_BALLOT = 0, EMUL_SHFL = 1, EMUL_SHFL_UP = 2, EMUL_SHFL_DOWN = 3, EMUL_SHFL_XOR = 4, EMUL_ANY = 5 };

@@ -840,6 +840,29 @@ template <> __device__ __forceinline__ uint32_t vec_candidates<uint32_t>(const u
     const bool last_ok = !next_known || next_first == b || next_first == 0xFFFFFFFFu;
     return ma & (((ms >> 1) & 0x7u) | (last_ok ? 8u : 0u));
 }
+// The A's of a vector that can start an occurrence as far as the next SLOT tells: the next slot holds B or a hole (the next
+// live token lies further on). next_first = the slot after the vector's last one. Same bit layout as vec_mask. Conservative
+// (an A whose next live token is B always qualifies) and cheap enough to run on every vector that holds an A: the packed
+// minimum of "slot != A or next slot != B" and "slot != A or next slot != hole" is zero exactly at the candidates.
+template <class TokT> __device__ __forceinline__ uint32_t vec_pair_candidates(const uint4& v, uint32_t a, uint32_t b, uint32_t next_first);
+template <> __device__ __forceinline__ uint32_t vec_pair_candidates<uint16_t>(const uint4& v, uint32_t a, uint32_t b, uint32_t next_first) {
+    const uint32_t aa = a | (a << 16), bb = b | (b << 16);
+    // y: every slot's successor slot
+    const uint32_t y0 = __funnelshift_r(v.x, v.y, 16), y1 = __funnelshift_r(v.y, v.z, 16), y2 = __funnelshift_r(v.z, v.w, 16),
+                   y3 = __funnelshift_r(v.w, next_first, 16);
+    auto c = [&](uint32_t w, uint32_t y) { const uint32_t x = w ^ aa; return __vminu2(x | (y ^ bb), x | ~y); };
+    const uint32_t c0 = c(v.x, y0), c1 = c(v.y, y1), c2 = c(v.z, y2), c3 = c(v.w, y3);
+    const uint32_t m = __vminu2(__vimin3_u16x2(c0, c1, c2), c3);
+    if (!((m - 0x00010001u) & ~m & 0x80008000u)) return 0u;  // no zero lane anywhere (exact, see vec_has)
+    auto z = [&](uint32_t x) { return ~(((x & 0x7FFF7FFFu) + 0x7FFF7FFFu) | x) & 0x80008000u; };
+    return (z(c0) >> 15) | (z(c1) >> 14) | (z(c2) >> 13) | (z(c3) >> 12);
+}
+template <> __device__ __forceinline__ uint32_t vec_pair_candidates<uint32_t>(const uint4& v, uint32_t a, uint32_t b, uint32_t next_first) {
+    const uint32_t H = 0xFFFFFFFFu;
+    auto ok = [&](uint32_t n) { return n == b || n == H; };
+    return ((v.x == a && ok(v.y)) ? 1u : 0u) | ((v.y == a && ok(v.z)) ? 2u : 0u) | ((v.z == a && ok(v.w)) ? 4u : 0u) |
+           ((v.w == a && ok(next_first)) ? 8u : 0u);
+}
 template <class TokT> __device__ __forceinline__ uint32_t vec_first_slot(const uint4& v);
 template <> __device__ __forceinline__ uint32_t vec_first_slot<uint16_t>(const uint4& v) { return v.x & 0xFFFFu; }
 template <> __device__ __forceinline__ uint32_t vec_first_slot<uint32_t>(const uint4& v) { return v.x; }
@@ -901,7 +924,7 @@ __device__ __forceinline__ void tile_stage(TokT* ext, const uint4 (&v)[NV], cons
 template <class TokT, bool DELTAS, bool STAGE_FROM_REGS, int NV, bool PRESTAGED = false>
 __device__ __forceinline__ void tile_staged_path(TokT* ext, const uint4 (&v)[NV], TokT* __restrict__ tok, size_t base,
                                                  const TileHalo<TokT>& h, uint32_t hitbits, uint32_t Au, uint32_t Bu, uint32_t Xu,
-                                                 bool use_bins, bool direct,
+                                                 bool use_bins, bool direct, bool pair_filter,
                                                  uint32_t* bin_key, uint32_t* bin_val, uint16_t* q_pos, uint32_t* q_n,
                                                  uint32_t* sh_runA, uint32_t* __restrict__ cntL, uint32_t* __restrict__ cntR,
                                                  uint32_t& nAB, uint32_t& nXX) {
@@ -966,8 +989,9 @@ __device__ __forceinline__ void tile_staged_path(TokT* ext, const uint4 (&v)[NV]
 #pragma unroll
             for (int k = 0; k < NV; k++) {
                 if (!((hitbits >> k) & 1u)) continue;
-                uint32_t mask = vec_mask<TokT>(getv(k), Au);
                 const int s0 = OFF + (k * THREADS + (int)threadIdx.x) * VEC;
+                // (the slot after the vector comes from the staged tile: the next thread's first slot, or the halo)
+                uint32_t mask = pair_filter ? vec_pair_candidates<TokT>(getv(k), Au, Bu, (uint32_t)ext[s0 + VEC]) : vec_mask<TokT>(getv(k), Au);
                 while (mask) {
                     const int bit = __ffs((int)mask) - 1;
                     mask &= mask - 1;
@@ -980,11 +1004,18 @@ __device__ __forceinline__ void tile_staged_path(TokT* ext, const uint4 (&v)[NV]
 #pragma unroll
         for (int k = 0; k < NV; k++) {
             // (the shuffle is executed by every lane; vectors k of neighbouring lanes are neighbours in the tile)
-            const uint4 vk = getv(k);
-            const uint32_t nf = __shfl_down_sync(0xffffffffu, vec_first_slot<TokT>(vk), 1);
-            if (!((hitbits >> k) & 1u)) continue;
-            uint32_t mask = vec_candidates<TokT>(vk, Au, Bu, nf, (threadIdx.x & 31u) != 31u);
             const int s0 = OFF + (k * THREADS + (int)threadIdx.x) * VEC;
+            uint32_t mask;
+            if (pair_filter) {  // the slot after the vector comes from the staged tile
+                if (!((hitbits >> k) & 1u)) continue;
+                mask = vec_pair_candidates<TokT>(getv(k), Au, Bu, (uint32_t)ext[s0 + VEC]);
+                if (!mask) continue;
+            } else {
+                const uint4 vk = getv(k);
+                const uint32_t nf = __shfl_down_sync(0xffffffffu, vec_first_slot<TokT>(vk), 1);
+                if (!((hitbits >> k) & 1u)) continue;
+                mask = vec_candidates<TokT>(vk, Au, Bu, nf, (threadIdx.x & 31u) != 31u);
+            }
             uint32_t at = atomicAdd(q_n, (uint32_t)__popc(mask));
             while (mask) {
                 const int bit = __ffs((int)mask) - 1;
@@ -1097,7 +1128,8 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(Tok
     const TokT H = (TokT)TokTraits<TokT>::hole;
     // odd steps walk the sequence backwards (`backwards`, chosen by the host from the step parity): the
     // tiles the previous pass touched last are still in the 126 MB L2 when this pass starts with them
-    const uint32_t tile = backwards ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
+    const bool pair_filter = !(backwards & 2);  // (bit 1 of `backwards`: direct path without the pair filter, for comparison)
+    const uint32_t tile = (backwards & 1) ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
     const size_t base = (size_t)tile * TILE;
 
     // 1. stream the tile through registers. The loads are issued before the control block is read so
@@ -1150,7 +1182,7 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(Tok
     if (PRESTAGE) tile_stage<TokT, true, NV>(ext, v, h, use_bins, bin_key, bin_val, &q_n, &sh_runA);
     if (!__syncthreads_or(any ? 1 : 0)) return;
     uint32_t nAB = 0, nXX = 0;
-    tile_staged_path<TokT, DELTAS, true, NV, PRESTAGE>(ext, v, tok, base, h, hitbits, Au, Bu, Xu, use_bins, direct, bin_key, bin_val, q_pos, &q_n, &sh_runA,
+    tile_staged_path<TokT, DELTAS, true, NV, PRESTAGE>(ext, v, tok, base, h, hitbits, Au, Bu, Xu, use_bins, direct, pair_filter, bin_key, bin_val, q_pos, &q_n, &sh_runA,
                                              cntL, cntR, nAB, nXX);
     if (nAB) atomicAdd(nab_out, nAB);
     if (DELTAS && nXX) atomicAdd(nxx_out, nXX);
@@ -1272,7 +1304,7 @@ __global__ void __launch_bounds__(THREADS, RING_CTAS_PER_SM) merge_tma_kernel(To
         any = hitbits != 0;
         if (threadIdx.x == 0 && h.l1 == A) any = true;  // possible head duty
         if (__syncthreads_or(any ? 1 : 0)) {
-            tile_staged_path<TokT, DELTAS, false, NV>(ext, v, tok, (size_t)tile * TILE, h, hitbits, Au, Bu, Xu, use_bins, false, bin_key, bin_val,
+            tile_staged_path<TokT, DELTAS, false, NV>(ext, v, tok, (size_t)tile * TILE, h, hitbits, Au, Bu, Xu, use_bins, false, false, bin_key, bin_val,
                                                       q_pos, &q_n, &sh_runA, cntL, cntR, nAB, nXX);
             __syncthreads();  // every thread is done with this stage
         }
