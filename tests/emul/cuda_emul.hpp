@@ -171,6 +171,8 @@ static inline void fence_proxy_async() {}
 static inline void mbar_arrive_expect_tx(uint64_t*, uint32_t) {}
 static inline void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t*) { memcpy(dst, src, bytes); }
 static inline void mbar_wait(uint64_t*, uint32_t) {}
+static inline void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
+static inline void cp_async_wait_all() {}
 // kernels that never call __syncthreads()/warp intrinsics: run threads as a plain loop
 #define BPE_LAUNCH_NS(kern, grid, block, stream, ...) \
     emul::launch(dim3(grid), dim3(block), [&]() { kern(__VA_ARGS__); }, false)

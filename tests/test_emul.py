@@ -42,6 +42,21 @@ def test_train_forced_replay_and_no_compaction(emu, ora):
     assert st["compactions"] > 0
 
 
+@pytest.mark.parametrize("loop,direct,pairfilter", [(1, 3, 1), (2, 0, 1), (3, 1 << 20, 0), (1000, 3, 1)])
+def test_train_resident_merge_ctas(emu, ora, taylor, loop, direct, pairfilter):
+    """merge_loop = CTAs per SM of the looped merge pass (a CTA takes every gridDim-th tile, the next tile and its halo are
+    prefetched, the delta bins live as long as the CTA); 1000 = as many CTAs as tiles (one round each). With a recount of
+    all pairs after every step."""
+    rng = np.random.default_rng(12)
+    try:
+        for data, vocab in ((taylor[:14000], 300), (bytes(rng.integers(97, 100, size=5000, dtype=np.uint8)), 290),
+                            (b"abab" * 300 + b"ba" * 200 + b"aab" * 100 + b"a" * 700, 275)):
+            _train_check(emu, ora, data, vocab, verify_recount=1, merge_loop=loop, merge_direct=direct, merge_pairfilter=pairfilter)
+    finally:
+        for k, v in (("merge_loop", 0), ("merge_direct", 3), ("merge_pairfilter", 1)):
+            emu.set_option(k, v)
+
+
 @pytest.mark.parametrize("direct", [0, 8, 1 << 20])
 def test_train_queued_and_queueless_step_paths(emu, ora, taylor, direct):
     """merge_direct: 0 = every staged tile fills the candidate queue, 2^20 = no step does, 8 = the default mix (by the
@@ -52,7 +67,7 @@ def test_train_queued_and_queueless_step_paths(emu, ora, taylor, direct):
                             (b"abab" * 300 + b"ba" * 200 + b"aab" * 100, 275)):
             _train_check(emu, ora, data, vocab, verify_recount=1, merge_direct=direct)
     finally:
-        emu.set_option("merge_direct", 8)
+        emu.set_option("merge_direct", 3)
 
 
 def test_train_golden_prefix(emu, ora, taylor):

@@ -924,7 +924,7 @@ __device__ __forceinline__ void tile_stage(TokT* ext, const uint4 (&v)[NV], cons
 template <class TokT, bool DELTAS, bool STAGE_FROM_REGS, int NV, bool PRESTAGED = false>
 __device__ __forceinline__ void tile_staged_path(TokT* ext, const uint4 (&v)[NV], TokT* __restrict__ tok, size_t base,
                                                  const TileHalo<TokT>& h, uint32_t hitbits, uint32_t Au, uint32_t Bu, uint32_t Xu,
-                                                 bool use_bins, bool direct, bool pair_filter,
+                                                 bool use_bins, bool direct, bool pair_filter, bool flush_bins,
                                                  uint32_t* bin_key, uint32_t* bin_val, uint16_t* q_pos, uint32_t* q_n,
                                                  uint32_t* sh_runA, uint32_t* __restrict__ cntL, uint32_t* __restrict__ cntR,
                                                  uint32_t& nAB, uint32_t& nXX) {
@@ -1097,7 +1097,7 @@ __device__ __forceinline__ void tile_staged_path(TokT* ext, const uint4 (&v)[NV]
             }
         }
     }
-    if (use_bins) {
+    if (use_bins && flush_bins) {
         __syncthreads();
         for (int i = (int)threadIdx.x; i < NBIN; i += THREADS) {
             const uint32_t k = bin_key[i];
@@ -1182,10 +1182,114 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(Tok
     if (PRESTAGE) tile_stage<TokT, true, NV>(ext, v, h, use_bins, bin_key, bin_val, &q_n, &sh_runA);
     if (!__syncthreads_or(any ? 1 : 0)) return;
     uint32_t nAB = 0, nXX = 0;
-    tile_staged_path<TokT, DELTAS, true, NV, PRESTAGE>(ext, v, tok, base, h, hitbits, Au, Bu, Xu, use_bins, direct, pair_filter, bin_key, bin_val, q_pos, &q_n, &sh_runA,
+    tile_staged_path<TokT, DELTAS, true, NV, PRESTAGE>(ext, v, tok, base, h, hitbits, Au, Bu, Xu, use_bins, direct, pair_filter, true, bin_key, bin_val, q_pos, &q_n, &sh_runA,
                                              cntL, cntR, nAB, nXX);
     if (nAB) atomicAdd(nab_out, nAB);
     if (DELTAS && nXX) atomicAdd(nxx_out, nXX);
+}
+
+#ifndef BPE_MERGE_LOOP_MINBLOCKS
+#define BPE_MERGE_LOOP_MINBLOCKS 5  // 51 registers: the prefetched tile (16 registers) stays in registers while the staged tile is worked on
+#endif
+// The train loop's merge pass with resident CTAs (merge_loop = CTAs per SM): a CTA takes the tiles blockIdx.x,
+// blockIdx.x + gridDim.x, ... The one-CTA-per-tile kernel above keeps only 57 % of the warp slots busy (a CTA lives for
+// ~2 us: launch, load, test, exit), so here (1) the next tile's four vectors and its halo are requested as soon as the
+// current tile is staged, and travel while the CTA waits at the barrier and works on the staged tile; (2) the control
+// block is read once per CTA; (3) the delta bins live as long as the CTA and are flushed once.
+__global__ void __launch_bounds__(THREADS, BPE_MERGE_LOOP_MINBLOCKS) merge_loop_kernel(uint16_t* __restrict__ tok, const TileHalo<uint16_t>* __restrict__ halo,
+                                                        const StepCtl* __restrict__ ctl, uint32_t* __restrict__ cntL,
+                                                        uint32_t* __restrict__ cntR, uint32_t* nxx_out, uint32_t* nab_out,
+                                                        uint32_t bins_min_count, int backwards, uint32_t direct_max_count, uint32_t ntiles) {
+    using TokT = uint16_t;
+    static_assert(sizeof(TileHalo<TokT>) == 16, "a halo travels as one 16-byte vector");
+    __shared__ __align__(16) TokT ext[EXT];
+    __shared__ uint32_t bin_key[MERGE_NBIN];
+    __shared__ uint32_t bin_val[MERGE_NBIN];
+    __shared__ uint16_t q_pos[MERGE_QCAP];
+    __shared__ uint32_t q_n;
+    __shared__ uint32_t sh_runA;
+    constexpr int VEC = 16 / (int)sizeof(TokT);
+    constexpr int NV = TILE / VEC / THREADS;
+    const bool pair_filter = !(backwards & 2);
+    const bool back = (backwards & 1) != 0;
+    uint32_t it = blockIdx.x;
+    if (it >= ntiles) return;
+    uint32_t tile = back ? ntiles - 1u - it : it;
+    uint4 v[NV];
+    __shared__ __align__(16) uint4 hraw[2];  // halo of the current / the next tile: {l2 | l1 << 16, r0 | r1 << 16, r2, runA}
+    uint32_t hsel = 0;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(tok + (size_t)tile * TILE);
+#pragma unroll
+        for (int k = 0; k < NV; k++) v[k] = src[k * THREADS + (int)threadIdx.x];
+    }
+    BPE_GRID_DEP_WAIT();
+    BPE_GRID_DEP_LAUNCH();
+    if (threadIdx.x == 0) cp_async16(&hraw[0], halo + tile);  // (asynchronous: no register, nothing waits for it here)
+    if (ctl->halt) return;
+    const uint32_t Au = ctl->A, Bu = ctl->B, Xu = ctl->X;
+    const uint32_t mc = ctl->max_count;
+    const bool use_bins = mc >= bins_min_count;
+    const bool direct = mc < direct_max_count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) const_cast<StepCtl*>(ctl)->pass_step = ctl->step + 1u;
+    if (use_bins) for (int i = (int)threadIdx.x; i < MERGE_NBIN; i += THREADS) { bin_key[i] = EMPTY_KEY; bin_val[i] = 0; }
+    if (threadIdx.x >= 1 && threadIdx.x < 32) {  // the margin slots beyond the halo tokens stay holes for the CTA's lifetime
+        const int i = (int)threadIdx.x - 1;
+        if (i < OFF - 2) ext[i] = (TokT)0xFFFFu;
+        else if (OFF + TILE + 3 + (i - (OFF - 2)) < EXT) ext[OFF + TILE + 3 + (i - (OFF - 2))] = (TokT)0xFFFFu;
+    }
+    uint32_t nAB = 0, nXX = 0;
+    const TileHalo<TokT> h_unused = {};
+    while (true) {
+        uint32_t hitbits = 0;
+#pragma unroll
+        for (int k = 0; k < NV; k++) hitbits |= vec_has<TokT>(v[k], Au) ? (1u << k) : 0u;
+        bool any = hitbits != 0;
+        {   // stage the tile and its halo
+            uint4* dst = reinterpret_cast<uint4*>(ext + OFF);
+#pragma unroll
+            for (int k = 0; k < NV; k++) dst[k * THREADS + (int)threadIdx.x] = v[k];
+            if (threadIdx.x == 0) {
+                cp_async_wait_all();
+                const uint4 hq = hraw[hsel];
+                if ((hq.x >> 16) == Au) any = true;  // possible head duty
+                *reinterpret_cast<uint32_t*>(ext + OFF - 2) = hq.x;
+                *reinterpret_cast<uint32_t*>(ext + OFF + TILE) = hq.y;
+                ext[OFF + TILE + 2] = (TokT)hq.z;
+                sh_runA = hq.w;
+                q_n = 0;
+            }
+        }
+        const size_t base = (size_t)tile * TILE;
+        // the next tile's data: on its way while this tile is worked on
+        const uint32_t it_next = it + gridDim.x;
+        const bool more = it_next < ntiles;
+        const uint32_t tile_next = more ? (back ? ntiles - 1u - it_next : it_next) : tile;
+        if (more) {
+            const uint4* src = reinterpret_cast<const uint4*>(tok + (size_t)tile_next * TILE);
+#pragma unroll
+            for (int k = 0; k < NV; k++) v[k] = src[k * THREADS + (int)threadIdx.x];
+            hsel ^= 1u;
+            if (threadIdx.x == 0) cp_async16(&hraw[hsel], halo + tile_next);
+        }
+        if (__syncthreads_or(any ? 1 : 0)) {
+            tile_staged_path<TokT, true, true, NV, true>(ext, v, tok, base, h_unused, hitbits, Au, Bu, Xu, use_bins, direct, pair_filter, false, bin_key,
+                                                         bin_val, q_pos, &q_n, &sh_runA, cntL, cntR, nAB, nXX);
+            if (more) __syncthreads();  // everybody has read the staged tile before the next one replaces it
+        }
+        if (!more) break;
+        it = it_next;
+        tile = tile_next;
+    }
+    if (nAB) atomicAdd(nab_out, nAB);
+    if (nXX) atomicAdd(nxx_out, nXX);
+    if (use_bins) {
+        __syncthreads();
+        for (int i = (int)threadIdx.x; i < MERGE_NBIN; i += THREADS) {
+            const uint32_t k = bin_key[i];
+            if (k != EMPTY_KEY) atomicAdd((k & 0x10000u) ? &cntR[k & 0xFFFFu] : &cntL[k], bin_val[i]);
+        }
+    }
 }
 
 // =========================================================================================
@@ -1304,7 +1408,7 @@ __global__ void __launch_bounds__(THREADS, RING_CTAS_PER_SM) merge_tma_kernel(To
         any = hitbits != 0;
         if (threadIdx.x == 0 && h.l1 == A) any = true;  // possible head duty
         if (__syncthreads_or(any ? 1 : 0)) {
-            tile_staged_path<TokT, DELTAS, false, NV>(ext, v, tok, (size_t)tile * TILE, h, hitbits, Au, Bu, Xu, use_bins, false, false, bin_key, bin_val,
+            tile_staged_path<TokT, DELTAS, false, NV>(ext, v, tok, (size_t)tile * TILE, h, hitbits, Au, Bu, Xu, use_bins, false, false, true, bin_key, bin_val,
                                                       q_pos, &q_n, &sh_runA, cntL, cntR, nAB, nXX);
             __syncthreads();  // every thread is done with this stage
         }
