@@ -129,10 +129,15 @@ const char* bpe_last_error(const bpe_ctx* ctx);
  *                         a tile goes through the staged path only if a candidate is left. 0 (default): every tile that
  *                         holds an A is staged (measured 14 % faster on C3: early steps stage nearly every tile anyway and
  *                         the filter's instructions sit on the streaming path).
- *   "merge_direct"        K (default 8): a train step whose pair occurs fewer than K times per tile on average takes the
+ *   "merge_direct"        K (default 3): a train step whose pair occurs fewer than K times per tile on average takes the
  *                         queue-less staged path (every thread looks its own A's up; no candidate masks, no
  *                         shared-memory queue); 0: always the queued path (round 2's first profile: 45 % of the merge
  *                         pass's instructions were candidate masks and queue traffic on steps with ~3 occurrences per tile)
+ *   "merge_loop"          T (default 6): the train loop's merge pass runs ceil(tiles / T) CTAs, each takes T tiles (strided by
+ *                         the grid size); the next tile's vectors are prefetched into registers and its halo by cp.async
+ *                         while the staged tile is worked on, the control block is read once and the delta bins are
+ *                         flushed once per CTA. 0: one CTA per tile (C3 on one B200: 1,417 ms per training against
+ *                         1,253 ms with T = 6; T = 2 / 4 / 8 / 12: 1,349 / 1,268 / 1,256 / 1,264 ms).
  *   "merge_pairfilter"    1 (default): on the queue-less path a vector's A's are reduced, in registers, to those whose next slot
  *                         holds B or a hole (packed 16-bit minimum) before anything is looked up; 0: every A is looked up
  *   "merge_prestage"      1 (default): the train loop's merge pass copies every tile into shared memory before the barrier

@@ -42,18 +42,18 @@ def test_train_forced_replay_and_no_compaction(emu, ora):
     assert st["compactions"] > 0
 
 
-@pytest.mark.parametrize("loop,direct,pairfilter", [(1, 3, 1), (2, 0, 1), (3, 1 << 20, 0), (1000, 3, 1)])
+@pytest.mark.parametrize("loop,direct,pairfilter", [(0, 3, 1), (1, 3, 1), (2, 0, 1), (3, 1 << 20, 0), (7, 3, 1), (1000, 3, 1)])
 def test_train_resident_merge_ctas(emu, ora, taylor, loop, direct, pairfilter):
-    """merge_loop = CTAs per SM of the looped merge pass (a CTA takes every gridDim-th tile, the next tile and its halo are
-    prefetched, the delta bins live as long as the CTA); 1000 = as many CTAs as tiles (one round each). With a recount of
-    all pairs after every step."""
+    """merge_loop = tiles per CTA of the looped merge pass (a CTA takes every gridDim-th tile, the next tile and its halo are
+    prefetched, the delta bins live as long as the CTA); 1 = one tile per CTA, 1000 = one CTA takes them all. With a recount
+    of all pairs after every step."""
     rng = np.random.default_rng(12)
     try:
         for data, vocab in ((taylor[:14000], 300), (bytes(rng.integers(97, 100, size=5000, dtype=np.uint8)), 290),
                             (b"abab" * 300 + b"ba" * 200 + b"aab" * 100 + b"a" * 700, 275)):
             _train_check(emu, ora, data, vocab, verify_recount=1, merge_loop=loop, merge_direct=direct, merge_pairfilter=pairfilter)
     finally:
-        for k, v in (("merge_loop", 0), ("merge_direct", 3), ("merge_pairfilter", 1)):
+        for k, v in (("merge_loop", 6), ("merge_direct", 3), ("merge_pairfilter", 1)):
             emu.set_option(k, v)
 
 
