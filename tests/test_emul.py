@@ -42,18 +42,20 @@ def test_train_forced_replay_and_no_compaction(emu, ora):
     assert st["compactions"] > 0
 
 
-@pytest.mark.parametrize("loop,direct,pairfilter", [(0, 3, 1), (1, 3, 1), (2, 0, 1), (3, 1 << 20, 0), (7, 3, 1), (1000, 3, 1)])
-def test_train_resident_merge_ctas(emu, ora, taylor, loop, direct, pairfilter):
+@pytest.mark.parametrize("loop,direct,pairfilter,dbuf", [(0, 3, 1, 0), (1, 3, 1, 0), (2, 0, 1, 1), (3, 1 << 20, 0, 0), (7, 3, 1, 0), (1000, 3, 1, 0),
+                                                        (3, 3, 1, 1), (2, 1 << 20, 1, 1), (1000, 3, 1, 1)])
+def test_train_resident_merge_ctas(emu, ora, taylor, loop, direct, pairfilter, dbuf):
     """merge_loop = tiles per CTA of the looped merge pass (a CTA takes every gridDim-th tile, the next tile and its halo are
-    prefetched, the delta bins live as long as the CTA); 1 = one tile per CTA, 1000 = one CTA takes them all. With a recount
-    of all pairs after every step."""
+    prefetched, the delta bins live as long as the CTA); 1 = one tile per CTA, 1000 = one CTA takes them all; merge_dbuf = two staging buffers. With a
+    recount of all pairs after every step."""
     rng = np.random.default_rng(12)
     try:
         for data, vocab in ((taylor[:14000], 300), (bytes(rng.integers(97, 100, size=5000, dtype=np.uint8)), 290),
                             (b"abab" * 300 + b"ba" * 200 + b"aab" * 100 + b"a" * 700, 275)):
-            _train_check(emu, ora, data, vocab, verify_recount=1, merge_loop=loop, merge_direct=direct, merge_pairfilter=pairfilter)
+            _train_check(emu, ora, data, vocab, verify_recount=1, merge_loop=loop, merge_direct=direct, merge_pairfilter=pairfilter,
+                         merge_dbuf=dbuf)
     finally:
-        for k, v in (("merge_loop", 6), ("merge_direct", 3), ("merge_pairfilter", 1)):
+        for k, v in (("merge_loop", 6), ("merge_direct", 3), ("merge_pairfilter", 1), ("merge_dbuf", 0)):
             emu.set_option(k, v)
 
 

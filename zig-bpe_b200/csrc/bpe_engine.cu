@@ -69,7 +69,7 @@ struct bpe_ctx {
     std::string err;
     // options
     long verify_recount = 0, force_slow_tiebreak = 0, check_tiebreak = 0, compact_pct = 85, table_log2 = 0,
-         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 6, encode_filter = 1, encode_geom = 4, encode_seg_min_steps = 450, encode_tile = 7936, encode_try_tiles = 1, fuse_halo = 1, count_limit_log2 = 32, stream_chunk_mb = 128, stream_chunk_bytes = 0, merge_filter = 0, merge_direct = 3, merge_prestage = 1, merge_pairfilter = 1, merge_loop = 6, batch_steps = 16, pdl = 1, cache_max_mb = 8192;
+         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 6, encode_filter = 1, encode_geom = 4, encode_seg_min_steps = 450, encode_tile = 7936, encode_try_tiles = 1, fuse_halo = 1, count_limit_log2 = 32, stream_chunk_mb = 128, stream_chunk_bytes = 0, merge_filter = 0, merge_direct = 3, merge_prestage = 1, merge_pairfilter = 1, merge_loop = 6, merge_dbuf = 0, batch_steps = 16, pdl = 1, cache_max_mb = 8192;
     int num_sms = 148;
     DistComm dist;  // world == 1 when single GPU
     uint64_t launches = 0;
@@ -520,7 +520,10 @@ static int launch_merge(bpe_ctx* ctx, TokT* tok, const TileHalo<TokT>* halo, uin
         if constexpr (FROMCTL && DELTAS && std::is_same<TokT, uint16_t>::value) {
             if (ctx->merge_loop > 0 && !ctx->merge_filter) {  // every CTA takes merge_loop tiles (strided by the grid size)
                 const unsigned grid = (unsigned)std::max<uint64_t>(1, ((uint64_t)nt + (uint64_t)ctx->merge_loop - 1) / (uint64_t)ctx->merge_loop);
-                BPE_LAUNCH_PDL(merge_loop_kernel, grid, THREADS, ctx->stream, pdl, tok, halo, d_ctl, cntL, cntR, nxx, nab, bins_min, backwards, direct_max, nt);
+                if (ctx->merge_dbuf)
+                    BPE_LAUNCH_PDL(merge_loop_kernel<true>, grid, THREADS, ctx->stream, pdl, tok, halo, d_ctl, cntL, cntR, nxx, nab, bins_min, backwards, direct_max, nt);
+                else
+                    BPE_LAUNCH_PDL(merge_loop_kernel<false>, grid, THREADS, ctx->stream, pdl, tok, halo, d_ctl, cntL, cntR, nxx, nab, bins_min, backwards, direct_max, nt);
                 ctx->launches++;
                 return BPE_OK;
             }
@@ -2007,6 +2010,7 @@ int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value) {
     else if (s == "merge_prestage") ctx->merge_prestage = value;
     else if (s == "merge_pairfilter") ctx->merge_pairfilter = value;
     else if (s == "merge_loop") ctx->merge_loop = value;
+    else if (s == "merge_dbuf") ctx->merge_dbuf = value;
     else if (s == "batch_steps") ctx->batch_steps = value;
     else if (s == "pdl") ctx->pdl = value;
     else if (s == "cache_max_mb") ctx->cache_max_mb = value;

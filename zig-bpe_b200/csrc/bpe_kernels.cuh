@@ -1196,13 +1196,18 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_MINBLOCKS) merge_kernel(Tok
 // ~2 us: launch, load, test, exit), so here (1) the next tile's four vectors and its halo are requested as soon as the
 // current tile is staged, and travel while the CTA waits at the barrier and works on the staged tile; (2) the control
 // block is read once per CTA; (3) the delta bins live as long as the CTA and are flushed once.
+// DBUF: two staging buffers, tiles alternate between them. A buffer is then rewritten only after the barrier of the tile
+// in between, which every thread reaches after it has finished with the buffer: a tile of the queue-less path needs no
+// barrier of its own any more (the queued path keeps it: its queue is single).
+template <bool DBUF>
 __global__ void __launch_bounds__(THREADS, BPE_MERGE_LOOP_MINBLOCKS) merge_loop_kernel(uint16_t* __restrict__ tok, const TileHalo<uint16_t>* __restrict__ halo,
                                                         const StepCtl* __restrict__ ctl, uint32_t* __restrict__ cntL,
                                                         uint32_t* __restrict__ cntR, uint32_t* nxx_out, uint32_t* nab_out,
                                                         uint32_t bins_min_count, int backwards, uint32_t direct_max_count, uint32_t ntiles) {
     using TokT = uint16_t;
     static_assert(sizeof(TileHalo<TokT>) == 16, "a halo travels as one 16-byte vector");
-    __shared__ __align__(16) TokT ext[EXT];
+    __shared__ __align__(16) TokT ext_all[DBUF ? 2 * EXT : EXT];
+    TokT* ext = ext_all;
     __shared__ uint32_t bin_key[MERGE_NBIN];
     __shared__ uint32_t bin_val[MERGE_NBIN];
     __shared__ uint16_t q_pos[MERGE_QCAP];
@@ -1235,8 +1240,11 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_LOOP_MINBLOCKS) merge_loop_
     if (use_bins) for (int i = (int)threadIdx.x; i < MERGE_NBIN; i += THREADS) { bin_key[i] = EMPTY_KEY; bin_val[i] = 0; }
     if (threadIdx.x >= 1 && threadIdx.x < 32) {  // the margin slots beyond the halo tokens stay holes for the CTA's lifetime
         const int i = (int)threadIdx.x - 1;
-        if (i < OFF - 2) ext[i] = (TokT)0xFFFFu;
-        else if (OFF + TILE + 3 + (i - (OFF - 2)) < EXT) ext[OFF + TILE + 3 + (i - (OFF - 2))] = (TokT)0xFFFFu;
+#pragma unroll
+        for (int b = 0; b < (DBUF ? 2 : 1); b++) {
+            if (i < OFF - 2) ext_all[b * EXT + i] = (TokT)0xFFFFu;
+            else if (OFF + TILE + 3 + (i - (OFF - 2)) < EXT) ext_all[b * EXT + OFF + TILE + 3 + (i - (OFF - 2))] = (TokT)0xFFFFu;
+        }
     }
     uint32_t nAB = 0, nXX = 0;
     const TileHalo<TokT> h_unused = {};
@@ -1275,11 +1283,13 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_LOOP_MINBLOCKS) merge_loop_
         if (__syncthreads_or(any ? 1 : 0)) {
             tile_staged_path<TokT, true, true, NV, true>(ext, v, tok, base, h_unused, hitbits, Au, Bu, Xu, use_bins, direct, pair_filter, false, bin_key,
                                                          bin_val, q_pos, &q_n, &sh_runA, cntL, cntR, nAB, nXX);
-            if (more) __syncthreads();  // everybody has read the staged tile before the next one replaces it
+            // everybody has read the staged tile (and the queue) before the next one replaces it
+            if (more && (!DBUF || !direct || Au == Bu)) __syncthreads();
         }
         if (!more) break;
         it = it_next;
         tile = tile_next;
+        if (DBUF) ext = (ext == ext_all) ? ext_all + EXT : ext_all;
     }
     if (nAB) atomicAdd(nab_out, nAB);
     if (nXX) atomicAdd(nxx_out, nXX);
