@@ -483,7 +483,7 @@ def main():
         "clocks": clk,
         "e2e": e2e,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                     "traffic": traffic, "kernel": "merge_kernel<u16>", "peak_source": peak_src,
+                     "traffic": traffic, "kernel": "merge_loop_kernel (u16)", "peak_source": peak_src,
                      "bytes_per_launch": samp_bytes / max(merge_calls, 1), "avg_launch_ms": merge_ms / max(merge_calls, 1),
                      "launches_timed": int(merge_calls), "sampling": "every 32nd merge step, CUDA events on the library's stream",
                      "kernel_share_of_step": est_merge_ms_all / dev_ms if dev_ms and est_merge_ms_all else None,

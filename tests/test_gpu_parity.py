@@ -411,6 +411,26 @@ def test_train_alternative_merge_paths(gpu, ora, synth, taylor, impl):
     _train_check(gpu, ora, data, 256 + 300, merge_impl=impl)
 
 
+@pytest.mark.parametrize("opts", [dict(merge_loop=0), dict(merge_loop=0, merge_prestage=0), dict(merge_loop=0, merge_direct=0),
+                                  dict(merge_loop=1), dict(merge_loop=3, merge_direct=1 << 20, merge_pairfilter=0),
+                                  dict(merge_loop=50, merge_direct=0), dict(merge_loop=4, merge_dbuf=1)])
+def test_train_merge_pass_variants(gpu, ora, synth, taylor, opts):
+    """The looped merge pass (merge_loop tiles per CTA, prefetch, optional second staging buffer), the one-CTA-per-tile pass
+    with / without pre-staging, the queued and the queue-less staged path with / without the packed pair filter: all learn
+    what the oracle learns, with a recount of all pairs after every step on the smaller inputs."""
+    defaults = dict(merge_loop=6, merge_prestage=1, merge_direct=3, merge_pairfilter=1, merge_dbuf=0)
+    rng = np.random.default_rng(32)
+    try:
+        _train_check(gpu, ora, taylor, 400, check_tiebreak=1, **opts)
+        _train_check(gpu, ora, bytes(rng.integers(97, 101, size=200000, dtype=np.uint8)), 350, verify_recount=1, **opts)
+        _train_check(gpu, ora, b"xyz" + b"a" * 40961 + b"b" + b"a" * 8192 + b"cc" + b"a" * 12287 + b"q" + b"ab" * 9000, 300,
+                     verify_recount=1, **opts)
+        data = bytes(synth.generate(3_000_000, synth.SEED_C3, synth.BYTE))
+        _train_check(gpu, ora, data, 256 + 300, **opts)
+    finally:
+        _opts(gpu, **defaults)
+
+
 def test_train_long_run_on_random_bytes(gpu, ora):
     """A long training on random bytes ends in the regime where the maximum is 1-2 and (hundreds of) thousands of
     pairs tie: the heavy list holds the whole table there and ties beyond 1,024 keys go to the replay."""
