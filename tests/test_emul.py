@@ -9,7 +9,7 @@ from test_oracle import MAIN_ZIG_STRING, MAIN_ZIG_TOKENS, REF_TEST_MERGES
 
 
 def _train_check(emu, ora, data, vocab, **opts):
-    for k, v in {"verify_recount": 0, "check_tiebreak": 1, "force_slow_tiebreak": 0, "compact_pct": 85, "merge_impl": 0, **opts}.items():
+    for k, v in {"verify_recount": 0, "check_tiebreak": 1, "force_slow_tiebreak": 0, "compact_pct": 93, "merge_impl": 0, **opts}.items():
         emu.set_option(k, v)
     m, c = emu.train(data, vocab)
     om, oc = ora.train(data, vocab, fast=True)
@@ -105,7 +105,7 @@ def test_fused_halo_equals_a_halo_pass_per_step(emu, ora, taylor):
         om, oc = ora.train(data, vocab, fast=True)
         for fh in (1, 0):
             try:
-                for k, v in {"verify_recount": 0, "check_tiebreak": 0, "force_slow_tiebreak": 0, "compact_pct": 85, "merge_impl": 0}.items():
+                for k, v in {"verify_recount": 0, "check_tiebreak": 0, "force_slow_tiebreak": 0, "compact_pct": 93, "merge_impl": 0}.items():
                     emu.set_option(k, v)  # (ties settled by the replay do not pass through the first == second halt)
                 emu.set_option("fuse_halo", fh)
                 m, c = emu.train(data, vocab)
@@ -271,4 +271,4 @@ def test_encode_levels_round_robin_tiles(emu, ora):
             emu.set_option("encode_grid", g)
             assert np.array_equal(emu.encode(text, merges), ora.encode(text, merges, linear=False))
     finally:
-        emu.set_option("encode_grid", 6)
+        emu.set_option("encode_grid", 24)

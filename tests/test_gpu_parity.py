@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _opts(eng, **opts):
-    for k, v in {"verify_recount": 0, "check_tiebreak": 0, "force_slow_tiebreak": 0, "compact_pct": 85, "table_log2": 0,
+    for k, v in {"verify_recount": 0, "check_tiebreak": 0, "force_slow_tiebreak": 0, "compact_pct": 93, "table_log2": 0,
                  "max_steps": 0, "merge_impl": 0, **opts}.items():
         eng.set_option(k, v)
 

@@ -68,8 +68,8 @@ struct bpe_ctx {
     cudaStream_t stream = 0;
     std::string err;
     // options
-    long verify_recount = 0, force_slow_tiebreak = 0, check_tiebreak = 0, compact_pct = 85, table_log2 = 0,
-         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 6, encode_filter = 1, encode_geom = 4, encode_seg_min_steps = 450, encode_tile = 7936, encode_try_tiles = 1, fuse_halo = 1, count_limit_log2 = 32, stream_chunk_mb = 128, stream_chunk_bytes = 0, merge_filter = 0, merge_direct = 3, merge_prestage = 1, merge_pairfilter = 1, merge_loop = 6, merge_dbuf = 0, batch_steps = 16, pdl = 1, cache_max_mb = 8192;
+    long verify_recount = 0, force_slow_tiebreak = 0, check_tiebreak = 0, compact_pct = 93, encode_compact_pct = 85, table_log2 = 0,
+         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 24, encode_filter = 1, encode_geom = 4, encode_seg_min_steps = 450, encode_tile = 7936, encode_try_tiles = 1, fuse_halo = 1, count_limit_log2 = 32, stream_chunk_mb = 128, stream_chunk_bytes = 0, merge_filter = 0, merge_direct = 3, merge_prestage = 1, merge_pairfilter = 1, merge_loop = 6, merge_dbuf = 0, batch_steps = 16, pdl = 1, cache_max_mb = 8192;
     int num_sms = 148;
     DistComm dist;  // world == 1 when single GPU
     uint64_t launches = 0;
@@ -1597,7 +1597,7 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
             rc = read_merged(&fresh);
             if (rc) return rc;
             since_check = 0;
-            if (sq.n_slots > (size_t)TILE && sq.live * 100 < (uint64_t)sq.n_slots * (uint64_t)ctx->compact_pct && !last_step) {
+            if (sq.n_slots > (size_t)TILE && sq.live * 100 < (uint64_t)sq.n_slots * (uint64_t)ctx->encode_compact_pct && !last_step) {
                 rc = seq_compact(ctx, sq, nullptr);
                 if (rc) return rc;
                 if (st) st->compactions++;
@@ -1989,6 +1989,7 @@ int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value) {
     else if (s == "force_slow_tiebreak") ctx->force_slow_tiebreak = value;
     else if (s == "check_tiebreak") ctx->check_tiebreak = value;
     else if (s == "compact_pct") ctx->compact_pct = value;
+    else if (s == "encode_compact_pct") ctx->encode_compact_pct = value;
     else if (s == "table_log2") ctx->table_log2 = value;
     else if (s == "max_steps") ctx->max_steps = value;
     else if (s == "time_phases") ctx->time_phases = value;
