@@ -272,3 +272,17 @@ def test_encode_levels_round_robin_tiles(emu, ora):
             assert np.array_equal(emu.encode(text, merges), ora.encode(text, merges, linear=False))
     finally:
         emu.set_option("encode_grid", 24)
+
+
+def test_packed_halfword_primitives(tmp_path):
+    """vec_has / vec_mask / vec_candidates / vec_pair_candidates (packed 16-bit minimum, funnel shifts, zero-halfword tricks)
+    against their slot-by-slot definitions on 2 x 2,000,000 random vectors (tests/emul/vec_check.cpp)"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "vec_check"
+    subprocess.run(["g++", "-O2", "-std=c++17", f"-I{root}/tests/emul", f"-I{root}/zig-bpe_b200/csrc", f"{root}/tests/emul/vec_check.cpp",
+                    f"{root}/tests/emul/cuda_emul.cpp", "-o", str(exe)], check=True)
+    for seed in ("1", "7"):
+        out = subprocess.run([str(exe), seed], capture_output=True, text=True).stdout.split()
+        assert out and int(out[0]) == 2000000 and int(out[1]) == 0, out
