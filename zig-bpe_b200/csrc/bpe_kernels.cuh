@@ -1231,7 +1231,7 @@ __global__ void __launch_bounds__(THREADS, BPE_MERGE_LOOP_MINBLOCKS) merge_loop_
     BPE_GRID_DEP_WAIT();
     BPE_GRID_DEP_LAUNCH();
     if (threadIdx.x == 0) cp_async16(&hraw[0], halo + tile);  // (asynchronous: no register, nothing waits for it here)
-    if (ctl->halt) return;
+    if (ctl->halt) { cp_async_wait_all(); return; }  // (no copy into shared memory may outlive the CTA)
     const uint32_t Au = ctl->A, Bu = ctl->B, Xu = ctl->X;
     const uint32_t mc = ctl->max_count;
     const bool use_bins = mc >= bins_min_count;
