@@ -286,3 +286,19 @@ def test_packed_halfword_primitives(tmp_path):
     for seed in ("1", "7"):
         out = subprocess.run([str(exe), seed], capture_output=True, text=True).stdout.split()
         assert out and int(out[0]) == 2000000 and int(out[1]) == 0, out
+
+
+def test_encode_into_a_caller_owned_buffer(emu, ora, taylor):
+    """Engine.encode(out=...) hands the caller's uint16 buffer to bpe_encode (the C ABI's own contract: the caller allocates
+    n ids) and returns a view of it"""
+    data = taylor[:3000]
+    m, _ = emu.train(data, 290)
+    want = emu.encode(data, m)
+    buf = np.full(len(data) + 5, 0xABCD, dtype=np.uint16)
+    got = emu.encode(data, m, out=buf)
+    assert np.array_equal(got, want) and got.base is buf and (buf[len(data):] == 0xABCD).all()
+    assert np.array_equal(got, ora.encode(data, merges_array(m)))
+    with pytest.raises(ValueError):
+        emu.encode(data, m, out=np.zeros(10, dtype=np.uint16))
+    with pytest.raises(ValueError):
+        emu.encode(data, m, out=np.zeros(len(data), dtype=np.int16))

@@ -221,16 +221,22 @@ class Engine:
         return merges[: out_n.value].copy(), counts[: out_n.value].copy()
 
     # ---- encode -----------------------------------------------------------------------
-    def encode(self, text, merges) -> np.ndarray:
+    def encode(self, text, merges, out=None) -> np.ndarray:
+        """out: optional caller-owned uint16 buffer of at least len(text) ids (e.g. page-locked and reused between calls, as
+        a C caller of bpe_encode would do); the result is then a view of it"""
         a = _as_u8(text)
         m = _as_merges(merges)
-        out = np.empty(max(a.size, 1), dtype=np.uint16)  # the caller-allocated upper bound of the C ABI (n ids)
+        own = out is None
+        if own:
+            out = np.empty(max(a.size, 1), dtype=np.uint16)  # the caller-allocated upper bound of the C ABI (n ids)
+        elif out.dtype != np.uint16 or not out.flags["C_CONTIGUOUS"] or out.size < max(a.size, 1):
+            raise ValueError("out must be a contiguous uint16 array of at least len(text) elements")
         out_n = c_size_t(0)
         st = bpe_stats_t()
         rc = self.lib.bpe_encode(self._ctx, a.ctypes.data, a.size, m.ctypes.data, len(m), out.ctypes.data, byref(out_n), byref(st))
         self.last_stats = st.as_dict()
         self._check(rc)
-        if out_n.value * 4 < out.size:  # small result in a big buffer: shrink (the Zig shim does the same with its allocator)
+        if own and out_n.value * 4 < out.size:  # small result in a big buffer: shrink (the Zig shim does the same with its allocator)
             return out[: out_n.value].copy()
         return out[: out_n.value]
 
