@@ -385,7 +385,10 @@ def main():
         if not args.no_e2e:
             # (ids land in a page-locked buffer allocated before the timed region, like the corpus: a fresh pageable 2 GB
             # array would put its page faults into the measurement)
-            ids_pinned = torch.empty(max(n, 1), dtype=torch.int16, pin_memory=True).numpy().view(np.uint16)
+            try:
+                ids_pinned = torch.empty(max(n, 1), dtype=torch.int16, pin_memory=True).numpy().view(np.uint16)
+            except Exception:  # no page-locked memory left: let the mirror allocate a pageable array
+                ids_pinned = None
             barrier()
             t4 = time.perf_counter()
             ids_h = eng.encode(host, merges, out=ids_pinned)
