@@ -4,10 +4,14 @@
 //   generateInitialTokens :155-170   -> widen_kernel
 //   generateCodePointPairs :234-255  -> fused away (pairs are formed from the staged tile)
 //   countCodePointPairs :257-278     -> byte_pair_hist_kernel + seed_table_kernel once, then
-//                                       incremental deltas from merge_kernel via apply_kernel
-//   sortCodePointPairs :280-306, [0] :193 -> argmax_kernel + ties_kernel + zig_* tie kernels
-//   replaceTopPairWithNewToken :207-232   -> halo_kernel + merge_kernel (+ compaction kernels)
-//   encode :71-88                    -> the same halo/merge kernels driven by the merge list
+//                                       incremental deltas from the merge pass via apply_kernel
+//   sortCodePointPairs :280-306, [0] :193 -> select_body (fused into apply_kernel) / select_kernel + the exact host replay
+//   replaceTopPairWithNewToken :207-232   -> the merge pass: merge_loop_kernel in the train loop (looped CTAs, next tile
+//                                       prefetched), merge_kernel elsewhere; halos gathered by apply_kernel / halo_kernel;
+//                                       compaction kernels between batches
+//   encode :71-88                    -> level_kernel (one pass per level of commuting merges), merge_kernel for
+//                                       first == second pairs and irregular entries; bpe_tilenc.cuh / bpe_segenc.cuh
+//   decode :90-138                   -> decode_len / tile_scan64 / decode_scatter
 #pragma once
 #include "bpe_common.cuh"
 
