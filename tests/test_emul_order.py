@@ -14,5 +14,5 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_emulated_kernels_are_order_independent(order, emu):  # `emu` makes sure the emulation library is built
     env = dict(os.environ, EMUL_ORDER=order)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_emul.py"), "-x", "-q", "-p", "no:cacheprovider",
-                        "-k", "encode or train_small or golden_prefix"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
+                        "-k", "encode or train_small or golden_prefix or resident or queueless"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
