@@ -31,7 +31,7 @@ CFG = {
     "c2": dict(bytes=100_000_000, seed=sc.SEED_C2, variant=sc.UTF8, vocab=4096),
     "c3": dict(bytes=1_000_000_000, seed=sc.SEED_C3, variant=sc.BYTE, vocab=8192),
 }
-PREFIXES = (1, 10, 40, 100, 250, 500, 1000, 2000, 3000, 3840, 4000, 5000, 6000, 7000, 7936)
+PREFIXES = (1, 10, 40, 100, 250, 500, 1000, 2000, 3000, 3840, 4000, 4971, 5000, 5500, 6000, 6500, 7000, 7500, 7936)
 LINE = re.compile(r"merge (\d+)/(\d+): \((\d+),(\d+)\) -> (\d+) had (\d+) occurrences")
 
 
@@ -40,6 +40,9 @@ def main():
     ap.add_argument("cfg", choices=sorted(CFG))
     ap.add_argument("--workdir", default="/tmp/gold")
     ap.add_argument("--collect", action="store_true", help="do not run the oracle, parse <workdir>/<cfg>.log")
+    ap.add_argument("--gpu-verified", type=int, default=None,
+                    help="record that a B200 training was compared with the first N merges of this list (tools/check_c3_golden.py); "
+                         "the GPU test asserts that many, bench.py reports the comparison with every prefix hash")
     a = ap.parse_args()
     c = CFG[a.cfg]
     os.makedirs(a.workdir, exist_ok=True)
@@ -78,6 +81,9 @@ def main():
            "how": "oracle/bpe_oracle train <corpus> <vocab> <out> -1 1 1 (fast mode, verbose), tools/make_golden_big.py"}
     p = os.path.join(gold, "big_sha256.json")
     allrec = json.load(open(p)) if os.path.exists(p) else {}
+    gv = a.gpu_verified if a.gpu_verified is not None else allrec.get(a.cfg, {}).get("gpu_verified_merges")
+    if gv is not None:
+        rec["gpu_verified_merges"] = min(int(gv), len(merges))
     allrec[a.cfg] = rec
     json.dump(allrec, open(p, "w"), indent=1, sort_keys=True)
     print(json.dumps(rec, indent=1))
