@@ -57,7 +57,8 @@ typedef struct bpe_stats_t {
      * the context's stream between launches, resolved after the run; no extra synchronisation):
      * [0] load+initial count  [1] argmax+ties  [2] tie occupancy kernels  [3] table replay
      * [4] halo  [5] merge  [6] apply deltas  [7] compaction  [8] table rebuild / zcnt rebuild
-     * [9] host gap (status read-back until the next launch)  [10] profile 3: slots scanned by the sampled
+     * [9] host gap (status read-back until the next launch); encode with "encode_fuse": kernel_calls[9] / kernel_calls[8] =
+     * fused level groups that went through / whose halos did not cover their levels (redone level by level)  [10] profile 3: slots scanned by the sampled
      * merge launches; encode: kernel_calls[10] = the encoder that produced the ids (0 passes, 1 segment kernel,
      * 2 tile kernel)  [11] encode: time of the tile / segment kernel; kernel_calls[11] = 1 when it produced the
      * result, 2 when it gave up (no common token at a seam, ...) and another encoder ran instead, 0 when not tried */
@@ -135,6 +136,12 @@ const char* bpe_last_error(const bpe_ctx* ctx);
  *                         queue-less staged path (every thread looks its own A's up; no candidate masks, no
  *                         shared-memory queue); 0: always the queued path (round 2's first profile: 45 % of the merge
  *                         pass's instructions were candidate masks and queue traffic on steps with ~3 occurrences per tile)
+ *   "encode_fuse"         K (2..8; default 0 = off): level passes of encode in groups of up to K consecutive levels per
+ *                         residency of a tile (bpe_groupenc.cuh): one role look-up per slot per group, per-level queues,
+ *                         30 live tokens of halo per side with a per-tile check that they covered the group (else the
+ *                         group is redone level by level). Single GPU, u16 ids below 16,384. Written after the round's last
+ *                         GPU lease: equal to the oracle under the CPU emulation (tests, tools/fuzz_emul_encode.py), not
+ *                         yet run on a GPU, hence off.
  *   "merge_loop"          T (default 6): the train loop's merge pass runs ceil(tiles / T) CTAs, each takes T tiles (strided by
  *                         the grid size); the next tile's vectors are prefetched into registers and its halo by cp.async
  *                         while the staged tile is worked on, the control block is read once and the delta bins are

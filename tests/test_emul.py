@@ -199,9 +199,15 @@ def _encode_both(emu, ora, data, merges):
             emu.set_option("encode_filter", filt)  # 1: byte role map + successor filter (MODE 1); 2: pair Bloom filter (MODE 2)
             got = emu.encode(data, merges)
             assert np.array_equal(got, want), (impl, filt, merges[:8])
+        emu.set_option("encode_impl", 2)
+        for fuse in (2, 3, 8):  # fused level groups (bpe_groupenc.cuh)
+            emu.set_option("encode_fuse", fuse)
+            got = emu.encode(data, merges)
+            assert np.array_equal(got, want), ("fuse", fuse, merges[:8])
     finally:
         emu.set_option("encode_impl", 0)
         emu.set_option("encode_filter", 2)
+        emu.set_option("encode_fuse", 0)
     return want
 
 

@@ -475,3 +475,17 @@ def test_encode_filter_variant(gpu, ora, synth):
     finally:
         gpu.set_option("encode_filter", 2)
         gpu.set_option("encode_impl", 0)
+
+
+@pytest.mark.xfail(strict=False, reason="bpe_groupenc.cuh was written after the round's last GPU lease: equal to the oracle under the CPU "
+                                        "emulation, never run on a GPU; off by default (encode_fuse = 0)")
+def test_encode_fused_level_groups_experimental():
+    """LAST test of the GPU tier, in a process of its own (a fault in the new kernel must not touch the tests above):
+    `encode_fuse` = 2 / 4 / 8 must give the ids of the level passes on a 50 MB corpus with 1,792 merges
+    (tools/fuse_gpu_check.py prints the timings)."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(GOLDEN), "..", "tools", "fuse_gpu_check.py"), "5e7", "2048"],
+                       capture_output=True, text=True, timeout=300)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]

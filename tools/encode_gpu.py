@@ -18,7 +18,7 @@ out = {"bytes": n, "merges": int(len(m)), "train_ms": round(eng.last_stats["devi
 if os.environ.get("ENC_DEBUG"):
     eng.set_option("debug", 1)  # the tile encoder reports ranges / rounds per window on stderr
 ref = None
-DEFAULTS = {"encode_grid": 24, "encode_filter": 1, "encode_geom": 4, "encode_tile": 7936}
+DEFAULTS = {"encode_fuse": 0, "encode_grid": 24, "encode_filter": 1, "encode_geom": 4, "encode_tile": 7936}
 for var in variants:
     parts = var.split(":")
     eng.set_option("encode_impl", int(parts[0]))

@@ -18,6 +18,7 @@
 #include "bpe_kernels.cuh"
 #include "bpe_segenc.cuh"
 #include "bpe_tilenc.cuh"
+#include "bpe_groupenc.cuh"
 #include "tiebreak_host.hpp"
 #include "dist_comm.hpp"
 
@@ -69,7 +70,7 @@ struct bpe_ctx {
     std::string err;
     // options
     long verify_recount = 0, force_slow_tiebreak = 0, check_tiebreak = 0, compact_pct = 93, encode_compact_pct = 85, table_log2 = 0,
-         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 24, encode_filter = 1, encode_geom = 4, encode_seg_min_steps = 450, encode_tile = 7936, encode_try_tiles = 1, fuse_halo = 1, count_limit_log2 = 32, stream_chunk_mb = 128, stream_chunk_bytes = 0, merge_filter = 0, merge_direct = 3, merge_prestage = 1, merge_pairfilter = 1, merge_loop = 6, merge_dbuf = 0, batch_steps = 16, pdl = 1, cache_max_mb = 8192;
+         max_steps = 0, time_phases = 0, profile = 0, debug = 0, merge_impl = 0, xchg_impl = 0, encode_impl = 0, encode_grid = 24, encode_filter = 1, encode_geom = 4, encode_seg_min_steps = 450, encode_tile = 7936, encode_try_tiles = 1, fuse_halo = 1, count_limit_log2 = 32, stream_chunk_mb = 128, stream_chunk_bytes = 0, merge_filter = 0, merge_direct = 3, merge_prestage = 1, merge_pairfilter = 1, merge_loop = 6, merge_dbuf = 0, encode_fuse = 0, batch_steps = 16, pdl = 1, cache_max_mb = 8192;
     int num_sms = 148;
     DistComm dist;  // world == 1 when single GPU
     uint64_t launches = 0;
@@ -1559,11 +1560,81 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
         if (st) st->scanned_slots += sq.n_slots;
         return BPE_OK;
     };
+    // encode_fuse = K > 1: up to K consecutive level steps go through ONE residency of every tile (bpe_groupenc.cuh)
+    const int fuse_k = (std::is_same<TokT, uint16_t>::value && !multi && max_id < (uint32_t)LVL_BYTE_IDS_MAX)
+                           ? (int)std::min<long>(std::max<long>(ctx->encode_fuse, 0), GRP_MAXLV) : 0;
+    DevBuf deep_halo, grp_res;
+    int fuse_now = fuse_k;  // halved when a group's halos did not cover its levels, grown back by one per group that went through
+    // steps [s0, s1): level steps with adjacent entries in `ents`. *ok = false: the taint reached a tile, nothing was changed.
+    auto group_pass = [&](size_t s0, size_t s1, bool* ok) -> int {
+        const uint32_t nt = sq.ntiles();
+        if (!deep_halo.p) {
+            CU(deep_halo.alloc((size_t)nt * sizeof(DeepHalo)));  // (the first group sees the largest tile count)
+            CU(grp_res.alloc(sizeof(GroupResult)));
+            CU(cudaFuncSetAttribute(group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)group_smem_bytes(GRP_HASH_MAX, LVL_BYTE_IDS_MAX)));
+        }
+        GroupDesc gd;
+        memset(&gd, 0, sizeof gd);
+        uint32_t total = 0;
+        for (size_t k = s0; k < s1; k++) { total += steps[k].cnt; gd.end[k - s0] = total; }
+        gd.nlev = (uint32_t)(s1 - s0);
+        for (uint32_t k = gd.nlev; k < (uint32_t)GRP_MAXLV; k++) gd.end[k] = total;
+        uint32_t hash_log2 = 6;
+        while ((1u << hash_log2) < 2u * total) hash_log2++;
+        const uint32_t role_bytes = ((max_id + 1u + 15u) / 16u) * 16u;
+        CU(cudaMemsetAsync(grp_res.p, 0, sizeof(GroupResult), ctx->stream));
+        BPE_LAUNCH(deep_halo_kernel, (nt + HALO_THREADS - 1) / HALO_THREADS, HALO_THREADS, ctx->stream, reinterpret_cast<const uint16_t*>(sq.tok()),
+                   sq.n_slots, nt, deep_halo.template as<DeepHalo>());
+        const uint32_t grid = ctx->encode_grid > 0   ? std::min<uint32_t>(nt, (uint32_t)ctx->encode_grid * (uint32_t)ctx->num_sms)
+                              : ctx->encode_grid < 0 ? std::min<uint32_t>(nt, (uint32_t)(-ctx->encode_grid))
+                                                     : nt;
+        const int backwards = (int)(pass_index++ & 1u);  // (not inside the launch: the emulation evaluates the arguments once per thread)
+        BPE_LAUNCH_SMEM(group_kernel, grid, THREADS, group_smem_bytes((int)(1u << hash_log2), (int)role_bytes), ctx->stream,
+                        reinterpret_cast<const uint16_t*>(sq.tok()), reinterpret_cast<uint16_t*>(sq.other()),
+                        (const DeepHalo*)deep_halo.template as<DeepHalo>(),
+                        (const LevelEntry*)ents_buf.template as<LevelEntry>() + steps[s0].off, gd, grp_res.template as<GroupResult>(), backwards, nt,
+                        hash_log2, role_bytes);
+        ctx->launches += 2;
+        CU(cudaGetLastError());
+        GroupResult gr;
+        CU(cudaMemcpyAsync(&gr, grp_res.p, sizeof gr, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (st) st->scanned_slots += sq.n_slots;
+        *ok = gr.fail == 0;
+        if (st) st->kernel_calls[*ok ? 9 : 8]++;  // encode: fused level groups that went through / that were redone level by level
+        if (*ok) {  // the other buffer now holds the sequence
+            sq.cur ^= 1;
+            sq.live -= gr.merged;
+        }
+        return BPE_OK;
+    };
     size_t since_check = 0;
     for (size_t si = 0; si < steps.size() && (n > 1 || multi); si++) {
         const EncStep& es = steps[si];
-        const bool last_step = si + 1 == steps.size();
-        if (es.single < 0) {
+        bool last_step = si + 1 == steps.size();
+        if (es.single < 0 && fuse_k > 1) {
+            size_t sj = si + 1;
+            uint32_t total = es.cnt;
+            while (sj < steps.size() && steps[sj].single < 0 && (int)(sj - si) < fuse_now && steps[sj].off == steps[sj - 1].off + steps[sj - 1].cnt &&
+                   total + steps[sj].cnt <= (uint32_t)GRP_PAIRS_MAX) { total += steps[sj].cnt; sj++; }
+            bool grouped = false;
+            if (sj - si > 1) {
+                rc = group_pass(si, sj, &grouped);
+                if (rc) return rc;
+                fuse_now = grouped ? std::min(fuse_k, fuse_now + 1) : std::max(1, fuse_now / 2);
+            } else if (fuse_now < fuse_k) {
+                fuse_now++;  // (single steps after a failure: try groups again, growing)
+            }
+            if (grouped) {
+                si = sj - 1;
+                last_step = si + 1 == steps.size();
+                since_check = 32;  // (the group's merges are in sq.live already; the compaction check below runs)
+            } else {
+                rc = one_pass(0, 0, 0, es.off, es.cnt);
+                if (rc) return rc;
+                since_check += (pass_index <= 8u) ? 32 : 8;
+            }
+        } else if (es.single < 0) {
             // a level pass can remove a large share of the tokens: the first ones do most of the merging, so the live count
             // is read back (one host round trip) after each of the first 8 level passes and after every 4th later on
             rc = one_pass(0, 0, 0, es.off, es.cnt);
@@ -2012,6 +2083,7 @@ int bpe_ctx_set_option(bpe_ctx* ctx, const char* name, long value) {
     else if (s == "merge_pairfilter") ctx->merge_pairfilter = value;
     else if (s == "merge_loop") ctx->merge_loop = value;
     else if (s == "merge_dbuf") ctx->merge_dbuf = value;
+    else if (s == "encode_fuse") ctx->encode_fuse = value;
     else if (s == "batch_steps") ctx->batch_steps = value;
     else if (s == "pdl") ctx->pdl = value;
     else if (s == "cache_max_mb") ctx->cache_max_mb = value;
