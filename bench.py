@@ -398,6 +398,19 @@ def main():
                 dist.all_reduce(te2, op=dist.ReduceOp.MAX)
             enc["e2e"] = {"value": total_bytes / 1e9 / (float(te2[0]) / 1000.0), "unit": "GB/s", "h2d_bytes_per_step": total_bytes, "d2h_bytes_per_step": 2 * ids_total}
             assert len(ids_h) == n_ids
+        # The fused level groups of encode (bpe_groupenc.cuh, "encode_fuse") were written after the round's last GPU lease and are
+        # off by default; this is their first run on a GPU, in a process of its own so that nothing it does can touch the numbers
+        # above: same corpus, same merges, device-resident, level passes vs groups of 4 / 8 levels, identical ids required.
+        if world == 1 and not args.max_steps and os.environ.get("BPE_BENCH_FUSED", "1") != "0":
+            try:
+                import subprocess
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "encode_gpu.py"), str(total_bytes), str(args.vocab),
+                                    "2,2:encode_fuse=4,2:encode_fuse=8"], capture_output=True, text=True, timeout=240)
+                last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+                enc["fused_groups_experimental"] = json.loads(last[-1]) if (r.returncode == 0 and last) else {
+                    "error": f"rc={r.returncode}", "stderr_tail": r.stderr[-300:]}
+            except Exception as e:  # noqa: BLE001 — never let the experiment break the bench line
+                enc["fused_groups_experimental"] = {"error": repr(e)[:300]}
         # N-invariant hash of the whole encoding: rank 0 hashes the ranks' ids in shard order
         ids_dev = d_out[:n_ids]
         if rank == 0:

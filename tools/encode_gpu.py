@@ -35,7 +35,8 @@ for var in variants:
         best = dt if best is None else min(best, dt)
     st = eng.last_stats
     out[f"impl{var}"] = {"s": round(best, 4), "GBps": round(n / 1e9 / best, 2), "launches": int(st["kernel_launches"]), "compactions": int(st["compactions"]), "ids": int(k),
-                          "encoder": int(st["kernel_calls"][10]), "verdict": int(st["kernel_calls"][11]), "kernel_ms": round(st["kernel_ms"][11], 3), "device_ms": round(st["device_ms"], 3)}
+                          "encoder": int(st["kernel_calls"][10]), "verdict": int(st["kernel_calls"][11]), "kernel_ms": round(st["kernel_ms"][11], 3), "device_ms": round(st["device_ms"], 3),
+                          "fused_groups_ok_redone": [int(st["kernel_calls"][9]), int(st["kernel_calls"][8])]}
     if ref is None:
         ref = d_ids[:k].clone()
     else:
