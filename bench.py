@@ -403,12 +403,11 @@ def main():
         # above: same corpus, same merges, device-resident, level passes vs groups of 4 / 8 levels, identical ids required.
         if world == 1 and not args.max_steps and os.environ.get("BPE_BENCH_FUSED", "1") != "0":
             try:
-                import subprocess
-                r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "encode_gpu.py"), str(total_bytes), str(args.vocab),
+                fr = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "encode_gpu.py"), str(total_bytes), str(args.vocab),
                                     "2,2:encode_fuse=4,2:encode_fuse=8"], capture_output=True, text=True, timeout=240)
-                last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-                enc["fused_groups_experimental"] = json.loads(last[-1]) if (r.returncode == 0 and last) else {
-                    "error": f"rc={r.returncode}", "stderr_tail": r.stderr[-300:]}
+                last = [ln for ln in fr.stdout.splitlines() if ln.startswith("{")]
+                enc["fused_groups_experimental"] = json.loads(last[-1]) if (fr.returncode == 0 and last) else {
+                    "error": f"rc={fr.returncode}", "stderr_tail": fr.stderr[-300:]}
             except Exception as e:  # noqa: BLE001 — never let the experiment break the bench line
                 enc["fused_groups_experimental"] = {"error": repr(e)[:300]}
         # N-invariant hash of the whole encoding: rank 0 hashes the ranks' ids in shard order
