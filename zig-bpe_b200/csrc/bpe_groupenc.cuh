@@ -57,19 +57,25 @@ __global__ void __launch_bounds__(HALO_THREADS) deep_halo_kernel(const uint16_t*
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles) return;
     DeepHalo h;
+    // (16-byte loads: ~5 dependent round trips per side instead of ~35; positions stay multiples of 8)
+    const uint4* tv = reinterpret_cast<const uint4*>(tok);
     int k = 0;
     size_t p = (size_t)t * TILE;
     while (k < GRP_H && p > 0) {
-        const uint16_t v = tok[--p];
-        if (v != 0xFFFFu) h.l[k++] = v;
+        p -= 8;
+        uint32_t w[8];
+        unpack_vec<uint16_t>(tv[p / 8], w);
+        for (int i = 7; i >= 0 && k < GRP_H; i--) if (w[i] != 0xFFFFu) h.l[k++] = (uint16_t)w[i];
     }
     h.lend = (k < GRP_H) ? 1 : 0;  // ran into the start of the sequence (a full halo may still have live tokens before it)
     for (; k < GRP_H; k++) h.l[k] = 0xFFFFu;
     k = 0;
     p = ((size_t)t + 1) * TILE;
     while (k < GRP_H && p < n_slots) {
-        const uint16_t v = tok[p++];
-        if (v != 0xFFFFu) h.r[k++] = v;
+        uint32_t w[8];
+        unpack_vec<uint16_t>(tv[p / 8], w);
+        p += 8;
+        for (int i = 0; i < 8 && k < GRP_H; i++) if (w[i] != 0xFFFFu) h.r[k++] = (uint16_t)w[i];
     }
     h.rend = (k < GRP_H) ? 1 : 0;
     for (; k < GRP_H; k++) h.r[k] = 0xFFFFu;
