@@ -1564,7 +1564,9 @@ static int encode_passes(bpe_ctx* ctx, const uint8_t* d_text, size_t n, const bp
     const int fuse_k = (std::is_same<TokT, uint16_t>::value && !multi && max_id < (uint32_t)LVL_BYTE_IDS_MAX)
                            ? (int)std::min<long>(std::max<long>(ctx->encode_fuse, 0), GRP_MAXLV) : 0;
     DevBuf deep_halo, grp_res;
-    int fuse_now = fuse_k;  // halved when a group's halos did not cover its levels, grown back by one per group that went through
+    // groups start small (the first levels merge a third of the tokens each, halos included), grow by one level per group that went
+    // through and are halved when a group's halos did not cover its levels
+    int fuse_now = std::min(fuse_k, 2);
     // steps [s0, s1): level steps with adjacent entries in `ents`. *ok = false: the taint reached a tile, nothing was changed.
     auto group_pass = [&](size_t s0, size_t s1, bool* ok) -> int {
         const uint32_t nt = sq.ntiles();
