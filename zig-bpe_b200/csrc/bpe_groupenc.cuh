@@ -185,7 +185,8 @@ __global__ void __launch_bounds__(THREADS, 3) group_kernel(const uint16_t* __res
         }
         if (threadIdx.x < GRP_MAXLV) qn[threadIdx.x] = 0u;
         if (threadIdx.x == GRP_MAXLV) qover = 0u;
-        for (int i = (int)threadIdx.x; i < GRP_EXT / 4; i += THREADS) reinterpret_cast<uint32_t*>(qmask)[i] = 0u;
+        static_assert(GRP_EXT % 16 == 0, "the queue masks are cleared in 16-byte stores");
+        for (int i = (int)threadIdx.x; i < GRP_EXT / 16; i += THREADS) reinterpret_cast<uint4*>(qmask)[i] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
         // ---- one look at every slot: queue it for the levels its token can start a pair in ----
         auto enqueue = [&](int s, uint32_t t) {
